@@ -750,7 +750,8 @@ class CrossSite:
     P_is_identity: Any = None
 
 
-def cross_site(m: Model, be, edge_rates_user: Optional[Sequence[float]] = None) -> CrossSite:
+def cross_site(m: Model, be, edge_rates_user: Optional[Sequence[float]] = None,
+               compute_P: bool = True) -> CrossSite:
     n = m.n
     t = m.tree
     prior_mp, rates_mp, expect_mp = rate_mixture_summary(m)
@@ -796,7 +797,7 @@ def cross_site(m: Model, be, edge_rates_user: Optional[Sequence[float]] = None) 
     for i in range(t.edge_count):
         er[t.order[i]] = be.num(er_user[i])
     P = np.empty((C, t.edge_count, n, n), dtype=(np.float64 if be.name == "fp64" else object))
-    for c in range(C):
+    for c in range(C if compute_P else 0):
         for e in range(t.edge_count):
             s = rates[c] * er[e]
             if s == 0:
@@ -1339,6 +1340,38 @@ def run_trans(root, mode="mp"):
                     if req_user[e]:
                         acc.accumulate([s, e, k2], X[k, t.order[e]])
     return acc.to_json()
+
+
+def per_site_marginal(m: Model, be, sites: Sequence[int]):
+    """[S', N, n] posterior marginals (arbplfmarginal.c:142-257), no reductions."""
+    t = m.tree
+    cs = cross_site(m, be)
+    base = _base_vectors(m, be, sites)
+    S = base.shape[0]
+    site_L = be.zeros(S)
+    out = be.zeros(S, t.node_count, m.n)
+    for c in range(cs.C):
+        lh, node, nconst, edge = site_lhood(m, cs, be, base, c, keep_edges=True)
+        post = cs.prior[c] * lh
+        live = np.array([bool(x != 0) for x in post])
+        site_L = site_L + np.where(live, post, be.num(0))
+        fn, fe = site_forward(m, cs, be, base, c, edge)
+        for a in range(t.node_count):
+            contrib = cs.prior[c] * (fn[a] * node[a])
+            out[:, a, :] = out[:, a, :] + np.where(live[:, None], contrib, be.num(0))
+    return out / site_L[:, None, None]
+
+
+def per_site_edge_expect(m: Model, be, sites: Sequence[int], L, trans: bool, requested_csr=None):
+    """[S', E] (csr order) dwell / trans expectations for a Frechet direction L."""
+    t = m.tree
+    cs = cross_site(m, be)
+    if requested_csr is None:
+        requested_csr = [True] * t.edge_count
+    base = _base_vectors(m, be, sites)
+    F = frechet_matrices(cs, be, be.asarray(L) if not isinstance(L, np.ndarray) or L.dtype != object else L,
+                         requested_csr)
+    return _edge_expectations(m, cs, be, base, F, requested_csr, trans=trans), cs
 
 
 PROGRAMS = {

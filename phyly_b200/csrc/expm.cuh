@@ -1,0 +1,194 @@
+/*
+ * K1/K2: batched matrix exponentials in double-double, one CTA per
+ * (rate category, edge).
+ *
+ * Replaces arb_mat_exp in _update_transition_matrices (cross_site_ws.c:150-168)
+ * and the 2n x 2n block exponential of _arb_mat_exp_frechet (util.c:500-548).
+ *
+ * Algorithm (not Arb's): A = r_c t_e Q is a rate matrix (off-diagonal >= 0, rows
+ * sum to 0).  With mu = max_i |A_ii| and s = ceil(log2 mu)^+,
+ *     exp(A) = ( e^{-mu/2^s} exp(B) )^(2^s),      B = (A + mu I)/2^s >= 0 .
+ * exp(B) is a Taylor series of non-negative terms (no cancellation, so every
+ * entry keeps full relative accuracy) and the squarings multiply non-negative
+ * matrices.  The Frechet block exp([[A,L],[0,A]]) keeps its block-triangular
+ * structure through both stages:
+ *     X_k = B X_{k-1}/k,  Y_k = (B Y_{k-1} + L_s X_{k-1})/k ;  (X,Y)^2 = (X X, X Y + Y X).
+ * Everything runs in double-double and is rounded to fp64 on output, together
+ * with D = scale * Q * P (the derivative matrices), which needs the extra
+ * digits when P is close to its stationary limit.
+ */
+#pragma once
+#include "dd.h"
+
+struct ExpmArgs {
+    int n, E, C;
+    const double *q_hi, *q_lo;       /* scaled rate matrix, n*n */
+    const double *l_hi, *l_lo;       /* Frechet direction or NULL */
+    const double *edge_rate;         /* [E] */
+    const double *cat_rate;          /* [C] */
+    const unsigned char *edge_mask;  /* [E] or NULL */
+    double *P;                       /* [C][E][n][n] or NULL */
+    double *D;                       /* [C][E][n][n] = cat_rate * Q * P, or NULL */
+    double *F;                       /* [C][E][n][n] Frechet block, or NULL */
+    int f_scale_mode;                /* 0: F ; 1: F * cat_rate * edge_rate */
+    dd_t *ws;                        /* global workspace (8*n*n dd per CTA) or NULL => shared */
+};
+
+__device__ __forceinline__ void dd_matmul(dd_t *Cm, const dd_t *A, const dd_t *B, int n, dd_t scale, bool use_scale)
+{
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+        int i = idx / n, j = idx - i * n;
+        dd_t acc = dd_make(0.0, 0.0);
+        for (int k = 0; k < n; k++) {
+            dd_t a = A[i * n + k];
+            if (a.hi == 0.0) continue;
+            acc = dd_add(acc, dd_mul(a, B[k * n + j]));
+        }
+        if (use_scale) acc = dd_mul(acc, scale);
+        Cm[idx] = acc;
+    }
+}
+
+/* Cm = (A*B + A2*B2) * scale */
+__device__ __forceinline__ void dd_matmul2(dd_t *Cm, const dd_t *A, const dd_t *B, const dd_t *A2, const dd_t *B2,
+                                           int n, dd_t scale, bool use_scale)
+{
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+        int i = idx / n, j = idx - i * n;
+        dd_t acc = dd_make(0.0, 0.0);
+        for (int k = 0; k < n; k++) {
+            dd_t a = A[i * n + k];
+            if (a.hi != 0.0) acc = dd_add(acc, dd_mul(a, B[k * n + j]));
+            dd_t a2 = A2[i * n + k];
+            if (a2.hi != 0.0) acc = dd_add(acc, dd_mul(a2, B2[k * n + j]));
+        }
+        if (use_scale) acc = dd_mul(acc, scale);
+        Cm[idx] = acc;
+    }
+}
+
+/* e^{-x} for 0 <= x <= 1 in double-double (Taylor of e^{x}, then reciprocal) */
+__device__ __forceinline__ dd_t dd_exp_neg_small(dd_t x)
+{
+    dd_t term = dd_make(1.0, 0.0), sum = dd_make(1.0, 0.0);
+    for (int k = 1; k <= 34; k++) {
+        term = dd_div_d(dd_mul(term, x), (double)k);
+        sum = dd_add(sum, term);
+        if (term.hi < 1e-36) break;
+    }
+    return dd_div(dd_make(1.0, 0.0), sum);
+}
+
+__global__ void __launch_bounds__(256) expm_dd_kernel(ExpmArgs a)
+{
+    extern __shared__ __align__(16) unsigned char expm_smem[];
+    const int n = a.n, nn = n * n;
+    const int e = blockIdx.x, c = blockIdx.y;
+    if (a.edge_mask && !a.edge_mask[e]) {
+        /* unrequested edge: leave zeros in F (evaluate_site_frechet.c:24-38 never uses them) */
+        if (a.F) for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) a.F[((size_t)c * a.E + e) * nn + idx] = 0.0;
+        if (!a.P && !a.D) return;
+    }
+    const bool want_f = (a.F != nullptr) && !(a.edge_mask && !a.edge_mask[e]);
+    dd_t *base = a.ws ? a.ws + ((size_t)(c * a.E + e)) * 8 * nn : reinterpret_cast<dd_t *>(expm_smem);
+    dd_t *B = base, *X = base + nn, *SX = base + 2 * nn, *T = base + 3 * nn;
+    dd_t *Ls = base + 4 * nn, *Y = base + 5 * nn, *SY = base + 6 * nn, *T2 = base + 7 * nn;
+
+    const double r = a.cat_rate[c], t = a.edge_rate[e];
+    const dd_t rt = dd_two_prod(r, t);
+
+    __shared__ double sh_mu;
+    __shared__ int sh_s;
+    /* A = rt * Q ; find mu */
+    if (threadIdx.x == 0) {
+        double mu = 0.0;
+        for (int i = 0; i < n; i++) {
+            dd_t q = dd_make(a.q_hi[i * n + i], a.q_lo ? a.q_lo[i * n + i] : 0.0);
+            double v = fabs(dd_to_d(dd_mul(q, rt)));
+            if (v > mu) mu = v;
+        }
+        int s = 0;
+        if (mu > 1.0) { int ex; frexp(mu, &ex); s = ex; /* mu < 2^ex */ }
+        sh_mu = mu; sh_s = s;
+    }
+    __syncthreads();
+    const double mu = sh_mu;
+    const int s = sh_s;
+    const double inv2s = scalbn(1.0, -s);
+    const dd_t mus = dd_make(mu * inv2s, 0.0);   /* exact: power of two scaling */
+
+    for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
+        int i = idx / n, j = idx - i * n;
+        dd_t q = dd_make(a.q_hi[idx], a.q_lo ? a.q_lo[idx] : 0.0);
+        dd_t v = dd_mul_pwr2(dd_mul(q, rt), inv2s);
+        if (i == j) v = dd_add(v, mus);
+        if (v.hi < 0.0) v = dd_make(0.0, 0.0);   /* the diagonal entry that defines mu */
+        B[idx] = v;
+        dd_t id = dd_make(i == j ? 1.0 : 0.0, 0.0);
+        X[idx] = id; SX[idx] = id;
+        if (want_f) {
+            dd_t l = dd_make(a.l_hi[idx], a.l_lo ? a.l_lo[idx] : 0.0);
+            Ls[idx] = dd_mul_pwr2(l, inv2s);
+            Y[idx] = dd_make(0.0, 0.0); SY[idx] = dd_make(0.0, 0.0);
+        }
+    }
+    __syncthreads();
+
+    /* number of Taylor terms: mus^k/k! < 2^-112 (mus <= 1 -> at most 32) */
+    int nterms = 1;
+    {
+        double bound = 1.0, m = mus.hi;
+        /* for the Frechet block the norm of the shifted block matrix is mus + |L_s|; be generous */
+        while (nterms < 40) { bound *= (m > 0.0 ? m : 0.0) / nterms; if (bound < 1.9e-34 && nterms >= 2) break; nterms++; }
+        if (m == 0.0) nterms = 2;
+        if (want_f) nterms += 4;
+    }
+    for (int k = 1; k <= nterms; k++) {
+        dd_t invk = dd_div(dd_make(1.0, 0.0), dd_make((double)k, 0.0));
+        /* T = B X / k ; T2 = (B Y + Ls X)/k */
+        dd_matmul(T, B, X, n, invk, true);
+        if (want_f) dd_matmul2(T2, B, Y, Ls, X, n, invk, true);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
+            X[idx] = T[idx]; SX[idx] = dd_add(SX[idx], T[idx]);
+            if (want_f) { Y[idx] = T2[idx]; SY[idx] = dd_add(SY[idx], T2[idx]); }
+        }
+        __syncthreads();
+    }
+    /* multiply by e^{-mus} */
+    {
+        dd_t em = dd_exp_neg_small(mus);
+        for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
+            SX[idx] = dd_mul(SX[idx], em);
+            if (want_f) SY[idx] = dd_mul(SY[idx], em);
+        }
+        __syncthreads();
+    }
+    /* squarings: (X,Y) <- (X X, X Y + Y X) */
+    for (int it = 0; it < s; it++) {
+        dd_matmul(T, SX, SX, n, dd_make(1.0, 0.0), false);
+        if (want_f) dd_matmul2(T2, SX, SY, SY, SX, n, dd_make(1.0, 0.0), false);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
+            SX[idx] = T[idx];
+            if (want_f) SY[idx] = T2[idx];
+        }
+        __syncthreads();
+    }
+    const size_t off = ((size_t)c * a.E + e) * nn;
+    if (a.P) for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) a.P[off + idx] = dd_to_d(SX[idx]);
+    if (want_f) {
+        double fs = (a.f_scale_mode == 1) ? r * t : 1.0;
+        dd_t fsd = (a.f_scale_mode == 1) ? rt : dd_make(1.0, 0.0);
+        (void)fs;
+        for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) a.F[off + idx] = dd_to_d(dd_mul(SY[idx], fsd));
+    }
+    if (a.D) {
+        /* D = r * Q * P in dd, T as scratch holding Q */
+        for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) T[idx] = dd_make(a.q_hi[idx], a.q_lo ? a.q_lo[idx] : 0.0);
+        __syncthreads();
+        dd_matmul(T2, T, SX, n, dd_make(r, 0.0), true);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) a.D[off + idx] = dd_to_d(T2[idx]);
+    }
+}

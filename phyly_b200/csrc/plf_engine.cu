@@ -1,0 +1,1051 @@
+/*
+ * plf_engine.cu -- implementation of the device seam declared in include/plf.h.
+ *
+ * Host side: buffer management, compilation of the tree into the fused-kernel
+ * program, kernel launches on one CUDA stream, second-stage reductions and the
+ * optional in-stream ncclAllReduce.  There is deliberately no CPU
+ * implementation of any query in this file: without a CUDA device plf_create
+ * fails and every entry point returns an error.
+ */
+#include <cuda_runtime.h>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <dlfcn.h>
+
+#include "../../include/plf.h"
+#include "dd.h"
+#include "expm.cuh"
+#include "generic.cuh"
+#include "fused4.cuh"
+
+/* ------------------------------------------------------------------ */
+/* small utilities                                                     */
+/* ------------------------------------------------------------------ */
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            if (cudaMalloc(&p, bytes) != cudaSuccess) { p = nullptr; return -1; }
+            want = bytes;
+        }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+/* NCCL through dlopen so that the library has no link-time dependency and
+ * shares whatever libnccl.so.2 the process already loaded (e.g. torch's). */
+typedef struct { char internal[128]; } plf_nccl_id;
+typedef void *plf_nccl_comm;
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(plf_nccl_id *) = nullptr;
+    int (*CommInitRank)(plf_nccl_comm *, int, plf_nccl_id, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, plf_nccl_comm, cudaStream_t) = nullptr;
+    int (*CommDestroy)(plf_nccl_comm) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool load()
+    {
+        if (lib) return true;
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return false;
+        GetUniqueId = (int (*)(plf_nccl_id *))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (int (*)(plf_nccl_comm *, int, plf_nccl_id, int))dlsym(lib, "ncclCommInitRank");
+        AllReduce = (int (*)(const void *, void *, size_t, int, int, plf_nccl_comm, cudaStream_t))dlsym(lib, "ncclAllReduce");
+        CommDestroy = (int (*)(plf_nccl_comm))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (const char *(*)(int))dlsym(lib, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+    }
+};
+static NcclApi g_nccl;
+
+struct plf_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int path = PLF_PATH_AUTO;
+    int sm_count = 0;
+
+    /* tree */
+    int N = 0, E = 0, root = -1;
+    std::vector<int> indptr, indices, preorder;
+    DevBuf d_indptr, d_indices, d_preorder, d_node_has_data;
+    bool tree_dirty = true;
+
+    /* model */
+    int n = 0, C = 0, root_mode = 0;
+    std::vector<double> q_hi, q_lo, edge_rates, cat_rates, cat_prior, root_vec;
+    DevBuf d_qhi, d_qlo, d_edge_rates, d_cat_rates, d_cat_prior, d_root_vec;
+    DevBuf d_P, d_D, d_F, d_lhi, d_llo, d_expm_ws;
+    bool model_dirty = true, P_valid = false, D_valid = false;
+
+    /* data */
+    int64_t S = 0;
+    int K = 0, code_bytes = 1;
+    DevBuf d_codes_in, d_codes, d_defs, d_def_const, d_def_ones, d_site_w;
+    bool have_w = false;
+    std::vector<unsigned char> def_const_h;
+
+    /* fused program */
+    std::vector<F4Op> ops;
+    std::vector<F4Child> children;
+    DevBuf d_ops, d_children, d_TP, d_TF;
+    int stack_depth = 0, nslots = 0, max_degree = 0;
+    bool TP_valid = false;
+
+    /* scratch */
+    DevBuf d_scratch, d_scratchS, d_block_ll, d_block_edge, d_edge_site, d_sum, d_site_ll, d_err, d_mask;
+    DevBuf g_Lg, g_Kg, g_Cg, g_Eg, g_Fg, g_FK, g_cat_lh, g_cat_k, g_site_m, g_site_k, g_edge_out, g_marg_out, g_tr;
+
+    /* timing / accounting */
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    float ms_mat = 0.f, ms_sites = 0.f;
+    int64_t launches = 0;
+
+    /* nccl */
+    plf_nccl_comm comm = nullptr;
+    int nranks = 1;
+};
+
+#define FAIL(e, ...) do { char _b[512]; snprintf(_b, sizeof(_b), __VA_ARGS__); (e)->err = _b; return -1; } while (0)
+#define CK(e, call) do { cudaError_t _r = (call); if (_r != cudaSuccess) { \
+        FAIL(e, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(_r)); } } while (0)
+#define ENSURE(e, buf, bytes) do { if ((buf).ensure(bytes)) FAIL(e, "out of device memory allocating %zu bytes (%s)", (size_t)(bytes), #buf); } while (0)
+#define KCHECK(e) do { (e)->launches++; CK(e, cudaGetLastError()); } while (0)
+
+/* ------------------------------------------------------------------ */
+/* small kernels                                                       */
+/* ------------------------------------------------------------------ */
+
+/* codes_in[S][N] (1 or 4 bytes) -> codes[N][S] (1 or 4 bytes); also flags nodes that carry data */
+template <typename TIn, typename TOut>
+__global__ void transpose_codes_kernel(const TIn *in, TOut *out, int64_t S, int N,
+                                       const unsigned char *def_ones, int *node_flags)
+{
+    __shared__ int tile[32][33];
+    const int64_t s0 = (int64_t)blockIdx.x * 32;
+    const int n0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int64_t s = s0 + r;
+        int nd = n0 + threadIdx.x;
+        tile[r][threadIdx.x] = (s < S && nd < N) ? (int)in[(size_t)s * N + nd] : -1;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int nd = n0 + r;
+        int64_t s = s0 + threadIdx.x;
+        int code = tile[threadIdx.x][r];
+        bool has = false;
+        if (nd < N && s < S) {
+            out[(size_t)nd * S + s] = (TOut)code;
+            has = !def_ones[code];
+        }
+        unsigned any = __ballot_sync(0xffffffffu, has);
+        if (any && threadIdx.x == 0 && nd < N) {
+            if (node_flags[nd] == 0) atomicOr(&node_flags[nd], 1);
+        }
+    }
+}
+
+__global__ void flags_to_bytes_kernel(const int *flags, unsigned char *out, int N)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) out[i] = flags[i] ? 1 : 0;
+}
+
+/* out[c][e][k][i] = sum_j M[c][e][i][j] def[k][j], leaf edges only.
+ * mode 0: stochastic matrix (constant rows map to the constant);
+ * mode 1: zero-row-sum matrix (constant rows map to exact 0); mode 2: no shortcut. */
+__global__ void tip_table_kernel(const double *M, const double *defs, const unsigned char *def_const,
+                                 const int *indptr, const int *indices, int C, int E, int K, int n,
+                                 int mode, double *out)
+{
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)C * E * K * n;
+    if (idx >= total) return;
+    int i = idx % n; size_t r = idx / n;
+    int k = r % K; r /= K;
+    int e = r % E; int c = r / E;
+    int b = indices[e];
+    if (indptr[b] != indptr[b + 1]) { out[idx] = 0.0; return; }
+    const double *row = M + (((size_t)c * E + e) * n + i) * n;
+    const double *d = defs + (size_t)k * n;
+    double v;
+    if (def_const[k] && mode == 0) v = d[0];
+    else if (def_const[k] && mode == 1) v = 0.0;
+    else {
+        v = 0.0;
+        for (int j = 0; j < n; j++) v = fma(row[j], d[j], v);
+    }
+    out[idx] = v;
+}
+
+/* weighted row sums: out[r] += sum_s w[s0+s] * val[r][s]  (one CTA per row, fixed order) */
+__global__ void wsum_rows_kernel(const double *val, const double *w, int64_t w_off, int cols, double *out, int *err, int check)
+{
+    __shared__ double red[256];
+    const int r = blockIdx.x;
+    const double *row = val + (size_t)r * cols;
+    double s = 0.0;
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) {
+        double wj = w ? w[w_off + j] : 1.0;
+        if (wj != 0.0) {
+            double v = row[j];
+            if (check && !isfinite(v)) atomicOr(err, 1);
+            s = fma(wj, v, s);
+        }
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[r] += red[0];
+}
+
+/* in[R][Cc] -> out[Cc][R] */
+__global__ void transpose_d_kernel(const double *in, double *out, int R, int Cc)
+{
+    __shared__ double tile[32][33];
+    int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int rr = r0 + r, cc = c0 + threadIdx.x;
+        tile[r][threadIdx.x] = (rr < R && cc < Cc) ? in[(size_t)rr * Cc + cc] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int cc = c0 + r, rr = r0 + threadIdx.x;
+        if (cc < Cc && rr < R) out[(size_t)cc * R + rr] = tile[threadIdx.x][r];
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* lifecycle                                                           */
+/* ------------------------------------------------------------------ */
+
+extern "C" int plf_create(plf_engine **out, int device)
+{
+    if (!out) return -1;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t r = cudaGetDeviceCount(&ndev);
+    if (r != cudaSuccess || ndev == 0) {
+        fprintf(stderr, "plf_create: no CUDA device available (%s); this engine has no CPU path\n",
+                r == cudaSuccess ? "device count is 0" : cudaGetErrorString(r));
+        return -1;
+    }
+    if (device < 0 || device >= ndev) {
+        fprintf(stderr, "plf_create: invalid device %d (have %d)\n", device, ndev);
+        return -1;
+    }
+    plf_engine *e = new plf_engine();
+    e->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        fprintf(stderr, "plf_create: cannot initialise device %d: %s\n", device, cudaGetErrorString(cudaGetLastError()));
+        delete e;
+        return -1;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    e->sm_count = prop.multiProcessorCount;
+    for (int i = 0; i < 3; i++) cudaEventCreate(&e->ev[i]);
+    *out = e;
+    return 0;
+}
+
+extern "C" void plf_destroy(plf_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    DevBuf *bufs[] = {&e->d_indptr, &e->d_indices, &e->d_preorder, &e->d_node_has_data, &e->d_qhi, &e->d_qlo,
+                      &e->d_edge_rates, &e->d_cat_rates, &e->d_cat_prior, &e->d_root_vec, &e->d_P, &e->d_D, &e->d_F,
+                      &e->d_lhi, &e->d_llo, &e->d_expm_ws, &e->d_codes_in, &e->d_codes, &e->d_defs, &e->d_def_const,
+                      &e->d_def_ones, &e->d_site_w, &e->d_ops, &e->d_children, &e->d_TP, &e->d_TF, &e->d_scratch,
+                      &e->d_scratchS, &e->d_block_ll, &e->d_block_edge, &e->d_edge_site, &e->d_sum, &e->d_site_ll,
+                      &e->d_err, &e->d_mask, &e->g_Lg, &e->g_Kg, &e->g_Cg, &e->g_Eg, &e->g_Fg, &e->g_FK, &e->g_cat_lh,
+                      &e->g_cat_k, &e->g_site_m, &e->g_site_k, &e->g_edge_out, &e->g_marg_out, &e->g_tr};
+    for (DevBuf *b : bufs) b->release();
+    for (int i = 0; i < 3; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+extern "C" const char *plf_last_error(const plf_engine *e) { return e ? e->err.c_str() : "null engine"; }
+
+extern "C" int plf_set_path(plf_engine *e, int path)
+{
+    if (!e) return -1;
+    if (path < PLF_PATH_AUTO || path > PLF_PATH_FUSED4) FAIL(e, "plf_set_path: invalid path %d", path);
+    e->path = path;
+    return 0;
+}
+
+extern "C" void *plf_stream(plf_engine *e) { return e ? (void *)e->stream : nullptr; }
+
+extern "C" int plf_synchronize(plf_engine *e)
+{
+    if (!e) return -1;
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int plf_last_timing(plf_engine *e, float *ms_matrices, float *ms_sites)
+{
+    if (!e) return -1;
+    if (ms_matrices) *ms_matrices = e->ms_mat;
+    if (ms_sites) *ms_sites = e->ms_sites;
+    return 0;
+}
+
+extern "C" int64_t plf_launch_count(plf_engine *e, int reset)
+{
+    if (!e) return -1;
+    int64_t v = e->launches;
+    if (reset) e->launches = 0;
+    return v;
+}
+
+/* ------------------------------------------------------------------ */
+/* tree                                                                */
+/* ------------------------------------------------------------------ */
+
+static int build_program(plf_engine *e)
+{
+    const int N = e->N;
+    std::vector<int> need(N, 0), slot(N, -1);
+    std::vector<std::vector<int>> ichild(N);   /* internal children (csr edge idx) sorted for visiting */
+    e->max_degree = 0;
+    auto is_leaf = [&](int v) { return e->indptr[v] == e->indptr[v + 1]; };
+    for (int u = N - 1; u >= 0; u--) {
+        int a = e->preorder[u];
+        int deg = e->indptr[a + 1] - e->indptr[a];
+        e->max_degree = std::max(e->max_degree, deg);
+        std::vector<int> &ic = ichild[a];
+        for (int idx = e->indptr[a]; idx < e->indptr[a + 1]; idx++)
+            if (!is_leaf(e->indices[idx])) ic.push_back(idx);
+        std::stable_sort(ic.begin(), ic.end(), [&](int x, int y) { return need[e->indices[x]] > need[e->indices[y]]; });
+        int nd = 0;
+        for (size_t j = 0; j < ic.size(); j++) nd = std::max(nd, (int)j + need[e->indices[ic[j]]]);
+        need[a] = nd;
+    }
+    /* iterative DFS emitting internal nodes in post-order */
+    std::vector<int> order;
+    {
+        std::vector<std::pair<int, size_t>> st;
+        st.push_back({e->root, 0});
+        while (!st.empty()) {
+            auto &top = st.back();
+            int a = top.first;
+            if (top.second < ichild[a].size()) {
+                int b = e->indices[ichild[a][top.second]];
+                top.second++;
+                st.push_back({b, 0});
+            } else {
+                order.push_back(a);
+                st.pop_back();
+            }
+        }
+    }
+    e->ops.clear(); e->children.clear();
+    for (size_t o = 0; o < order.size(); o++) slot[order[o]] = (int)o;
+    std::vector<int> stk;
+    int cur = -1, maxdepth = 0;
+    for (size_t o = 0; o < order.size(); o++) {
+        int a = order[o];
+        F4Op op;
+        op.node = a; op.first_child = (int)e->children.size(); op.nchild = 0; op.slot = (int)o;
+        op.has_data = 0; op.spill_before = 0;
+        const std::vector<int> &ic = ichild[a];
+        int cur_edge = -1;
+        for (int idx : ic) if (e->indices[idx] == cur) cur_edge = idx;
+        if (cur != -1 && cur_edge == -1) {
+            op.spill_before = 1;
+            stk.push_back(cur);
+            maxdepth = std::max(maxdepth, (int)stk.size());
+        }
+        if (cur_edge != -1) {
+            F4Child ch = {cur_edge, cur, slot[cur], F4_KIND_CUR};
+            e->children.push_back(ch); op.nchild++;
+        }
+        size_t nstack = ic.size() - (cur_edge != -1 ? 1 : 0);
+        for (size_t j = 0; j < nstack; j++) {
+            if (stk.empty()) { e->err = "internal error: fused program stack underflow"; return -1; }
+            int b = stk.back(); stk.pop_back();
+            int be = -1;
+            for (int idx : ic) if (e->indices[idx] == b) be = idx;
+            if (be == -1) { e->err = "internal error: fused program stack mismatch"; return -1; }
+            F4Child ch = {be, b, slot[b], F4_KIND_STACK};
+            e->children.push_back(ch); op.nchild++;
+        }
+        for (int idx = e->indptr[a]; idx < e->indptr[a + 1]; idx++) {
+            int b = e->indices[idx];
+            if (is_leaf(b)) {
+                F4Child ch = {idx, b, -1, F4_KIND_TIP};
+                e->children.push_back(ch); op.nchild++;
+            }
+        }
+        e->ops.push_back(op);
+        cur = a;
+    }
+    if (!stk.empty()) { e->err = "internal error: fused program leaves a non-empty stack"; return -1; }
+    e->stack_depth = maxdepth;
+    e->nslots = (int)order.size();
+    return 0;
+}
+
+extern "C" int plf_set_tree(plf_engine *e, int node_count, const int *indptr, const int *indices, const int *preorder)
+{
+    if (!e) return -1;
+    if (node_count < 2 || !indptr || !indices || !preorder) FAIL(e, "plf_set_tree: invalid arguments");
+    const int N = node_count, E = N - 1;
+    if (indptr[0] != 0 || indptr[N] != E) FAIL(e, "plf_set_tree: indptr does not describe %d edges", E);
+    std::vector<int> indeg(N, 0), seen(N, 0), pos(N, -1);
+    for (int i = 0; i < N; i++) if (indptr[i + 1] < indptr[i]) FAIL(e, "plf_set_tree: indptr is not monotone");
+    for (int j = 0; j < E; j++) {
+        if (indices[j] < 0 || indices[j] >= N) FAIL(e, "plf_set_tree: child index out of range");
+        indeg[indices[j]]++;
+    }
+    for (int u = 0; u < N; u++) {
+        int a = preorder[u];
+        if (a < 0 || a >= N || seen[a]) FAIL(e, "plf_set_tree: preorder is not a permutation");
+        seen[a] = 1; pos[a] = u;
+    }
+    if (indeg[preorder[0]] != 0) FAIL(e, "plf_set_tree: preorder[0] is not the root");
+    for (int a = 0; a < N; a++) {
+        if (a != preorder[0] && indeg[a] != 1) FAIL(e, "plf_set_tree: not a rooted tree");
+        for (int j = indptr[a]; j < indptr[a + 1]; j++)
+            if (pos[indices[j]] <= pos[a]) FAIL(e, "plf_set_tree: preorder visits a child before its parent");
+    }
+    e->N = N; e->E = E; e->root = preorder[0];
+    e->indptr.assign(indptr, indptr + N + 1);
+    e->indices.assign(indices, indices + E);
+    e->preorder.assign(preorder, preorder + N);
+    if (build_program(e)) return -1;
+    CK(e, cudaSetDevice(e->device));
+    ENSURE(e, e->d_indptr, sizeof(int) * (N + 1));
+    ENSURE(e, e->d_indices, sizeof(int) * E);
+    ENSURE(e, e->d_preorder, sizeof(int) * N);
+    ENSURE(e, e->d_ops, sizeof(F4Op) * e->ops.size());
+    ENSURE(e, e->d_children, sizeof(F4Child) * e->children.size());
+    CK(e, cudaMemcpyAsync(e->d_indptr.p, indptr, sizeof(int) * (N + 1), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->d_indices.p, indices, sizeof(int) * E, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->d_preorder.p, preorder, sizeof(int) * N, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->d_ops.p, e->ops.data(), sizeof(F4Op) * e->ops.size(), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->d_children.p, e->children.data(), sizeof(F4Child) * e->children.size(), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    e->P_valid = e->D_valid = e->TP_valid = false;
+    e->S = 0;   /* data must be (re)set after the tree */
+    return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* model                                                               */
+/* ------------------------------------------------------------------ */
+
+extern "C" int plf_set_model(plf_engine *e, int n, int C, const double *q_hi, const double *q_lo,
+                             const double *edge_rates, const double *cat_rates, const double *cat_prior,
+                             int root_mode, const double *root_vec)
+{
+    if (!e) return -1;
+    if (e->N == 0) FAIL(e, "plf_set_model: set the tree first");
+    if (n < 1 || n > 128 || C < 1 || !q_hi || !edge_rates || !cat_rates || !cat_prior)
+        FAIL(e, "plf_set_model: invalid arguments (n=%d C=%d)", n, C);
+    if (root_mode < PLF_ROOT_NONE || root_mode > PLF_ROOT_CUSTOM) FAIL(e, "plf_set_model: invalid root mode");
+    if ((root_mode == PLF_ROOT_EQUILIBRIUM || root_mode == PLF_ROOT_CUSTOM) && !root_vec)
+        FAIL(e, "plf_set_model: root_vec is required for this root mode");
+    for (int i = 0; i < e->E; i++) if (!(edge_rates[i] >= 0.0) || !std::isfinite(edge_rates[i]))
+        FAIL(e, "plf_set_model: edge rate %d is not a finite non-negative number", i);
+    for (int i = 0; i < C; i++) if (!(cat_rates[i] >= 0.0) || !std::isfinite(cat_rates[i]) || !(cat_prior[i] >= 0.0))
+        FAIL(e, "plf_set_model: category %d has an invalid rate or prior", i);
+    if (n != e->n) e->S = 0;
+    e->n = n; e->C = C; e->root_mode = root_mode;
+    e->q_hi.assign(q_hi, q_hi + n * n);
+    if (q_lo) e->q_lo.assign(q_lo, q_lo + n * n); else e->q_lo.assign(n * n, 0.0);
+    e->edge_rates.assign(edge_rates, edge_rates + e->E);
+    e->cat_rates.assign(cat_rates, cat_rates + C);
+    e->cat_prior.assign(cat_prior, cat_prior + C);
+    e->root_vec.assign(n, 1.0);
+    if (root_vec) e->root_vec.assign(root_vec, root_vec + n);
+    CK(e, cudaSetDevice(e->device));
+    ENSURE(e, e->d_qhi, sizeof(double) * n * n);
+    ENSURE(e, e->d_qlo, sizeof(double) * n * n);
+    ENSURE(e, e->d_edge_rates, sizeof(double) * e->E);
+    ENSURE(e, e->d_cat_rates, sizeof(double) * C);
+    ENSURE(e, e->d_cat_prior, sizeof(double) * C);
+    ENSURE(e, e->d_root_vec, sizeof(double) * n);
+    CK(e, cudaMemcpyAsync(e->d_qhi.p, e->q_hi.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->d_qlo.p, e->q_lo.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->d_edge_rates.p, e->edge_rates.data(), sizeof(double) * e->E, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->d_cat_rates.p, e->cat_rates.data(), sizeof(double) * C, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->d_cat_prior.p, e->cat_prior.data(), sizeof(double) * C, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->d_root_vec.p, e->root_vec.data(), sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    e->P_valid = e->D_valid = e->TP_valid = false;
+    return 0;
+}
+
+extern "C" int plf_set_edge_rates(plf_engine *e, const double *edge_rates)
+{
+    if (!e) return -1;
+    if (e->n == 0) FAIL(e, "plf_set_edge_rates: set the model first");
+    for (int i = 0; i < e->E; i++) if (!(edge_rates[i] >= 0.0) || !std::isfinite(edge_rates[i]))
+        FAIL(e, "plf_set_edge_rates: edge rate %d is not a finite non-negative number", i);
+    e->edge_rates.assign(edge_rates, edge_rates + e->E);
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaMemcpyAsync(e->d_edge_rates.p, e->edge_rates.data(), sizeof(double) * e->E, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    e->P_valid = e->D_valid = e->TP_valid = false;
+    return 0;
+}
+
+/* launch the expm kernel; which outputs are produced depends on the pointers */
+static int run_expm(plf_engine *e, double *P, double *D, double *F, int f_scale_mode, const unsigned char *d_mask,
+                    const double *d_lhi, const double *d_llo)
+{
+    ExpmArgs a;
+    a.n = e->n; a.E = e->E; a.C = e->C;
+    a.q_hi = e->d_qhi.as<double>(); a.q_lo = e->d_qlo.as<double>();
+    a.l_hi = d_lhi; a.l_lo = d_llo;
+    a.edge_rate = e->d_edge_rates.as<double>(); a.cat_rate = e->d_cat_rates.as<double>();
+    a.edge_mask = d_mask;
+    a.P = P; a.D = D; a.F = F; a.f_scale_mode = f_scale_mode;
+    const size_t nn = (size_t)e->n * e->n;
+    size_t smem = 0;
+    if (e->n <= 16) { a.ws = nullptr; smem = 8 * nn * sizeof(dd_t); }
+    else {
+        ENSURE(e, e->d_expm_ws, (size_t)e->C * e->E * 8 * nn * sizeof(dd_t));
+        a.ws = e->d_expm_ws.as<dd_t>();
+    }
+    int threads = (int)std::min<size_t>(256, ((nn + 31) / 32) * 32);
+    dim3 grid(e->E, e->C);
+    expm_dd_kernel<<<grid, threads, smem, e->stream>>>(a);
+    KCHECK(e);
+    return 0;
+}
+
+static int ensure_matrices(plf_engine *e, bool need_D)
+{
+    const size_t bytes = sizeof(double) * e->C * e->E * e->n * e->n;
+    if (e->P_valid && (!need_D || e->D_valid)) return 0;
+    ENSURE(e, e->d_P, bytes);
+    if (need_D) ENSURE(e, e->d_D, bytes);
+    if (run_expm(e, e->d_P.as<double>(), need_D ? e->d_D.as<double>() : nullptr, nullptr, 0, nullptr, nullptr, nullptr)) return -1;
+    e->P_valid = true;
+    if (need_D) e->D_valid = true;
+    e->TP_valid = false;
+    return 0;
+}
+
+static int upload_L(plf_engine *e, const double *l_hi, const double *l_lo)
+{
+    const size_t nn = (size_t)e->n * e->n;
+    if (!l_hi) FAIL(e, "Frechet direction matrix is required");
+    std::vector<double> zero(nn, 0.0);
+    ENSURE(e, e->d_lhi, sizeof(double) * nn);
+    ENSURE(e, e->d_llo, sizeof(double) * nn);
+    CK(e, cudaMemcpyAsync(e->d_lhi.p, l_hi, sizeof(double) * nn, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->d_llo.p, l_lo ? l_lo : zero.data(), sizeof(double) * nn, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* data                                                                */
+/* ------------------------------------------------------------------ */
+
+extern "C" int plf_set_data(plf_engine *e, int64_t S, int K, const double *defs, const void *codes, int code_bytes)
+{
+    if (!e) return -1;
+    if (e->N == 0 || e->n == 0) FAIL(e, "plf_set_data: set the tree and the model first");
+    if (S < 1 || K < 1 || !defs || !codes || (code_bytes != 1 && code_bytes != 4)) FAIL(e, "plf_set_data: invalid arguments");
+    if (code_bytes == 1 && K > 256) FAIL(e, "plf_set_data: %d definitions do not fit 1-byte codes", K);
+    const int n = e->n, N = e->N;
+    CK(e, cudaSetDevice(e->device));
+    std::vector<unsigned char> dconst(K), dones(K);
+    for (int k = 0; k < K; k++) {
+        bool c = true, o = true;
+        for (int i = 0; i < n; i++) {
+            double v = defs[(size_t)k * n + i];
+            if (!(v >= 0.0) || !std::isfinite(v)) FAIL(e, "plf_set_data: definition %d has an invalid entry", k);
+            if (v != defs[(size_t)k * n]) c = false;
+            if (v != 1.0) o = false;
+        }
+        dconst[k] = c; dones[k] = o;
+    }
+    e->def_const_h = dconst;
+    const int dev_bytes = (K <= 256) ? 1 : 4;
+    ENSURE(e, e->d_defs, sizeof(double) * K * n);
+    ENSURE(e, e->d_def_const, K);
+    ENSURE(e, e->d_def_ones, K);
+    ENSURE(e, e->d_codes_in, (size_t)S * N * code_bytes);
+    ENSURE(e, e->d_codes, (size_t)S * N * dev_bytes);
+    ENSURE(e, e->d_node_has_data, N);
+    ENSURE(e, e->d_err, sizeof(int) * (N + 4));
+    CK(e, cudaMemcpyAsync(e->d_defs.p, defs, sizeof(double) * K * n, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->d_def_const.p, dconst.data(), K, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->d_def_ones.p, dones.data(), K, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->d_codes_in.p, codes, (size_t)S * N * code_bytes, cudaMemcpyHostToDevice, e->stream));
+    int *flags = e->d_err.as<int>() + 4;
+    CK(e, cudaMemsetAsync(e->d_err.p, 0, sizeof(int) * (N + 4), e->stream));
+    dim3 blk(32, 8), grid((unsigned)((S + 31) / 32), (unsigned)((N + 31) / 32));
+    if (code_bytes == 1)
+        transpose_codes_kernel<unsigned char, unsigned char><<<grid, blk, 0, e->stream>>>(
+            e->d_codes_in.as<unsigned char>(), e->d_codes.as<unsigned char>(), S, N, e->d_def_ones.as<unsigned char>(), flags);
+    else if (dev_bytes == 1)
+        transpose_codes_kernel<int, unsigned char><<<grid, blk, 0, e->stream>>>(
+            e->d_codes_in.as<int>(), e->d_codes.as<unsigned char>(), S, N, e->d_def_ones.as<unsigned char>(), flags);
+    else
+        transpose_codes_kernel<int, int><<<grid, blk, 0, e->stream>>>(
+            e->d_codes_in.as<int>(), e->d_codes.as<int>(), S, N, e->d_def_ones.as<unsigned char>(), flags);
+    KCHECK(e);
+    flags_to_bytes_kernel<<<(N + 127) / 128, 128, 0, e->stream>>>(flags, e->d_node_has_data.as<unsigned char>(), N);
+    KCHECK(e);
+    /* host-side range check of the codes would cost a pass over S*N bytes; the
+     * caller (the JSON front end) has already validated them (parsemodel.c:600-613). */
+    CK(e, cudaStreamSynchronize(e->stream));
+    e->S = S; e->K = K; e->code_bytes = dev_bytes;
+    e->TP_valid = false;
+    e->have_w = false;
+    return 0;
+}
+
+extern "C" int plf_set_site_weights(plf_engine *e, const double *w)
+{
+    if (!e) return -1;
+    if (e->S == 0) FAIL(e, "plf_set_site_weights: set the data first");
+    CK(e, cudaSetDevice(e->device));
+    if (!w) { e->have_w = false; return 0; }
+    ENSURE(e, e->d_site_w, sizeof(double) * e->S);
+    CK(e, cudaMemcpyAsync(e->d_site_w.p, w, sizeof(double) * e->S, cudaMemcpyHostToDevice, e->stream));
+    e->have_w = true;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* queries                                                             */
+/* ------------------------------------------------------------------ */
+
+struct Query {
+    bool want_edge = false, want_marg = false;
+    const double *Fm = nullptr;      /* device [C][E][n][n] */
+    int f_zero_rowsum = 0;
+    const unsigned char *edge_mask_h = nullptr;
+    /* host outputs (any may be NULL) */
+    double *site_ll = nullptr, *sum_ll = nullptr;
+    double *site_edge = nullptr, *sum_edge = nullptr;   /* [S][E], [E] */
+    double *site_marg = nullptr, *sum_marg = nullptr;   /* [S][N][n], [N][n] */
+};
+
+static bool fused_applicable(const plf_engine *e)
+{
+    return e->n == 4 && e->C <= 4 && e->code_bytes == 1 && e->K <= 256 && e->max_degree <= F4_MAXD;
+}
+
+static int ensure_tip_tables(plf_engine *e, const double *Fm, int f_mode)
+{
+    const size_t cnt = (size_t)e->C * e->E * e->K * e->n;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((cnt + threads - 1) / threads);
+    if (!e->TP_valid) {
+        ENSURE(e, e->d_TP, sizeof(double) * cnt);
+        tip_table_kernel<<<blocks, threads, 0, e->stream>>>(e->d_P.as<double>(), e->d_defs.as<double>(),
+            e->d_def_const.as<unsigned char>(), e->d_indptr.as<int>(), e->d_indices.as<int>(),
+            e->C, e->E, e->K, e->n, 0, e->d_TP.as<double>());
+        KCHECK(e);
+        e->TP_valid = true;
+    }
+    if (Fm) {
+        ENSURE(e, e->d_TF, sizeof(double) * cnt);
+        tip_table_kernel<<<blocks, threads, 0, e->stream>>>(Fm, e->d_defs.as<double>(),
+            e->d_def_const.as<unsigned char>(), e->d_indptr.as<int>(), e->d_indices.as<int>(),
+            e->C, e->E, e->K, e->n, f_mode, e->d_TF.as<double>());
+        KCHECK(e);
+    }
+    return 0;
+}
+
+static int finish_sums(plf_engine *e, double *d_sum, size_t count)
+{
+    if (e->comm) {
+        int r = g_nccl.AllReduce(d_sum, d_sum, count, /*ncclDouble*/ 8, /*ncclSum*/ 0, e->comm, e->stream);
+        if (r != 0) FAIL(e, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    }
+    return 0;
+}
+
+static int copy_site_matrix(plf_engine *e, const double *d_rows /*[R][cols]*/, int R, int64_t cols, double *host /*[cols][R]*/)
+{
+    /* transpose in column chunks to bound the staging buffer */
+    const int64_t chunk = std::max<int64_t>(32, std::min<int64_t>(cols, (int64_t)(64u << 20) / std::max(1, R)));
+    ENSURE(e, e->g_tr, sizeof(double) * (size_t)chunk * R * 2);
+    double *src_c = e->g_tr.as<double>();
+    double *dst_c = src_c + (size_t)chunk * R;
+    for (int64_t c0 = 0; c0 < cols; c0 += chunk) {
+        int cc = (int)std::min<int64_t>(chunk, cols - c0);
+        /* gather the column block into a dense [R][cc] array */
+        CK(e, cudaMemcpy2DAsync(src_c, sizeof(double) * cc, d_rows + c0, sizeof(double) * cols,
+                                sizeof(double) * cc, R, cudaMemcpyDeviceToDevice, e->stream));
+        dim3 blk(32, 8), grid((cc + 31) / 32, (R + 31) / 32);
+        transpose_d_kernel<<<grid, blk, 0, e->stream>>>(src_c, dst_c, R, cc);
+        KCHECK(e);
+        CK(e, cudaMemcpyAsync(host + (size_t)c0 * R, dst_c, sizeof(double) * (size_t)cc * R, cudaMemcpyDeviceToHost, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+    }
+    return 0;
+}
+
+static int run_fused(plf_engine *e, Query &q)
+{
+    const bool edge = q.want_edge;
+    const int bd = 128;
+    F4Args a;
+    memset(&a, 0, sizeof(a));
+    a.nops = (int)e->ops.size();
+    a.ops = e->d_ops.as<F4Op>(); a.children = e->d_children.as<F4Child>();
+    a.C = e->C; a.E = e->E; a.K = e->K; a.S = e->S;
+    a.codes = e->d_codes.as<unsigned char>();
+    a.defs = e->d_defs.as<double>(); a.def_const = e->d_def_const.as<unsigned char>();
+    a.node_has_data = e->d_node_has_data.as<unsigned char>();
+    a.P = e->d_P.as<double>(); a.TP = e->d_TP.as<double>();
+    a.Fm = q.Fm; a.TF = edge ? e->d_TF.as<double>() : nullptr;
+    a.f_zero_rowsum = q.f_zero_rowsum;
+    a.cat_prior = e->d_cat_prior.as<double>();
+    a.root_mode = e->root_mode;
+    for (int i = 0; i < 4; i++) a.root_vec[i] = e->root_vec[i];
+    a.site_w = e->have_w ? e->d_site_w.as<double>() : nullptr;
+    a.stack_depth = e->stack_depth; a.nslots = e->nslots;
+
+    const size_t smem = (size_t)bd * ((size_t)e->stack_depth * 36 + 16) + (size_t)(bd / 32) * e->E * 8 + 16;
+    auto kern = edge ? fused4_kernel<true> : fused4_kernel<false>;
+    if (smem > 48 * 1024) CK(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 227 * 1024) FAIL(e, "fused kernel needs %zu bytes of shared memory", smem);
+    int per_sm = 0;
+    CK(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, bd, smem));
+    if (per_sm < 1) FAIL(e, "fused kernel cannot be resident (smem %zu)", smem);
+    const int64_t ntiles = (e->S + bd - 1) / bd;
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)per_sm * e->sm_count);
+    const size_t T = (size_t)grid * bd;
+
+    ENSURE(e, e->d_block_ll, sizeof(double) * grid);
+    ENSURE(e, e->d_sum, sizeof(double) * (1 + e->E + (size_t)e->N * e->n));
+    ENSURE(e, e->d_err, sizeof(int) * (e->N + 4));
+    CK(e, cudaMemsetAsync(e->d_err.p, 0, sizeof(int), e->stream));
+    a.block_ll = e->d_block_ll.as<double>();
+    a.error_flag = e->d_err.as<int>();
+    if (q.site_ll) { ENSURE(e, e->d_site_ll, sizeof(double) * e->S); a.site_ll = e->d_site_ll.as<double>(); }
+    if (edge) {
+        ENSURE(e, e->d_scratch, sizeof(double4) * (size_t)e->C * e->nslots * T);
+        ENSURE(e, e->d_scratchS, (size_t)e->C * e->nslots * T);
+        ENSURE(e, e->d_block_edge, sizeof(double) * (size_t)grid * e->E);
+        a.scratch = e->d_scratch.as<double4>(); a.scratchS = e->d_scratchS.as<signed char>();
+        a.block_edge = e->d_block_edge.as<double>();
+        if (q.edge_mask_h) {
+            ENSURE(e, e->d_mask, e->E);
+            CK(e, cudaMemcpyAsync(e->d_mask.p, q.edge_mask_h, e->E, cudaMemcpyHostToDevice, e->stream));
+            a.edge_mask = e->d_mask.as<unsigned char>();
+        }
+        if (q.site_edge) {
+            ENSURE(e, e->d_edge_site, sizeof(double) * (size_t)e->E * e->S);
+            CK(e, cudaMemsetAsync(e->d_edge_site.p, 0, sizeof(double) * (size_t)e->E * e->S, e->stream));
+            a.edge_site_out = e->d_edge_site.as<double>();
+        }
+    }
+    kern<<<grid, bd, smem, e->stream>>>(a);
+    KCHECK(e);
+    double *dsum = e->d_sum.as<double>();
+    sum_rows_kernel<<<1, 32, 0, e->stream>>>(a.block_ll, grid, 1, dsum);
+    KCHECK(e);
+    size_t nsum = 1;
+    if (edge && !q.site_edge) {
+        sum_rows_kernel<<<(e->E + 127) / 128, 128, 0, e->stream>>>(a.block_edge, grid, e->E, dsum + 1);
+        KCHECK(e);
+        nsum = 1 + e->E;
+    }
+    if (edge && q.site_edge && q.sum_edge) {
+        /* per-site outputs requested together with sums: reduce the per-site rows with the weights */
+        CK(e, cudaMemsetAsync(dsum + 1, 0, sizeof(double) * e->E, e->stream));
+        wsum_rows_kernel<<<e->E, 256, 0, e->stream>>>(a.edge_site_out, a.site_w, 0, (int)e->S, dsum + 1, a.error_flag, 0);
+        KCHECK(e);
+        nsum = 1 + e->E;
+    }
+    if (finish_sums(e, dsum, nsum)) return -1;
+    CK(e, cudaEventRecord(e->ev[2], e->stream));
+    std::vector<double> hs(nsum);
+    int herr = 0;
+    CK(e, cudaMemcpyAsync(hs.data(), dsum, sizeof(double) * nsum, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaMemcpyAsync(&herr, e->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    if (q.site_ll) CK(e, cudaMemcpyAsync(q.site_ll, e->d_site_ll.p, sizeof(double) * e->S, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    if (q.site_edge && copy_site_matrix(e, e->d_edge_site.as<double>(), e->E, e->S, q.site_edge)) return -1;
+    if (herr && (q.sum_ll || q.sum_edge)) FAIL(e, "a site with non-zero weight has zero likelihood");
+    if (q.sum_ll) *q.sum_ll = hs[0];
+    if (q.sum_edge && nsum > 1) memcpy(q.sum_edge, hs.data() + 1, sizeof(double) * e->E);
+    return 0;
+}
+
+static int run_generic(plf_engine *e, Query &q)
+{
+    const int n = e->n, C = e->C, N = e->N, E = e->E;
+    const bool outside = q.want_edge || q.want_marg;
+    /* chunk size from a memory budget */
+    size_t per_site = (size_t)C * ((size_t)N * n * 8 + N * 5 + (size_t)E * n * 8 + 16) + 16;
+    if (outside) per_site += (size_t)C * ((size_t)N * n * 8 + N * 4) + (size_t)E * 8 + (size_t)N * n * 8;
+    size_t free_b = 0, total_b = 0;
+    CK(e, cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = std::min<size_t>((size_t)24 << 30, free_b / 2);
+    int64_t Sc = std::max<int64_t>(PLF_TS, std::min<int64_t>(e->S, (int64_t)(budget / per_site)));
+    Sc = std::min<int64_t>(Sc, 1 << 20);
+    if (Sc < e->S) Sc = (Sc / PLF_TS) * PLF_TS;
+
+    ENSURE(e, e->g_Lg, sizeof(double) * (size_t)C * N * n * Sc);
+    ENSURE(e, e->g_Kg, sizeof(int) * (size_t)C * N * Sc);
+    ENSURE(e, e->g_Cg, (size_t)C * N * Sc);
+    ENSURE(e, e->g_Eg, sizeof(double) * (size_t)C * E * n * Sc);
+    ENSURE(e, e->g_cat_lh, sizeof(double) * (size_t)C * Sc);
+    ENSURE(e, e->g_cat_k, sizeof(int) * (size_t)C * Sc);
+    ENSURE(e, e->g_site_m, sizeof(double) * Sc);
+    ENSURE(e, e->g_site_k, sizeof(int) * Sc);
+    ENSURE(e, e->d_site_ll, sizeof(double) * e->S);
+    ENSURE(e, e->d_sum, sizeof(double) * (1 + E + (size_t)N * n));
+    ENSURE(e, e->d_err, sizeof(int) * (N + 4));
+    if (outside) {
+        ENSURE(e, e->g_Fg, sizeof(double) * (size_t)C * N * n * Sc);
+        ENSURE(e, e->g_FK, sizeof(int) * (size_t)C * N * Sc);
+    }
+    if (q.want_edge) ENSURE(e, e->g_edge_out, sizeof(double) * (size_t)E * Sc);
+    if (q.want_marg) ENSURE(e, e->g_marg_out, sizeof(double) * (size_t)N * n * Sc);
+    if (q.edge_mask_h) {
+        ENSURE(e, e->d_mask, E);
+        CK(e, cudaMemcpyAsync(e->d_mask.p, q.edge_mask_h, E, cudaMemcpyHostToDevice, e->stream));
+    }
+    double *dsum = e->d_sum.as<double>();
+    CK(e, cudaMemsetAsync(dsum, 0, sizeof(double) * (1 + E + (size_t)N * n), e->stream));
+    CK(e, cudaMemsetAsync(e->d_err.p, 0, sizeof(int), e->stream));
+
+    GenericArgs a;
+    memset(&a, 0, sizeof(a));
+    a.t.N = N; a.t.E = E; a.t.root = e->root;
+    a.t.indptr = e->d_indptr.as<int>(); a.t.indices = e->d_indices.as<int>(); a.t.preorder = e->d_preorder.as<int>();
+    a.t.node_has_data = e->d_node_has_data.as<unsigned char>();
+    a.n = n; a.C = C; a.K = e->K; a.S = e->S;
+    a.codes = e->d_codes.p; a.code_bytes = e->code_bytes;
+    a.defs = e->d_defs.as<double>(); a.def_const = e->d_def_const.as<unsigned char>();
+    a.P = e->d_P.as<double>(); a.Fm = q.Fm; a.f_zero_rowsum = q.f_zero_rowsum;
+    a.edge_coef = nullptr;
+    a.edge_mask = q.edge_mask_h ? e->d_mask.as<unsigned char>() : nullptr;
+    a.cat_prior = e->d_cat_prior.as<double>();
+    a.root_mode = e->root_mode; a.root_vec = e->d_root_vec.as<double>();
+    a.Lg = e->g_Lg.as<double>(); a.Kg = e->g_Kg.as<int>(); a.Cg = e->g_Cg.as<unsigned char>();
+    a.Eg = e->g_Eg.as<double>(); a.Fg = e->g_Fg.as<double>(); a.FK = e->g_FK.as<int>();
+    a.cat_lh = e->g_cat_lh.as<double>(); a.cat_k = e->g_cat_k.as<int>();
+    a.site_m = e->g_site_m.as<double>(); a.site_k = e->g_site_k.as<int>();
+    a.site_ll = e->d_site_ll.as<double>();
+    a.edge_out = q.want_edge ? e->g_edge_out.as<double>() : nullptr;
+    a.marg_out = q.want_marg ? e->g_marg_out.as<double>() : nullptr;
+    a.want_edge = q.want_edge; a.want_marg = q.want_marg;
+
+    const size_t smem_in = sizeof(double) * 2 * n * PLF_TS, smem_out = sizeof(double) * 3 * n * PLF_TS;
+    if (smem_in > 48 * 1024) CK(e, cudaFuncSetAttribute(generic_inside_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_in));
+    if (smem_out > 48 * 1024) CK(e, cudaFuncSetAttribute(generic_outside_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_out));
+    if (smem_out > 227 * 1024) FAIL(e, "state count %d is too large for the generic kernels", n);
+    const double *w = e->have_w ? e->d_site_w.as<double>() : nullptr;
+
+    for (int64_t s0 = 0; s0 < e->S; s0 += Sc) {
+        a.s0 = s0; a.Sc = (int)std::min<int64_t>(Sc, e->S - s0);
+        const unsigned gx = (unsigned)((a.Sc + PLF_TS - 1) / PLF_TS);
+        generic_inside_kernel<<<dim3(gx, C), PLF_TS, smem_in, e->stream>>>(a);
+        KCHECK(e);
+        generic_site_kernel<<<(a.Sc + 255) / 256, 256, 0, e->stream>>>(a);
+        KCHECK(e);
+        if (q.sum_ll) {
+            wsum_rows_kernel<<<1, 256, 0, e->stream>>>(a.site_ll + s0, w, s0, a.Sc, dsum, e->d_err.as<int>(), 1);
+            KCHECK(e);
+        }
+        if (outside) {
+            if (q.want_edge) CK(e, cudaMemsetAsync(a.edge_out, 0, sizeof(double) * (size_t)E * a.Sc, e->stream));
+            if (q.want_marg) CK(e, cudaMemsetAsync(a.marg_out, 0, sizeof(double) * (size_t)N * n * a.Sc, e->stream));
+            generic_outside_kernel<<<gx, PLF_TS, smem_out, e->stream>>>(a);
+            KCHECK(e);
+            if (q.want_edge && q.sum_edge) {
+                wsum_rows_kernel<<<E, 256, 0, e->stream>>>(a.edge_out, w, s0, a.Sc, dsum + 1, e->d_err.as<int>(), 0);
+                KCHECK(e);
+            }
+            if (q.want_marg && q.sum_marg) {
+                wsum_rows_kernel<<<N * n, 256, 0, e->stream>>>(a.marg_out, w, s0, a.Sc, dsum + 1 + E, e->d_err.as<int>(), 0);
+                KCHECK(e);
+            }
+            if (q.want_edge && q.site_edge) {
+                CK(e, cudaStreamSynchronize(e->stream));
+                if (copy_site_matrix(e, a.edge_out, E, a.Sc, q.site_edge + (size_t)s0 * E)) return -1;
+            }
+            if (q.want_marg && q.site_marg) {
+                CK(e, cudaStreamSynchronize(e->stream));
+                if (copy_site_matrix(e, a.marg_out, N * n, a.Sc, q.site_marg + (size_t)s0 * N * n)) return -1;
+            }
+        }
+    }
+    const size_t nsum = 1 + E + (size_t)N * n;
+    if (finish_sums(e, dsum, nsum)) return -1;
+    CK(e, cudaEventRecord(e->ev[2], e->stream));
+    std::vector<double> hs(nsum);
+    int herr = 0;
+    CK(e, cudaMemcpyAsync(hs.data(), dsum, sizeof(double) * nsum, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaMemcpyAsync(&herr, e->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    if (q.site_ll) CK(e, cudaMemcpyAsync(q.site_ll, e->d_site_ll.p, sizeof(double) * e->S, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    if (herr && q.sum_ll) FAIL(e, "a site with non-zero weight has zero likelihood");
+    if (q.sum_ll) *q.sum_ll = hs[0];
+    if (q.sum_edge) memcpy(q.sum_edge, hs.data() + 1, sizeof(double) * E);
+    if (q.sum_marg) memcpy(q.sum_marg, hs.data() + 1 + E, sizeof(double) * (size_t)N * n);
+    return 0;
+}
+
+/* common driver: matrices, path selection, timing */
+static int run_query(plf_engine *e, Query &q, bool need_D, const double *l_hi, const double *l_lo, int kind)
+{
+    if (e->S == 0 || e->n == 0 || e->N == 0) FAIL(e, "engine is not fully configured (tree, model and data are required)");
+    CK(e, cudaSetDevice(e->device));
+    bool use_fused = fused_applicable(e) && !q.want_marg;
+    if (e->path == PLF_PATH_GENERIC) use_fused = false;
+    if (e->path == PLF_PATH_FUSED4 && !use_fused) FAIL(e, "the fused 4-state path does not apply to this query");
+    CK(e, cudaEventRecord(e->ev[0], e->stream));
+    if (ensure_matrices(e, need_D)) return -1;
+    int f_mode = 2;
+    if (need_D) { q.Fm = e->d_D.as<double>(); q.f_zero_rowsum = 1; f_mode = 1; }
+    if (l_hi) {
+        if (upload_L(e, l_hi, l_lo)) return -1;
+        ENSURE(e, e->d_F, sizeof(double) * (size_t)e->C * e->E * e->n * e->n);
+        if (q.edge_mask_h) {
+            ENSURE(e, e->d_mask, e->E);
+            CK(e, cudaMemcpyAsync(e->d_mask.p, q.edge_mask_h, e->E, cudaMemcpyHostToDevice, e->stream));
+        }
+        if (run_expm(e, nullptr, nullptr, e->d_F.as<double>(), kind == PLF_KIND_TRANS ? 1 : 0,
+                     q.edge_mask_h ? e->d_mask.as<unsigned char>() : nullptr, e->d_lhi.as<double>(), e->d_llo.as<double>())) return -1;
+        q.Fm = e->d_F.as<double>(); q.f_zero_rowsum = 0; f_mode = 2;
+    }
+    if (use_fused && ensure_tip_tables(e, q.want_edge ? q.Fm : nullptr, f_mode)) return -1;
+    CK(e, cudaEventRecord(e->ev[1], e->stream));
+    int rc = use_fused ? run_fused(e, q) : run_generic(e, q);
+    if (rc) return rc;
+    cudaEventElapsedTime(&e->ms_mat, e->ev[0], e->ev[1]);
+    cudaEventElapsedTime(&e->ms_sites, e->ev[1], e->ev[2]);
+    return 0;
+}
+
+extern "C" int plf_ll(plf_engine *e, double *site_ll, double *sum)
+{
+    if (!e) return -1;
+    Query q;
+    q.site_ll = site_ll; q.sum_ll = sum;
+    return run_query(e, q, false, nullptr, nullptr, 0);
+}
+
+extern "C" int plf_deriv(plf_engine *e, const unsigned char *edge_mask, double *site_ll, double *sum_ll,
+                         double *site_deriv, double *sum_deriv)
+{
+    if (!e) return -1;
+    Query q;
+    q.want_edge = true; q.edge_mask_h = edge_mask;
+    q.site_ll = site_ll; q.sum_ll = sum_ll; q.site_edge = site_deriv; q.sum_edge = sum_deriv;
+    return run_query(e, q, true, nullptr, nullptr, 0);
+}
+
+extern "C" int plf_marginal(plf_engine *e, double *site_marg, double *sum_marg)
+{
+    if (!e) return -1;
+    Query q;
+    q.want_marg = true; q.site_marg = site_marg; q.sum_marg = sum_marg;
+    return run_query(e, q, false, nullptr, nullptr, 0);
+}
+
+extern "C" int plf_edge_expect(plf_engine *e, int kind, const double *l_hi, const double *l_lo,
+                               const unsigned char *edge_mask, double *site_out, double *sum_out)
+{
+    if (!e) return -1;
+    if (kind != PLF_KIND_DWELL && kind != PLF_KIND_TRANS) FAIL(e, "plf_edge_expect: invalid kind %d", kind);
+    if (!l_hi) FAIL(e, "plf_edge_expect: l_hi is required");
+    Query q;
+    q.want_edge = true; q.edge_mask_h = edge_mask; q.site_edge = site_out; q.sum_edge = sum_out;
+    return run_query(e, q, false, l_hi, l_lo, kind);
+}
+
+extern "C" int plf_get_transition_matrices(plf_engine *e, double *p_out)
+{
+    if (!e) return -1;
+    if (e->n == 0) FAIL(e, "model not set");
+    CK(e, cudaSetDevice(e->device));
+    if (ensure_matrices(e, false)) return -1;
+    CK(e, cudaMemcpyAsync(p_out, e->d_P.p, sizeof(double) * (size_t)e->C * e->E * e->n * e->n, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int plf_get_derivative_matrices(plf_engine *e, double *d_out)
+{
+    if (!e) return -1;
+    if (e->n == 0) FAIL(e, "model not set");
+    CK(e, cudaSetDevice(e->device));
+    if (ensure_matrices(e, true)) return -1;
+    CK(e, cudaMemcpyAsync(d_out, e->d_D.p, sizeof(double) * (size_t)e->C * e->E * e->n * e->n, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int plf_get_frechet_matrices(plf_engine *e, const double *l_hi, const double *l_lo, double *f_out)
+{
+    if (!e) return -1;
+    if (e->n == 0) FAIL(e, "model not set");
+    CK(e, cudaSetDevice(e->device));
+    if (upload_L(e, l_hi, l_lo)) return -1;
+    ENSURE(e, e->d_F, sizeof(double) * (size_t)e->C * e->E * e->n * e->n);
+    if (run_expm(e, nullptr, nullptr, e->d_F.as<double>(), 0, nullptr, e->d_lhi.as<double>(), e->d_llo.as<double>())) return -1;
+    CK(e, cudaMemcpyAsync(f_out, e->d_F.p, sizeof(double) * (size_t)e->C * e->E * e->n * e->n, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* multi-GPU                                                           */
+/* ------------------------------------------------------------------ */
+
+extern "C" int plf_comm_unique_id(char id[128])
+{
+    if (!g_nccl.load()) { fprintf(stderr, "plf_comm_unique_id: cannot load libnccl.so.2\n"); return -1; }
+    plf_nccl_id u;
+    if (g_nccl.GetUniqueId(&u) != 0) return -1;
+    memcpy(id, u.internal, 128);
+    return 0;
+}
+
+extern "C" int plf_comm_init(plf_engine *e, int nranks, int rank, const char id[128])
+{
+    if (!e) return -1;
+    if (!g_nccl.load()) FAIL(e, "cannot load libnccl.so.2: %s", dlerror());
+    CK(e, cudaSetDevice(e->device));
+    plf_nccl_id u;
+    memcpy(u.internal, id, 128);
+    int r = g_nccl.CommInitRank(&e->comm, nranks, u, rank);
+    if (r != 0) { e->comm = nullptr; FAIL(e, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); }
+    e->nranks = nranks;
+    return 0;
+}

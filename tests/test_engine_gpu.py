@@ -1,0 +1,207 @@
+"""
+GPU parity tests of the device seam (include/plf.h) against the oracle.
+
+Every comparison is against the oracle in 320-bit mode (which reproduces the
+reference's golden outputs bit for bit, tests/test_oracle_golden.py), at the
+tolerance the north star states: 1e-11 relative.  Exact zeros / ones that the
+reference produces through its constant-column shortcut must stay exact.
+The oracle values are cached in tests/golden/seam/*.npz (see
+tests/helpers.py:seam_reference; regenerate by deleting the cache).
+"""
+import numpy as np
+import pytest
+
+from oracle import arbplf_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-11
+
+
+def _engine():
+    from phyly_b200.engine import Engine
+    return Engine(0)
+
+
+def _assert_close(got, want, what, rtol=RTOL, atol=0.0):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    err = np.abs(got - want)
+    tol = rtol * np.abs(want) + atol
+    bad = ~(err <= tol)
+    if bad.any():
+        i = tuple(np.argwhere(bad)[0])
+        raise AssertionError("%s: %d mismatches, first at %s: got %r want %r (rel %.3e)" % (
+            what, bad.sum(), i, got[i], want[i], err[i] / max(abs(want[i]), 1e-300)))
+
+
+def _paths(m, C, K):
+    from phyly_b200 import engine as E
+    t = m.tree
+    maxdeg = max(t.indptr[i + 1] - t.indptr[i] for i in range(t.node_count))
+    p = [E.PATH_GENERIC]
+    if m.n == 4 and C <= 4 and maxdeg <= 3 and K <= 256:
+        p.append(E.PATH_FUSED4)
+    return p
+
+
+GOLDEN_MODELS = ["fels_deriv", "beast_gtrg", "beast_hky85i", "beast_gtrgi", "jc_long_deriv", "bpp_deriv",
+                 "mj_jumps", "beast_anc_marginal", "jc29_same_deriv", "jc30_diff_deriv", "fels_ll2"]
+
+RANDOM = [
+    dict(seed=1, ntips=8, n=4, S=9, ncat=1),
+    dict(seed=2, ntips=12, n=4, S=33, ncat=4, mixture="gamma", missing=0.2),
+    dict(seed=3, ntips=9, n=4, S=17, ncat=3, root="equilibrium_distribution", root_degree=3),
+    dict(seed=4, ntips=10, n=4, S=8, ncat=2, root="uniform_distribution", internal_data=True),
+    dict(seed=5, ntips=7, n=4, S=6, ncat=5, mixture="median_inv"),
+    dict(seed=6, ntips=6, n=2, S=7, ncat=2, root=None, divisor=None),
+    dict(seed=7, ntips=6, n=5, S=7, ncat=1, soft=True, internal_data=True),
+    dict(seed=8, ntips=4, n=20, S=5, ncat=1),
+    dict(seed=9, ntips=9, n=4, S=12, ncat=1, max_degree=4),
+    dict(seed=10, ntips=40, n=4, S=24, ncat=4, mixture="gamma", edge_scale=0.05),
+    dict(seed=11, ntips=6, n=3, S=300, ncat=2, missing=0.5),
+    dict(seed=12, ntips=24, n=4, S=70, ncat=2, root="equilibrium_distribution", missing=0.3),
+]
+
+
+def _problems():
+    out = []
+    for name in GOLDEN_MODELS:
+        out.append((name, H.golden_in(name)))
+    for kw in RANDOM:
+        out.append(("random%d" % kw["seed"], H.random_problem(**kw)))
+    return out
+
+
+PROBLEMS = _problems()
+IDS = [p[0] for p in PROBLEMS]
+
+
+def _setup(name, prob):
+    m = O.parse_model(prob["model_and_data"])
+    ref = H.seam_reference(name, prob)
+    defs, codes = H.dedupe_rows(m.dense_pmat())
+    return m, ref, defs.shape[0]
+
+
+@pytest.mark.parametrize("name,prob", PROBLEMS, ids=IDS)
+def test_matrices(name, prob):
+    m, ref, K = _setup(name, prob)
+    eng = _engine()
+    cs = H.fill_engine(eng, m)
+    P = eng.transition_matrices()
+    D = eng.derivative_matrices()
+    Ld, Lt, Lt_hi, Lt_lo, Lg = H.frechet_directions(m, cs)
+    F = eng.frechet_matrices(Lg)
+    _assert_close(P, ref["P"], name + " P", rtol=1e-14, atol=1e-300)
+    for c in range(P.shape[0]):
+        for e in range(P.shape[1]):
+            # entries of Q.P cancel: accurate relative to the scale of |Q||P|
+            _assert_close(D[c, e], ref["Dm"][c, e], "%s D[%d,%d]" % (name, c, e), rtol=1e-13,
+                          atol=1e-28 * ref["Dscale"][c, e])
+            _assert_close(F[c, e], ref["F"][c, e], "%s F[%d,%d]" % (name, c, e), rtol=1e-13,
+                          atol=1e-28 * np.abs(ref["F"][c, e]).max())
+    eng.close()
+
+
+@pytest.mark.parametrize("name,prob", PROBLEMS, ids=IDS)
+def test_ll_and_deriv(name, prob):
+    m, ref, K = _setup(name, prob)
+    S = m.site_count
+    ll_w, D_w = ref["ll"], ref["D"]
+    E = D_w.shape[1]
+    rng = np.random.default_rng(0)
+    w = rng.integers(0, 4, S).astype(np.float64) + rng.random(S)
+    for path in _paths(m, int(ref["C"]), K):
+        eng = _engine()
+        H.fill_engine(eng, m)
+        eng.set_path(path)
+        site_ll, tot = eng.ll()
+        _assert_close(site_ll, ll_w, "%s ll path%d" % (name, path))
+        assert H.close(tot, float(np.sum(ll_w)), 1e-11, 1e-13), (name, path, tot, np.sum(ll_w))
+        r = eng.deriv(per_site=True, per_site_ll=True)
+        _assert_close(r["site_ll"], ll_w, "%s deriv-ll path%d" % (name, path))
+        _assert_close(r["site_deriv"], D_w, "%s deriv path%d" % (name, path), atol=1e-300)
+        assert np.all(r["site_deriv"][D_w == 0.0] == 0.0), (name, path)     # exact zeros stay exact
+        # weighted sums through the reduction kernels
+        eng.set_site_weights(w)
+        r2 = eng.deriv(per_site=False)
+        want = (w[:, None] * D_w).sum(axis=0)
+        mag = (np.abs(w[:, None] * D_w)).sum(axis=0).max()
+        _assert_close(r2["sum_deriv"], want, "%s sum deriv path%d" % (name, path), atol=1e-13 * mag)
+        assert H.close(r2["sum_ll"], float((w * ll_w).sum()), 1e-11, 1e-13), (name, path)
+        mask = np.zeros(E, dtype=np.uint8)
+        mask[::2] = 1
+        r3 = eng.deriv(edge_mask=mask, per_site=False)
+        _assert_close(r3["sum_deriv"][mask == 1], want[mask == 1], "%s masked deriv path%d" % (name, path),
+                      atol=1e-13 * mag)
+        assert np.all(r3["sum_deriv"][mask == 0] == 0.0)
+        eng.close()
+
+
+@pytest.mark.parametrize("name,prob", PROBLEMS, ids=IDS)
+def test_marginal(name, prob):
+    m, ref, K = _setup(name, prob)
+    want = ref["marg"]
+    eng = _engine()
+    H.fill_engine(eng, m)
+    sm, tot = eng.marginal()
+    _assert_close(sm, want, "%s marginal" % name, atol=1e-300)
+    assert np.all(sm[want == 0.0] == 0.0)
+    assert np.all(sm[want == 1.0] == 1.0)
+    _assert_close(tot, want.sum(axis=0), "%s marginal sums" % name, atol=1e-13 * m.site_count)
+    eng.close()
+
+
+@pytest.mark.parametrize("name,prob", PROBLEMS, ids=IDS)
+def test_dwell_and_trans(name, prob):
+    m, ref, K = _setup(name, prob)
+    S = m.site_count
+    Xd, Xt = ref["Xd"], ref["Xt"]
+    from phyly_b200 import engine as E
+    for path in _paths(m, int(ref["C"]), K):
+        eng = _engine()
+        cs = H.fill_engine(eng, m)
+        Ld, Lt, Lt_hi, Lt_lo, Lg = H.frechet_directions(m, cs)
+        eng.set_path(path)
+        so, tot = eng.edge_expect(E.KIND_DWELL, Ld)
+        _assert_close(so, Xd, "%s dwell path%d" % (name, path), atol=1e-300)
+        _assert_close(tot, Xd.sum(axis=0), "%s dwell sums path%d" % (name, path), atol=1e-13 * S)
+        so, tot = eng.edge_expect(E.KIND_TRANS, Lt_hi, Lt_lo)
+        _assert_close(so, Xt, "%s trans path%d" % (name, path), atol=1e-300)
+        so2, tot2 = eng.edge_expect(E.KIND_TRANS, Lt_hi, Lt_lo, per_site=False)
+        _assert_close(tot2, Xt.sum(axis=0), "%s trans sums path%d" % (name, path), atol=1e-13 * S)
+        eng.close()
+
+
+def test_deep_tree_scaling():
+    """A 600-taxon tree underflows fp64 without per-site rescaling."""
+    prob = H.random_problem(21, ntips=600, n=4, S=40, ncat=2, missing=0.02, edge_scale=0.3)
+    m = O.parse_model(prob["model_and_data"])
+    ref = H.seam_reference("deep600", prob)
+    sites = ref["sites"]
+    assert ref["ll"][0] < -745.0          # below log(min double): plain fp64 would underflow
+    from phyly_b200 import engine as E
+    for path in (E.PATH_GENERIC, E.PATH_FUSED4):
+        eng = _engine()
+        H.fill_engine(eng, m)
+        eng.set_path(path)
+        r = eng.deriv(per_site=True, per_site_ll=True)
+        _assert_close(r["site_ll"][sites], ref["ll"], "deep ll path%d" % path)
+        _assert_close(r["site_deriv"][sites], ref["D"], "deep deriv path%d" % path, atol=1e-300)
+        eng.close()
+
+
+def test_zero_likelihood_is_an_error():
+    prob = H.golden_in("fels_ll")
+    md = prob["model_and_data"]
+    md["edge_rate_coefficients"] = [0.0] * 7     # P = I everywhere, data disagree -> likelihood 0
+    m = O.parse_model(md)
+    from phyly_b200.engine import EngineError
+    eng = _engine()
+    H.fill_engine(eng, m)
+    with pytest.raises(EngineError):
+        eng.ll()
+    eng.close()
