@@ -1116,10 +1116,12 @@ def run_ll(root, mode="mp"):
 
 
 def per_site_ll_and_deriv(m: Model, be, sites: Sequence[int], want_deriv=True,
-                          requested_csr=None, literal=False):
+                          requested_csr=None, literal=False, absQ=False):
     """
     Returns (ll[S'], deriv[S', E] in csr edge order).  Used by the tests to
-    check the device seam directly.
+    check the device seam directly.  With absQ=True the derivative sum is
+    formed with |Q| instead of Q: the magnitude of the terms that cancel, i.e.
+    the scale against which a floating-point evaluation can be accurate.
     """
     cs = cross_site(m, be)
     t = m.tree
@@ -1144,9 +1146,9 @@ def per_site_ll_and_deriv(m: Model, be, sites: Sequence[int], want_deriv=True,
                 if not requested_csr[idx]:
                     continue
                 b = t.indices[idx]
-                qe = _matvec(cs.Q, edge[idx])
+                qe = _matvec(abs(cs.Q) if absQ else cs.Q, edge[idx])
                 ec = nconst[b]
-                if ec.any():
+                if ec.any() and not absQ:
                     qe[ec] = 0
                 v = (fe[idx] * qe).sum(axis=1)
                 D[:, idx] = D[:, idx] + cs.prior[c] * cs.rates[c] * v

@@ -216,6 +216,10 @@ def seam_reference(name, prob):
         sites = [0, 7, 39]
     ll, D, cs = O.per_site_ll_and_deriv(m, be, sites)
     out = {"sites": np.array(sites), "ll": _fl(ll), "D": _fl(D), "C": np.array(cs.C)}
+    # magnitude of the cancelling terms of each derivative (fp64 is plenty for a scale)
+    _, Dabs, _ = O.per_site_ll_and_deriv(m, be if name.startswith("deep") else O.get_backend("fp64"),
+                                         sites, absQ=True)
+    out["Dabs"] = _fl(Dabs)
     if not name.startswith("deep"):
         Ld, Lt, Lt_hi, Lt_lo, Lg = frechet_directions(m, cs)
         out["marg"] = _fl(O.per_site_marginal(m, be, sites))

