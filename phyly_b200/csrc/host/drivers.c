@@ -1,0 +1,519 @@
+/*
+ * Per-query drivers: JSON in -> device seam -> JSON out.
+ *
+ * Each driver mirrors the reference's _parse / _query / _nd_accum_update trio
+ * (arbplfll.c:110-323, arbplfderiv.c:210-531, arbplfmarginal.c:111-446,
+ * arbplfdwell.c:116-610, arbplftrans.c:115-660) except that the loop nest
+ * over sites x categories x nodes and the precision loop are replaced by one
+ * call into the CUDA engine (include/plf.h).  What stays on the host is the
+ * reference's outer, precision-agnostic layer: schema validation, selection /
+ * aggregation weights and the output table.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "arbplf.h"
+#include "plf.h"
+#include "json.h"
+#include "model.h"
+#include "reduce.h"
+#include "dd.h"
+
+static plf_engine *g_engine = NULL;
+static int g_device = -1;
+
+void arbplf_set_device(int device)
+{
+    if (g_engine && device != g_device) { plf_destroy(g_engine); g_engine = NULL; }
+    g_device = device;
+}
+
+static plf_engine *get_engine(void)
+{
+    if (g_engine) return g_engine;
+    if (g_device < 0) {
+        const char *s = getenv("ARBPLF_DEVICE");
+        g_device = s ? atoi(s) : 0;
+    }
+    if (plf_create(&g_engine, g_device)) {
+        fprintf(stderr, "error: cannot create the CUDA engine on device %d (this build has no CPU path)\n", g_device);
+        g_engine = NULL;
+    }
+    return g_engine;
+}
+
+typedef struct {
+    jv *root;
+    plf_model m;
+    plf_derived d;
+    plf_engine *e;
+    int loaded;
+} ctx;
+
+static void ctx_clear(ctx *c)
+{
+    json_free(c->root);
+    plf_model_clear(&c->m);
+    plf_derived_clear(&c->d);
+    memset(c, 0, sizeof(*c));
+}
+
+/* parse the document and the model; keys: NULL-terminated list for the strict top-level unpack */
+static int ctx_parse(ctx *c, const char *json_in, const char *const *keys, const jv **out)
+{
+    char err[256];
+    memset(c, 0, sizeof(*c));
+    plf_model_init(&c->m);
+    c->root = json_parse(json_in, err, sizeof err);
+    if (!c->root) { fprintf(stderr, "%s\n", err); return -1; }
+    if (jv_unpack_strict(c->root, keys, out)) return -1;
+    if (plf_model_parse(&c->m, out[0])) return -1;
+    return 0;
+}
+
+/* push tree, model and data to the device */
+static int ctx_load(ctx *c)
+{
+    if (plf_derive(&c->d, &c->m)) return -1;
+    c->e = get_engine();
+    if (!c->e) return -1;
+    const plf_model *m = &c->m;
+    const plf_derived *d = &c->d;
+#define EK(call) do { if (call) { fprintf(stderr, "error: %s\n", plf_last_error(c->e)); return -1; } } while (0)
+    EK(plf_set_tree(c->e, m->N, m->indptr, m->indices, m->preorder));
+    EK(plf_set_model(c->e, m->n, d->C, d->q_hi, d->q_lo, d->edge_rates_csr, d->cat_rates, d->cat_prior,
+                     m->root_mode, d->root_vec));
+    if (m->S > 0) EK(plf_set_data(c->e, m->S, m->K, m->defs, m->codes, m->code_bytes));
+    c->loaded = 1;
+    return 0;
+}
+
+static unsigned char *edge_mask_csr(const plf_model *m, const axis *edge_axis)
+{
+    unsigned char *mask = calloc(m->E > 0 ? m->E : 1, 1);
+    for (int e = 0; e < m->E; e++) mask[m->order[e]] = edge_axis->requested[e];
+    return mask;
+}
+
+static char *finish(ctx *c, char *out, int rc, int *retcode)
+{
+    ctx_clear(c);
+    *retcode = rc;
+    if (rc) { free(out); return NULL; }
+    return out;
+}
+
+/* ------------------------------------------------------------------ */
+/* arbplf-ll                                                           */
+/* ------------------------------------------------------------------ */
+
+char *arbplf_ll(const char *json_in, int *retcode)
+{
+    static const char *const keys[] = {"model_and_data", "?site_reduction", NULL};
+    const jv *v[2];
+    ctx c;
+    reduction r_site; reduction_init(&r_site);
+    axis ax[1]; memset(ax, 0, sizeof ax);
+    double *val = NULL, *site_ll = NULL;
+    char *out = NULL;
+    int rc = -1;
+    if (ctx_parse(&c, json_in, keys, v)) goto done;
+    const int64_t S = c.m.S;
+    if (reduction_parse(&r_site, (int)S, "site", v[1])) goto done;
+    if (axis_init(&ax[0], "site", (int)S, &r_site)) goto done;
+    val = calloc(ax[0].aggregated ? 1 : (S > 0 ? S : 1), sizeof(double));
+    if (S > 0) {
+        if (ctx_load(&c)) goto done;
+        if (ax[0].aggregated) {
+            if (plf_set_site_weights(c.e, ax[0].w) || plf_ll(c.e, NULL, &val[0])) {
+                fprintf(stderr, "error: %s\n", plf_last_error(c.e)); goto done;
+            }
+        } else {
+            site_ll = malloc(sizeof(double) * S);
+            if (plf_set_site_weights(c.e, NULL) || plf_ll(c.e, site_ll, NULL)) {
+                fprintf(stderr, "error: %s\n", plf_last_error(c.e)); goto done;
+            }
+            for (int64_t s = 0; s < S; s++) {
+                if (!ax[0].requested[s]) continue;
+                if (!isfinite(site_ll[s])) { fprintf(stderr, "error: site %lld has zero likelihood\n", (long long)s); goto done; }
+                val[s] = site_ll[s];
+            }
+        }
+    }
+    out = table_to_json(ax, 1, val);
+    rc = 0;
+done:
+    free(val); free(site_ll);
+    axis_clear(&ax[0]); reduction_clear(&r_site);
+    return finish(&c, out, rc, retcode);
+}
+
+/* ------------------------------------------------------------------ */
+/* shared by deriv / dwell / trans: values over (site, edge[, third])  */
+/* ------------------------------------------------------------------ */
+
+/*
+ * One engine call producing edge values for all sites (kind < 0: derivative).
+ * Fills val over (site, user edge) at third-axis coordinate `third` (stride 1,
+ * extent third_n), applying the site / edge aggregation weights.
+ */
+static int edge_pass(ctx *c, int kind, const double *l_hi, const double *l_lo,
+                     const axis *ax_site, const axis *ax_edge, const unsigned char *mask,
+                     double *val, int third, int third_n)
+{
+    const plf_model *m = &c->m;
+    const int E = m->E;
+    const int64_t S = m->S;
+    int rc = -1;
+    double *sum = NULL, *per_site = NULL, *site_ll = NULL;
+    const size_t edge_ext = ax_edge->aggregated ? 1 : (size_t)E;
+    if (ax_site->aggregated) {
+        sum = calloc(E > 0 ? E : 1, sizeof(double));
+        double dummy = 0;
+        int r;
+        if (plf_set_site_weights(c->e, ax_site->w)) goto engine_error;
+        if (kind < 0) r = plf_deriv(c->e, mask, NULL, &dummy, NULL, sum);
+        else r = plf_edge_expect(c->e, kind, l_hi, l_lo, mask, NULL, sum);
+        if (r) goto engine_error;
+        for (int e = 0; e < E; e++) {
+            if (!ax_edge->requested[e]) continue;
+            double x = sum[m->order[e]];
+            if (!isfinite(x)) { fprintf(stderr, "error: a requested site has zero likelihood\n"); goto done; }
+            if (ax_edge->aggregated) val[third] += x * ax_edge->w[e];
+            else val[(size_t)e * third_n + third] = x;
+        }
+    } else {
+        per_site = malloc(sizeof(double) * (size_t)S * (E > 0 ? E : 1));
+        int r;
+        if (plf_set_site_weights(c->e, NULL)) goto engine_error;
+        if (kind < 0) r = plf_deriv(c->e, mask, NULL, NULL, per_site, NULL);
+        else r = plf_edge_expect(c->e, kind, l_hi, l_lo, mask, per_site, NULL);
+        if (r) goto engine_error;
+        for (int64_t s = 0; s < S; s++) {
+            if (!ax_site->requested[s]) continue;
+            for (int e = 0; e < E; e++) {
+                if (!ax_edge->requested[e]) continue;
+                double x = per_site[(size_t)s * E + m->order[e]];
+                if (!isfinite(x)) { fprintf(stderr, "error: site %lld has zero likelihood\n", (long long)s); goto done; }
+                if (ax_edge->aggregated) val[(size_t)s * third_n + third] += x * ax_edge->w[e];
+                else val[((size_t)s * edge_ext + e) * third_n + third] = x;
+            }
+        }
+    }
+    rc = 0;
+    goto done;
+engine_error:
+    fprintf(stderr, "error: %s\n", plf_last_error(c->e));
+done:
+    free(sum); free(per_site); free(site_ll);
+    return rc;
+}
+
+char *arbplf_deriv(const char *json_in, int *retcode)
+{
+    static const char *const keys[] = {"model_and_data", "?site_reduction", "?edge_reduction", NULL};
+    const jv *v[3];
+    ctx c;
+    reduction r_site, r_edge; reduction_init(&r_site); reduction_init(&r_edge);
+    axis ax[2]; memset(ax, 0, sizeof ax);
+    double *val = NULL;
+    unsigned char *mask = NULL;
+    char *out = NULL;
+    int rc = -1;
+    if (ctx_parse(&c, json_in, keys, v)) goto done;
+    if (reduction_parse(&r_site, (int)c.m.S, "site", v[1])) goto done;
+    if (reduction_parse(&r_edge, c.m.E, "edge", v[2])) goto done;
+    if (axis_init(&ax[0], "site", (int)c.m.S, &r_site) || axis_init(&ax[1], "edge", c.m.E, &r_edge)) goto done;
+    {
+        size_t cells = (ax[0].aggregated ? 1 : (size_t)c.m.S) * (ax[1].aggregated ? 1 : (size_t)c.m.E);
+        val = calloc(cells ? cells : 1, sizeof(double));
+    }
+    if (c.m.S > 0) {
+        if (ctx_load(&c)) goto done;
+        mask = edge_mask_csr(&c.m, &ax[1]);
+        if (edge_pass(&c, -1, NULL, NULL, &ax[0], &ax[1], mask, val, 0, 1)) goto done;
+    }
+    out = table_to_json(ax, 2, val);
+    rc = 0;
+done:
+    free(val); free(mask);
+    axis_clear(&ax[0]); axis_clear(&ax[1]);
+    reduction_clear(&r_site); reduction_clear(&r_edge);
+    return finish(&c, out, rc, retcode);
+}
+
+/* ------------------------------------------------------------------ */
+/* arbplf-marginal                                                     */
+/* ------------------------------------------------------------------ */
+
+char *arbplf_marginal(const char *json_in, int *retcode)
+{
+    static const char *const keys[] = {"model_and_data", "?site_reduction", "?node_reduction", "?state_reduction", NULL};
+    const jv *v[4];
+    ctx c;
+    reduction r_site, r_node, r_state;
+    reduction_init(&r_site); reduction_init(&r_node); reduction_init(&r_state);
+    axis ax[3]; memset(ax, 0, sizeof ax);
+    double *val = NULL, *buf = NULL;
+    char *out = NULL;
+    int rc = -1;
+    if (ctx_parse(&c, json_in, keys, v)) goto done;
+    const int N = c.m.N, n = c.m.n;
+    const int64_t S = c.m.S;
+    if (reduction_parse(&r_site, (int)S, "site", v[1])) goto done;
+    if (reduction_parse(&r_node, N, "node", v[2])) goto done;
+    if (reduction_parse(&r_state, n, "state", v[3])) goto done;
+    if (axis_init(&ax[0], "site", (int)S, &r_site) || axis_init(&ax[1], "node", N, &r_node) ||
+        axis_init(&ax[2], "state", n, &r_state)) goto done;
+    const size_t e1 = ax[1].aggregated ? 1 : (size_t)N, e2 = ax[2].aggregated ? 1 : (size_t)n;
+    val = calloc((ax[0].aggregated ? 1 : (size_t)(S > 0 ? S : 1)) * e1 * e2, sizeof(double));
+    if (S > 0) {
+        if (ctx_load(&c)) goto done;
+        const int64_t rows = ax[0].aggregated ? 1 : S;
+        buf = malloc(sizeof(double) * (size_t)rows * N * n);
+        int r;
+        if (ax[0].aggregated) r = plf_set_site_weights(c.e, ax[0].w) || plf_marginal(c.e, NULL, buf);
+        else r = plf_set_site_weights(c.e, NULL) || plf_marginal(c.e, buf, NULL);
+        if (r) { fprintf(stderr, "error: %s\n", plf_last_error(c.e)); goto done; }
+        for (int64_t s = 0; s < rows; s++) {
+            if (!ax[0].aggregated && !ax[0].requested[s]) continue;
+            for (int a = 0; a < N; a++) {
+                if (!ax[1].requested[a]) continue;
+                for (int j = 0; j < n; j++) {
+                    if (!ax[2].requested[j]) continue;
+                    double x = buf[((size_t)s * N + a) * n + j];
+                    if (!isfinite(x)) { fprintf(stderr, "error: a requested site has zero likelihood\n"); goto done; }
+                    if (ax[1].aggregated) x *= ax[1].w[a];
+                    if (ax[2].aggregated) x *= ax[2].w[j];
+                    size_t off = ((size_t)s * e1 + (ax[1].aggregated ? 0 : a)) * e2 + (ax[2].aggregated ? 0 : j);
+                    val[off] += x;
+                }
+            }
+        }
+    }
+    out = table_to_json(ax, 3, val);
+    rc = 0;
+done:
+    free(val); free(buf);
+    for (int i = 0; i < 3; i++) axis_clear(&ax[i]);
+    reduction_clear(&r_site); reduction_clear(&r_node); reduction_clear(&r_state);
+    return finish(&c, out, rc, retcode);
+}
+
+/* ------------------------------------------------------------------ */
+/* arbplf-dwell / arbplf-trans                                         */
+/* ------------------------------------------------------------------ */
+
+char *arbplf_dwell(const char *json_in, int *retcode)
+{
+    static const char *const keys[] = {"model_and_data", "?site_reduction", "?edge_reduction", "?state_reduction", NULL};
+    const jv *v[4];
+    ctx c;
+    reduction r_site, r_edge, r_state;
+    reduction_init(&r_site); reduction_init(&r_edge); reduction_init(&r_state);
+    axis ax[3]; memset(ax, 0, sizeof ax);
+    double *val = NULL, *L = NULL;
+    unsigned char *mask = NULL;
+    char *out = NULL;
+    int rc = -1;
+    if (ctx_parse(&c, json_in, keys, v)) goto done;
+    const int n = c.m.n, E = c.m.E;
+    const int64_t S = c.m.S;
+    if (reduction_parse(&r_site, (int)S, "site", v[1])) goto done;
+    if (reduction_parse(&r_edge, E, "edge", v[2])) goto done;
+    if (reduction_parse(&r_state, n, "state", v[3])) goto done;
+    if (axis_init(&ax[0], "site", (int)S, &r_site) || axis_init(&ax[1], "edge", E, &r_edge) ||
+        axis_init(&ax[2], "state", n, &r_state)) goto done;
+    /* state aggregation is folded into the Frechet direction: ndim = 2 (arbplfdwell.c:462-468) */
+    const int state_agg = ax[2].aggregated;
+    const int third_n = state_agg ? 1 : n;
+    {
+        size_t cells = (ax[0].aggregated ? 1 : (size_t)(S > 0 ? S : 1)) * (ax[1].aggregated ? 1 : (size_t)E) * third_n;
+        val = calloc(cells ? cells : 1, sizeof(double));
+    }
+    if (S > 0) {
+        if (ctx_load(&c)) goto done;
+        mask = edge_mask_csr(&c.m, &ax[1]);
+        L = calloc((size_t)n * n, sizeof(double));
+        if (state_agg) {
+            for (int s = 0; s < n; s++) L[s * n + s] = ax[2].w[s];     /* arbplfdwell.c:173-178 */
+            if (edge_pass(&c, PLF_KIND_DWELL, L, NULL, &ax[0], &ax[1], mask, val, 0, 1)) goto done;
+        } else {
+            for (int s = 0; s < n; s++) {
+                if (!ax[2].requested[s]) continue;
+                memset(L, 0, sizeof(double) * n * n);
+                L[s * n + s] = 1.0;                                     /* arbplfdwell.c:133 */
+                if (edge_pass(&c, PLF_KIND_DWELL, L, NULL, &ax[0], &ax[1], mask, val, s, n)) goto done;
+            }
+        }
+    }
+    out = table_to_json(ax, state_agg ? 2 : 3, val);
+    rc = 0;
+done:
+    free(val); free(L); free(mask);
+    for (int i = 0; i < 3; i++) axis_clear(&ax[i]);
+    reduction_clear(&r_site); reduction_clear(&r_edge); reduction_clear(&r_state);
+    return finish(&c, out, rc, retcode);
+}
+
+char *arbplf_trans(const char *json_in, int *retcode)
+{
+    static const char *const keys[] = {"model_and_data", "?site_reduction", "?edge_reduction", "?trans_reduction", NULL};
+    const jv *v[4];
+    ctx c;
+    reduction r_site, r_edge, r_trans;
+    reduction_init(&r_site); reduction_init(&r_edge); reduction_init(&r_trans);
+    axis ax[3]; memset(ax, 0, sizeof ax);
+    double *val = NULL, *Lh = NULL, *Ll = NULL;
+    unsigned char *mask = NULL;
+    char *out = NULL;
+    int rc = -1;
+    if (ctx_parse(&c, json_in, keys, v)) goto done;
+    const int n = c.m.n, E = c.m.E;
+    const int64_t S = c.m.S;
+    if (reduction_parse(&r_site, (int)S, "site", v[1])) goto done;
+    if (reduction_parse(&r_edge, E, "edge", v[2])) goto done;
+    if (reduction_parse_pairs(&r_trans, n, "trans", v[3])) goto done;
+    const int T = r_trans.selection_len;
+    if (axis_init(&ax[0], "site", (int)S, &r_site) || axis_init(&ax[1], "edge", E, &r_edge) ||
+        axis_init(&ax[2], "trans", T, &r_trans)) goto done;
+    ax[2].ncomp = 2;
+    ax[2].comp_name[0] = "first_state"; ax[2].comp_name[1] = "second_state";
+    ax[2].comp_idx[0] = r_trans.first_idx; ax[2].comp_idx[1] = r_trans.second_idx;
+    const int trans_agg = ax[2].aggregated;
+    const int third_n = trans_agg ? 1 : (T > 0 ? T : 1);
+    {
+        size_t cells = (ax[0].aggregated ? 1 : (size_t)(S > 0 ? S : 1)) * (ax[1].aggregated ? 1 : (size_t)E) * third_n;
+        val = calloc(cells ? cells : 1, sizeof(double));
+    }
+    if (S > 0) {
+        if (ctx_load(&c)) goto done;
+        mask = edge_mask_csr(&c.m, &ax[1]);
+        Lh = calloc((size_t)n * n, sizeof(double));
+        Ll = calloc((size_t)n * n, sizeof(double));
+        if (trans_agg) {
+            /* L = (sum_k w_k E_{a_k b_k}) .* Q / divisor  (arbplftrans.c:179-193) */
+            double *W = calloc((size_t)n * n, sizeof(double));
+            for (int k = 0; k < T; k++) W[r_trans.first_idx[k] * n + r_trans.second_idx[k]] += ax[2].w[k];
+            for (int i = 0; i < n * n; i++) {
+                dd_t q = dd_mul_d(dd_make(c.d.q_hi[i], c.d.q_lo[i]), W[i]);
+                Lh[i] = q.hi; Ll[i] = q.lo;
+            }
+            free(W);
+            if (edge_pass(&c, PLF_KIND_TRANS, Lh, Ll, &ax[0], &ax[1], mask, val, 0, 1)) goto done;
+        } else {
+            for (int k = 0; k < T; k++) {
+                if (!ax[2].requested[k]) continue;
+                memset(Lh, 0, sizeof(double) * n * n); memset(Ll, 0, sizeof(double) * n * n);
+                int idx = r_trans.first_idx[k] * n + r_trans.second_idx[k];
+                Lh[idx] = c.d.q_hi[idx]; Ll[idx] = c.d.q_lo[idx];      /* arbplftrans.c:133-134 */
+                if (edge_pass(&c, PLF_KIND_TRANS, Lh, Ll, &ax[0], &ax[1], mask, val, k, third_n)) goto done;
+            }
+        }
+    }
+    out = table_to_json(ax, trans_agg ? 2 : 3, val);
+    rc = 0;
+done:
+    free(val); free(Lh); free(Ll); free(mask);
+    for (int i = 0; i < 3; i++) axis_clear(&ax[i]);
+    reduction_clear(&r_site); reduction_clear(&r_edge); reduction_clear(&r_trans);
+    return finish(&c, out, rc, retcode);
+}
+
+/* ------------------------------------------------------------------ */
+/* model summary, unsupported programs, stdio shell                    */
+/* ------------------------------------------------------------------ */
+
+static void put_darray(jbuf *b, const char *key, const double *x, size_t n)
+{
+    jbuf_puts(b, "\""); jbuf_puts(b, key); jbuf_puts(b, "\": ");
+    if (!x) { jbuf_puts(b, "null"); return; }
+    jbuf_puts(b, "[");
+    for (size_t i = 0; i < n; i++) { if (i) jbuf_puts(b, ", "); jbuf_real(b, x[i]); }
+    jbuf_puts(b, "]");
+}
+
+static void put_iarray(jbuf *b, const char *key, const int *x, size_t n)
+{
+    jbuf_puts(b, "\""); jbuf_puts(b, key); jbuf_puts(b, "\": [");
+    for (size_t i = 0; i < n; i++) { if (i) jbuf_puts(b, ", "); jbuf_int(b, x[i]); }
+    jbuf_puts(b, "]");
+}
+
+char *arbplf_model_summary(const char *json_in, int *retcode)
+{
+    static const char *const keys[] = {"model_and_data", NULL};
+    const jv *v[1];
+    ctx c;
+    char *out = NULL;
+    int rc = -1;
+    if (ctx_parse(&c, json_in, keys, v)) goto done;
+    if (plf_derive(&c.d, &c.m)) goto done;
+    {
+        jbuf b; jbuf_init(&b);
+        const int n = c.m.n;
+        jbuf_puts(&b, "{\"state_count\": "); jbuf_int(&b, n);
+        jbuf_puts(&b, ", \"category_count\": "); jbuf_int(&b, c.d.C);
+        jbuf_puts(&b, ", \"site_count\": "); jbuf_int(&b, c.m.S);
+        jbuf_puts(&b, ", \"root_mode\": "); jbuf_int(&b, c.m.root_mode);
+        jbuf_puts(&b, ", \"rate_mix_expect\": "); jbuf_real(&b, c.d.expect);
+        jbuf_puts(&b, ", "); put_darray(&b, "cat_rates", c.d.cat_rates, c.d.C);
+        jbuf_puts(&b, ", "); put_darray(&b, "cat_prior", c.d.cat_prior, c.d.C);
+        jbuf_puts(&b, ", "); put_darray(&b, "equilibrium", c.d.equilibrium, n);
+        jbuf_puts(&b, ", "); put_darray(&b, "root_vec", c.d.root_vec, n);
+        jbuf_puts(&b, ", "); put_darray(&b, "q_hi", c.d.q_hi, (size_t)n * n);
+        jbuf_puts(&b, ", "); put_darray(&b, "q_lo", c.d.q_lo, (size_t)n * n);
+        jbuf_puts(&b, ", "); put_darray(&b, "edge_rates_csr", c.d.edge_rates_csr, c.m.E);
+        jbuf_puts(&b, ", "); put_iarray(&b, "indptr", c.m.indptr, c.m.N + 1);
+        jbuf_puts(&b, ", "); put_iarray(&b, "indices", c.m.indices, c.m.E);
+        jbuf_puts(&b, ", "); put_iarray(&b, "preorder", c.m.preorder, c.m.N);
+        jbuf_puts(&b, ", "); put_iarray(&b, "order", c.m.order, c.m.E);
+        jbuf_puts(&b, "}");
+        out = jbuf_take(&b);
+    }
+    rc = 0;
+done:
+    return finish(&c, out, rc, retcode);
+}
+
+static char *unsupported(const char *name, int *retcode)
+{
+    fprintf(stderr, "error: %s is outside the hot path of this build (second-order / EM programs of "
+                    "arbplfhess.c and arbplfem.c are not implemented)\n", name);
+    *retcode = -1;
+    return NULL;
+}
+
+char *arbplf_hess(const char *j, int *rc) { (void)j; return unsupported("arbplf-hess", rc); }
+char *arbplf_inv_hess(const char *j, int *rc) { (void)j; return unsupported("arbplf-inv-hess", rc); }
+char *arbplf_newton_delta(const char *j, int *rc) { (void)j; return unsupported("arbplf-newton-delta", rc); }
+char *arbplf_newton_update(const char *j, int *rc) { (void)j; return unsupported("arbplf-newton-update", rc); }
+char *arbplf_newton_refine(const char *j, int *rc) { (void)j; return unsupported("arbplf-newton-refine", rc); }
+char *arbplf_em_update(const char *j, int *rc) { (void)j; return unsupported("arbplf-em-update", rc); }
+
+/* runjson.c:88-147 */
+int arbplf_run_stdio(char *(*f)(const char *, int *))
+{
+    size_t cap = 1 << 16, len = 0;
+    char *s = malloc(cap);
+    if (!s) return -1;
+    for (;;) {
+        size_t got = fread(s + len, 1, cap - len - 1, stdin);
+        len += got;
+        if (got == 0) break;
+        if (len + 1 >= cap) {
+            cap *= 2;
+            char *t = realloc(s, cap);
+            if (!t) { fprintf(stderr, "failed to read string from stdin\n"); free(s); return -1; }
+            s = t;
+        }
+    }
+    s[len] = 0;
+    int rc = 0;
+    char *out = f(s, &rc);
+    free(s);
+    if (out) { puts(out); free(out); }
+    return rc;
+}

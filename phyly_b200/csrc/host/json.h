@@ -1,0 +1,61 @@
+/*
+ * Minimal strict JSON reader / writer for the arbplf front end.
+ *
+ * The reference uses jansson (json_loads / json_unpack_ex with JSON_STRICT /
+ * json_dumps, runjson.c:10-66); no jansson header exists in this image, so the
+ * host layer carries its own.  What matters for parity:
+ *   - integer and real tokens are distinguished (json_is_integer,
+ *     parsemodel.c:592,771; parsereduction.c:47);
+ *   - duplicate / unknown keys can be rejected by the caller;
+ *   - reals are printed with 17 significant digits and always carry a '.0' or
+ *     an exponent, like jansson's json_dumps.
+ */
+#ifndef PLF_JSON_H
+#define PLF_JSON_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+enum { JV_NULL = 0, JV_FALSE, JV_TRUE, JV_INT, JV_REAL, JV_STRING, JV_ARRAY, JV_OBJECT };
+
+typedef struct jv {
+    uint8_t type;
+    uint32_t len;                 /* array: items; object: pairs; string: bytes */
+    union {
+        int64_t i;
+        double d;
+        char *s;
+        struct jv *items;         /* array: len values; object: 2*len (key, value) */
+    } u;
+} jv;
+
+/* Parse a whole document.  On failure returns NULL and writes a message. */
+jv *json_parse(const char *text, char *err, size_t errlen);
+void json_free(jv *v);
+
+static inline int jv_is_number(const jv *v) { return v && (v->type == JV_INT || v->type == JV_REAL); }
+static inline int jv_is_int(const jv *v) { return v && v->type == JV_INT; }
+static inline int jv_is_string(const jv *v) { return v && v->type == JV_STRING; }
+static inline int jv_is_array(const jv *v) { return v && v->type == JV_ARRAY; }
+static inline int jv_is_object(const jv *v) { return v && v->type == JV_OBJECT; }
+static inline int jv_is_null(const jv *v) { return v && v->type == JV_NULL; }
+static inline double jv_number(const jv *v) { return v->type == JV_INT ? (double)v->u.i : v->u.d; }
+const jv *jv_get(const jv *obj, const char *key);
+
+/*
+ * json_unpack_ex(..., JSON_STRICT, "{s:o, s?o ...}") equivalent: keys is a
+ * NULL-terminated list; a leading '?' marks an optional key.  out[i] receives
+ * the value or NULL.  Returns 0 or -1 (message on stderr like the reference:
+ * "error: on line %d: %s").
+ */
+int jv_unpack_strict(const jv *obj, const char *const *keys, const jv **out);
+
+/* growing output buffer */
+typedef struct { char *p; size_t len, cap; } jbuf;
+void jbuf_init(jbuf *b);
+void jbuf_puts(jbuf *b, const char *s);
+void jbuf_int(jbuf *b, long long v);
+void jbuf_real(jbuf *b, double d);   /* jansson formatting, -0.0 scrubbed (util.c:44-48) */
+char *jbuf_take(jbuf *b);            /* malloc'd, NUL terminated; caller frees */
+
+#endif

@@ -240,3 +240,92 @@ def seam_reference(name, prob):
     os.makedirs(SEAM_CACHE, exist_ok=True)
     np.savez_compressed(path, **out)
     return out
+
+
+JSON_CACHE = os.path.join(GOLDEN, "json_cases")
+
+
+def reduction_cases():
+    """
+    (name, program, document) triples exercising the selection / aggregation
+    semantics of every axis (test_ll.py:64-94, test_ll_deriv.py:103-389,
+    test_marginal.py:89-126, test_dwell.py, test_trans.py of the reference).
+    """
+    cases = []
+    base = random_problem(31, ntips=7, n=4, S=6, ncat=2, root_degree=3)
+    E = len(base["model_and_data"]["edges"])
+    N = E + 1
+
+    def doc(**red):
+        d = {"model_and_data": base["model_and_data"]}
+        d.update(red)
+        return d
+    cases += [
+        ("ll_plain", "ll", doc()),
+        ("ll_sum", "ll", doc(site_reduction={"aggregation": "sum"})),
+        ("ll_avg", "ll", doc(site_reduction={"aggregation": "avg"})),
+        ("ll_sel", "ll", doc(site_reduction={"selection": [4, 1, 1, 0]})),
+        ("ll_sel_sum", "ll", doc(site_reduction={"selection": [4, 1, 1, 0], "aggregation": "sum"})),
+        ("ll_sel_avg", "ll", doc(site_reduction={"selection": [4, 1, 1, 0], "aggregation": "avg"})),
+        ("ll_only", "ll", doc(site_reduction={"selection": [3], "aggregation": "only"})),
+        ("ll_weighted", "ll", doc(site_reduction={"aggregation": [1, 2.5, 0, -1, 3, 0.125]})),
+        ("ll_sel_weighted", "ll", doc(site_reduction={"selection": [2, 2, 5], "aggregation": [1.5, -0.5, 2]})),
+        ("deriv_plain", "deriv", doc()),
+        ("deriv_site_sum", "deriv", doc(site_reduction={"aggregation": "sum"})),
+        ("deriv_edge_sum", "deriv", doc(edge_reduction={"aggregation": "sum"})),
+        ("deriv_both", "deriv", doc(site_reduction={"aggregation": "avg"}, edge_reduction={"aggregation": "sum"})),
+        ("deriv_sel", "deriv", doc(site_reduction={"selection": [5, 0]}, edge_reduction={"selection": [E - 1, 0, 3]})),
+        ("deriv_sel_w", "deriv", doc(site_reduction={"selection": [5, 0, 0], "aggregation": [1, 2, 3]},
+                                     edge_reduction={"selection": [E - 1, 0, 3], "aggregation": [0.5, -1, 2]})),
+        ("deriv_edge_only", "deriv", doc(edge_reduction={"selection": [2], "aggregation": "only"})),
+        ("marg_plain", "marginal", doc()),
+        ("marg_site_sum", "marginal", doc(site_reduction={"aggregation": "sum"})),
+        ("marg_node_sel", "marginal", doc(node_reduction={"selection": [N - 1, 0, 2]})),
+        ("marg_state_w", "marginal", doc(state_reduction={"aggregation": [1, 0, 2, 0.5]})),
+        ("marg_all", "marginal", doc(site_reduction={"aggregation": "avg"}, node_reduction={"selection": [1, 3], "aggregation": "sum"},
+                                     state_reduction={"selection": [0, 3], "aggregation": "sum"})),
+        ("dwell_plain", "dwell", doc()),
+        ("dwell_state_sum", "dwell", doc(state_reduction={"selection": [1, 3], "aggregation": "sum"})),
+        ("dwell_state_w", "dwell", doc(state_reduction={"aggregation": [0.1, 0.2, 0.3, 0.4]}, site_reduction={"aggregation": "sum"})),
+        ("dwell_state_sel", "dwell", doc(state_reduction={"selection": [2, 0]}, edge_reduction={"selection": [1, 4], "aggregation": "avg"})),
+        ("dwell_only", "dwell", doc(state_reduction={"selection": [0], "aggregation": "only"}, edge_reduction={"aggregation": "sum"},
+                                    site_reduction={"aggregation": "sum"})),
+        ("trans_all_sum", "trans", doc(trans_reduction={"aggregation": "sum"})),
+        ("trans_all_avg", "trans", doc(trans_reduction={"aggregation": "avg"}, site_reduction={"aggregation": "sum"})),
+        ("trans_none", "trans", doc(site_reduction={"selection": [1]}, edge_reduction={"selection": [0, 2]})),
+        ("trans_sel", "trans", doc(trans_reduction={"selection": [[0, 1], [2, 3], [0, 1]]}, site_reduction={"aggregation": "sum"})),
+        ("trans_sel_w", "trans", doc(trans_reduction={"selection": [[0, 1], [2, 3], [3, 0]], "aggregation": [1, 2, -0.5]},
+                                     edge_reduction={"aggregation": "sum"})),
+        ("trans_only", "trans", doc(trans_reduction={"selection": [[1, 2]], "aggregation": "only"})),
+    ]
+    # other models through the whole stack
+    gam = random_problem(32, ntips=9, n=4, S=20, ncat=4, mixture="gamma", missing=0.3, root="equilibrium_distribution")
+    cases.append(("gamma_ll_sum", "ll", dict(gam, site_reduction={"aggregation": "sum"})))
+    cases.append(("gamma_deriv_sum", "deriv", dict(gam, site_reduction={"aggregation": "sum"})))
+    cases.append(("gamma_marg_avg", "marginal", dict(gam, site_reduction={"aggregation": "avg"})))
+    inv = random_problem(33, ntips=6, n=4, S=8, ncat=5, mixture="median_inv", root="uniform_distribution")
+    cases.append(("inv_deriv", "deriv", inv))
+    cases.append(("inv_trans_sum", "trans", dict(inv, trans_reduction={"aggregation": "sum"}, site_reduction={"aggregation": "sum"})))
+    n3 = random_problem(34, ntips=5, n=3, S=4, ncat=2, soft=True, internal_data=True, root=None, divisor=2.5)
+    for prog in ("ll", "deriv", "marginal", "dwell", "trans"):
+        cases.append(("soft3_" + prog, prog, n3))
+    path = {"model_and_data": {
+        "edges": [[0, 1], [1, 2], [2, 3]], "edge_rate_coefficients": [0.5, 0.0, 1.5],
+        "rate_matrix": [[0, 1], [0, 0]], "root_prior": [1, 0],
+        "probability_array": [[[1, 0], [1, 1], [1, 1], [0, 1]], [[1, 0], [1, 1], [1, 1], [1, 0]]]}}
+    for prog in ("ll", "deriv", "marginal", "dwell", "trans"):
+        cases.append(("absorbing_path_" + prog, prog, path))
+    return cases
+
+
+def expected_json(name, program, doc):
+    """Oracle (320-bit) output for a JSON case, cached under tests/golden/json_cases/."""
+    path = os.path.join(JSON_CACHE, name + ".json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    out = O.run(program, doc, mode="mp")
+    os.makedirs(JSON_CACHE, exist_ok=True)
+    with open(path, "w") as f:
+        json.dump(out, f)
+    return out

@@ -1,0 +1,223 @@
+"""
+CPU-side tests of the C host layer and of the library boundary (no GPU work):
+  * the shared library loads and exports every symbol declared in include/*.h;
+  * the integer front end (CSR tree, BFS order, edge map) is bit exact against
+    the oracle;
+  * site-independent model quantities (mixture rates, equilibrium, scaled rate
+    matrix in double-double) match the 320-bit oracle;
+  * malformed models are rejected (test_scripts/test_bad_model_args.py of the
+    reference) and nothing silently falls back to a CPU computation.
+"""
+import copy
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import arbplf_oracle as O
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib():
+    from phyly_b200 import _lib
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib()
+    names = []
+    for hdr in ("plf.h", "arbplf.h"):
+        text = open(os.path.join(ROOT, "include", hdr)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names += re.findall(r"\b((?:plf|arbplf)_[a-z0-9_]+)\s*\(", text)
+    names = sorted(set(names))
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), "symbol %s declared in include/ but not exported" % n
+
+
+def _summary(doc):
+    import phyly_b200.arbplf as A
+    return json.loads(A.arbplf_model_summary(json.dumps({"model_and_data": doc["model_and_data"]})))
+
+
+CASES = [c["name"] for c in H.manifest()]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_integer_front_end_is_bit_exact(name):
+    doc = H.golden_in(name)
+    s = _summary(doc)
+    t = O.build_tree(doc["model_and_data"]["edges"])
+    assert s["indptr"] == t.indptr
+    assert s["indices"] == t.indices
+    assert s["preorder"] == t.preorder
+    assert s["order"] == t.order
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_integer_front_end_random_trees(seed):
+    doc = H.random_problem(100 + seed, ntips=5 + 7 * seed, n=4, S=1, max_degree=2 + seed % 3)
+    s = _summary(doc)
+    t = O.build_tree(doc["model_and_data"]["edges"])
+    assert (s["indptr"], s["indices"], s["preorder"], s["order"]) == (t.indptr, t.indices, t.preorder, t.order)
+
+
+@pytest.mark.parametrize("name", ["beast_gtrg", "beast_hky85g", "beast_hky85i", "beast_gtrgi", "beast_gtri", "bpp_ll",
+                                  "gell_test", "gell_driver", "beast_k80", "fels_ll", "mj_jumps"])
+def test_model_quantities_match_oracle(name):
+    doc = H.golden_in(name)
+    s = _summary(doc)
+    m = O.parse_model(doc["model_and_data"])
+    params, cs = H.model_params(m)
+    np.testing.assert_allclose(s["cat_rates"], params["cat_rates"], rtol=4e-16, atol=0)
+    np.testing.assert_allclose(s["cat_prior"], params["cat_prior"], rtol=4e-16, atol=0)
+    n = m.n
+    q = np.array(s["q_hi"]).reshape(n, n)
+    np.testing.assert_allclose(q, params["q_hi"], rtol=4e-16, atol=0)
+    # hi + lo together carry ~31 digits
+    from mpmath import mpf
+    for i in range(n):
+        for j in range(n):
+            got = mpf(s["q_hi"][i * n + j]) + mpf(s["q_lo"][i * n + j])
+            want = cs.Q[i, j]
+            assert abs(got - want) <= abs(want) * mpf(10) ** -18, (i, j)
+    np.testing.assert_allclose(s["edge_rates_csr"], params["edge_rates"], rtol=0, atol=0)
+    if params["root_vec"] is not None:
+        np.testing.assert_allclose(s["root_vec"], params["root_vec"], rtol=4e-16)
+
+
+def test_gamma_rates_known_answers():
+    # test_scripts/test_gamma_discretization.py:101-107 (Yang 1994, shape 0.5, 4 categories)
+    doc = H.golden_in("fels_ll")
+    doc["model_and_data"]["gamma_rate_mixture"] = {"gamma_shape": 0.5, "gamma_categories": 4}
+    s = _summary(doc)
+    want = [0.0333877533835995, 0.251915917593438, 0.820268481973649, 2.89442784704931]
+    np.testing.assert_allclose(s["cat_rates"], want, rtol=2e-15)
+    # tiny shape: effectively one category with rate 4 (test_gamma_discretization.py:146-184)
+    doc["model_and_data"]["gamma_rate_mixture"] = {"gamma_shape": 1e-6, "gamma_categories": 4}
+    s = _summary(doc)
+    np.testing.assert_allclose(s["cat_rates"], [0, 0, 0, 4], atol=1e-12)
+    # invariant sites: rates divided by (1-p), extra category of rate 0
+    doc["model_and_data"]["gamma_rate_mixture"] = {"gamma_shape": 0.5, "gamma_categories": 4, "invariable_prior": 0.3}
+    s = _summary(doc)
+    np.testing.assert_allclose(s["cat_rates"], [w / 0.7 for w in want] + [0.0], rtol=2e-15)
+    np.testing.assert_allclose(s["cat_prior"], [0.7 / 4] * 4 + [0.3], rtol=2e-16)
+
+
+@pytest.mark.parametrize("shape", [0.05, 0.137064, 0.19249, 0.5, 1.0, 3.7, 25.0])
+@pytest.mark.parametrize("ncat", [2, 4, 8])
+def test_gamma_rates_vs_oracle(shape, ncat):
+    from mpmath import mp
+    mp.prec = O.MP_PREC_BITS
+    doc = H.golden_in("fels_ll")
+    for key, fn in (("gamma_rate_mixture", O.gamma_rates_mean), ("normalized_median_gamma_rate_mixture", O.gamma_rates_median)):
+        d = copy.deepcopy(doc)
+        d["model_and_data"][key] = {"gamma_shape": shape, "gamma_categories": ncat}
+        got = _summary(d)["cat_rates"]
+        want = [float(x) for x in fn(ncat, shape)]
+        np.testing.assert_allclose(got, want, rtol=1e-14, atol=1e-300)
+
+
+GOOD = {
+    "model_and_data": {
+        "edges": [[0, 1], [1, 2], [1, 3]],
+        "edge_rate_coefficients": [2.0, 4.2, 0.5],
+        "rate_matrix": [[0, 4.2, 3.0], [1.0, 0, 5.0], [6.0, 0.5, 0]],
+        "probability_array": [
+            [[0.6, 0.2, 0.2], [1, 1, 1], [1, 0, 0], [0, 0, 1]],
+            [[0.6, 0.2, 0.2], [1, 1, 1], [0, 0, 1], [0, 0, 1]]]},
+    "site_reduction": {"aggregation": "sum"},
+}
+
+
+def _bad_models():
+    # test_scripts/test_bad_model_args.py:31-260
+    def mod(f):
+        x = copy.deepcopy(GOOD)
+        f(x["model_and_data"])
+        return x
+    out = []
+    for bad in ({"hello": "world"}, "hello", 0, [-1, 3], [0, 1, 2], [0], [1.0, 3]):
+        out.append(mod(lambda m, b=bad: m["edges"].__setitem__(2, b)))
+    for edges in ([[0, 1], [1, 5], [1, 6]], [[0, 1], [1, 2], [2, 2]], [[0, 1], [1, 2], [3, 3]],
+                  [[0, 1], [1, 2], [1, 3], [2, 3]], [[0, 1], [1, 2], [2, 0]], [[0, 1], [2, 3], [3, 2]],
+                  [[0, 1], [2, 1], [3, 1]], [[0, 1], [2, 3], [2, 4], [4, 3]]):
+        out.append(mod(lambda m, e=edges: m.__setitem__("edges", e)))
+    for erc in ("hello", [2.0, 4.2, 0.5, 1.0], [2.0, 4.2], [2.0, "x", 0.5], [2.0, "4.2", 0.5], [2.0, -4.2, 0.5]):
+        out.append(mod(lambda m, e=erc: m.__setitem__("edge_rate_coefficients", e)))
+    out.append(mod(lambda m: m.__setitem__("rate_matrix", "hello")))
+    out.append(mod(lambda m: m["rate_matrix"].__setitem__(1, "hello")))
+    out.append(mod(lambda m: m["rate_matrix"].__setitem__(1, [1.0, 0, 5.0, 1.0])))
+    out.append(mod(lambda m: m["rate_matrix"].__setitem__(1, [1.0, 0])))
+    out.append(mod(lambda m: m["rate_matrix"][1].__setitem__(2, "hello")))
+    out.append(mod(lambda m: m["rate_matrix"][1].__setitem__(2, "5.0")))
+    out.append(mod(lambda m: m["rate_matrix"][1].__setitem__(2, -5.0)))
+    out.append(mod(lambda m: m.__setitem__("probability_array", "hello")))
+    out.append(mod(lambda m: m["probability_array"].__setitem__(0, "hello")))
+    out.append(mod(lambda m: m["probability_array"].__setitem__(0, {"a": 1})))
+    out.append(mod(lambda m: m["probability_array"][0].__setitem__(1, "hello")))
+    out.append(mod(lambda m: m["probability_array"][0].__setitem__(1, {"a": 1})))
+    out.append(mod(lambda m: m["probability_array"][0][1].__setitem__(1, "hello")))
+    out.append(mod(lambda m: m["probability_array"][0][1].__setitem__(1, -0.5)))
+    out.append(mod(lambda m: m["probability_array"][0].append([1, 1, 1])))
+    out.append(mod(lambda m: m["probability_array"][0].pop()))
+    out.append(mod(lambda m: m["probability_array"][0][1].append(1)))
+    out.append(mod(lambda m: m["probability_array"][0][1].pop()))
+    # schema level
+    out.append(mod(lambda m: m.__setitem__("unknown_key", 1)))
+    out.append(mod(lambda m: m.pop("edges")))
+    out.append(mod(lambda m: m.__setitem__("rate_divisor", -1)))
+    out.append(mod(lambda m: m.__setitem__("rate_divisor", "bogus")))
+    out.append(mod(lambda m: m.__setitem__("root_prior", "bogus")))
+    out.append(mod(lambda m: m.__setitem__("root_prior", [0.5, 0.5])))
+    out.append(mod(lambda m: (m.__setitem__("rate_mixture", {"rates": [1, 2], "prior": [0.5, 0.5]}),
+                              m.__setitem__("gamma_rate_mixture", {"gamma_shape": 1, "gamma_categories": 2}))))
+    out.append(mod(lambda m: m.__setitem__("gamma_rate_mixture", {"gamma_shape": 1, "gamma_categories": 2.0})))
+    out.append(mod(lambda m: (m.__setitem__("character_data", [[0, 0, 0, 0]]), m.__setitem__("character_definitions", [[1, 1, 1]]))))
+    return out
+
+
+@pytest.mark.parametrize("i", range(len(_bad_models())))
+def test_bad_models_are_rejected(i):
+    import phyly_b200.arbplf as A
+    doc = _bad_models()[i]
+    with pytest.raises(O.OracleError):
+        O.run("ll", doc, mode="fp64")
+    with pytest.raises(RuntimeError):
+        A.arbplf_model_summary(json.dumps({"model_and_data": doc["model_and_data"]}))
+    with pytest.raises(RuntimeError):
+        A.arbplf_ll(json.dumps(doc))
+
+
+def test_malformed_json_is_rejected():
+    import phyly_b200.arbplf as A
+    for s in ("", "{", "[1, 2", '{"model_and_data": }', "3", '{"a": 1} trailing'):
+        with pytest.raises(RuntimeError):
+            A.arbplf_ll(s)
+
+
+def test_unsupported_programs_fail_cleanly():
+    import phyly_b200.arbplf as A
+    for f in (A.arbplf_hess, A.arbplf_inv_hess, A.arbplf_newton_delta, A.arbplf_newton_update,
+              A.arbplf_newton_refine, A.arbplf_em_update):
+        with pytest.raises(RuntimeError):
+            f(json.dumps(GOOD))
+
+
+def test_no_cpu_fallback_without_gpu():
+    """Without a CUDA device the product must fail loudly, not compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import phyly_b200.arbplf as A
+    from phyly_b200.engine import Engine, EngineError
+    with pytest.raises(RuntimeError):
+        A.arbplf_ll(json.dumps(GOOD))
+    with pytest.raises(EngineError):
+        Engine(0)

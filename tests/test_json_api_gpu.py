@@ -1,0 +1,186 @@
+"""
+GPU tests of the reference-facing boundary: JSON string in -> JSON string out
+through the C ABI (include/arbplf.h), the Python mirror of the reference's
+module, and the arbplf-* executables.
+
+1. Every golden input/output pair shipped by the reference (tests/golden,
+   SURVEY.md appendix B) must be reproduced to 1e-11 relative.
+2. The reduction semantics (selection order, duplicates, sum / avg / only /
+   weighted) are checked against the 320-bit oracle.
+3. The reference's invariance tests (site weights vs duplicated sites, rate
+   matrix scaling, relabelling) are replayed.
+"""
+import copy
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES = H.manifest()
+SUPPORTED = {"ll", "deriv", "marginal", "dwell", "trans"}
+
+# Absolute floors, only where the reference's exact arithmetic cancels to a
+# value far below the magnitude of the terms (see tests/test_engine_gpu.py):
+# value = tolerance on |got - want| in units of the largest |entry| of the table.
+CANCEL_FLOOR = 4e-15
+
+
+def _run(program, doc):
+    import phyly_b200.arbplf as A
+    return json.loads(getattr(A, "arbplf_" + program)(json.dumps(doc)))
+
+
+def _check(got, want, what, rtol=1e-11):
+    assert got["columns"] == want["columns"], what
+    assert len(got["data"]) == len(want["data"]), what
+    scale = max([abs(r[-1]) for r in want["data"]] + [1.0])
+    for r1, r2 in zip(got["data"], want["data"]):
+        assert r1[:-1] == r2[:-1], (what, r1, r2)
+        a, b = r1[-1], r2[-1]
+        assert isinstance(a, float), (what, r1)
+        assert abs(a - b) <= rtol * abs(b) + CANCEL_FLOOR * scale, (what, r1, r2)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_golden(case):
+    assert case["program"] in SUPPORTED
+    got = _run(case["program"], H.golden_in(case["name"]))
+    _check(got, H.golden_out(case["name"]), case["name"])
+
+
+def test_golden_long_branch_derivatives_relative():
+    """examples/JC.long.branch: naive fp64 loses these (4e-5 relative); the
+    double-double matrix kernel keeps them to 1e-11 relative with NO absolute floor."""
+    for name in ("jc_long_deriv", "jc29_same_deriv", "jc29_diff_deriv", "jc30_same_deriv", "jc30_diff_deriv"):
+        got = _run("deriv", H.golden_in(name))
+        want = H.golden_out(name)
+        for r1, r2 in zip(got["data"], want["data"]):
+            if r2[-1] != 0.0:
+                assert abs(r1[-1] - r2[-1]) <= 1e-11 * abs(r2[-1]), (name, r1, r2)
+
+
+def test_golden_exact_zeros():
+    """Derivatives at data-free sites / edges are literal 0.0 (constant-column shortcut)."""
+    got = _run("deriv", H.golden_in("fels_deriv"))
+    want = H.golden_out("fels_deriv")
+    for r1, r2 in zip(got["data"], want["data"]):
+        if r2[0] == 0:
+            assert r1[-1] == 0.0 and r2[-1] == 0.0
+    got = _run("ll", H.golden_in("fels_ll2"))
+    assert got["data"][0][-1] == 0.0
+
+
+RCASES = H.reduction_cases()
+
+
+@pytest.mark.parametrize("name,program,doc", RCASES, ids=[c[0] for c in RCASES])
+def test_reductions_against_oracle(name, program, doc):
+    want = H.expected_json(name, program, doc)
+    got = _run(program, doc)
+    _check(got, want, name)
+
+
+def test_cli_executables():
+    exe = os.path.join(ROOT, "phyly_b200", "bin")
+    for name, prog in (("fels_ll", "ll"), ("bpp_deriv", "deriv"), ("beast_anc_marginal", "marginal"),
+                       ("mj_rewards", "dwell"), ("mj_jumps", "trans")):
+        text = json.dumps(H.golden_in(name))
+        p = subprocess.run([os.path.join(exe, "arbplf-" + prog)], input=text, capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        assert p.stdout.endswith("\n")
+        _check(json.loads(p.stdout), H.golden_out(name), name)
+    # errors: non-zero exit status, message on stderr, nothing on stdout (arbplf-ll.c:13-14)
+    p = subprocess.run([os.path.join(exe, "arbplf-ll")], input='{"model_and_data": {}}', capture_output=True, text=True)
+    assert p.returncode != 0 and p.stdout == "" and "error" in p.stderr
+    p = subprocess.run([os.path.join(exe, "arbplf-hess")], input=json.dumps(H.golden_in("fels_ll")), capture_output=True, text=True)
+    assert p.returncode != 0
+
+
+def test_output_formatting_matches_jansson():
+    import phyly_b200.arbplf as A
+    s = A.arbplf_ll(json.dumps(H.golden_in("fels_ll")))
+    assert s == '{"columns": ["site", "value"], "data": [[0, -11.297288182875496]]}'
+    s = A.arbplf_ll(json.dumps(H.golden_in("fels_ll2")))
+    assert '[0, 0.0]' in s
+    s = A.arbplf_dwell(json.dumps(H.golden_in("fels_dwell_adenine")))
+    assert "7.4565883396650014e-6" in s or "e-6" in s
+
+
+BAD_REDUCTIONS = [
+    {"site_reduction": "hello"}, {"site_reduction": {"aggregation": {"a": 1}}}, {"site_reduction": {"aggregation": "hello"}},
+    {"site_reduction": {"aggregation": [1, "x"]}}, {"site_reduction": {"aggregation": [1]}},
+    {"site_reduction": {"aggregation": [1, 2, 3]}}, {"site_reduction": {"selection": {"a": 1}}},
+    {"site_reduction": {"selection": "hello"}}, {"site_reduction": {"selection": [-1]}},
+    {"site_reduction": {"selection": [2]}}, {"site_reduction": {"selection": [0.5]}},
+    {"site_reduction": {"selection": ["a"]}}, {"site_reduction": {"selection": [{"a": 1}]}},
+    {"site_reduction": {"selection": [0, 1, 1], "aggregation": [1, 2]}},
+    {"site_reduction": {"selection": [0], "aggregation": [1, 2]}},
+    {"site_reduction": {"selection": [0, 1], "aggregation": "only"}},
+    {"site_reduction": {"selection": None}}, {"site_reduction": {"bogus": 1}}, {"bogus_reduction": {}},
+]
+
+
+@pytest.mark.parametrize("i", range(len(BAD_REDUCTIONS)))
+def test_bad_reductions_are_rejected(i):
+    # test_scripts/test_bad_reduction_args.py:31-112
+    import phyly_b200.arbplf as A
+    from tests.test_host_cpu import GOOD
+    doc = copy.deepcopy(GOOD)
+    doc.pop("site_reduction")
+    A.arbplf_ll(json.dumps(doc))            # the unmodified document is fine
+    doc.update(BAD_REDUCTIONS[i])
+    with pytest.raises(RuntimeError):
+        A.arbplf_ll(json.dumps(doc))
+
+
+def test_site_weights_equal_duplicated_sites():
+    # test_scripts/test_site_weights.py:60-97
+    base = H.random_problem(41, ntips=6, n=4, S=3, ncat=2)
+    md = base["model_and_data"]
+    dup = copy.deepcopy(md)
+    dup["character_data"] = [md["character_data"][i] for i in (0, 0, 1, 2, 2, 2)]
+    for prog, extra in (("ll", {}), ("deriv", {}), ("marginal", {}), ("dwell", {"state_reduction": {"aggregation": "sum"}}),
+                        ("trans", {"trans_reduction": {"aggregation": "sum"}})):
+        a = _run(prog, dict({"model_and_data": md, "site_reduction": {"aggregation": [2, 1, 3]}}, **extra))
+        b = _run(prog, dict({"model_and_data": dup, "site_reduction": {"aggregation": "sum"}}, **extra))
+        _check(a, b, "weights vs duplicates " + prog, rtol=1e-13)
+
+
+def test_rate_matrix_scaling_invariance():
+    # test_scripts/test_rate_divisor.py:96-262
+    base = H.random_problem(42, ntips=5, n=4, S=4, ncat=1, divisor=3.0)
+    md = base["model_and_data"]
+    scaled = copy.deepcopy(md)
+    scaled["rate_matrix"] = [[8 * x for x in row] for row in md["rate_matrix"]]
+    scaled["rate_divisor"] = 24.0
+    diag = copy.deepcopy(md)
+    for i in range(4):
+        diag["rate_matrix"][i][i] = 123.0          # the diagonal is ignored
+    for prog in ("ll", "deriv", "marginal"):
+        a = _run(prog, {"model_and_data": md})
+        _check(_run(prog, {"model_and_data": scaled}), a, "scaled " + prog, rtol=1e-13)
+        _check(_run(prog, {"model_and_data": diag}), a, "diag " + prog, rtol=1e-13)
+
+
+def test_edge_permutation_equivariance():
+    # test_scripts/test_ll_deriv.py / test_path.py:133-195
+    base = H.random_problem(43, ntips=6, n=4, S=3, ncat=2)
+    md = base["model_and_data"]
+    E = len(md["edges"])
+    perm = list(np.random.default_rng(5).permutation(E))
+    pm = copy.deepcopy(md)
+    pm["edges"] = [md["edges"][i] for i in perm]
+    pm["edge_rate_coefficients"] = [md["edge_rate_coefficients"][i] for i in perm]
+    a = _run("deriv", {"model_and_data": md, "site_reduction": {"aggregation": "sum"}})
+    b = _run("deriv", {"model_and_data": pm, "site_reduction": {"aggregation": "sum"}})
+    va = {r[0]: r[1] for r in a["data"]}
+    vb = {perm[r[0]]: r[1] for r in b["data"]}
+    for e in range(E):
+        assert abs(va[e] - vb[e]) <= 1e-12 * abs(va[e]) + 1e-14
