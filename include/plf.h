@@ -128,6 +128,8 @@ int plf_get_frechet_matrices(plf_engine *e, const double *l_hi, const double *l_
  * kernels, and the number of kernel launches since the last reset.
  */
 int plf_last_timing(plf_engine *e, float *ms_matrices, float *ms_sites);
+/* duration of the dominant per-site kernel alone (the fused 4-state kernel), 0 if it did not run */
+int plf_last_kernel_ms(plf_engine *e, float *ms_kernel);
 int64_t plf_launch_count(plf_engine *e, int reset);
 
 /*

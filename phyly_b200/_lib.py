@@ -47,6 +47,8 @@ def load():
     lib.plf_get_derivative_matrices.argtypes = [P, P]
     lib.plf_get_frechet_matrices.argtypes = [P, P, P, P]
     lib.plf_last_timing.argtypes = [P, c.POINTER(c.c_float), c.POINTER(c.c_float)]
+    lib.plf_last_kernel_ms.argtypes = [P, c.POINTER(c.c_float)]
+    lib.plf_last_kernel_ms.restype = c.c_int
     lib.plf_launch_count.argtypes = [P, c.c_int]
     lib.plf_launch_count.restype = c.c_int64
     lib.plf_comm_unique_id.argtypes = [c.c_char_p]

@@ -114,8 +114,9 @@ struct plf_engine {
     DevBuf g_Lg, g_Kg, g_Cg, g_Eg, g_Fg, g_FK, g_cat_lh, g_cat_k, g_site_m, g_site_k, g_edge_out, g_marg_out, g_tr;
 
     /* timing / accounting */
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-    float ms_mat = 0.f, ms_sites = 0.f;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float ms_mat = 0.f, ms_sites = 0.f, ms_kernel = 0.f;
+    bool kernel_timed = false;
     int64_t launches = 0;
 
     /* nccl */
@@ -265,7 +266,7 @@ extern "C" int plf_create(plf_engine **out, int device)
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     e->sm_count = prop.multiProcessorCount;
-    for (int i = 0; i < 3; i++) cudaEventCreate(&e->ev[i]);
+    for (int i = 0; i < 5; i++) cudaEventCreate(&e->ev[i]);
     *out = e;
     return 0;
 }
@@ -284,7 +285,7 @@ extern "C" void plf_destroy(plf_engine *e)
                       &e->d_err, &e->d_mask, &e->g_Lg, &e->g_Kg, &e->g_Cg, &e->g_Eg, &e->g_Fg, &e->g_FK, &e->g_cat_lh,
                       &e->g_cat_k, &e->g_site_m, &e->g_site_k, &e->g_edge_out, &e->g_marg_out, &e->g_tr};
     for (DevBuf *b : bufs) b->release();
-    for (int i = 0; i < 3; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -314,6 +315,13 @@ extern "C" int plf_last_timing(plf_engine *e, float *ms_matrices, float *ms_site
     if (!e) return -1;
     if (ms_matrices) *ms_matrices = e->ms_mat;
     if (ms_sites) *ms_sites = e->ms_sites;
+    return 0;
+}
+
+extern "C" int plf_last_kernel_ms(plf_engine *e, float *ms_kernel)
+{
+    if (!e || !ms_kernel) return -1;
+    *ms_kernel = e->ms_kernel;
     return 0;
 }
 
@@ -770,8 +778,11 @@ static int run_fused(plf_engine *e, Query &q)
             a.edge_site_out = e->d_edge_site.as<double>();
         }
     }
+    CK(e, cudaEventRecord(e->ev[3], e->stream));
     kern<<<grid, bd, smem, e->stream>>>(a);
     KCHECK(e);
+    CK(e, cudaEventRecord(e->ev[4], e->stream));
+    e->kernel_timed = true;
     double *dsum = e->d_sum.as<double>();
     sum_rows_kernel<<<1, 32, 0, e->stream>>>(a.block_ll, grid, 1, dsum);
     KCHECK(e);
@@ -945,10 +956,13 @@ static int run_query(plf_engine *e, Query &q, bool need_D, const double *l_hi, c
     }
     if (use_fused && ensure_tip_tables(e, q.want_edge ? q.Fm : nullptr, f_mode)) return -1;
     CK(e, cudaEventRecord(e->ev[1], e->stream));
+    e->kernel_timed = false;
     int rc = use_fused ? run_fused(e, q) : run_generic(e, q);
     if (rc) return rc;
     cudaEventElapsedTime(&e->ms_mat, e->ev[0], e->ev[1]);
     cudaEventElapsedTime(&e->ms_sites, e->ev[1], e->ev[2]);
+    e->ms_kernel = 0.f;
+    if (e->kernel_timed) cudaEventElapsedTime(&e->ms_kernel, e->ev[3], e->ev[4]);
     return 0;
 }
 

@@ -141,6 +141,11 @@ class Engine:
         self._lib.plf_last_timing(self._h, ctypes.byref(a), ctypes.byref(b))
         return a.value, b.value
 
+    def last_kernel_ms(self):
+        a = ctypes.c_float()
+        self._lib.plf_last_kernel_ms(self._h, ctypes.byref(a))
+        return a.value
+
     def launch_count(self, reset=False):
         return int(self._lib.plf_launch_count(self._h, 1 if reset else 0))
 
