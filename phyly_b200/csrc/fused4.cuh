@@ -7,20 +7,29 @@
  *   _prune_update_prob util.c:241-301), then per requested edge a root-path
  *   recomputation (arbplfderiv.c:144-205).
  *
- * B200 design: one thread owns one site pattern and walks the whole tree
- * on chip.  The tree is compiled on the host into a post-order "program" of
- * node operations with Sethi-Ullman child ordering; the most recent partial
- * stays in registers, older pending partials sit on a small per-thread stack
- * in shared memory.  Tips never touch fp64 matrix-vector work: P_e.def_k and
- * F_e.def_k are precomputed per (category, edge, character) ("tip tables").
- * The derivative / edge-expectation outputs come from an outside (pre-order)
- * pass that runs the same program backwards, using the identity
- *     d L_c / d t_e = rate_c * fe_e^T (Q P_e) L_b
- * instead of the reference's O(depth) walk per edge.  Per-edge values are
- * reduced over the 32 sites of a warp with shuffles and accumulated per warp in
- * shared memory; one deterministic second-stage kernel adds the per-CTA rows.
- * HBM traffic: 1 byte per (site, tip) of codes, plus the inside partials of the
- * internal nodes (32 B per node, category, site) when the outside pass runs.
+ * B200 design
+ *   - one thread owns one site pattern and walks the whole tree; all rate
+ *     categories are advanced together (compile-time C, unrolled), so tree
+ *     decoding, tip codes and addresses are shared by the categories and each
+ *     thread carries 4*C independent fp64 chains.
+ *   - the tree is compiled on the host into a post-order program with
+ *     Sethi-Ullman child ordering; the program, the transition / derivative
+ *     matrices of the internal edges and the tip tables (P_e.def_k, F_e.def_k
+ *     per character k) are staged in shared memory once per CTA; the tile's tip
+ *     codes are staged in shared memory once per tile (coalesced 1-byte loads).
+ *   - the newest partial of each category lives in shared memory ("cur");
+ *     inside partials of internal nodes are written once to a per-thread slab
+ *     in HBM ([slot][category][thread] double4: every warp access is one
+ *     contiguous 1 KB run) and read once by the outside pass.
+ *   - derivative / dwell / trans outputs come from an outside (pre-order) pass
+ *     that runs the same program backwards with the identity
+ *         d L_c / d t_e = rate_c * fe_e^T (Q P_e) L_b ,
+ *     replacing the reference's O(depth) walk per edge.  Per-edge values are
+ *     summed over categories in registers, over the 32 sites of a warp with
+ *     shuffles, over the warps of the CTA in shared memory, and over CTAs by a
+ *     deterministic second-stage kernel.
+ * Algorithmic HBM traffic: 1 byte per (site, tip) of codes plus, when the
+ * outside pass runs, 2 x 33 bytes per (internal node, category, site).
  */
 #pragma once
 #include <stdint.h>
@@ -35,41 +44,46 @@ struct F4Op {
     int first_child;
     int nchild;
     int slot;            /* scratch slot of this node's inside vector */
-    int has_data;
-    int spill_before;    /* push the register-resident partial before this op */
+    int code_row;        /* row of the codes tile if the node carries data, else -1 */
+    int spill_before;    /* the register-resident partial is not consumed by this op */
 };
 
 struct F4Child {
-    int edge;            /* csr idx */
-    int node;
-    int slot;            /* scratch slot if internal, else -1 */
     int kind;
+    int slot;            /* scratch slot if internal, else -1 */
+    int mat;             /* internal child: index into the compact internal-edge matrices;
+                            tip child: index into the compact tip tables */
+    int code_row;        /* tip child: row of the codes tile */
+    int edge;            /* csr idx (output position) */
+    int pad[3];
 };
 
 struct F4Args {
-    int nops;
+    int nops, nchildren;
     const F4Op *ops;
     const F4Child *children;
-    int C, E, K;
+    int E, K, Ei, Et;                /* edges, characters, internal-child edges, tip edges */
     int64_t S;
+    int ncode_rows;
+    const int *code_row_node;        /* [ncode_rows] node whose codes fill the row */
     const unsigned char *codes;      /* [N][S] */
-    const unsigned char *node_has_data; /* [N] */
     const double *defs;              /* [K][4] */
     const unsigned char *def_const;  /* [K] */
-    const double *P;                 /* [C][E][16] */
-    const double *TP;                /* [C][E][K][4] */
-    const double *Fm;                /* [C][E][16] or NULL */
-    const double *TF;                /* [C][E][K][4] or NULL */
+    const double *Pint;              /* [C][Ei][16] */
+    const double *TP;                /* [C][Et][K][4] */
+    const double *Fint;              /* [C][Ei][16] or NULL */
+    const double *TF;                /* [C][Et][K][4] or NULL */
+    int stage_mask;                  /* bit0 Pint, bit1 TP, bit2 Fint, bit3 TF staged in shared memory */
     int f_zero_rowsum;
     const double *cat_prior;
     int root_mode;
     double root_vec[4];
     const double *site_w;            /* [S] or NULL */
     const unsigned char *edge_mask;  /* [E] or NULL */
-    int stack_depth;
+    int stack_depth;                 /* ll-only mode: shared-memory stack entries */
     int nslots;
-    double4 *scratch;                /* [C][nslots][T] */
-    signed char *scratchS;           /* [C][nslots][T] */
+    double4 *scratch;                /* [nslots][C][T] */
+    unsigned char *scratchS;         /* [nslots][C][T] */
     double *site_ll;                 /* [S] or NULL */
     double *edge_site_out;           /* [E][S] or NULL */
     double *block_ll;                /* [grid] */
@@ -79,11 +93,10 @@ struct F4Args {
 
 __device__ __forceinline__ void f4_matvec(const double *__restrict__ M, const double v[4], double out[4])
 {
-    /* M row-major 4x4, uniform address across the warp: broadcast loads */
     const double2 *M2 = reinterpret_cast<const double2 *>(M);
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        double2 a = __ldg(M2 + 2 * i), b = __ldg(M2 + 2 * i + 1);
+        double2 a = M2[2 * i], b = M2[2 * i + 1];
         double r = a.x * v[0];
         r = fma(a.y, v[1], r);
         r = fma(b.x, v[2], r);
@@ -96,11 +109,11 @@ __device__ __forceinline__ void f4_matvec(const double *__restrict__ M, const do
 __device__ __forceinline__ void f4_matvec_t(const double *__restrict__ M, const double v[4], double out[4])
 {
     const double2 *M2 = reinterpret_cast<const double2 *>(M);
-    double2 a0 = __ldg(M2 + 0), b0 = __ldg(M2 + 1);
+    double2 a0 = M2[0], b0 = M2[1];
     out[0] = a0.x * v[0]; out[1] = a0.y * v[0]; out[2] = b0.x * v[0]; out[3] = b0.y * v[0];
 #pragma unroll
     for (int i = 1; i < 4; i++) {
-        double2 a = __ldg(M2 + 2 * i), b = __ldg(M2 + 2 * i + 1);
+        double2 a = M2[2 * i], b = M2[2 * i + 1];
         out[0] = fma(a.x, v[i], out[0]);
         out[1] = fma(a.y, v[i], out[1]);
         out[2] = fma(b.x, v[i], out[2]);
@@ -111,19 +124,24 @@ __device__ __forceinline__ void f4_matvec_t(const double *__restrict__ M, const 
 __device__ __forceinline__ void f4_ld4(const double *__restrict__ p, double out[4])
 {
     const double2 *p2 = reinterpret_cast<const double2 *>(p);
-    double2 a = __ldg(p2), b = __ldg(p2 + 1);
+    double2 a = p2[0], b = p2[1];
     out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
 }
 
+/* number of 2^256 up-scalings applied so that max(v) >= 2^-256 (v >= 0) */
 __device__ __forceinline__ int f4_rescale_up(double v[4])
 {
-    double m = fmax(fmax(v[0], v[1]), fmax(v[2], v[3]));
+    /* non-negative doubles order like their high words */
+    int h = max(max(__double2hiint(v[0]), __double2hiint(v[1])), max(__double2hiint(v[2]), __double2hiint(v[3])));
     int s = 0;
-    while (m > 0.0 && m < PLF_TWO_M256) {
+    if (h < 0x2FF00000) {          /* high word of 2^-256 */
+        double m = fmax(fmax(v[0], v[1]), fmax(v[2], v[3]));
+        while (m > 0.0 && m < PLF_TWO_M256) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) v[i] *= PLF_TWO_P256;
-        m *= PLF_TWO_P256;
-        s++;
+            for (int i = 0; i < 4; i++) v[i] *= PLF_TWO_P256;
+            m *= PLF_TWO_P256;
+            s++;
+        }
     }
     return s;
 }
@@ -135,140 +153,208 @@ __device__ __forceinline__ double f4_warp_sum(double x)
     return x;
 }
 
+__host__ __device__ inline size_t f4_align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
 /*
- * EDGE = false : log-likelihood only (no scratch, no outside pass)
- * EDGE = true  : log-likelihood + per-edge bilinear forms with matrices Fm
- * Launch: persistent grid; dynamic shared memory =
- *   blockDim*(stack_depth*36 + 4*4) + (blockDim/32)*E*8 bytes
+ * C     : number of rate categories (1..4)
+ * EDGE  : false = log-likelihood only; true = log-likelihood + per-edge bilinear forms
+ * The dynamic shared memory layout below is mirrored on the host by f4_smem_bytes().
  */
-template <bool EDGE>
+template <int C, bool EDGE>
 __global__ void __launch_bounds__(256) fused4_kernel(F4Args a)
 {
     extern __shared__ __align__(16) unsigned char f4_smem[];
     const int tid = threadIdx.x, bd = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = bd >> 5;
-    double *stack = reinterpret_cast<double *>(f4_smem);                    /* [depth][4][bd] */
-    int *stackf = reinterpret_cast<int *>(stack + (size_t)a.stack_depth * 4 * bd);   /* [depth][bd] */
-    int *kcat = stackf + (size_t)a.stack_depth * bd;                        /* [4][bd] */
-    double *accE = reinterpret_cast<double *>(kcat + 4 * bd);               /* [nwarp][E] */
     const int64_t T = (int64_t)gridDim.x * bd;
     const int64_t gtid = (int64_t)blockIdx.x * bd + tid;
 
-    if (EDGE) {
-        for (int i = tid; i < nwarp * a.E; i += bd) accE[i] = 0.0;
-        __syncthreads();
+    /* ---- carve shared memory ---- */
+    size_t off = 0;
+    F4Op *ops = reinterpret_cast<F4Op *>(f4_smem + off); off = f4_align16(off + sizeof(F4Op) * a.nops);
+    F4Child *chs = reinterpret_cast<F4Child *>(f4_smem + off); off = f4_align16(off + sizeof(F4Child) * a.nchildren);
+    double *cur = reinterpret_cast<double *>(f4_smem + off); off = f4_align16(off + sizeof(double) * 4 * C * bd);   /* [C][4][bd] */
+    double *accE = reinterpret_cast<double *>(f4_smem + off); off = f4_align16(off + (EDGE ? sizeof(double) * nwarp * a.E : 0));
+    double *stack = reinterpret_cast<double *>(f4_smem + off); off = f4_align16(off + (EDGE ? 0 : sizeof(double) * 4 * C * bd * a.stack_depth));
+    int *stackf = reinterpret_cast<int *>(f4_smem + off); off = f4_align16(off + (EDGE ? 0 : sizeof(int) * bd * a.stack_depth));
+    int *kcat = reinterpret_cast<int *>(f4_smem + off); off = f4_align16(off + sizeof(int) * C * bd);
+    unsigned char *tile = f4_smem + off; off = f4_align16(off + (size_t)a.ncode_rows * bd);
+    unsigned char *dconst = f4_smem + off; off = f4_align16(off + a.K);
+    double *defs_s = reinterpret_cast<double *>(f4_smem + off); off = f4_align16(off + sizeof(double) * 4 * a.K);
+    const double *Pint = a.Pint, *TP = a.TP, *Fint = a.Fint, *TF = a.TF;
+    {
+        const size_t nP = (size_t)C * a.Ei * 16, nT = (size_t)C * a.Et * a.K * 4;
+        if (a.stage_mask & 1) { double *d = reinterpret_cast<double *>(f4_smem + off); off += sizeof(double) * nP;
+            for (size_t i = tid; i < nP; i += bd) d[i] = a.Pint[i]; Pint = d; }
+        if (a.stage_mask & 2) { double *d = reinterpret_cast<double *>(f4_smem + off); off += sizeof(double) * nT;
+            for (size_t i = tid; i < nT; i += bd) d[i] = a.TP[i]; TP = d; }
+        if (EDGE && (a.stage_mask & 4)) { double *d = reinterpret_cast<double *>(f4_smem + off); off += sizeof(double) * nP;
+            for (size_t i = tid; i < nP; i += bd) d[i] = a.Fint[i]; Fint = d; }
+        if (EDGE && (a.stage_mask & 8)) { double *d = reinterpret_cast<double *>(f4_smem + off); off += sizeof(double) * nT;
+            for (size_t i = tid; i < nT; i += bd) d[i] = a.TF[i]; TF = d; }
     }
+    for (int i = tid; i < a.nops; i += bd) ops[i] = a.ops[i];
+    for (int i = tid; i < a.nchildren; i += bd) chs[i] = a.children[i];
+    for (int i = tid; i < a.K; i += bd) dconst[i] = a.def_const[i];
+    for (int i = tid; i < 4 * a.K; i += bd) defs_s[i] = a.defs[i];
+    if (EDGE) for (int i = tid; i < nwarp * a.E; i += bd) accE[i] = 0.0;
+    __syncthreads();
+
+    const int tpstride = a.Et * a.K * 4;     /* doubles per category in the tip tables */
+    const int pstride = a.Ei * 16;
+    double prior[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) prior[c] = a.cat_prior[c];
+
     double ll_acc = 0.0;
     const int64_t ntiles = (a.S + bd - 1) / bd;
 
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t site_raw = tile * bd + tid;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t site_raw = t * bd + tid;
         const bool valid = site_raw < a.S;
         const int64_t site = valid ? site_raw : a.S - 1;
         const double w = valid ? (a.site_w ? a.site_w[site] : 1.0) : 0.0;
+        /* stage this tile's character codes: each thread only ever reads its own column */
+        for (int r = 0; r < a.ncode_rows; r++)
+            tile[r * bd + tid] = a.codes[(size_t)a.code_row_node[r] * a.S + site];
 
-        /* ---------------- inside pass, one category at a time ---------------- */
+        /* ---------------- inside pass (all categories together) ---------------- */
+        int curf = 1, sp = 0;
+        int ktot[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) ktot[c] = 0;
+#pragma unroll 1
+        for (int o = 0; o < a.nops; o++) {
+            const F4Op op = ops[o];
+            if (!EDGE && op.spill_before) {
+#pragma unroll
+                for (int c = 0; c < C; c++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) stack[((sp * C + c) * 4 + i) * bd + tid] = cur[(c * 4 + i) * bd + tid];
+                stackf[sp * bd + tid] = curf;
+                sp++;
+            }
+            double acc[C][4];
+            int cst = 1;
+            bool first = true;
+            if (op.code_row >= 0) {
+                const int code = tile[op.code_row * bd + tid];
+                double b[4];
+                f4_ld4(defs_s + code * 4, b);
+#pragma unroll
+                for (int c = 0; c < C; c++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) acc[c][i] = b[i];
+                cst = dconst[code];
+                first = false;
+            }
+#pragma unroll 1
+            for (int j = 0; j < op.nchild; j++) {
+                const F4Child ch = chs[op.first_child + j];
+                double em[C][4];
+                int bc;
+                if (ch.kind == F4_KIND_TIP) {
+                    const int code = tile[ch.code_row * bd + tid];
+                    bc = dconst[code];
+                    const double *tp = TP + (ch.mat * a.K + code) * 4;
+#pragma unroll
+                    for (int c = 0; c < C; c++) f4_ld4(tp + c * tpstride, em[c]);
+                } else {
+                    double v[C][4];
+                    if (ch.kind == F4_KIND_CUR) {
+                        bc = curf;
+#pragma unroll
+                        for (int c = 0; c < C; c++)
+#pragma unroll
+                            for (int i = 0; i < 4; i++) v[c][i] = cur[(c * 4 + i) * bd + tid];
+                    } else if (EDGE) {
+                        const size_t so = ((size_t)ch.slot * C) * T + gtid;
+                        bc = (a.scratchS[so] >> 6) & 1;
+#pragma unroll
+                        for (int c = 0; c < C; c++) {
+                            double4 l4 = a.scratch[so + (size_t)c * T];
+                            v[c][0] = l4.x; v[c][1] = l4.y; v[c][2] = l4.z; v[c][3] = l4.w;
+                        }
+                    } else {
+                        sp--;
+                        bc = stackf[sp * bd + tid];
+#pragma unroll
+                        for (int c = 0; c < C; c++)
+#pragma unroll
+                            for (int i = 0; i < 4; i++) v[c][i] = stack[((sp * C + c) * 4 + i) * bd + tid];
+                    }
+                    if (bc) {
+#pragma unroll
+                        for (int c = 0; c < C; c++)
+#pragma unroll
+                            for (int i = 0; i < 4; i++) em[c][i] = v[c][i];
+                    } else {
+                        const double *pm = Pint + ch.mat * 16;
+#pragma unroll
+                        for (int c = 0; c < C; c++) f4_matvec(pm + c * pstride, v[c], em[c]);
+                    }
+                }
+                if (first) {
+#pragma unroll
+                    for (int c = 0; c < C; c++)
+#pragma unroll
+                        for (int i = 0; i < 4; i++) acc[c][i] = em[c][i];
+                    first = false;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < C; c++)
+#pragma unroll
+                        for (int i = 0; i < 4; i++) acc[c][i] *= em[c][i];
+                }
+                cst &= bc;
+            }
+            /* one rescale check per node is enough for out-degree <= 3 (each factor has max >= 2^-256 p_min) */
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const int sloc = f4_rescale_up(acc[c]);
+                ktot[c] -= sloc;
+#pragma unroll
+                for (int i = 0; i < 4; i++) cur[(c * 4 + i) * bd + tid] = acc[c][i];
+                if (EDGE) {
+                    const size_t so = ((size_t)op.slot * C + c) * T + gtid;
+                    a.scratch[so] = make_double4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+                    a.scratchS[so] = (unsigned char)(sloc | (cst << 6));
+                }
+            }
+            curf = cst;
+        }
+        /* ---------------- root: site likelihood (model.c:282-350, arbplfll.c:149-169) ---------------- */
         double site_m = 0.0;
         int site_k = 0;
         bool have = false;
-#pragma unroll 1
-        for (int c = 0; c < a.C; c++) {
-            double cur[4] = {1.0, 1.0, 1.0, 1.0};
-            int curf = 1;
-            int sp = 0;
-            int ktot = 0;
-            const double *Pc = a.P + (size_t)c * a.E * 16;
-            const double *TPc = a.TP + (size_t)c * a.E * a.K * 4;
-#pragma unroll 1
-            for (int o = 0; o < a.nops; o++) {
-                const F4Op op = a.ops[o];
-                if (op.spill_before) {
 #pragma unroll
-                    for (int i = 0; i < 4; i++) stack[((size_t)sp * 4 + i) * bd + tid] = cur[i];
-                    stackf[(size_t)sp * bd + tid] = curf;
-                    sp++;
-                }
-                double acc[4];
-                int cst = 1;
-                if (a.node_has_data[op.node]) {
-                    int code = a.codes[(size_t)op.node * a.S + site];
-                    f4_ld4(a.defs + code * 4, acc);
-                    cst = a.def_const[code];
-                } else {
-                    acc[0] = acc[1] = acc[2] = acc[3] = 1.0;
-                }
-                int sloc = 0;
-#pragma unroll 1
-                for (int j = 0; j < op.nchild; j++) {
-                    const F4Child ch = a.children[op.first_child + j];
-                    double em[4];
-                    int bc;
-                    if (ch.kind == F4_KIND_TIP) {
-                        int code = a.codes[(size_t)ch.node * a.S + site];
-                        f4_ld4(TPc + ((size_t)ch.edge * a.K + code) * 4, em);
-                        bc = a.def_const[code];
-                    } else {
-                        double v[4];
-                        if (ch.kind == F4_KIND_CUR) {
+        for (int c = 0; c < C; c++) {
+            double r[4];
 #pragma unroll
-                            for (int i = 0; i < 4; i++) v[i] = cur[i];
-                            bc = curf;
-                        } else {
-                            sp--;
-#pragma unroll
-                            for (int i = 0; i < 4; i++) v[i] = stack[((size_t)sp * 4 + i) * bd + tid];
-                            bc = stackf[(size_t)sp * bd + tid];
-                        }
-                        if (bc) {
-#pragma unroll
-                            for (int i = 0; i < 4; i++) em[i] = v[i];
-                        } else {
-                            f4_matvec(Pc + (size_t)ch.edge * 16, v, em);
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; i++) acc[i] *= em[i];
-                    sloc += f4_rescale_up(acc);
-                    cst &= bc;
-                }
-                ktot -= sloc;
-#pragma unroll
-                for (int i = 0; i < 4; i++) cur[i] = acc[i];
-                curf = cst;
-                if (EDGE) {
-                    const size_t off = ((size_t)c * a.nslots + op.slot) * T + gtid;
-                    a.scratch[off] = make_double4(acc[0], acc[1], acc[2], acc[3]);
-                    a.scratchS[off] = (signed char)(sloc | (cst << 6));
-                }
-            }
-            /* root prior expectation (model.c:282-350) */
+            for (int i = 0; i < 4; i++) r[i] = cur[(c * 4 + i) * bd + tid];
             double lh;
-            if (a.root_mode == PLF_ROOT_NONE) {
-                lh = (cur[0] + cur[1]) + (cur[2] + cur[3]);
-            } else if (a.root_mode == PLF_ROOT_UNIFORM) {
-                lh = curf ? cur[0] : ((cur[0] + cur[1]) + (cur[2] + cur[3])) * 0.25;
-            } else if (a.root_mode == PLF_ROOT_EQUILIBRIUM && curf) {
-                lh = cur[0];
-            } else {
-                lh = a.root_vec[0] * cur[0];
-                lh = fma(a.root_vec[1], cur[1], lh);
-                lh = fma(a.root_vec[2], cur[2], lh);
-                lh = fma(a.root_vec[3], cur[3], lh);
+            if (a.root_mode == PLF_ROOT_NONE) lh = (r[0] + r[1]) + (r[2] + r[3]);
+            else if (a.root_mode == PLF_ROOT_UNIFORM) lh = curf ? r[0] : ((r[0] + r[1]) + (r[2] + r[3])) * 0.25;
+            else if (a.root_mode == PLF_ROOT_EQUILIBRIUM && curf) lh = r[0];
+            else {
+                lh = a.root_vec[0] * r[0];
+                lh = fma(a.root_vec[1], r[1], lh);
+                lh = fma(a.root_vec[2], r[2], lh);
+                lh = fma(a.root_vec[3], r[3], lh);
             }
-            const double v = a.cat_prior[c] * lh;
-            kcat[c * bd + tid] = (v > 0.0) ? ktot : INT_MIN;
+            const double v = prior[c] * lh;
+            kcat[c * bd + tid] = (v > 0.0) ? ktot[c] : INT_MIN;
             if (v > 0.0) {
-                if (!have) { site_m = v; site_k = ktot; have = true; }
-                else if (ktot > site_k) { site_m = scalbn(site_m, PLF_SCALE_BITS * (site_k - ktot)) + v; site_k = ktot; }
-                else site_m += scalbn(v, PLF_SCALE_BITS * (ktot - site_k));
+                if (!have) { site_m = v; site_k = ktot[c]; have = true; }
+                else if (ktot[c] > site_k) { site_m = scalbn(site_m, PLF_SCALE_BITS * (site_k - ktot[c])) + v; site_k = ktot[c]; }
+                else if (ktot[c] == site_k) site_m += v;
+                else site_m += scalbn(v, PLF_SCALE_BITS * (ktot[c] - site_k));
             }
         }
-        /* ---------------- site log-likelihood ---------------- */
         {
-            const double c_hi = 177.445678223346, c_lo = 5.936759843446527e-15;
+            const double c_hi = 177.445678223346, c_lo = 5.936759843446527e-15;   /* 256 ln 2 */
             double ll = log(site_m);
-            ll = fma((double)site_k, c_hi, ll);
-            ll = fma((double)site_k, c_lo, ll);
+            if (site_k != 0) { ll = fma((double)site_k, c_hi, ll); ll = fma((double)site_k, c_lo, ll); }
             if (valid) {
                 if (a.site_ll) a.site_ll[site] = ll;
                 if (w != 0.0) {
@@ -281,89 +367,81 @@ __global__ void __launch_bounds__(256) fused4_kernel(F4Args a)
 
         /* ---------------- outside pass ---------------- */
         const double inv_site = (have && w != 0.0) ? (a.edge_site_out ? 1.0 : w) / site_m : 0.0;
-#pragma unroll 1
-        for (int c = 0; c < a.C; c++) {
+        /* fn_root = root prior vector * prior_c * w / site_L, scaled so that fn .* L is O(1) */
+#pragma unroll
+        for (int c = 0; c < C; c++) {
             const int kc = kcat[c * bd + tid];
-            const bool alive = (kc != INT_MIN);
-            /* fn_root = root prior vector * prior_c * w / site_L, scaled so that fn .* L is O(1) */
-            const double sc0 = alive ? scalbn(a.cat_prior[c] * inv_site, PLF_SCALE_BITS * (kc - site_k)) : 0.0;
-            double curF[4];
+            const double sc0 = (kc != INT_MIN) ? scalbn(prior[c] * inv_site, PLF_SCALE_BITS * (kc - site_k)) : 0.0;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 double r = 1.0;
                 if (a.root_mode == PLF_ROOT_UNIFORM) r = 0.25;
                 else if (a.root_mode == PLF_ROOT_EQUILIBRIUM || a.root_mode == PLF_ROOT_CUSTOM) r = a.root_vec[i];
-                curF[i] = r * sc0;
+                cur[(c * 4 + i) * bd + tid] = r * sc0;
             }
-            int sp = 0;
-            const double *Pc = a.P + (size_t)c * a.E * 16;
-            const double *Fc = a.Fm + (size_t)c * a.E * 16;
-            const double *TPc = a.TP + (size_t)c * a.E * a.K * 4;
-            const double *TFc = a.TF + (size_t)c * a.E * a.K * 4;
+        }
 #pragma unroll 1
-            for (int o = a.nops - 1; o >= 0; o--) {
-                const F4Op op = a.ops[o];
-                double fa[4];
-                if (o != a.nops - 1 && a.ops[o + 1].spill_before) {
-                    sp--;
+        for (int o = a.nops - 1; o >= 0; o--) {
+            const F4Op op = ops[o];
+            /* fn_a comes from "cur" if this node was consumed from registers by its parent, else from its slot */
+            const bool from_slot = (o != a.nops - 1) && ops[o + 1].spill_before;
+            double basev[4] = {1.0, 1.0, 1.0, 1.0};
+            if (op.code_row >= 0) f4_ld4(defs_s + tile[op.code_row * bd + tid] * 4, basev);
+            /* children descriptors and category-independent lookups */
+            int kinds[F4_MAXD], mats[F4_MAXD], slots[F4_MAXD], edges[F4_MAXD], codes[F4_MAXD], bcs[F4_MAXD];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) fa[i] = stack[((size_t)sp * 4 + i) * bd + tid];
+            for (int j = 0; j < F4_MAXD; j++) {
+                kinds[j] = -1; mats[j] = 0; slots[j] = 0; edges[j] = 0; codes[j] = 0; bcs[j] = 0;
+                if (j < op.nchild) {
+                    const F4Child ch = chs[op.first_child + j];
+                    kinds[j] = ch.kind; mats[j] = ch.mat; slots[j] = ch.slot; edges[j] = ch.edge;
+                    if (ch.kind == F4_KIND_TIP) codes[j] = tile[ch.code_row * bd + tid];
+                    else bcs[j] = (a.scratchS[((size_t)ch.slot * C) * T + gtid] >> 6) & 1;
+                }
+            }
+            double x[F4_MAXD] = {0.0, 0.0, 0.0};
+#pragma unroll 1
+            for (int c = 0; c < C; c++) {
+                double fa[4];
+                const size_t so_a = ((size_t)op.slot * C + c) * T + gtid;
+                if (from_slot) {
+                    double4 f4v = a.scratch[so_a];
+                    fa[0] = f4v.x; fa[1] = f4v.y; fa[2] = f4v.z; fa[3] = f4v.w;
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 4; i++) fa[i] = curF[i];
+                    for (int i = 0; i < 4; i++) fa[i] = cur[(c * 4 + i) * bd + tid];
                 }
-                /* tmp = fn_a .* base_a * 2^(256 s_a) */
-                {
-                    const size_t off = ((size_t)c * a.nslots + op.slot) * T + gtid;
-                    int sa = a.scratchS[off] & 63;
-                    if (a.node_has_data[op.node]) {
-                        int code = a.codes[(size_t)op.node * a.S + site];
-                        double b[4];
-                        f4_ld4(a.defs + code * 4, b);
+                int sa = a.scratchS[so_a] & 63;
 #pragma unroll
-                        for (int i = 0; i < 4; i++) fa[i] *= b[i];
-                    }
-                    while (sa > 0) {
+                for (int i = 0; i < 4; i++) fa[i] *= basev[i];
+                while (sa > 0) {
 #pragma unroll
-                        for (int i = 0; i < 4; i++) fa[i] *= PLF_TWO_P256;
-                        sa--;
-                    }
+                    for (int i = 0; i < 4; i++) fa[i] *= PLF_TWO_P256;
+                    sa--;
                 }
                 double em[F4_MAXD][4], y[F4_MAXD][4];
-                int kinds[F4_MAXD], edges[F4_MAXD];
 #pragma unroll
                 for (int j = 0; j < F4_MAXD; j++) {
-                    kinds[j] = -1; edges[j] = 0;
 #pragma unroll
                     for (int i = 0; i < 4; i++) { em[j][i] = 1.0; y[j][i] = 0.0; }
-                    if (j < op.nchild) {
-                        const F4Child ch = a.children[op.first_child + j];
-                        kinds[j] = ch.kind; edges[j] = ch.edge;
-                        if (ch.kind == F4_KIND_TIP) {
-                            int code = a.codes[(size_t)ch.node * a.S + site];
-                            f4_ld4(TPc + ((size_t)ch.edge * a.K + code) * 4, em[j]);
-                            f4_ld4(TFc + ((size_t)ch.edge * a.K + code) * 4, y[j]);
-                        } else {
-                            const size_t off = ((size_t)c * a.nslots + ch.slot) * T + gtid;
-                            double4 l4 = a.scratch[off];
-                            int bc = (a.scratchS[off] >> 6) & 1;
-                            double lv[4] = {l4.x, l4.y, l4.z, l4.w};
-                            if (bc) {
+                    if (kinds[j] == F4_KIND_TIP) {
+                        f4_ld4(TP + c * tpstride + (mats[j] * a.K + codes[j]) * 4, em[j]);
+                        f4_ld4(TF + c * tpstride + (mats[j] * a.K + codes[j]) * 4, y[j]);
+                    } else if (kinds[j] >= 0) {
+                        double4 l4 = a.scratch[((size_t)slots[j] * C + c) * T + gtid];
+                        double lv[4] = {l4.x, l4.y, l4.z, l4.w};
+                        if (bcs[j]) {
 #pragma unroll
-                                for (int i = 0; i < 4; i++) em[j][i] = lv[i];
-                            } else {
-                                f4_matvec(Pc + (size_t)ch.edge * 16, lv, em[j]);
-                            }
-                            if (!(bc && a.f_zero_rowsum)) f4_matvec(Fc + (size_t)ch.edge * 16, lv, y[j]);
+                            for (int i = 0; i < 4; i++) em[j][i] = lv[i];
+                        } else {
+                            f4_matvec(Pint + c * pstride + mats[j] * 16, lv, em[j]);
                         }
+                        if (!(bcs[j] && a.f_zero_rowsum)) f4_matvec(Fint + c * pstride + mats[j] * 16, lv, y[j]);
                     }
                 }
-                /* per child: fe_j = tmp .* prod_{i != j} em_i ; x_j = fe_j . y_j ; fn_j = P_j^T fe_j */
-                double newcur[4] = {0.0, 0.0, 0.0, 0.0};
-                double push[F4_MAXD][4];
 #pragma unroll
                 for (int j = 0; j < F4_MAXD; j++) {
-                    if (j < op.nchild) {
+                    if (kinds[j] >= 0) {
                         double fe[4];
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
@@ -372,43 +450,38 @@ __global__ void __launch_bounds__(256) fused4_kernel(F4Args a)
                             for (int j2 = 0; j2 < F4_MAXD; j2++) if (j2 != j) f *= em[j2][i];
                             fe[i] = f;
                         }
-                        double x = fe[0] * y[j][0];
-                        x = fma(fe[1], y[j][1], x);
-                        x = fma(fe[2], y[j][2], x);
-                        x = fma(fe[3], y[j][3], x);
-                        const int e = edges[j];
-                        if (!a.edge_mask || a.edge_mask[e]) {
-                            if (a.edge_site_out) {
-                                if (valid) a.edge_site_out[(size_t)e * a.S + site] += x;
-                            } else {
-                                double xs = f4_warp_sum(x);
-                                if (lane == 0) accE[warp * a.E + e] += xs;
-                            }
-                        }
+                        double xv = fe[0] * y[j][0];
+                        xv = fma(fe[1], y[j][1], xv);
+                        xv = fma(fe[2], y[j][2], xv);
+                        xv = fma(fe[3], y[j][3], xv);
+                        x[j] += xv;
                         if (kinds[j] != F4_KIND_TIP) {
                             double fb[4];
-                            f4_matvec_t(Pc + (size_t)e * 16, fe, fb);
+                            f4_matvec_t(Pint + c * pstride + mats[j] * 16, fe, fb);
                             if (kinds[j] == F4_KIND_CUR) {
 #pragma unroll
-                                for (int i = 0; i < 4; i++) newcur[i] = fb[i];
+                                for (int i = 0; i < 4; i++) cur[(c * 4 + i) * bd + tid] = fb[i];
                             } else {
-#pragma unroll
-                                for (int i = 0; i < 4; i++) push[j][i] = fb[i];
+                                /* the child's inside vector is dead after this op: its slot carries fn down */
+                                a.scratch[((size_t)slots[j] * C + c) * T + gtid] = make_double4(fb[0], fb[1], fb[2], fb[3]);
                             }
                         }
                     }
                 }
-                /* push stack children in reverse list order (mirror of the inside pops) */
+            }
 #pragma unroll
-                for (int j = F4_MAXD - 1; j >= 0; j--) {
-                    if (j < op.nchild && kinds[j] == F4_KIND_STACK) {
-#pragma unroll
-                        for (int i = 0; i < 4; i++) stack[((size_t)sp * 4 + i) * bd + tid] = push[j][i];
-                        sp++;
+            for (int j = 0; j < F4_MAXD; j++) {
+                if (kinds[j] >= 0) {
+                    const int e = edges[j];
+                    if (!a.edge_mask || a.edge_mask[e]) {
+                        if (a.edge_site_out) {
+                            if (valid) a.edge_site_out[(size_t)e * a.S + site] = x[j];
+                        } else {
+                            double xs = f4_warp_sum(x[j]);
+                            if (lane == 0) accE[warp * a.E + e] += xs;
+                        }
                     }
                 }
-#pragma unroll
-                for (int i = 0; i < 4; i++) curF[i] = newcur[i];
             }
         }
     }
@@ -416,8 +489,8 @@ __global__ void __launch_bounds__(256) fused4_kernel(F4Args a)
     /* ---------------- CTA-level reductions ---------------- */
     {
         __shared__ double red[32];
-        double x = f4_warp_sum(ll_acc);
-        if (lane == 0) red[warp] = x;
+        double xx = f4_warp_sum(ll_acc);
+        if (lane == 0) red[warp] = xx;
         __syncthreads();
         if (tid == 0) {
             double s = 0.0;
@@ -434,7 +507,7 @@ __global__ void __launch_bounds__(256) fused4_kernel(F4Args a)
     }
 }
 
-/* second stage: out[j] = sum over rows of part[row][j], fixed order */
+/* second stage: out[j] = sum over rows of part[row][j], fixed order (Kahan) */
 __global__ void sum_rows_kernel(const double *part, int rows, int cols, double *out)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -447,4 +520,15 @@ __global__ void sum_rows_kernel(const double *part, int rows, int cols, double *
         s = tsum;
     }
     out[j] = s;
+}
+
+/* gather the matrices of internal-child edges: out[c][ie] = M[c][edge_of[ie]] (16 doubles each) */
+__global__ void compact_matrices_kernel(const double *M, const int *edge_of, int C, int E, int Ei, double *out)
+{
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = C * Ei * 16;
+    if (idx >= total) return;
+    int k = idx & 15, r = idx >> 4;
+    int ie = r % Ei, c = r / Ei;
+    out[idx] = M[((size_t)c * E + edge_of[ie]) * 16 + k];
 }

@@ -105,9 +105,11 @@ struct plf_engine {
     /* fused program */
     std::vector<F4Op> ops;
     std::vector<F4Child> children;
-    DevBuf d_ops, d_children, d_TP, d_TF;
+    DevBuf d_ops, d_children, d_TP, d_TF, d_Pint, d_Fint, d_edge_of_int, d_edge_of_tip, d_code_row_node;
+    std::vector<int> edge_of_int, edge_of_tip, code_row_node;
+    std::vector<unsigned char> node_has_data_h;
     int stack_depth = 0, nslots = 0, max_degree = 0;
-    bool TP_valid = false;
+    bool TP_valid = false, program_dirty = true;
 
     /* scratch */
     DevBuf d_scratch, d_scratchS, d_block_ll, d_block_edge, d_edge_site, d_sum, d_site_ll, d_err, d_mask;
@@ -170,22 +172,20 @@ __global__ void flags_to_bytes_kernel(const int *flags, unsigned char *out, int 
     if (i < N) out[i] = flags[i] ? 1 : 0;
 }
 
-/* out[c][e][k][i] = sum_j M[c][e][i][j] def[k][j], leaf edges only.
+/* compact tip tables: out[c][te][k][i] = sum_j M[c][edge_of_tip[te]][i][j] def[k][j].
  * mode 0: stochastic matrix (constant rows map to the constant);
  * mode 1: zero-row-sum matrix (constant rows map to exact 0); mode 2: no shortcut. */
 __global__ void tip_table_kernel(const double *M, const double *defs, const unsigned char *def_const,
-                                 const int *indptr, const int *indices, int C, int E, int K, int n,
+                                 const int *edge_of_tip, int C, int E, int Et, int K, int n,
                                  int mode, double *out)
 {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t total = (size_t)C * E * K * n;
+    size_t total = (size_t)C * Et * K * n;
     if (idx >= total) return;
     int i = idx % n; size_t r = idx / n;
     int k = r % K; r /= K;
-    int e = r % E; int c = r / E;
-    int b = indices[e];
-    if (indptr[b] != indptr[b + 1]) { out[idx] = 0.0; return; }
-    const double *row = M + (((size_t)c * E + e) * n + i) * n;
+    int te = r % Et; int c = r / Et;
+    const double *row = M + (((size_t)c * E + edge_of_tip[te]) * n + i) * n;
     const double *d = defs + (size_t)k * n;
     double v;
     if (def_const[k] && mode == 0) v = d[0];
@@ -375,14 +375,21 @@ static int build_program(plf_engine *e)
         }
     }
     e->ops.clear(); e->children.clear();
+    e->edge_of_int.clear(); e->edge_of_tip.clear(); e->code_row_node.clear();
     for (size_t o = 0; o < order.size(); o++) slot[order[o]] = (int)o;
+    std::vector<int> code_row(N, -1);
+    auto row_of = [&](int node) {
+        if (code_row[node] < 0) { code_row[node] = (int)e->code_row_node.size(); e->code_row_node.push_back(node); }
+        return code_row[node];
+    };
     std::vector<int> stk;
     int cur = -1, maxdepth = 0;
     for (size_t o = 0; o < order.size(); o++) {
         int a = order[o];
         F4Op op;
         op.node = a; op.first_child = (int)e->children.size(); op.nchild = 0; op.slot = (int)o;
-        op.has_data = 0; op.spill_before = 0;
+        op.code_row = (!e->node_has_data_h.empty() && e->node_has_data_h[a]) ? row_of(a) : -1;
+        op.spill_before = 0;
         const std::vector<int> &ic = ichild[a];
         int cur_edge = -1;
         for (int idx : ic) if (e->indices[idx] == cur) cur_edge = idx;
@@ -391,10 +398,14 @@ static int build_program(plf_engine *e)
             stk.push_back(cur);
             maxdepth = std::max(maxdepth, (int)stk.size());
         }
-        if (cur_edge != -1) {
-            F4Child ch = {cur_edge, cur, slot[cur], F4_KIND_CUR};
+        auto add_internal = [&](int idx, int b, int kind) {
+            F4Child ch;
+            memset(&ch, 0, sizeof(ch));
+            ch.kind = kind; ch.slot = slot[b]; ch.mat = (int)e->edge_of_int.size(); ch.code_row = -1; ch.edge = idx;
+            e->edge_of_int.push_back(idx);
             e->children.push_back(ch); op.nchild++;
-        }
+        };
+        if (cur_edge != -1) add_internal(cur_edge, cur, F4_KIND_CUR);
         size_t nstack = ic.size() - (cur_edge != -1 ? 1 : 0);
         for (size_t j = 0; j < nstack; j++) {
             if (stk.empty()) { e->err = "internal error: fused program stack underflow"; return -1; }
@@ -402,13 +413,15 @@ static int build_program(plf_engine *e)
             int be = -1;
             for (int idx : ic) if (e->indices[idx] == b) be = idx;
             if (be == -1) { e->err = "internal error: fused program stack mismatch"; return -1; }
-            F4Child ch = {be, b, slot[b], F4_KIND_STACK};
-            e->children.push_back(ch); op.nchild++;
+            add_internal(be, b, F4_KIND_STACK);
         }
         for (int idx = e->indptr[a]; idx < e->indptr[a + 1]; idx++) {
             int b = e->indices[idx];
             if (is_leaf(b)) {
-                F4Child ch = {idx, b, -1, F4_KIND_TIP};
+                F4Child ch;
+                memset(&ch, 0, sizeof(ch));
+                ch.kind = F4_KIND_TIP; ch.slot = -1; ch.mat = (int)e->edge_of_tip.size(); ch.code_row = row_of(b); ch.edge = idx;
+                e->edge_of_tip.push_back(idx);
                 e->children.push_back(ch); op.nchild++;
             }
         }
@@ -448,18 +461,17 @@ extern "C" int plf_set_tree(plf_engine *e, int node_count, const int *indptr, co
     e->indptr.assign(indptr, indptr + N + 1);
     e->indices.assign(indices, indices + E);
     e->preorder.assign(preorder, preorder + N);
-    if (build_program(e)) return -1;
+    e->node_has_data_h.clear();
+    e->program_dirty = true;
+    e->max_degree = 0;
+    for (int a = 0; a < N; a++) e->max_degree = std::max(e->max_degree, indptr[a + 1] - indptr[a]);
     CK(e, cudaSetDevice(e->device));
     ENSURE(e, e->d_indptr, sizeof(int) * (N + 1));
     ENSURE(e, e->d_indices, sizeof(int) * E);
     ENSURE(e, e->d_preorder, sizeof(int) * N);
-    ENSURE(e, e->d_ops, sizeof(F4Op) * e->ops.size());
-    ENSURE(e, e->d_children, sizeof(F4Child) * e->children.size());
     CK(e, cudaMemcpyAsync(e->d_indptr.p, indptr, sizeof(int) * (N + 1), cudaMemcpyHostToDevice, e->stream));
     CK(e, cudaMemcpyAsync(e->d_indices.p, indices, sizeof(int) * E, cudaMemcpyHostToDevice, e->stream));
     CK(e, cudaMemcpyAsync(e->d_preorder.p, preorder, sizeof(int) * N, cudaMemcpyHostToDevice, e->stream));
-    CK(e, cudaMemcpyAsync(e->d_ops.p, e->ops.data(), sizeof(F4Op) * e->ops.size(), cudaMemcpyHostToDevice, e->stream));
-    CK(e, cudaMemcpyAsync(e->d_children.p, e->children.data(), sizeof(F4Child) * e->children.size(), cudaMemcpyHostToDevice, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
     e->P_valid = e->D_valid = e->TP_valid = false;
     e->S = 0;   /* data must be (re)set after the tree */
@@ -630,7 +642,12 @@ extern "C" int plf_set_data(plf_engine *e, int64_t S, int K, const double *defs,
     KCHECK(e);
     /* host-side range check of the codes would cost a pass over S*N bytes; the
      * caller (the JSON front end) has already validated them (parsemodel.c:600-613). */
-    CK(e, cudaStreamSynchronize(e->stream));
+    {
+        std::vector<unsigned char> flags_h(N);
+        CK(e, cudaMemcpyAsync(flags_h.data(), e->d_node_has_data.p, N, cudaMemcpyDeviceToHost, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+        if (flags_h != e->node_has_data_h) { e->node_has_data_h = flags_h; e->program_dirty = true; }
+    }
     e->S = S; e->K = K; e->code_bytes = dev_bytes;
     e->TP_valid = false;
     e->have_w = false;
@@ -669,25 +686,63 @@ static bool fused_applicable(const plf_engine *e)
     return e->n == 4 && e->C <= 4 && e->code_bytes == 1 && e->K <= 256 && e->max_degree <= F4_MAXD;
 }
 
+static int ensure_program(plf_engine *e)
+{
+    if (!e->program_dirty) return 0;
+    if (build_program(e)) return -1;
+    ENSURE(e, e->d_ops, sizeof(F4Op) * e->ops.size());
+    ENSURE(e, e->d_children, sizeof(F4Child) * e->children.size());
+    ENSURE(e, e->d_edge_of_int, sizeof(int) * (e->edge_of_int.size() + 1));
+    ENSURE(e, e->d_edge_of_tip, sizeof(int) * (e->edge_of_tip.size() + 1));
+    ENSURE(e, e->d_code_row_node, sizeof(int) * (e->code_row_node.size() + 1));
+    CK(e, cudaMemcpyAsync(e->d_ops.p, e->ops.data(), sizeof(F4Op) * e->ops.size(), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->d_children.p, e->children.data(), sizeof(F4Child) * e->children.size(), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->d_edge_of_int.p, e->edge_of_int.data(), sizeof(int) * e->edge_of_int.size(), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->d_edge_of_tip.p, e->edge_of_tip.data(), sizeof(int) * e->edge_of_tip.size(), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->d_code_row_node.p, e->code_row_node.data(), sizeof(int) * e->code_row_node.size(), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    e->program_dirty = false;
+    e->TP_valid = false;
+    return 0;
+}
+
+/* compact matrices of the internal-child edges and tip tables for the fused kernel */
 static int ensure_tip_tables(plf_engine *e, const double *Fm, int f_mode)
 {
-    const size_t cnt = (size_t)e->C * e->E * e->K * e->n;
+    if (ensure_program(e)) return -1;
+    const int Ei = (int)e->edge_of_int.size(), Et = (int)e->edge_of_tip.size();
+    const size_t cntT = (size_t)e->C * Et * e->K * e->n, cntP = (size_t)e->C * Ei * 16;
     const int threads = 256;
-    const unsigned blocks = (unsigned)((cnt + threads - 1) / threads);
     if (!e->TP_valid) {
-        ENSURE(e, e->d_TP, sizeof(double) * cnt);
-        tip_table_kernel<<<blocks, threads, 0, e->stream>>>(e->d_P.as<double>(), e->d_defs.as<double>(),
-            e->d_def_const.as<unsigned char>(), e->d_indptr.as<int>(), e->d_indices.as<int>(),
-            e->C, e->E, e->K, e->n, 0, e->d_TP.as<double>());
-        KCHECK(e);
+        ENSURE(e, e->d_TP, sizeof(double) * (cntT + 1));
+        ENSURE(e, e->d_Pint, sizeof(double) * (cntP + 1));
+        if (cntT) {
+            tip_table_kernel<<<(unsigned)((cntT + threads - 1) / threads), threads, 0, e->stream>>>(
+                e->d_P.as<double>(), e->d_defs.as<double>(), e->d_def_const.as<unsigned char>(),
+                e->d_edge_of_tip.as<int>(), e->C, e->E, Et, e->K, e->n, 0, e->d_TP.as<double>());
+            KCHECK(e);
+        }
+        if (cntP) {
+            compact_matrices_kernel<<<(unsigned)((cntP + threads - 1) / threads), threads, 0, e->stream>>>(
+                e->d_P.as<double>(), e->d_edge_of_int.as<int>(), e->C, e->E, Ei, e->d_Pint.as<double>());
+            KCHECK(e);
+        }
         e->TP_valid = true;
     }
     if (Fm) {
-        ENSURE(e, e->d_TF, sizeof(double) * cnt);
-        tip_table_kernel<<<blocks, threads, 0, e->stream>>>(Fm, e->d_defs.as<double>(),
-            e->d_def_const.as<unsigned char>(), e->d_indptr.as<int>(), e->d_indices.as<int>(),
-            e->C, e->E, e->K, e->n, f_mode, e->d_TF.as<double>());
-        KCHECK(e);
+        ENSURE(e, e->d_TF, sizeof(double) * (cntT + 1));
+        ENSURE(e, e->d_Fint, sizeof(double) * (cntP + 1));
+        if (cntT) {
+            tip_table_kernel<<<(unsigned)((cntT + threads - 1) / threads), threads, 0, e->stream>>>(
+                Fm, e->d_defs.as<double>(), e->d_def_const.as<unsigned char>(),
+                e->d_edge_of_tip.as<int>(), e->C, e->E, Et, e->K, e->n, f_mode, e->d_TF.as<double>());
+            KCHECK(e);
+        }
+        if (cntP) {
+            compact_matrices_kernel<<<(unsigned)((cntP + threads - 1) / threads), threads, 0, e->stream>>>(
+                Fm, e->d_edge_of_int.as<int>(), e->C, e->E, Ei, e->d_Fint.as<double>());
+            KCHECK(e);
+        }
     }
     return 0;
 }
@@ -722,20 +777,61 @@ static int copy_site_matrix(plf_engine *e, const double *d_rows /*[R][cols]*/, i
     return 0;
 }
 
+typedef void (*f4_kernel_t)(F4Args);
+
+static f4_kernel_t f4_select(int C, bool edge)
+{
+    switch (C * 2 + (edge ? 1 : 0)) {
+    case 2: return fused4_kernel<1, false>;
+    case 3: return fused4_kernel<1, true>;
+    case 4: return fused4_kernel<2, false>;
+    case 5: return fused4_kernel<2, true>;
+    case 6: return fused4_kernel<3, false>;
+    case 7: return fused4_kernel<3, true>;
+    case 8: return fused4_kernel<4, false>;
+    case 9: return fused4_kernel<4, true>;
+    }
+    return nullptr;
+}
+
+/* mirrors the shared-memory carve-up at the top of fused4_kernel */
+static size_t f4_smem_bytes(const plf_engine *e, bool edge, int bd, int stage_mask)
+{
+    const int C = e->C, Ei = (int)e->edge_of_int.size(), Et = (int)e->edge_of_tip.size();
+    size_t off = 0;
+    off = f4_align16(off + sizeof(F4Op) * e->ops.size());
+    off = f4_align16(off + sizeof(F4Child) * e->children.size());
+    off = f4_align16(off + sizeof(double) * 4 * C * bd);
+    off = f4_align16(off + (edge ? sizeof(double) * (bd / 32) * e->E : 0));
+    off = f4_align16(off + (edge ? 0 : sizeof(double) * 4 * C * bd * e->stack_depth));
+    off = f4_align16(off + (edge ? 0 : sizeof(int) * bd * e->stack_depth));
+    off = f4_align16(off + sizeof(int) * C * bd);
+    off = f4_align16(off + e->code_row_node.size() * bd);
+    off = f4_align16(off + e->K);
+    off = f4_align16(off + sizeof(double) * 4 * e->K);
+    const size_t nP = (size_t)C * Ei * 16 * sizeof(double), nT = (size_t)C * Et * e->K * 4 * sizeof(double);
+    if (stage_mask & 1) off += nP;
+    if (stage_mask & 2) off += nT;
+    if (edge && (stage_mask & 4)) off += nP;
+    if (edge && (stage_mask & 8)) off += nT;
+    return off + 16;
+}
+
 static int run_fused(plf_engine *e, Query &q)
 {
     const bool edge = q.want_edge;
-    const int bd = 128;
     F4Args a;
     memset(&a, 0, sizeof(a));
-    a.nops = (int)e->ops.size();
+    a.nops = (int)e->ops.size(); a.nchildren = (int)e->children.size();
     a.ops = e->d_ops.as<F4Op>(); a.children = e->d_children.as<F4Child>();
-    a.C = e->C; a.E = e->E; a.K = e->K; a.S = e->S;
+    a.E = e->E; a.K = e->K; a.S = e->S;
+    a.Ei = (int)e->edge_of_int.size(); a.Et = (int)e->edge_of_tip.size();
+    a.ncode_rows = (int)e->code_row_node.size();
+    a.code_row_node = e->d_code_row_node.as<int>();
     a.codes = e->d_codes.as<unsigned char>();
     a.defs = e->d_defs.as<double>(); a.def_const = e->d_def_const.as<unsigned char>();
-    a.node_has_data = e->d_node_has_data.as<unsigned char>();
-    a.P = e->d_P.as<double>(); a.TP = e->d_TP.as<double>();
-    a.Fm = q.Fm; a.TF = edge ? e->d_TF.as<double>() : nullptr;
+    a.Pint = e->d_Pint.as<double>(); a.TP = e->d_TP.as<double>();
+    a.Fint = edge ? e->d_Fint.as<double>() : nullptr; a.TF = edge ? e->d_TF.as<double>() : nullptr;
     a.f_zero_rowsum = q.f_zero_rowsum;
     a.cat_prior = e->d_cat_prior.as<double>();
     a.root_mode = e->root_mode;
@@ -743,10 +839,25 @@ static int run_fused(plf_engine *e, Query &q)
     a.site_w = e->have_w ? e->d_site_w.as<double>() : nullptr;
     a.stack_depth = e->stack_depth; a.nslots = e->nslots;
 
-    const size_t smem = (size_t)bd * ((size_t)e->stack_depth * 36 + 16) + (size_t)(bd / 32) * e->E * 8 + 16;
-    auto kern = edge ? fused4_kernel<true> : fused4_kernel<false>;
-    if (smem > 48 * 1024) CK(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (smem > 227 * 1024) FAIL(e, "fused kernel needs %zu bytes of shared memory", smem);
+    f4_kernel_t kern = f4_select(e->C, edge);
+    if (!kern) FAIL(e, "fused kernel: unsupported category count %d", e->C);
+    /* block size and which tables live in shared memory: prefer everything on chip */
+    const size_t smem_cap = 227 * 1024;
+    int bd = 256, stage_mask = 15;
+    size_t smem = 0;
+    for (;;) {
+        smem = f4_smem_bytes(e, edge, bd, stage_mask);
+        if (smem <= smem_cap) break;
+        if (stage_mask & 8) stage_mask &= ~8;
+        else if (stage_mask & 4) stage_mask &= ~4;
+        else if (bd > 128) { bd = 128; stage_mask = 15; }
+        else if (stage_mask & 2) stage_mask &= ~2;
+        else if (stage_mask & 1) stage_mask &= ~1;
+        else if (bd > 64) bd = 64;
+        else FAIL(e, "fused kernel needs %zu bytes of shared memory", smem);
+    }
+    a.stage_mask = stage_mask;
+    CK(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CK(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, bd, smem));
     if (per_sm < 1) FAIL(e, "fused kernel cannot be resident (smem %zu)", smem);
@@ -765,7 +876,7 @@ static int run_fused(plf_engine *e, Query &q)
         ENSURE(e, e->d_scratch, sizeof(double4) * (size_t)e->C * e->nslots * T);
         ENSURE(e, e->d_scratchS, (size_t)e->C * e->nslots * T);
         ENSURE(e, e->d_block_edge, sizeof(double) * (size_t)grid * e->E);
-        a.scratch = e->d_scratch.as<double4>(); a.scratchS = e->d_scratchS.as<signed char>();
+        a.scratch = e->d_scratch.as<double4>(); a.scratchS = e->d_scratchS.as<unsigned char>();
         a.block_edge = e->d_block_edge.as<double>();
         if (q.edge_mask_h) {
             ENSURE(e, e->d_mask, e->E);
