@@ -109,7 +109,7 @@ struct plf_engine {
     std::vector<int> edge_of_int, edge_of_tip, code_row_node;
     std::vector<unsigned char> node_has_data_h;
     int stack_depth = 0, nslots = 0, max_degree = 0;
-    bool TP_valid = false, program_dirty = true, fused_shapes_ok = true;
+    bool TP_valid = false, program_dirty = true;
 
     /* scratch */
     DevBuf d_scratch, d_scratchS, d_block_ll, d_block_edge, d_edge_site, d_sum, d_site_ll, d_err, d_mask;
@@ -219,12 +219,6 @@ __global__ void wsum_rows_kernel(const double *val, const double *w, int64_t w_o
         __syncthreads();
     }
     if (threadIdx.x == 0) out[r] += red[0];
-}
-
-__global__ void add_vec_kernel(double *dst, const double *src, int n)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] += src[i];
 }
 
 /* in[R][Cc] -> out[Cc][R] */
@@ -381,7 +375,6 @@ static int build_program(plf_engine *e)
         }
     }
     e->ops.clear(); e->children.clear();
-    e->fused_shapes_ok = true;
     e->edge_of_int.clear(); e->edge_of_tip.clear(); e->code_row_node.clear();
     for (size_t o = 0; o < order.size(); o++) slot[order[o]] = (int)o;
     std::vector<int> code_row(N, -1);
@@ -431,19 +424,6 @@ static int build_program(plf_engine *e)
                 e->edge_of_tip.push_back(idx);
                 e->children.push_back(ch); op.nchild++;
             }
-        }
-        {
-            int ntip = 0, nst = 0, hc = 0;
-            for (int j = 0; j < op.nchild; j++) {
-                int k = e->children[op.first_child + j].kind;
-                if (k == F4_KIND_TIP) ntip++; else if (k == F4_KIND_STACK) nst++; else hc++;
-            }
-            op.shape = hc * 16 + nst * 4 + ntip;
-            op.pad = 0;
-            static const int allowed[] = {16, 17, 18, 20, 21, 24, 1, 2, 3};
-            bool ok = false;
-            for (int v : allowed) ok |= (v == op.shape);
-            if (!ok) e->fused_shapes_ok = false;
         }
         e->ops.push_back(op);
         cur = a;
@@ -707,6 +687,7 @@ static bool fused_applicable(const plf_engine *e)
 }
 
 static bool fused_fits(const plf_engine *e, bool edge);
+static int ensure_program(plf_engine *e);
 
 static int ensure_program(plf_engine *e)
 {
@@ -801,63 +782,55 @@ static int copy_site_matrix(plf_engine *e, const double *d_rows /*[R][cols]*/, i
 
 typedef void (*f4_kernel_t)(F4Args);
 
-/* mirrors f4_setup_smem */
-static size_t f4_smem_bytes(const plf_engine *e, bool outside, int bd, bool staged)
+template <int BD, bool STAGED>
+static f4_kernel_t f4_select_c(int C, bool edge)
+{
+    switch (C * 2 + (edge ? 1 : 0)) {
+    case 2: return fused4_kernel<1, false, BD, STAGED>;
+    case 3: return fused4_kernel<1, true, BD, STAGED>;
+    case 4: return fused4_kernel<2, false, BD, STAGED>;
+    case 5: return fused4_kernel<2, true, BD, STAGED>;
+    case 6: return fused4_kernel<3, false, BD, STAGED>;
+    case 7: return fused4_kernel<3, true, BD, STAGED>;
+    case 8: return fused4_kernel<4, false, BD, STAGED>;
+    case 9: return fused4_kernel<4, true, BD, STAGED>;
+    }
+    return nullptr;
+}
+
+/* mirrors the shared-memory carve-up at the top of fused4_kernel */
+static size_t f4_smem_bytes(const plf_engine *e, bool edge, int bd, bool staged)
 {
     const int C = e->C, Ei = (int)e->edge_of_int.size(), Et = (int)e->edge_of_tip.size();
-    const int spc = (32 / C) * (bd / 32);
     size_t off = 0;
     off = f4_align16(off + sizeof(F4Op) * e->ops.size());
     off = f4_align16(off + sizeof(F4Child) * e->children.size());
-    off = f4_align16(off + e->code_row_node.size() * spc);
+    off = f4_align16(off + sizeof(double) * 4 * C * bd);
+    off = f4_align16(off + (edge ? sizeof(double) * (bd / 32) * e->E : 0));
+    off = f4_align16(off + (edge ? 0 : sizeof(double) * 4 * C * bd * e->stack_depth));
+    off = f4_align16(off + (edge ? 0 : sizeof(int) * bd * e->stack_depth));
+    off = f4_align16(off + sizeof(int) * C * bd);
+    off = f4_align16(off + e->code_row_node.size() * bd);
     off = f4_align16(off + e->K);
     off = f4_align16(off + sizeof(double) * 4 * e->K);
-    off = f4_align16(off + (outside ? sizeof(double) * (bd / 32) * e->E : 0));
-    off = f4_align16(off + (outside ? 0 : sizeof(double) * 4 * bd * e->stack_depth));
-    off = f4_align16(off + (outside ? 0 : sizeof(int) * bd * e->stack_depth));
     const size_t nP = (size_t)C * Ei * 16 * sizeof(double), nT = (size_t)C * Et * e->K * 4 * sizeof(double);
-    if (staged) off += (nP + nT) * (outside ? 2 : 1);
+    if (staged) off += (nP + nT) * (edge ? 2 : 1);
     return off + 16;
 }
 
 static bool fused_fits(const plf_engine *e, bool edge)
 {
-    if (!e->fused_shapes_ok) return false;
-    if (f4_smem_bytes(e, false, 256, false) > 227 * 1024) return false;
-    if (edge && f4_smem_bytes(e, true, 256, false) > 227 * 1024) return false;
-    return true;
-}
-
-struct F4Launch { f4_kernel_t k; int bd; size_t smem; int grid; };
-
-static int f4_configure(plf_engine *e, F4Launch &L, bool edge, int64_t S)
-{
-    const size_t cap = 227 * 1024;
-    L.k = nullptr;
-    const size_t s512 = f4_smem_bytes(e, edge, 512, true), s256 = f4_smem_bytes(e, edge, 256, true);
-    if (s512 <= cap) { L.bd = 512; L.smem = s512; L.k = edge ? fused4_kernel<512, true, true> : fused4_kernel<512, false, true>; }
-    else if (s256 <= cap) { L.bd = 256; L.smem = s256; L.k = edge ? fused4_kernel<256, true, true> : fused4_kernel<256, false, true>; }
-    else { L.bd = 256; L.smem = f4_smem_bytes(e, edge, 256, false); L.k = edge ? fused4_kernel<256, true, false> : fused4_kernel<256, false, false>; }
-    if (L.smem > cap) FAIL(e, "fused kernel needs %zu bytes of shared memory", L.smem);
-    CK(e, cudaFuncSetAttribute(L.k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-    int per_sm = 0;
-    CK(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, L.k, L.bd, L.smem));
-    if (per_sm < 1) FAIL(e, "fused kernel cannot be resident (smem %zu)", L.smem);
-    const int spc = (32 / e->C) * (L.bd / 32);
-    const int64_t ntiles = (S + spc - 1) / spc;
-    L.grid = (int)std::min<int64_t>(ntiles, (int64_t)per_sm * e->sm_count);
-    return 0;
+    return f4_smem_bytes(e, edge, 128, false) <= 227 * 1024;
 }
 
 static int run_fused(plf_engine *e, Query &q)
 {
     const bool edge = q.want_edge;
-    const int C = e->C, E = e->E;
     F4Args a;
     memset(&a, 0, sizeof(a));
     a.nops = (int)e->ops.size(); a.nchildren = (int)e->children.size();
     a.ops = e->d_ops.as<F4Op>(); a.children = e->d_children.as<F4Child>();
-    a.C = C; a.E = E; a.K = e->K;
+    a.E = e->E; a.K = e->K; a.S = e->S;
     a.Ei = (int)e->edge_of_int.size(); a.Et = (int)e->edge_of_tip.size();
     a.ncode_rows = (int)e->code_row_node.size();
     a.code_row_node = e->d_code_row_node.as<int>();
@@ -871,57 +844,77 @@ static int run_fused(plf_engine *e, Query &q)
     for (int i = 0; i < 4; i++) a.root_vec[i] = e->root_vec[i];
     a.site_w = e->have_w ? e->d_site_w.as<double>() : nullptr;
     a.stack_depth = e->stack_depth; a.nslots = e->nslots;
-    a.S_total = e->S; a.S = e->S; a.s0 = 0;
 
-    F4Launch L;
-    if (f4_configure(e, L, edge, e->S)) return -1;
-    const int spc = (32 / C) * (L.bd / 32);
-    ENSURE(e, e->d_block_ll, sizeof(double) * L.grid);
-    ENSURE(e, e->d_sum, sizeof(double) * (1 + E + (size_t)e->N * e->n));
+    /* block size, and whether the matrices / tip tables live in shared memory: prefer everything on chip */
+    const size_t smem_cap = 227 * 1024;
+    int bd = 256;
+    f4_kernel_t kern = nullptr;
+    size_t smem = f4_smem_bytes(e, edge, 256, true);
+    if (smem <= smem_cap) kern = f4_select_c<256, true>(e->C, edge);
+    else {
+        bd = 128;
+        smem = f4_smem_bytes(e, edge, 128, true);
+        if (smem <= smem_cap) kern = f4_select_c<128, true>(e->C, edge);
+        else {
+            smem = f4_smem_bytes(e, edge, 128, false);
+            if (smem > smem_cap) FAIL(e, "fused kernel needs %zu bytes of shared memory", smem);
+            kern = f4_select_c<128, false>(e->C, edge);
+        }
+    }
+    if (!kern) FAIL(e, "fused kernel: unsupported category count %d", e->C);
+    CK(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CK(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, bd, smem));
+    if (per_sm < 1) FAIL(e, "fused kernel cannot be resident (smem %zu)", smem);
+    const int64_t ntiles = (e->S + bd - 1) / bd;
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)per_sm * e->sm_count);
+    const size_t T = (size_t)grid * bd;
+
+    ENSURE(e, e->d_block_ll, sizeof(double) * grid);
+    ENSURE(e, e->d_sum, sizeof(double) * (1 + e->E + (size_t)e->N * e->n));
     ENSURE(e, e->d_err, sizeof(int) * (e->N + 4));
     CK(e, cudaMemsetAsync(e->d_err.p, 0, sizeof(int), e->stream));
-    double *dsum = e->d_sum.as<double>();
     a.block_ll = e->d_block_ll.as<double>();
     a.error_flag = e->d_err.as<int>();
     if (q.site_ll) { ENSURE(e, e->d_site_ll, sizeof(double) * e->S); a.site_ll = e->d_site_ll.as<double>(); }
     if (edge) {
-        /* one private slab per CTA, reused for every tile the CTA processes */
-        const size_t slab_elems = (size_t)L.grid * e->nslots * C * spc;
-        ENSURE(e, e->d_scratch, sizeof(double4) * slab_elems);
-        ENSURE(e, e->d_scratchS, slab_elems);
-        ENSURE(e, e->d_block_edge, sizeof(double) * (size_t)L.grid * E);
-        a.slab = e->d_scratch.as<double4>(); a.slabF = e->d_scratchS.as<unsigned char>();
+        ENSURE(e, e->d_scratch, sizeof(double4) * (size_t)e->C * e->nslots * T);
+        ENSURE(e, e->d_scratchS, sizeof(unsigned int) * (size_t)e->nslots * T);
+        ENSURE(e, e->d_block_edge, sizeof(double) * (size_t)grid * e->E);
+        a.scratch = e->d_scratch.as<double4>(); a.scratchS = e->d_scratchS.as<unsigned int>();
         a.block_edge = e->d_block_edge.as<double>();
         if (q.edge_mask_h) {
-            ENSURE(e, e->d_mask, E);
-            CK(e, cudaMemcpyAsync(e->d_mask.p, q.edge_mask_h, E, cudaMemcpyHostToDevice, e->stream));
+            ENSURE(e, e->d_mask, e->E);
+            CK(e, cudaMemcpyAsync(e->d_mask.p, q.edge_mask_h, e->E, cudaMemcpyHostToDevice, e->stream));
             a.edge_mask = e->d_mask.as<unsigned char>();
         }
         if (q.site_edge) {
-            ENSURE(e, e->d_edge_site, sizeof(double) * (size_t)E * e->S);
-            CK(e, cudaMemsetAsync(e->d_edge_site.p, 0, sizeof(double) * (size_t)E * e->S, e->stream));
+            ENSURE(e, e->d_edge_site, sizeof(double) * (size_t)e->E * e->S);
+            CK(e, cudaMemsetAsync(e->d_edge_site.p, 0, sizeof(double) * (size_t)e->E * e->S, e->stream));
             a.edge_site_out = e->d_edge_site.as<double>();
         }
     }
     CK(e, cudaEventRecord(e->ev[3], e->stream));
-    L.k<<<L.grid, L.bd, L.smem, e->stream>>>(a);
+    CK(e, cudaEventRecord(e->ev[3], e->stream));
+    kern<<<grid, bd, smem, e->stream>>>(a);
     KCHECK(e);
     CK(e, cudaEventRecord(e->ev[4], e->stream));
     e->kernel_timed = true;
-    sum_rows_kernel<<<1, 32, 0, e->stream>>>(a.block_ll, L.grid, 1, dsum);
+    double *dsum = e->d_sum.as<double>();
+    sum_rows_kernel<<<1, 32, 0, e->stream>>>(a.block_ll, grid, 1, dsum);
     KCHECK(e);
     size_t nsum = 1;
     if (edge && !q.site_edge) {
-        sum_rows_kernel<<<(E + 127) / 128, 128, 0, e->stream>>>(a.block_edge, L.grid, E, dsum + 1);
+        sum_rows_kernel<<<(e->E + 127) / 128, 128, 0, e->stream>>>(a.block_edge, grid, e->E, dsum + 1);
         KCHECK(e);
-        nsum = 1 + E;
+        nsum = 1 + e->E;
     }
     if (edge && q.site_edge && q.sum_edge) {
         /* per-site outputs requested together with sums: reduce the per-site rows with the weights */
-        CK(e, cudaMemsetAsync(dsum + 1, 0, sizeof(double) * E, e->stream));
-        wsum_rows_kernel<<<E, 256, 0, e->stream>>>(a.edge_site_out, a.site_w, 0, (int)e->S, dsum + 1, a.error_flag, 0);
+        CK(e, cudaMemsetAsync(dsum + 1, 0, sizeof(double) * e->E, e->stream));
+        wsum_rows_kernel<<<e->E, 256, 0, e->stream>>>(a.edge_site_out, a.site_w, 0, (int)e->S, dsum + 1, a.error_flag, 0);
         KCHECK(e);
-        nsum = 1 + E;
+        nsum = 1 + e->E;
     }
     if (finish_sums(e, dsum, nsum)) return -1;
     CK(e, cudaEventRecord(e->ev[2], e->stream));
@@ -931,10 +924,10 @@ static int run_fused(plf_engine *e, Query &q)
     CK(e, cudaMemcpyAsync(&herr, e->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     if (q.site_ll) CK(e, cudaMemcpyAsync(q.site_ll, e->d_site_ll.p, sizeof(double) * e->S, cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
-    if (q.site_edge && copy_site_matrix(e, e->d_edge_site.as<double>(), E, e->S, q.site_edge)) return -1;
+    if (q.site_edge && copy_site_matrix(e, e->d_edge_site.as<double>(), e->E, e->S, q.site_edge)) return -1;
     if (herr && (q.sum_ll || q.sum_edge)) FAIL(e, "a site with non-zero weight has zero likelihood");
     if (q.sum_ll) *q.sum_ll = hs[0];
-    if (q.sum_edge && nsum > 1) memcpy(q.sum_edge, hs.data() + 1, sizeof(double) * E);
+    if (q.sum_edge && nsum > 1) memcpy(q.sum_edge, hs.data() + 1, sizeof(double) * e->E);
     return 0;
 }
 
