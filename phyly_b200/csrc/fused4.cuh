@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
                     }
                 }
             }
-#pragma unroll 1
+#pragma unroll 2
             for (int c = 0; c < C; c++) {
                 double fa[4];
                 const size_t so_a = ((size_t)op.slot * C + c) * T + gtid;
