@@ -1,0 +1,208 @@
+"""
+Parity at BASELINE.json's sizes, where the 320-bit oracle is too slow:
+  cfg2  1M sites x 64 taxa, GTR+Gamma4: fused kernel vs the C restatement (itself pinned on the
+        320-bit oracle, tests/test_oracle_c.py) on ALL sites, plus linearity in the site weights;
+  cfg3  HKY85+I marginals on 128 taxa: posterior marginals sum to 1 at every (site, node);
+  cfg4  61-state codon model: generic kernels vs the C restatement, matrices vs scipy expm;
+  cfg5  dwell / trans on the cfg2 model: dwell over all states is exactly the edge (1 per site),
+        fused path vs generic path (independent kernels) for a weighted trans direction.
+"""
+import json
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _bench():
+    import bench
+    return bench
+
+
+def _problem(sites, taxa=64):
+    b = _bench()
+
+    class A:
+        pass
+    args = A()
+    args.taxa = taxa
+    args.sites = sites
+    return b, b.build_problem(args, 0, 0)
+
+
+def test_cfg2_full_size_against_c_port():
+    from oracle import c_port
+    b, pb = _problem(1000000)
+    eng = pb["eng"]
+    defs = np.array(b.DEFS, dtype=np.float64)
+    eng.set_data(defs, pb["codes"])
+    rng = np.random.default_rng(7)
+    w = 1.0 + rng.poisson(3.0, pb["S"]).astype(np.float64)        # weights ~ 1 + Poisson(3)
+    eng.set_site_weights(w)
+    r = eng.deriv(per_site=False)
+    s = pb["summary"]
+    D = eng.derivative_matrices()
+    P = eng.transition_matrices()
+    _, sum_ll, sum_d = c_port.ll_deriv(s["indptr"], s["indices"], s["preorder"], P, D, np.array(s["cat_prior"]),
+                                       s["root_mode"], np.array(s["root_vec"]), pb["codes"], defs, w=w,
+                                       want_site_ll=False)
+    assert abs(r["sum_ll"] - sum_ll) <= 1e-11 * abs(sum_ll)
+    scale = np.abs(sum_d).max()
+    assert np.all(np.abs(r["sum_deriv"] - sum_d) <= 1e-11 * np.abs(sum_d) + 1e-12 * scale)
+    # linearity in the weights: two halves add up to the whole
+    w1 = w.copy(); w1[pb["S"] // 2:] = 0
+    w2 = w - w1
+    eng.set_site_weights(w1); r1 = eng.deriv(per_site=False)
+    eng.set_site_weights(w2); r2 = eng.deriv(per_site=False)
+    assert abs(r1["sum_ll"] + r2["sum_ll"] - r["sum_ll"]) <= 1e-12 * abs(r["sum_ll"])
+    assert np.all(np.abs(r1["sum_deriv"] + r2["sum_deriv"] - r["sum_deriv"]) <= 1e-11 * np.abs(r["sum_deriv"]) + 1e-12 * scale)
+    # per-site log-likelihoods of a subsample against the C port
+    site_ll, _ = eng.ll(per_site=True)
+    idx = rng.choice(pb["S"], 5000, replace=False)
+    ref_ll, _, _ = c_port.ll_deriv(s["indptr"], s["indices"], s["preorder"], P, None, np.array(s["cat_prior"]),
+                                   s["root_mode"], np.array(s["root_vec"]), pb["codes"][idx], defs, want_deriv=False)
+    np.testing.assert_allclose(site_ll[idx], ref_ll, rtol=1e-11, atol=2e-15)
+    eng.close()
+
+
+def test_cfg5_dwell_is_one_and_paths_agree():
+    from phyly_b200 import engine as E
+    b, pb = _problem(60000)
+    eng = pb["eng"]
+    defs = np.array(b.DEFS, dtype=np.float64)
+    eng.set_data(defs, pb["codes"])
+    n = 4
+    # dwell with all states: the chain is always somewhere -> exactly 1 per (site, edge)
+    so, tot = eng.edge_expect(E.KIND_DWELL, np.eye(n), per_site=False)
+    np.testing.assert_allclose(tot, pb["S"], rtol=1e-12)
+    # a weighted trans direction through both kernel families
+    q = np.array(pb["summary"]["q_hi"]).reshape(n, n)
+    L = q * (1.0 + np.arange(16).reshape(4, 4) % 3)
+    np.fill_diagonal(L, 0.0)
+    eng.set_path(E.PATH_FUSED4)
+    _, t_f = eng.edge_expect(E.KIND_TRANS, L, per_site=False)
+    eng.set_path(E.PATH_GENERIC)
+    _, t_g = eng.edge_expect(E.KIND_TRANS, L, per_site=False)
+    np.testing.assert_allclose(t_f, t_g, rtol=1e-11)
+    eng.close()
+
+
+def _hky_doc(taxa, kappa=2.0, pi=(0.3, 0.2, 0.25, 0.25)):
+    b = _bench()
+    edges, N = b.yule_tree(taxa, seed=11)
+    rng = np.random.default_rng(12)
+    Q = [[0.0] * 4 for _ in range(4)]
+    for i in range(4):
+        for j in range(4):
+            if i != j:
+                ts = (i, j) in ((0, 2), (2, 0), (1, 3), (3, 1))
+                Q[i][j] = pi[j] * (kappa if ts else 1.0)
+    md = {"edges": edges, "edge_rate_coefficients": [float(x) for x in rng.exponential(0.05, len(edges))],
+          "rate_matrix": Q, "root_prior": list(pi), "rate_divisor": "equilibrium_exit_rate",
+          "rate_mixture": {"rates": [0.0, 2.0], "prior": [0.5, 0.5]},
+          "character_definitions": b.DEFS, "character_data": [[4] * N]}
+    return {"model_and_data": md}, N
+
+
+def test_cfg3_marginals_sum_to_one():
+    import phyly_b200.arbplf as A
+    from phyly_b200.engine import Engine
+    b = _bench()
+    doc, N = _hky_doc(128)
+    s = json.loads(A.arbplf_model_summary(json.dumps(doc)))
+    eng = Engine(0)
+    eng.set_tree(s["indptr"], s["indices"], s["preorder"])
+    eng.set_model(np.array(s["q_hi"]).reshape(4, 4), np.array(s["q_lo"]).reshape(4, 4), s["edge_rates_csr"],
+                  s["cat_rates"], s["cat_prior"], s["root_mode"], s["root_vec"])
+    P = eng.transition_matrices()
+    S = 4096
+    codes = np.empty((S, N), dtype=np.uint8)
+    b.simulate_codes(s, P, S, seed=13, out=codes)
+    eng.set_data(np.array(b.DEFS, dtype=np.float64), codes)
+    sm, tot = eng.marginal()
+    np.testing.assert_allclose(sm.sum(axis=2), 1.0, rtol=0, atol=1e-12)
+    # observed leaves are certain
+    leaf = [a for a in range(N) if s["indptr"][a] == s["indptr"][a + 1]][0]
+    obs = codes[:, leaf] < 4
+    assert np.allclose(sm[obs, leaf, :].max(axis=1), 1.0, atol=1e-12)
+    np.testing.assert_allclose(tot, sm.sum(axis=0), rtol=1e-11, atol=1e-9)
+    eng.close()
+
+
+def _codon_model(kappa=2.0, omega=0.5, seed=4):
+    """GY94-style 61-state rate matrix with F3x4 frequencies."""
+    rng = np.random.default_rng(seed)
+    nts = "TCAG"
+    code = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"
+    codons = [(a, b_, c) for a in range(4) for b_ in range(4) for c in range(4)]
+    aa = {cd: code[16 * cd[0] + 4 * cd[1] + cd[2]] for cd in codons}
+    sense = [cd for cd in codons if aa[cd] != "*"]
+    f = rng.dirichlet(np.ones(4) * 5, size=3)
+    pi = np.array([f[0][cd[0]] * f[1][cd[1]] * f[2][cd[2]] for cd in sense])
+    pi /= pi.sum()
+    n = len(sense)
+    Q = np.zeros((n, n))
+    transitions = {(0, 1), (1, 0), (2, 3), (3, 2)}       # T<->C, A<->G
+    for i, ci in enumerate(sense):
+        for j, cj in enumerate(sense):
+            diff = [k for k in range(3) if ci[k] != cj[k]]
+            if len(diff) != 1:
+                continue
+            k = diff[0]
+            r = pi[j]
+            if (ci[k], cj[k]) in transitions:
+                r *= kappa
+            if aa[ci] != aa[cj]:
+                r *= omega
+            Q[i, j] = r
+    return Q, pi
+
+
+def test_cfg4_codon_generic_path_against_c_port():
+    import scipy.linalg
+    import phyly_b200.arbplf as A
+    from oracle import c_port
+    from phyly_b200.engine import Engine
+    b = _bench()
+    Q, pi = _codon_model()
+    n = Q.shape[0]
+    assert n == 61
+    edges, N = b.yule_tree(16, seed=21)
+    rng = np.random.default_rng(22)
+    defs = np.vstack([np.eye(n), np.ones((1, n))])
+    md = {"edges": edges, "edge_rate_coefficients": [float(x) for x in rng.exponential(0.1, len(edges))],
+          "rate_matrix": Q.tolist(), "root_prior": "equilibrium_distribution", "rate_divisor": "equilibrium_exit_rate",
+          "character_definitions": defs.tolist(), "character_data": [[n] * N]}
+    s = json.loads(A.arbplf_model_summary(json.dumps({"model_and_data": md})))
+    np.testing.assert_allclose(s["equilibrium"], pi, rtol=1e-12)
+    eng = Engine(0)
+    eng.set_tree(s["indptr"], s["indices"], s["preorder"])
+    qh = np.array(s["q_hi"]).reshape(n, n)
+    eng.set_model(qh, np.array(s["q_lo"]).reshape(n, n), s["edge_rates_csr"], s["cat_rates"], s["cat_prior"],
+                  s["root_mode"], s["root_vec"])
+    P = eng.transition_matrices()
+    D = eng.derivative_matrices()
+    for e in range(0, N - 1, 7):
+        Pw = scipy.linalg.expm(qh * s["edge_rates_csr"][e])
+        np.testing.assert_allclose(P[0, e], Pw, rtol=1e-10, atol=1e-15)
+        np.testing.assert_allclose(D[0, e], qh @ Pw, rtol=1e-9, atol=1e-13)
+    # data: random codons at the leaves (5 % missing), internal nodes unobserved
+    S = 300
+    codes = np.full((S, N), n, dtype=np.uint8)
+    for a in range(N):
+        if s["indptr"][a] == s["indptr"][a + 1]:
+            col = rng.integers(0, n, S)
+            col[rng.random(S) < 0.05] = n
+            codes[:, a] = col
+    eng.set_data(defs, codes)
+    w = rng.random(S) + 0.5
+    eng.set_site_weights(w)
+    r = eng.deriv(per_site=False)
+    site_ll, _ = eng.ll()
+    ref_ll, sum_ll, sum_d = c_port.ll_deriv(s["indptr"], s["indices"], s["preorder"], P, D, np.array(s["cat_prior"]),
+                                            s["root_mode"], np.array(s["root_vec"]), codes, defs, w=w)
+    np.testing.assert_allclose(site_ll, ref_ll, rtol=1e-11)
+    assert abs(r["sum_ll"] - sum_ll) <= 1e-11 * abs(sum_ll)
+    np.testing.assert_allclose(r["sum_deriv"], sum_d, rtol=1e-10, atol=1e-10 * np.abs(sum_d).max())
+    eng.close()
