@@ -164,7 +164,8 @@ __device__ __forceinline__ void f4_prefetch(const void *p)
  * EDGE  : false = log-likelihood only; true = log-likelihood + per-edge bilinear forms
  * The dynamic shared memory layout below is mirrored on the host by f4_smem_bytes().
  */
-template <int C, bool EDGE, int BD, bool STAGED>
+/* STAGED: 2 = all tables in shared memory, 1 = all but TF (read through L1), 0 = none */
+template <int C, bool EDGE, int BD, int STAGED>
 __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
 {
     extern __shared__ __align__(16) unsigned char f4_smem[];
@@ -183,7 +184,6 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
     double *accE = reinterpret_cast<double *>(f4_smem + off); off = f4_align16(off + (EDGE ? sizeof(double) * nwarp * a.E : 0));
     double *stack = reinterpret_cast<double *>(f4_smem + off); off = f4_align16(off + (EDGE ? 0 : sizeof(double) * 4 * C * bd * a.stack_depth));
     int *stackf = reinterpret_cast<int *>(f4_smem + off); off = f4_align16(off + (EDGE ? 0 : sizeof(int) * bd * a.stack_depth));
-    int *kcat = reinterpret_cast<int *>(f4_smem + off); off = f4_align16(off + sizeof(int) * C * bd);
     unsigned char *tile = f4_smem + off; off = f4_align16(off + (size_t)a.ncode_rows * bd);
     unsigned char *dconst = f4_smem + off; off = f4_align16(off + a.K);
     double *defs_s = reinterpret_cast<double *>(f4_smem + off); off = f4_align16(off + sizeof(double) * 4 * a.K);
@@ -193,10 +193,11 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
         double *sP = reinterpret_cast<double *>(f4_smem + off); off += sizeof(double) * nP;
         double *sT = reinterpret_cast<double *>(f4_smem + off); off += sizeof(double) * nT;
         double *sF = reinterpret_cast<double *>(f4_smem + off); off += EDGE ? sizeof(double) * nP : 0;
-        double *sTF = reinterpret_cast<double *>(f4_smem + off); off += EDGE ? sizeof(double) * nT : 0;
+        double *sTF = reinterpret_cast<double *>(f4_smem + off); off += (EDGE && STAGED == 2) ? sizeof(double) * nT : 0;
         for (size_t i = tid; i < nP; i += bd) { sP[i] = a.Pint[i]; if (EDGE) sF[i] = a.Fint[i]; }
-        for (size_t i = tid; i < nT; i += bd) { sT[i] = a.TP[i]; if (EDGE) sTF[i] = a.TF[i]; }
-        Pint = sP; TP = sT; Fint = sF; TF = sTF;
+        for (size_t i = tid; i < nT; i += bd) { sT[i] = a.TP[i]; if (EDGE && STAGED == 2) sTF[i] = a.TF[i]; }
+        Pint = sP; TP = sT; Fint = sF;
+        if (STAGED == 2) TF = sTF;
     }
     for (int i = tid; i < a.nops; i += bd) ops[i] = a.ops[i];
     for (int i = tid; i < a.nchildren; i += bd) chs[i] = a.children[i];
@@ -334,6 +335,7 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
         double site_m = 0.0;
         int site_k = 0;
         bool have = false;
+        int kcat[C];
 #pragma unroll
         for (int c = 0; c < C; c++) {
             double r[4];
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
                 lh = fma(a.root_vec[3], r[3], lh);
             }
             const double v = prior[c] * lh;
-            kcat[c * bd + tid] = (v > 0.0) ? ktot[c] : INT_MIN;
+            kcat[c] = (v > 0.0) ? ktot[c] : INT_MIN;
             if (v > 0.0) {
                 if (!have) { site_m = v; site_k = ktot[c]; have = true; }
                 else if (ktot[c] > site_k) { site_m = scalbn(site_m, PLF_SCALE_BITS * (site_k - ktot[c])) + v; site_k = ktot[c]; }
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
         /* fn_root = root prior vector * prior_c * w / site_L, scaled so that fn .* L is O(1) */
 #pragma unroll
         for (int c = 0; c < C; c++) {
-            const int kc = kcat[c * bd + tid];
+            const int kc = kcat[c];
             const double sc0 = (kc != INT_MIN) ? scalbn(prior[c] * inv_site, PLF_SCALE_BITS * (kc - site_k)) : 0.0;
 #pragma unroll
             for (int i = 0; i < 4; i++) {

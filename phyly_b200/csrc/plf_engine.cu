@@ -782,7 +782,7 @@ static int copy_site_matrix(plf_engine *e, const double *d_rows /*[R][cols]*/, i
 
 typedef void (*f4_kernel_t)(F4Args);
 
-template <int BD, bool STAGED>
+template <int BD, int STAGED>
 static f4_kernel_t f4_select_c(int C, bool edge)
 {
     switch (C * 2 + (edge ? 1 : 0)) {
@@ -799,7 +799,7 @@ static f4_kernel_t f4_select_c(int C, bool edge)
 }
 
 /* mirrors the shared-memory carve-up at the top of fused4_kernel */
-static size_t f4_smem_bytes(const plf_engine *e, bool edge, int bd, bool staged)
+static size_t f4_smem_bytes(const plf_engine *e, bool edge, int bd, int staged)
 {
     const int C = e->C, Ei = (int)e->edge_of_int.size(), Et = (int)e->edge_of_tip.size();
     size_t off = 0;
@@ -809,18 +809,17 @@ static size_t f4_smem_bytes(const plf_engine *e, bool edge, int bd, bool staged)
     off = f4_align16(off + (edge ? sizeof(double) * (bd / 32) * e->E : 0));
     off = f4_align16(off + (edge ? 0 : sizeof(double) * 4 * C * bd * e->stack_depth));
     off = f4_align16(off + (edge ? 0 : sizeof(int) * bd * e->stack_depth));
-    off = f4_align16(off + sizeof(int) * C * bd);
     off = f4_align16(off + e->code_row_node.size() * bd);
     off = f4_align16(off + e->K);
     off = f4_align16(off + sizeof(double) * 4 * e->K);
     const size_t nP = (size_t)C * Ei * 16 * sizeof(double), nT = (size_t)C * Et * e->K * 4 * sizeof(double);
-    if (staged) off += (nP + nT) * (edge ? 2 : 1);
+    if (staged) off += nP + nT + (edge ? nP : 0) + ((edge && staged == 2) ? nT : 0);
     return off + 16;
 }
 
 static bool fused_fits(const plf_engine *e, bool edge)
 {
-    return f4_smem_bytes(e, edge, 128, false) <= 227 * 1024;
+    return f4_smem_bytes(e, edge, 128, 0) <= 227 * 1024;
 }
 
 static int run_fused(plf_engine *e, Query &q)
@@ -849,17 +848,25 @@ static int run_fused(plf_engine *e, Query &q)
     const size_t smem_cap = 227 * 1024;
     int bd = 256;
     f4_kernel_t kern = nullptr;
-    size_t smem = f4_smem_bytes(e, edge, 256, true);
-    if (smem <= smem_cap) kern = f4_select_c<256, true>(e->C, edge);
-    else {
-        bd = 128;
-        smem = f4_smem_bytes(e, edge, 128, true);
-        if (smem <= smem_cap) kern = f4_select_c<128, true>(e->C, edge);
-        else {
-            smem = f4_smem_bytes(e, edge, 128, false);
-            if (smem > smem_cap) FAIL(e, "fused kernel needs %zu bytes of shared memory", smem);
-            kern = f4_select_c<128, false>(e->C, edge);
+    size_t smem = 0;
+    {
+        /* candidate configurations, best first; PLF_F4_CONFIG=<index> forces one (tuning aid) */
+        struct Cand { int bd, staged; f4_kernel_t k; };
+        const Cand cands[] = {
+            {512, 1, f4_select_c<512, 1>(e->C, edge)},
+            {384, 1, f4_select_c<384, 1>(e->C, edge)},
+            {256, 2, f4_select_c<256, 2>(e->C, edge)},
+            {256, 1, f4_select_c<256, 1>(e->C, edge)},
+            {128, 2, f4_select_c<128, 2>(e->C, edge)},
+            {128, 0, f4_select_c<128, 0>(e->C, edge)},
+        };
+        const char *force = edge ? getenv("PLF_F4_CONFIG") : nullptr;
+        for (int i = 0; i < 6; i++) {
+            if (force && atoi(force) != i) continue;
+            smem = f4_smem_bytes(e, edge, cands[i].bd, cands[i].staged);
+            if (smem <= smem_cap) { kern = cands[i].k; bd = cands[i].bd; break; }
         }
+        if (!kern) FAIL(e, "fused kernel needs %zu bytes of shared memory", smem);
     }
     if (!kern) FAIL(e, "fused kernel: unsupported category count %d", e->C);
     CK(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
