@@ -159,6 +159,117 @@ __device__ __forceinline__ void f4_prefetch(const void *p)
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 
+
+/* sums of two values over the warp in one butterfly: sum(a) lands in lanes < 16, sum(b) in lanes >= 16 */
+__device__ __forceinline__ double f4_warp_sum2(double a, double b, int lane)
+{
+    const bool hi = lane >= 16;
+    double keep = hi ? b : a, send = hi ? a : b;
+    keep += __shfl_xor_sync(0xffffffffu, send, 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+    return keep;
+}
+
+/*
+ * Outside step specialised for a node with exactly two children of kinds (K0, K1) in
+ * {(CUR, TIP), (CUR, STACK), (TIP, TIP)}: straight-line code, no filler factors.
+ */
+template <int C, int BD, int K0, int K1>
+__device__ __forceinline__ void f4_outside2(const F4Args &a, const F4Op &op, const F4Child &c0, const F4Child &c1,
+                                            bool from_slot, double *cur, const unsigned char *tile, const double *defs_s,
+                                            const double *Pint, const double *Fint, const double *TP, const double *TF,
+                                            int pstride, int tpstride, size_t T, size_t gtid, int tid,
+                                            double &x0, double &x1)
+{
+    double basev[4] = {1.0, 1.0, 1.0, 1.0};
+    const bool has_base = op.code_row >= 0;
+    if (has_base) f4_ld4(defs_s + tile[op.code_row * BD + tid] * 4, basev);
+    const unsigned int sword_a = a.scratchS[(size_t)op.slot * T + gtid];
+    int code0 = 0, code1 = 0, bc0 = 0, bc1 = 0;
+    if (K0 == F4_KIND_TIP) code0 = tile[c0.code_row * BD + tid]; else bc0 = (a.scratchS[(size_t)c0.slot * T + gtid] >> 6) & 1;
+    if (K1 == F4_KIND_TIP) code1 = tile[c1.code_row * BD + tid]; else bc1 = (a.scratchS[(size_t)c1.slot * T + gtid] >> 6) & 1;
+    x0 = 0.0; x1 = 0.0;
+#pragma unroll 2
+    for (int c = 0; c < C; c++) {
+        /* loads of this category first */
+        double l0[4], l1[4], fa[4];
+        if (K0 != F4_KIND_TIP) {
+            double4 v = a.scratch[((size_t)c0.slot * C + c) * T + gtid];
+            l0[0] = v.x; l0[1] = v.y; l0[2] = v.z; l0[3] = v.w;
+        }
+        if (K1 != F4_KIND_TIP) {
+            double4 v = a.scratch[((size_t)c1.slot * C + c) * T + gtid];
+            l1[0] = v.x; l1[1] = v.y; l1[2] = v.z; l1[3] = v.w;
+        }
+        if (from_slot) {
+            double4 v = a.scratch[((size_t)op.slot * C + c) * T + gtid];
+            fa[0] = v.x; fa[1] = v.y; fa[2] = v.z; fa[3] = v.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) fa[i] = cur[(c * 4 + i) * BD + tid];
+        }
+        if (has_base) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) fa[i] *= basev[i];
+        }
+        const int sa = (sword_a >> (8 * c)) & 63;
+        if (sa) {
+            const double sc = __hiloint2double((1023 + PLF_SCALE_BITS * sa) << 20, 0);
+#pragma unroll
+            for (int i = 0; i < 4; i++) fa[i] *= sc;
+        }
+        double em0[4], y0[4], em1[4], y1[4];
+        if (K0 == F4_KIND_TIP) {
+            f4_ld4(TP + c * tpstride + (c0.mat * a.K + code0) * 4, em0);
+            f4_ld4(TF + c * tpstride + (c0.mat * a.K + code0) * 4, y0);
+        } else {
+            f4_matvec(Pint + c * pstride + c0.mat * 16, l0, em0);
+            f4_matvec(Fint + c * pstride + c0.mat * 16, l0, y0);
+            if (bc0) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) { em0[i] = l0[i]; if (a.f_zero_rowsum) y0[i] = 0.0; }
+            }
+        }
+        if (K1 == F4_KIND_TIP) {
+            f4_ld4(TP + c * tpstride + (c1.mat * a.K + code1) * 4, em1);
+            f4_ld4(TF + c * tpstride + (c1.mat * a.K + code1) * 4, y1);
+        } else {
+            f4_matvec(Pint + c * pstride + c1.mat * 16, l1, em1);
+            f4_matvec(Fint + c * pstride + c1.mat * 16, l1, y1);
+            if (bc1) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) { em1[i] = l1[i]; if (a.f_zero_rowsum) y1[i] = 0.0; }
+            }
+        }
+        double fe0[4], fe1[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { fe0[i] = fa[i] * em1[i]; fe1[i] = fa[i] * em0[i]; }
+        double xv = fe0[0] * y0[0];
+        xv = fma(fe0[1], y0[1], xv); xv = fma(fe0[2], y0[2], xv); xv = fma(fe0[3], y0[3], xv);
+        x0 += xv;
+        xv = fe1[0] * y1[0];
+        xv = fma(fe1[1], y1[1], xv); xv = fma(fe1[2], y1[2], xv); xv = fma(fe1[3], y1[3], xv);
+        x1 += xv;
+        if (K0 != F4_KIND_TIP) {
+            double fb[4];
+            f4_matvec_t(Pint + c * pstride + c0.mat * 16, fe0, fb);
+            if (K0 == F4_KIND_CUR) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) cur[(c * 4 + i) * BD + tid] = fb[i];
+            } else {
+                a.scratch[((size_t)c0.slot * C + c) * T + gtid] = make_double4(fb[0], fb[1], fb[2], fb[3]);
+            }
+        }
+        if (K1 != F4_KIND_TIP) {
+            double fb[4];
+            f4_matvec_t(Pint + c * pstride + c1.mat * 16, fe1, fb);
+            /* the child's inside vector is dead after this op: its slot carries fn down */
+            a.scratch[((size_t)c1.slot * C + c) * T + gtid] = make_double4(fb[0], fb[1], fb[2], fb[3]);
+        }
+    }
+}
+
 /*
  * C     : number of rate categories (1..4)
  * EDGE  : false = log-likelihood only; true = log-likelihood + per-edge bilinear forms
@@ -394,6 +505,41 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
             const F4Op op = ops[o];
             /* fn_a comes from "cur" if this node was consumed from registers by its parent, else from its slot */
             const bool from_slot = (o != a.nops - 1) && ops[o + 1].spill_before;
+            /* the next node (o-1) reads these slab lines: start fetching them */
+            if (o > 0) {
+                const F4Op nx = ops[o - 1];
+                for (int j = 0; j < nx.nchild; j++) {
+                    const F4Child nc = chs[nx.first_child + j];
+                    if (nc.kind != F4_KIND_TIP) {
+#pragma unroll
+                        for (int c = 0; c < C; c++) f4_prefetch(&a.scratch[((size_t)nc.slot * C + c) * T + gtid]);
+                    }
+                }
+            }
+            if (op.nchild == 2) {
+                const F4Child c0 = chs[op.first_child], c1 = chs[op.first_child + 1];
+                double x0, x1;
+                if (c0.kind == F4_KIND_CUR && c1.kind == F4_KIND_TIP)
+                    f4_outside2<C, BD, F4_KIND_CUR, F4_KIND_TIP>(a, op, c0, c1, from_slot, cur, tile, defs_s, Pint, Fint, TP, TF,
+                                                                 pstride, tpstride, (size_t)T, (size_t)gtid, tid, x0, x1);
+                else if (c0.kind == F4_KIND_CUR)
+                    f4_outside2<C, BD, F4_KIND_CUR, F4_KIND_STACK>(a, op, c0, c1, from_slot, cur, tile, defs_s, Pint, Fint, TP, TF,
+                                                                   pstride, tpstride, (size_t)T, (size_t)gtid, tid, x0, x1);
+                else
+                    f4_outside2<C, BD, F4_KIND_TIP, F4_KIND_TIP>(a, op, c0, c1, from_slot, cur, tile, defs_s, Pint, Fint, TP, TF,
+                                                                 pstride, tpstride, (size_t)T, (size_t)gtid, tid, x0, x1);
+                const bool m0 = !a.edge_mask || a.edge_mask[c0.edge];
+                const bool m1 = !a.edge_mask || a.edge_mask[c1.edge];
+                if (a.edge_site_out) {
+                    if (valid && m0) a.edge_site_out[(size_t)c0.edge * a.S + site] = x0;
+                    if (valid && m1) a.edge_site_out[(size_t)c1.edge * a.S + site] = x1;
+                } else if (m0 || m1) {
+                    const double r = f4_warp_sum2(m0 ? x0 : 0.0, m1 ? x1 : 0.0, lane);
+                    if (lane == 0 && m0) accE[warp * a.E + c0.edge] += r;
+                    if (lane == 16 && m1) accE[warp * a.E + c1.edge] += r;
+                }
+                continue;
+            }
             double basev[4] = {1.0, 1.0, 1.0, 1.0};
             if (op.code_row >= 0) f4_ld4(defs_s + tile[op.code_row * bd + tid] * 4, basev);
             /* children descriptors and category-independent lookups */
@@ -410,18 +556,7 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
             }
             double x[F4_MAXD] = {0.0, 0.0, 0.0};
             const unsigned int sword_a = a.scratchS[(size_t)op.slot * T + gtid];
-            /* the next node (o-1) reads these slab lines: start fetching them */
-            if (o > 0) {
-                const F4Op nx = ops[o - 1];
-                for (int j = 0; j < nx.nchild; j++) {
-                    const F4Child nc = chs[nx.first_child + j];
-                    if (nc.kind != F4_KIND_TIP) {
-#pragma unroll
-                        for (int c = 0; c < C; c++) f4_prefetch(&a.scratch[((size_t)nc.slot * C + c) * T + gtid]);
-                    }
-                }
-            }
-#pragma unroll 2
+#pragma unroll 1
             for (int c = 0; c < C; c++) {
                 double fa[4];
                 const size_t so_a = ((size_t)op.slot * C + c) * T + gtid;
