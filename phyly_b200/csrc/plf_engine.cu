@@ -853,15 +853,16 @@ static int run_fused(plf_engine *e, Query &q)
         /* candidate configurations, best first; PLF_F4_CONFIG=<index> forces one (tuning aid) */
         struct Cand { int bd, staged; f4_kernel_t k; };
         const Cand cands[] = {
-            {512, 1, f4_select_c<512, 1>(e->C, edge)},
             {384, 1, f4_select_c<384, 1>(e->C, edge)},
+            {512, 1, f4_select_c<512, 1>(e->C, edge)},
             {256, 2, f4_select_c<256, 2>(e->C, edge)},
             {256, 1, f4_select_c<256, 1>(e->C, edge)},
             {128, 2, f4_select_c<128, 2>(e->C, edge)},
             {128, 0, f4_select_c<128, 0>(e->C, edge)},
         };
+        const int ncand = (int)(sizeof(cands) / sizeof(cands[0]));
         const char *force = edge ? getenv("PLF_F4_CONFIG") : nullptr;
-        for (int i = 0; i < 6; i++) {
+        for (int i = 0; i < ncand; i++) {
             if (force && atoi(force) != i) continue;
             smem = f4_smem_bytes(e, edge, cands[i].bd, cands[i].staged);
             if (smem <= smem_cap) { kern = cands[i].k; bd = cands[i].bd; break; }
