@@ -23,6 +23,7 @@
 #include "expm.cuh"
 #include "generic.cuh"
 #include "fused4.cuh"
+#include "tile.cuh"
 
 /* ------------------------------------------------------------------ */
 /* small utilities                                                     */
@@ -1005,12 +1006,23 @@ static int run_generic(plf_engine *e, Query &q)
     if (smem_out > 48 * 1024) CK(e, cudaFuncSetAttribute(generic_outside_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_out));
     if (smem_out > 227 * 1024) FAIL(e, "state count %d is too large for the generic kernels", n);
     const double *w = e->have_w ? e->d_site_w.as<double>() : nullptr;
+    /* 16 < n <= 64 (amino-acid, codon): inside pass on the FP64 tensor pipe (tile.cuh) */
+    const bool use_tile = n > 16 && n <= TL_NP && !getenv("PLF_NO_TILE");
+    const size_t smem_tile = sizeof(double) * (TL_NP * TL_PS + TL_NP * TL_LS + 8 * TL_TS + TL_TS) + sizeof(int) * 5 * TL_TS;
+    if (use_tile) CK(e, cudaFuncSetAttribute(tile_inside_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile));
 
     for (int64_t s0 = 0; s0 < e->S; s0 += Sc) {
         a.s0 = s0; a.Sc = (int)std::min<int64_t>(Sc, e->S - s0);
         const unsigned gx = (unsigned)((a.Sc + PLF_TS - 1) / PLF_TS);
-        generic_inside_kernel<<<dim3(gx, C), PLF_TS, smem_in, e->stream>>>(a);
-        KCHECK(e);
+        if (use_tile) {
+            generic_leaf_kernel<<<dim3((a.Sc + 255) / 256, C), 256, 0, e->stream>>>(a);
+            KCHECK(e);
+            tile_inside_kernel<<<dim3((a.Sc + TL_TS - 1) / TL_TS, C), 256, smem_tile, e->stream>>>(a, outside ? 1 : 0);
+            KCHECK(e);
+        } else {
+            generic_inside_kernel<<<dim3(gx, C), PLF_TS, smem_in, e->stream>>>(a);
+            KCHECK(e);
+        }
         generic_site_kernel<<<(a.Sc + 255) / 256, 256, 0, e->stream>>>(a);
         KCHECK(e);
         if (q.sum_ll) {

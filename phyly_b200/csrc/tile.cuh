@@ -1,0 +1,232 @@
+/*
+ * Inside (pruning) pass for large state spaces (16 < n <= 64: amino-acid, codon) on the FP64
+ * tensor pipe.
+ *
+ * For these models the per-node contraction P_e . L_b of evaluate_site_lhood
+ * (evaluate_site_lhood.c:32-56, _arb_mat_mul_stochastic arb_mat_extras.c:54-113) is a dense
+ * GEMM over sites: [n x n] . [n x TS] for a tile of TS sites.  One CTA owns a tile of 64
+ * sites of one rate category and walks the tree in post order; for every child edge it stages
+ * P_e (padded to 64 x 64) and the child's partials (64 x 64 sites) in shared memory and
+ * multiplies them with mma.sync.m8n8k4.f64 (DMMA): warp w owns output rows [8w, 8w+8) for
+ * all 64 sites, i.e. 8 accumulator fragments, and keeps the node's running product in the
+ * same fragment layout.  Partials live in HBM as [category][node][state][site] with the site
+ * index fastest (the layout of the generic kernels, which consume the results in the outside
+ * pass).  Row strides of the shared tiles are padded (68 and 72 doubles) so that both
+ * fragment loads are bank-conflict free.
+ *
+ * Algorithmic work per (site, child edge): 2 n^2 flops (here counted on the padded 64 x 64);
+ * HBM traffic per (site, internal node): n*8 B written + n*8 B per internal child read
+ * (+ the same again for the edge vectors kept for the outside pass).
+ */
+#pragma once
+#include <stdint.h>
+
+#define TL_NP 64          /* padded state count */
+#define TL_TS 64          /* sites per tile */
+#define TL_PS 68          /* row stride of the staged P (doubles) */
+#define TL_LS 72          /* row stride of the staged child partials (doubles) */
+
+__device__ __forceinline__ void tl_dmma(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+/* grid = (site tiles, categories), 256 threads */
+__global__ void __launch_bounds__(256) tile_inside_kernel(GenericArgs a, int keep_edges)
+{
+    extern __shared__ __align__(16) double tl_sm[];
+    double *Psm = tl_sm;                              /* [64][TL_PS] */
+    double *Lsm = Psm + TL_NP * TL_PS;                /* [64][TL_LS] */
+    double *colmax = Lsm + TL_NP * TL_LS;             /* [8][64] */
+    double *scale = colmax + 8 * TL_TS;               /* [64] */
+    int *kacc = reinterpret_cast<int *>(scale + TL_TS);      /* [64] */
+    int *kb = kacc + TL_TS;                           /* [64] */
+    int *bcs = kb + TL_TS;                            /* [64] */
+    int *cst = bcs + TL_TS;                           /* [64] */
+    int *codes_s = cst + TL_TS;                       /* [64] */
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;            /* fragment coordinates */
+    const int c = blockIdx.y;
+    const int n = a.n, Sc = a.Sc;
+    const int s0 = blockIdx.x * TL_TS;
+    const int row = warp * 8 + g;                     /* output row owned by this thread */
+    const size_t cN = (size_t)c * a.t.N, cE = (size_t)c * a.t.E;
+
+    for (int u = a.t.N - 1; u >= 0; u--) {
+        const int nd = a.t.preorder[u];
+        const int start = a.t.indptr[nd], stop = a.t.indptr[nd + 1];
+        if (start == stop) continue;                  /* leaves are written by generic_leaf_kernel */
+        double acc[8][2];
+        bool first = true;
+        __syncthreads();
+        if (tid < TL_TS) {
+            kacc[tid] = 0;
+            int cf = 1, code = -1;
+            if (a.t.node_has_data[nd] && s0 + tid < Sc) {
+                code = plf_code_at(a.codes, a.code_bytes, a.S, nd, a.s0 + s0 + tid);
+                cf = a.def_const[code];
+            }
+            cst[tid] = cf;
+            codes_s[tid] = code;
+        }
+        for (int idx = start; idx < stop; idx++) {
+            const int b = a.t.indices[idx];
+            __syncthreads();
+            /* stage P_e (zero padded) and the child's tile */
+            {
+                const double *Pm = a.P + (cE + idx) * n * n;
+                for (int i = tid; i < TL_NP * TL_NP; i += 256) {
+                    const int r = i >> 6, k = i & 63;
+                    Psm[r * TL_PS + k] = (r < n && k < n) ? Pm[r * n + k] : 0.0;
+                }
+                const double *Lb = a.Lg + ((cN + b) * n) * Sc;
+                for (int i = tid; i < TL_NP * TL_TS; i += 256) {
+                    const int k = i >> 6, s = i & 63;
+                    Lsm[k * TL_LS + s] = (k < n && s0 + s < Sc) ? Lb[(size_t)k * Sc + s0 + s] : 0.0;
+                }
+                if (tid < TL_TS) {
+                    const bool in = s0 + tid < Sc;
+                    kb[tid] = in ? a.Kg[(cN + b) * Sc + s0 + tid] : 0;
+                    bcs[tid] = in ? a.Cg[(cN + b) * Sc + s0 + tid] : 0;
+                }
+            }
+            __syncthreads();
+            /* em = P_e . L_b on the FP64 tensor pipe */
+            double em[8][2];
+#pragma unroll
+            for (int nb = 0; nb < 8; nb++) { em[nb][0] = 0.0; em[nb][1] = 0.0; }
+#pragma unroll 4
+            for (int kk = 0; kk < TL_NP / 4; kk++) {
+                const double af = Psm[row * TL_PS + kk * 4 + q];
+#pragma unroll
+                for (int nb = 0; nb < 8; nb++) {
+                    const double bf = Lsm[(kk * 4 + q) * TL_LS + nb * 8 + g];
+                    tl_dmma(em[nb][0], em[nb][1], af, bf);
+                }
+            }
+            /* constant column maps to itself (arb_mat_extras.c:84-91); keep edge vectors; multiply in */
+#pragma unroll
+            for (int nb = 0; nb < 8; nb++) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int s = nb * 8 + q * 2 + h;
+                    if (bcs[s] && row < n) em[nb][h] = Lsm[s];           /* row 0 of the child tile */
+                }
+                if (keep_edges && row < n) {
+                    const int s = nb * 8 + q * 2;
+                    double *Eo = a.Eg + ((cE + idx) * n + row) * Sc + s0 + s;
+                    if (s0 + s + 1 < Sc && (((size_t)(Eo - a.Eg)) & 1) == 0) *reinterpret_cast<double2 *>(Eo) = make_double2(em[nb][0], em[nb][1]);
+                    else { if (s0 + s < Sc) Eo[0] = em[nb][0]; if (s0 + s + 1 < Sc) Eo[1] = em[nb][1]; }
+                }
+                if (first) { acc[nb][0] = em[nb][0]; acc[nb][1] = em[nb][1]; }
+                else { acc[nb][0] *= em[nb][0]; acc[nb][1] *= em[nb][1]; }
+            }
+            first = false;
+            /* per-site max over all rows -> rescale (exponents in units of 2^256) */
+            {
+                double mx[8][2];
+#pragma unroll
+                for (int nb = 0; nb < 8; nb++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        double m = acc[nb][h];
+                        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 4));
+                        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 8));
+                        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 16));
+                        mx[nb][h] = m;
+                    }
+                if (g == 0) {
+#pragma unroll
+                    for (int nb = 0; nb < 8; nb++) {
+                        colmax[warp * TL_TS + nb * 8 + q * 2] = mx[nb][0];
+                        colmax[warp * TL_TS + nb * 8 + q * 2 + 1] = mx[nb][1];
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid < TL_TS) {
+                double m = 0.0;
+                for (int w = 0; w < 8; w++) m = fmax(m, colmax[w * TL_TS + tid]);
+                int k = kacc[tid] + kb[tid];
+                double sc = 1.0;
+                while (m > 0.0 && m < PLF_TWO_M256) { m *= PLF_TWO_P256; sc *= PLF_TWO_P256; k -= 1; }
+                kacc[tid] = k;
+                scale[tid] = sc;
+                cst[tid] &= bcs[tid];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int nb = 0; nb < 8; nb++) {
+                acc[nb][0] *= scale[nb * 8 + q * 2];
+                acc[nb][1] *= scale[nb * 8 + q * 2 + 1];
+            }
+        }
+        /* base vector of a node that carries data (rare) */
+        if (a.t.node_has_data[nd]) {
+#pragma unroll
+            for (int nb = 0; nb < 8; nb++)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int code = codes_s[nb * 8 + q * 2 + h];
+                    if (code >= 0 && row < n) acc[nb][h] *= a.defs[(size_t)code * n + row];
+                }
+        }
+        /* store the node's partials, exponents and flags */
+        if (row < n) {
+            double *La = a.Lg + ((cN + nd) * n + row) * Sc + s0;
+#pragma unroll
+            for (int nb = 0; nb < 8; nb++) {
+                const int s = nb * 8 + q * 2;
+                if (s0 + s < Sc) La[s] = acc[nb][0];
+                if (s0 + s + 1 < Sc) La[s + 1] = acc[nb][1];
+            }
+        }
+        if (tid < TL_TS && s0 + tid < Sc) {
+            a.Kg[(cN + nd) * Sc + s0 + tid] = kacc[tid];
+            a.Cg[(cN + nd) * Sc + s0 + tid] = (unsigned char)cst[tid];
+        }
+        if (nd == a.t.root) {
+            /* root_prior_expectation (model.c:282-350): weighted column sums */
+            double part[8][2];
+#pragma unroll
+            for (int nb = 0; nb < 8; nb++)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    double r = 0.0;
+                    if (row < n) {
+                        if (a.root_mode == PLF_ROOT_NONE) r = 1.0;
+                        else if (a.root_mode == PLF_ROOT_UNIFORM) r = 1.0 / (double)n;
+                        else r = a.root_vec[row];
+                    }
+                    double v = r * acc[nb][h];
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    part[nb][h] = v;
+                }
+            __syncthreads();
+            if (g == 0) {
+#pragma unroll
+                for (int nb = 0; nb < 8; nb++) {
+                    colmax[warp * TL_TS + nb * 8 + q * 2] = part[nb][0];
+                    colmax[warp * TL_TS + nb * 8 + q * 2 + 1] = part[nb][1];
+                }
+            }
+            /* acc row 0 for the constant-column shortcut of the uniform / equilibrium priors */
+            if (warp == 0 && g == 0) {
+#pragma unroll
+                for (int nb = 0; nb < 8; nb++) { scale[nb * 8 + q * 2] = acc[nb][0]; scale[nb * 8 + q * 2 + 1] = acc[nb][1]; }
+            }
+            __syncthreads();
+            if (tid < TL_TS && s0 + tid < Sc) {
+                double lh = 0.0;
+                for (int w = 0; w < 8; w++) lh += colmax[w * TL_TS + tid];
+                if (cst[tid] && (a.root_mode == PLF_ROOT_UNIFORM || a.root_mode == PLF_ROOT_EQUILIBRIUM)) lh = scale[tid];
+                a.cat_lh[(size_t)c * Sc + s0 + tid] = lh;
+                a.cat_k[(size_t)c * Sc + s0 + tid] = kacc[tid];
+            }
+        }
+    }
+}
