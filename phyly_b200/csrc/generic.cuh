@@ -59,6 +59,10 @@ struct GenericArgs {
     double *edge_out;     /* [E][Sc] per-site edge forms (already divided by site lhood) or NULL */
     double *marg_out;     /* [N][n][Sc] or NULL */
     int want_edge, want_marg;
+    /* tip tables for the tile kernel: TP[c][tip edge][k][i] = (P_e def_k)_i, tip_of_edge[csr idx] = tip edge or -1 */
+    const double *TP;
+    const int *tip_of_edge;
+    int Et;
 };
 
 __device__ __forceinline__ int plf_code_at(const void *codes, int code_bytes, int64_t S, int node, int64_t site)

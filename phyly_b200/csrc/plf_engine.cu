@@ -106,7 +106,7 @@ struct plf_engine {
     /* fused program */
     std::vector<F4Op> ops;
     std::vector<F4Child> children;
-    DevBuf d_ops, d_children, d_TP, d_TF, d_Pint, d_Fint, d_edge_of_int, d_edge_of_tip, d_code_row_node;
+    DevBuf d_ops, d_children, d_TP, d_TF, d_Pint, d_Fint, d_edge_of_int, d_edge_of_tip, d_code_row_node, d_tip_of_edge, d_TPg;
     std::vector<int> edge_of_int, edge_of_tip, code_row_node;
     std::vector<unsigned char> node_has_data_h;
     int stack_depth = 0, nslots = 0, max_degree = 0;
@@ -1008,6 +1008,25 @@ static int run_generic(plf_engine *e, Query &q)
     const double *w = e->have_w ? e->d_site_w.as<double>() : nullptr;
     /* 16 < n <= 64 (amino-acid, codon): inside pass on the FP64 tensor pipe (tile.cuh) */
     const bool use_tile = n > 16 && n <= TL_NP && !getenv("PLF_NO_TILE");
+    if (use_tile && e->K <= 4096 && !getenv("PLF_NO_TIPTABLE")) {
+        /* tip tables (P_e def_k) so that tip children need no GEMM */
+        if (ensure_program(e)) return -1;
+        const int Et = (int)e->edge_of_tip.size();
+        std::vector<int> toe(E, -1);
+        for (int te = 0; te < Et; te++) toe[e->edge_of_tip[te]] = te;
+        ENSURE(e, e->d_tip_of_edge, sizeof(int) * E);
+        CK(e, cudaMemcpyAsync(e->d_tip_of_edge.p, toe.data(), sizeof(int) * E, cudaMemcpyHostToDevice, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+        const size_t cnt = (size_t)C * Et * e->K * n;
+        ENSURE(e, e->d_TPg, sizeof(double) * (cnt + 1));
+        if (cnt) {
+            tip_table_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, e->stream>>>(
+                e->d_P.as<double>(), e->d_defs.as<double>(), e->d_def_const.as<unsigned char>(),
+                e->d_edge_of_tip.as<int>(), C, E, Et, e->K, n, 0, e->d_TPg.as<double>());
+            KCHECK(e);
+        }
+        a.TP = e->d_TPg.as<double>(); a.tip_of_edge = e->d_tip_of_edge.as<int>(); a.Et = Et;
+    }
     const size_t smem_tile = sizeof(double) * (TL_NP * TL_PS + TL_NP * TL_LS + 8 * TL_TS + TL_TS) + sizeof(int) * 5 * TL_TS;
     if (use_tile) CK(e, cudaFuncSetAttribute(tile_inside_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile));
 

@@ -74,13 +74,36 @@ __global__ void __launch_bounds__(256) tile_inside_kernel(GenericArgs a, int kee
         for (int idx = start; idx < stop; idx++) {
             const int b = a.t.indices[idx];
             __syncthreads();
-            /* stage P_e (zero padded) and the child's tile */
-            {
-                const double *Pm = a.P + (cE + idx) * n * n;
-                for (int i = tid; i < TL_NP * TL_NP; i += 256) {
-                    const int r = i >> 6, k = i & 63;
-                    Psm[r * TL_PS + k] = (r < n && k < n) ? Pm[r * n + k] : 0.0;
+            const int te = a.tip_of_edge ? a.tip_of_edge[idx] : -1;
+            double em[8][2];
+            if (te >= 0) {
+                /* tip child: no GEMM, gather the column from the tip table (P_e def_k) through L1 */
+                const double *Tt = a.TP + (((size_t)c * a.Et + te) * a.K) * n;
+                if (tid < TL_TS) {
+                    int code = 0;
+                    if (s0 + tid < Sc) code = plf_code_at(a.codes, a.code_bytes, a.S, b, a.s0 + s0 + tid);
+                    kb[tid] = code;                       /* reused as the code of this site */
+                    bcs[tid] = a.def_const[code];
                 }
+                __syncthreads();
+#pragma unroll
+                for (int nb = 0; nb < 8; nb++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++)
+                        em[nb][h] = (row < n) ? __ldg(Tt + (size_t)kb[nb * 8 + q * 2 + h] * n + row) : 0.0;
+                __syncthreads();
+                if (tid < TL_TS) kb[tid] = 0;             /* a tip carries no exponent */
+                __syncthreads();
+            } else {
+                /* A fragments of P_e straight from global memory (hot in L1/L2, shared by all CTAs) */
+                const double *Pm = a.P + (cE + idx) * n * n;
+                double af[TL_NP / 4];
+#pragma unroll
+                for (int kk = 0; kk < TL_NP / 4; kk++) {
+                    const int k = kk * 4 + q;
+                    af[kk] = (row < n && k < n) ? __ldg(Pm + row * n + k) : 0.0;
+                }
+                /* stage the child's tile [state][site] */
                 const double *Lb = a.Lg + ((cN + b) * n) * Sc;
                 for (int i = tid; i < TL_NP * TL_TS; i += 256) {
                     const int k = i >> 6, s = i & 63;
@@ -91,19 +114,17 @@ __global__ void __launch_bounds__(256) tile_inside_kernel(GenericArgs a, int kee
                     kb[tid] = in ? a.Kg[(cN + b) * Sc + s0 + tid] : 0;
                     bcs[tid] = in ? a.Cg[(cN + b) * Sc + s0 + tid] : 0;
                 }
-            }
-            __syncthreads();
-            /* em = P_e . L_b on the FP64 tensor pipe */
-            double em[8][2];
+                __syncthreads();
+                /* em = P_e . L_b on the FP64 tensor pipe */
 #pragma unroll
-            for (int nb = 0; nb < 8; nb++) { em[nb][0] = 0.0; em[nb][1] = 0.0; }
-#pragma unroll 4
-            for (int kk = 0; kk < TL_NP / 4; kk++) {
-                const double af = Psm[row * TL_PS + kk * 4 + q];
+                for (int nb = 0; nb < 8; nb++) { em[nb][0] = 0.0; em[nb][1] = 0.0; }
 #pragma unroll
-                for (int nb = 0; nb < 8; nb++) {
-                    const double bf = Lsm[(kk * 4 + q) * TL_LS + nb * 8 + g];
-                    tl_dmma(em[nb][0], em[nb][1], af, bf);
+                for (int kk = 0; kk < TL_NP / 4; kk++) {
+#pragma unroll
+                    for (int nb = 0; nb < 8; nb++) {
+                        const double bf = Lsm[(kk * 4 + q) * TL_LS + nb * 8 + g];
+                        tl_dmma(em[nb][0], em[nb][1], af[kk], bf);
+                    }
                 }
             }
             /* constant column maps to itself (arb_mat_extras.c:84-91); keep edge vectors; multiply in */
@@ -112,7 +133,7 @@ __global__ void __launch_bounds__(256) tile_inside_kernel(GenericArgs a, int kee
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int s = nb * 8 + q * 2 + h;
-                    if (bcs[s] && row < n) em[nb][h] = Lsm[s];           /* row 0 of the child tile */
+                    if (te < 0 && bcs[s] && row < n) em[nb][h] = Lsm[s];   /* row 0 of the child tile */
                 }
                 if (keep_edges && row < n) {
                     const int s = nb * 8 + q * 2;
