@@ -1028,7 +1028,11 @@ static int run_generic(plf_engine *e, Query &q)
         a.TP = e->d_TPg.as<double>(); a.tip_of_edge = e->d_tip_of_edge.as<int>(); a.Et = Et;
     }
     const size_t smem_tile = sizeof(double) * (TL_NP * TL_PS + TL_NP * TL_LS + 8 * TL_TS + TL_TS) + sizeof(int) * 5 * TL_TS;
-    if (use_tile) CK(e, cudaFuncSetAttribute(tile_inside_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile));
+    const size_t smem_tile_out = sizeof(double) * (TL_NP * TL_LS + 8 * TL_TS + 3 * TL_TS) + sizeof(int) * 6 * TL_TS;
+    if (use_tile) {
+        CK(e, cudaFuncSetAttribute(tile_inside_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile));
+        CK(e, cudaFuncSetAttribute(tile_outside_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile_out));
+    }
 
     for (int64_t s0 = 0; s0 < e->S; s0 += Sc) {
         a.s0 = s0; a.Sc = (int)std::min<int64_t>(Sc, e->S - s0);
@@ -1051,8 +1055,13 @@ static int run_generic(plf_engine *e, Query &q)
         if (outside) {
             if (q.want_edge) CK(e, cudaMemsetAsync(a.edge_out, 0, sizeof(double) * (size_t)E * a.Sc, e->stream));
             if (q.want_marg) CK(e, cudaMemsetAsync(a.marg_out, 0, sizeof(double) * (size_t)N * n * a.Sc, e->stream));
-            generic_outside_kernel<<<gx, PLF_TS, smem_out, e->stream>>>(a);
-            KCHECK(e);
+            if (use_tile) {
+                tile_outside_kernel<<<(a.Sc + TL_TS - 1) / TL_TS, 256, smem_tile_out, e->stream>>>(a);
+                KCHECK(e);
+            } else {
+                generic_outside_kernel<<<gx, PLF_TS, smem_out, e->stream>>>(a);
+                KCHECK(e);
+            }
             if (q.want_edge && q.sum_edge) {
                 wsum_rows_kernel<<<E, 256, 0, e->stream>>>(a.edge_out, w, s0, a.Sc, dsum + 1, e->d_err.as<int>(), 0);
                 KCHECK(e);

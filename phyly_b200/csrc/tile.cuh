@@ -251,3 +251,252 @@ __global__ void __launch_bounds__(256) tile_inside_kernel(GenericArgs a, int kee
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* outside pass on the FP64 tensor pipe                                                         */
+/* ------------------------------------------------------------------------------------------ */
+
+/* fragment helpers: a thread owns row `row` and the 16 sites {8 nb + 2 q + h} of the tile */
+#define TL_FOR_FRAG(nb, h) _Pragma("unroll") for (int nb = 0; nb < 8; nb++) _Pragma("unroll") for (int h = 0; h < 2; h++)
+
+__device__ __forceinline__ void tl_load_frag(double (&f)[8][2], const double *rows0, int row, int n, int Sc, int s0, int q)
+{
+    const double *p = rows0 + (size_t)row * Sc + s0;
+    TL_FOR_FRAG(nb, h) {
+        const int s = nb * 8 + q * 2 + h;
+        f[nb][h] = (row < n && s0 + s < Sc) ? p[s] : 0.0;
+    }
+}
+
+/* per-site (column) reduction over all 64 rows: result[s] for s = tid < 64, valid after the call */
+template <bool IS_MAX>
+__device__ __forceinline__ void tl_col_reduce(const double (&f)[8][2], double *colbuf, double *out, int warp, int g, int q, int tid)
+{
+    double r[8][2];
+    TL_FOR_FRAG(nb, h) {
+        double m = f[nb][h];
+        if (IS_MAX) {
+            m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 4));
+            m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 8));
+            m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 16));
+        } else {
+            m += __shfl_xor_sync(0xffffffffu, m, 4);
+            m += __shfl_xor_sync(0xffffffffu, m, 8);
+            m += __shfl_xor_sync(0xffffffffu, m, 16);
+        }
+        r[nb][h] = m;
+    }
+    __syncthreads();
+    if (g == 0) {
+        TL_FOR_FRAG(nb, h) colbuf[warp * TL_TS + nb * 8 + q * 2 + h] = r[nb][h];
+    }
+    __syncthreads();
+    if (tid < TL_TS) {
+        double m = 0.0;
+        for (int w = 0; w < 8; w++) m = IS_MAX ? fmax(m, colbuf[w * TL_TS + tid]) : m + colbuf[w * TL_TS + tid];
+        out[tid] = m;
+    }
+    __syncthreads();
+}
+
+/*
+ * Outside pass for 16 < n <= 64 (evaluate_site_forward.c:52-102, evaluate_site_frechet.c:18-39,
+ * evaluate_site_marginal.c:14-20).  One CTA owns 64 sites and loops over the categories (so that
+ * every output cell has a single writer).  Per child edge: fe = fn_a .* base_a .* prod of the
+ * siblings' edge vectors (kept by the inside pass), y = F_e L_b and fn_b = P_e^T fe on DMMA.
+ * grid = (site tiles), 256 threads.
+ */
+__global__ void __launch_bounds__(256) tile_outside_kernel(GenericArgs a)
+{
+    extern __shared__ __align__(16) double tl_sm[];
+    double *Bsm = tl_sm;                              /* [64][TL_LS] B operand: child partials or fe */
+    double *colbuf = Bsm + TL_NP * TL_LS;             /* [8][64] */
+    double *colres = colbuf + 8 * TL_TS;              /* [64] */
+    double *coef = colres + TL_TS;                    /* [64] prior_c / site likelihood (0 if the category is dead) */
+    double *scl = coef + TL_TS;                       /* [64] */
+    int *ka = reinterpret_cast<int *>(scl + TL_TS);   /* [64] exponent of fn_a */
+    int *kfe = ka + TL_TS;                            /* [64] */
+    int *kbv = kfe + TL_TS;                           /* [64] exponent of the child's partial */
+    int *bcv = kbv + TL_TS;                           /* [64] constant-column flag of the child */
+    int *codev = bcv + TL_TS;                         /* [64] */
+    int *sitek = codev + TL_TS;                       /* [64] */
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int n = a.n, Sc = a.Sc;
+    const int s0 = blockIdx.x * TL_TS;
+    const int row = warp * 8 + g;
+    const bool site_in = (tid < TL_TS) && (s0 + tid < Sc);
+
+    for (int c = 0; c < a.C; c++) {
+        const size_t cN = (size_t)c * a.t.N, cE = (size_t)c * a.t.E;
+        __syncthreads();
+        if (tid < TL_TS) {
+            double cf = 0.0;
+            int sk = 0;
+            if (site_in) {
+                const double pl = a.cat_prior[c] * a.cat_lh[(size_t)c * Sc + s0 + tid];
+                const double m = a.site_m[s0 + tid];
+                if (pl > 0.0 && m > 0.0) cf = a.cat_prior[c] / m;       /* arbplfmarginal.c:184-191 */
+                sk = a.site_k[s0 + tid];
+            }
+            coef[tid] = cf;
+            sitek[tid] = sk;
+        }
+        /* forward vector at the root: root_prior_mul_col_vec (model.c:225-280) */
+        if (row < n) {
+            double r = 1.0;
+            if (a.root_mode == PLF_ROOT_UNIFORM) r = 1.0 / (double)n;
+            else if (a.root_mode == PLF_ROOT_EQUILIBRIUM || a.root_mode == PLF_ROOT_CUSTOM) r = a.root_vec[row];
+            double *Fr = a.Fg + ((cN + a.t.root) * n + row) * Sc + s0;
+            TL_FOR_FRAG(nb, h) { const int s = nb * 8 + q * 2 + h; if (s0 + s < Sc) Fr[s] = r; }
+        }
+        if (site_in) a.FK[(cN + a.t.root) * Sc + s0 + tid] = 0;
+        __syncthreads();
+
+        for (int u = 0; u < a.t.N; u++) {
+            const int nd = a.t.preorder[u];
+            const int start = a.t.indptr[nd], stop = a.t.indptr[nd + 1];
+            const bool leaf = start == stop;
+            if (leaf && !a.want_marg) continue;
+            double fa[8][2];
+            tl_load_frag(fa, a.Fg + (cN + nd) * n * Sc, row, n, Sc, s0, q);
+            __syncthreads();
+            if (tid < TL_TS) ka[tid] = site_in ? a.FK[(cN + nd) * Sc + s0 + tid] : 0;
+            __syncthreads();
+            if (a.want_marg) {
+                /* marg_a += prior_c fn_a .* L_a / site_L */
+                double la[8][2];
+                tl_load_frag(la, a.Lg + (cN + nd) * n * Sc, row, n, Sc, s0, q);
+                if (tid < TL_TS) kbv[tid] = site_in ? a.Kg[(cN + nd) * Sc + s0 + tid] : 0;
+                __syncthreads();
+                if (row < n) {
+                    double *Mo = a.marg_out + ((size_t)nd * n + row) * Sc + s0;
+                    TL_FOR_FRAG(nb, h) {
+                        const int s = nb * 8 + q * 2 + h;
+                        if (s0 + s < Sc && coef[s] != 0.0)
+                            Mo[s] += scalbn(coef[s] * fa[nb][h] * la[nb][h], PLF_SCALE_BITS * (ka[s] + kbv[s] - sitek[s]));
+                    }
+                }
+                __syncthreads();
+            }
+            if (leaf) continue;
+            if (a.t.node_has_data[nd]) {
+                TL_FOR_FRAG(nb, h) {
+                    const int s = nb * 8 + q * 2 + h;
+                    if (row < n && s0 + s < Sc) {
+                        const int code = plf_code_at(a.codes, a.code_bytes, a.S, nd, a.s0 + s0 + s);
+                        fa[nb][h] *= a.defs[(size_t)code * n + row];
+                    }
+                }
+            }
+            for (int idx = start; idx < stop; idx++) {
+                const int b = a.t.indices[idx];
+                const bool b_leaf = a.t.indptr[b] == a.t.indptr[b + 1];
+                const bool want_x = a.want_edge && (!a.edge_mask || a.edge_mask[idx]);
+                const bool want_fn = !b_leaf || a.want_marg;
+                if (!want_x && !want_fn) continue;
+                /* fe = fa .* prod_{sib != idx} Em_sib ; exponent kfe = ka + sum K_sib */
+                double fe[8][2];
+                TL_FOR_FRAG(nb, h) fe[nb][h] = fa[nb][h];
+                __syncthreads();
+                if (tid < TL_TS) kfe[tid] = ka[tid];
+                for (int idx2 = start; idx2 < stop; idx2++) {
+                    if (idx2 == idx) continue;
+                    double es[8][2];
+                    tl_load_frag(es, a.Eg + (cE + idx2) * n * Sc, row, n, Sc, s0, q);
+                    TL_FOR_FRAG(nb, h) fe[nb][h] *= es[nb][h];
+                    __syncthreads();
+                    if (site_in) kfe[tid] += a.Kg[(cN + a.t.indices[idx2]) * Sc + s0 + tid];
+                    /* keep the mantissas in range */
+                    tl_col_reduce<true>(fe, colbuf, colres, warp, g, q, tid);
+                    if (tid < TL_TS) {
+                        double m = colres[tid], sc = 1.0;
+                        int k = kfe[tid];
+                        while (m > 0.0 && m < PLF_TWO_M256) { m *= PLF_TWO_P256; sc *= PLF_TWO_P256; k -= 1; }
+                        while (m > PLF_TWO_P256) { m *= PLF_TWO_M256; sc *= PLF_TWO_M256; k += 1; }
+                        kfe[tid] = k; scl[tid] = sc;
+                    }
+                    __syncthreads();
+                    TL_FOR_FRAG(nb, h) fe[nb][h] *= scl[nb * 8 + q * 2 + h];
+                }
+                __syncthreads();
+                /* the child's partial: tile as B operand (internal child) or code (tip) */
+                if (tid < TL_TS) {
+                    kbv[tid] = site_in ? a.Kg[(cN + b) * Sc + s0 + tid] : 0;
+                    bcv[tid] = site_in ? a.Cg[(cN + b) * Sc + s0 + tid] : 0;
+                    codev[tid] = (site_in && b_leaf && a.t.node_has_data[b]) ? plf_code_at(a.codes, a.code_bytes, a.S, b, a.s0 + s0 + tid) : -1;
+                }
+                if (want_x) {
+                    /* x_e = fe^T (F_e L_b)  (evaluate_site_frechet.c:18-39) */
+                    const double *Lb = a.Lg + ((cN + b) * n) * Sc;
+                    for (int i = tid; i < TL_NP * TL_TS; i += 256) {
+                        const int k = i >> 6, s = i & 63;
+                        Bsm[k * TL_LS + s] = (k < n && s0 + s < Sc) ? Lb[(size_t)k * Sc + s0 + s] : 0.0;
+                    }
+                    const double *Fm = a.Fm + (cE + idx) * n * n;
+                    double af[TL_NP / 4];
+#pragma unroll
+                    for (int kk = 0; kk < TL_NP / 4; kk++) {
+                        const int k = kk * 4 + q;
+                        af[kk] = (row < n && k < n) ? __ldg(Fm + row * n + k) : 0.0;
+                    }
+                    __syncthreads();
+                    double y[8][2];
+                    TL_FOR_FRAG(nb, h) y[nb][h] = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < TL_NP / 4; kk++) {
+#pragma unroll
+                        for (int nb = 0; nb < 8; nb++) tl_dmma(y[nb][0], y[nb][1], af[kk], Bsm[(kk * 4 + q) * TL_LS + nb * 8 + g]);
+                    }
+                    TL_FOR_FRAG(nb, h) {
+                        const int s = nb * 8 + q * 2 + h;
+                        y[nb][h] = (a.f_zero_rowsum && bcv[s]) ? 0.0 : y[nb][h] * fe[nb][h];
+                    }
+                    tl_col_reduce<false>(y, colbuf, colres, warp, g, q, tid);
+                    if (site_in && coef[tid] != 0.0)
+                        a.edge_out[(size_t)idx * Sc + s0 + tid] += scalbn(colres[tid] * coef[tid], PLF_SCALE_BITS * (kfe[tid] + kbv[tid] - sitek[tid]));
+                    __syncthreads();
+                }
+                if (want_fn) {
+                    /* fn_b = P_e^T fe  (util.c:464-498): fe becomes the B operand */
+                    __syncthreads();
+                    TL_FOR_FRAG(nb, h) Bsm[row * TL_LS + nb * 8 + q * 2 + h] = fe[nb][h];
+                    const double *Pm = a.P + (cE + idx) * n * n;
+                    double af[TL_NP / 4];
+#pragma unroll
+                    for (int kk = 0; kk < TL_NP / 4; kk++) {
+                        const int k = kk * 4 + q;
+                        af[kk] = (row < n && k < n) ? __ldg(Pm + k * n + row) : 0.0;     /* A = P^T */
+                    }
+                    __syncthreads();
+                    double fb[8][2];
+                    TL_FOR_FRAG(nb, h) fb[nb][h] = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < TL_NP / 4; kk++) {
+#pragma unroll
+                        for (int nb = 0; nb < 8; nb++) tl_dmma(fb[nb][0], fb[nb][1], af[kk], Bsm[(kk * 4 + q) * TL_LS + nb * 8 + g]);
+                    }
+                    tl_col_reduce<true>(fb, colbuf, colres, warp, g, q, tid);
+                    if (tid < TL_TS) {
+                        double m = colres[tid], sc = 1.0;
+                        int k = kfe[tid];
+                        while (m > PLF_TWO_P256) { m *= PLF_TWO_M256; sc *= PLF_TWO_M256; k += 1; }
+                        while (m > 0.0 && m < PLF_TWO_M256) { m *= PLF_TWO_P256; sc *= PLF_TWO_P256; k -= 1; }
+                        scl[tid] = sc;
+                        if (site_in) a.FK[(cN + b) * Sc + s0 + tid] = k;
+                    }
+                    __syncthreads();
+                    if (row < n) {
+                        double *Fb = a.Fg + ((cN + b) * n + row) * Sc + s0;
+                        TL_FOR_FRAG(nb, h) {
+                            const int s = nb * 8 + q * 2 + h;
+                            if (s0 + s < Sc) Fb[s] = fb[nb][h] * scl[s];
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+    }
+}
