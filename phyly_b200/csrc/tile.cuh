@@ -306,7 +306,7 @@ __device__ __forceinline__ void tl_col_reduce(const double (&f)[8][2], double *c
  * siblings' edge vectors (kept by the inside pass), y = F_e L_b and fn_b = P_e^T fe on DMMA.
  * grid = (site tiles), 256 threads.
  */
-__global__ void __launch_bounds__(256) tile_outside_kernel(GenericArgs a)
+__global__ void __launch_bounds__(256, 2) tile_outside_kernel(GenericArgs a)
 {
     extern __shared__ __align__(16) double tl_sm[];
     double *Bsm = tl_sm;                              /* [64][TL_LS] B operand: child partials or fe */
