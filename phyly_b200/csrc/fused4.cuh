@@ -154,6 +154,14 @@ __device__ __forceinline__ double f4_warp_sum(double x)
 
 __host__ __device__ inline size_t f4_align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
+/* character code of this thread's site for tile row r */
+template <int BD, bool PACK>
+__device__ __forceinline__ int f4_code(const unsigned char *tile, int r, int tid)
+{
+    if (PACK) return (tile[(r >> 1) * BD + tid] >> ((r & 1) * 4)) & 15;
+    return tile[r * BD + tid];
+}
+
 __device__ __forceinline__ void f4_prefetch(const void *p)
 {
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
@@ -175,7 +183,7 @@ __device__ __forceinline__ double f4_warp_sum2(double a, double b, int lane)
  * Outside step specialised for a node with exactly two children of kinds (K0, K1) in
  * {(CUR, TIP), (CUR, STACK), (TIP, TIP)}: straight-line code, no filler factors.
  */
-template <int C, int BD, int K0, int K1>
+template <int C, int BD, int K0, int K1, bool PACK>
 __device__ __forceinline__ void f4_outside2(const F4Args &a, const F4Op &op, const F4Child &c0, const F4Child &c1,
                                             bool from_slot, double *cur, const unsigned char *tile, const double *defs_s,
                                             const double *Pint, const double *Fint, const double *TP, const double *TF,
@@ -184,11 +192,11 @@ __device__ __forceinline__ void f4_outside2(const F4Args &a, const F4Op &op, con
 {
     double basev[4] = {1.0, 1.0, 1.0, 1.0};
     const bool has_base = op.code_row >= 0;
-    if (has_base) f4_ld4(defs_s + tile[op.code_row * BD + tid] * 4, basev);
+    if (has_base) f4_ld4(defs_s + f4_code<BD, PACK>(tile, op.code_row, tid) * 4, basev);
     const unsigned int sword_a = a.scratchS[(size_t)op.slot * T + gtid];
     int code0 = 0, code1 = 0, bc0 = 0, bc1 = 0;
-    if (K0 == F4_KIND_TIP) code0 = tile[c0.code_row * BD + tid]; else bc0 = (a.scratchS[(size_t)c0.slot * T + gtid] >> 6) & 1;
-    if (K1 == F4_KIND_TIP) code1 = tile[c1.code_row * BD + tid]; else bc1 = (a.scratchS[(size_t)c1.slot * T + gtid] >> 6) & 1;
+    if (K0 == F4_KIND_TIP) code0 = f4_code<BD, PACK>(tile, c0.code_row, tid); else bc0 = (a.scratchS[(size_t)c0.slot * T + gtid] >> 6) & 1;
+    if (K1 == F4_KIND_TIP) code1 = f4_code<BD, PACK>(tile, c1.code_row, tid); else bc1 = (a.scratchS[(size_t)c1.slot * T + gtid] >> 6) & 1;
     x0 = 0.0; x1 = 0.0;
 #pragma unroll 2
     for (int c = 0; c < C; c++) {
@@ -275,8 +283,9 @@ __device__ __forceinline__ void f4_outside2(const F4Args &a, const F4Op &op, con
  * EDGE  : false = log-likelihood only; true = log-likelihood + per-edge bilinear forms
  * The dynamic shared memory layout below is mirrored on the host by f4_smem_bytes().
  */
-/* STAGED: 2 = all tables in shared memory, 1 = all but TF (read through L1), 0 = none */
-template <int C, bool EDGE, int BD, int STAGED>
+/* STAGED: 2 = all tables in shared memory, 1 = all but TF (read through L1), 0 = none.
+ * PACK: the tile's character codes are stored two per byte (needs K <= 16). */
+template <int C, bool EDGE, int BD, int STAGED, bool PACK>
 __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
 {
     extern __shared__ __align__(16) unsigned char f4_smem[];
@@ -295,7 +304,7 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
     double *accE = reinterpret_cast<double *>(f4_smem + off); off = f4_align16(off + (EDGE ? sizeof(double) * nwarp * a.E : 0));
     double *stack = reinterpret_cast<double *>(f4_smem + off); off = f4_align16(off + (EDGE ? 0 : sizeof(double) * 4 * C * bd * a.stack_depth));
     int *stackf = reinterpret_cast<int *>(f4_smem + off); off = f4_align16(off + (EDGE ? 0 : sizeof(int) * bd * a.stack_depth));
-    unsigned char *tile = f4_smem + off; off = f4_align16(off + (size_t)a.ncode_rows * bd);
+    unsigned char *tile = f4_smem + off; off = f4_align16(off + (size_t)(PACK ? (a.ncode_rows + 1) / 2 : a.ncode_rows) * bd);
     unsigned char *dconst = f4_smem + off; off = f4_align16(off + a.K);
     double *defs_s = reinterpret_cast<double *>(f4_smem + off); off = f4_align16(off + sizeof(double) * 4 * a.K);
     const double *Pint = a.Pint, *TP = a.TP, *Fint = a.Fint, *TF = a.TF;
@@ -332,8 +341,16 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
         const int64_t site = valid ? site_raw : a.S - 1;
         const double w = valid ? (a.site_w ? a.site_w[site] : 1.0) : 0.0;
         /* stage this tile's character codes: each thread only ever reads its own column */
-        for (int r = 0; r < a.ncode_rows; r++)
-            tile[r * bd + tid] = a.codes[(size_t)a.code_row_node[r] * a.S + site];
+        if (PACK) {
+            for (int r = 0; r < a.ncode_rows; r += 2) {
+                unsigned int lo = a.codes[(size_t)a.code_row_node[r] * a.S + site];
+                unsigned int hi = (r + 1 < a.ncode_rows) ? a.codes[(size_t)a.code_row_node[r + 1] * a.S + site] : 0u;
+                tile[(r >> 1) * bd + tid] = (unsigned char)(lo | (hi << 4));
+            }
+        } else {
+            for (int r = 0; r < a.ncode_rows; r++)
+                tile[r * bd + tid] = a.codes[(size_t)a.code_row_node[r] * a.S + site];
+        }
 
         /* ---------------- inside pass (all categories together) ---------------- */
         int curf = 1, sp = 0;
@@ -355,7 +372,7 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
             int cst = 1;
             bool first = true;
             if (op.code_row >= 0) {
-                const int code = tile[op.code_row * bd + tid];
+                const int code = f4_code<BD, PACK>(tile, op.code_row, tid);
                 double b[4];
                 f4_ld4(defs_s + code * 4, b);
 #pragma unroll
@@ -371,7 +388,7 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
                 double em[C][4];
                 int bc;
                 if (ch.kind == F4_KIND_TIP) {
-                    const int code = tile[ch.code_row * bd + tid];
+                    const int code = f4_code<BD, PACK>(tile, ch.code_row, tid);
                     bc = dconst[code];
                     const double *tp = TP + (ch.mat * a.K + code) * 4;
 #pragma unroll
@@ -520,13 +537,13 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
                 const F4Child c0 = chs[op.first_child], c1 = chs[op.first_child + 1];
                 double x0, x1;
                 if (c0.kind == F4_KIND_CUR && c1.kind == F4_KIND_TIP)
-                    f4_outside2<C, BD, F4_KIND_CUR, F4_KIND_TIP>(a, op, c0, c1, from_slot, cur, tile, defs_s, Pint, Fint, TP, TF,
+                    f4_outside2<C, BD, F4_KIND_CUR, F4_KIND_TIP, PACK>(a, op, c0, c1, from_slot, cur, tile, defs_s, Pint, Fint, TP, TF,
                                                                  pstride, tpstride, (size_t)T, (size_t)gtid, tid, x0, x1);
                 else if (c0.kind == F4_KIND_CUR)
-                    f4_outside2<C, BD, F4_KIND_CUR, F4_KIND_STACK>(a, op, c0, c1, from_slot, cur, tile, defs_s, Pint, Fint, TP, TF,
+                    f4_outside2<C, BD, F4_KIND_CUR, F4_KIND_STACK, PACK>(a, op, c0, c1, from_slot, cur, tile, defs_s, Pint, Fint, TP, TF,
                                                                    pstride, tpstride, (size_t)T, (size_t)gtid, tid, x0, x1);
                 else
-                    f4_outside2<C, BD, F4_KIND_TIP, F4_KIND_TIP>(a, op, c0, c1, from_slot, cur, tile, defs_s, Pint, Fint, TP, TF,
+                    f4_outside2<C, BD, F4_KIND_TIP, F4_KIND_TIP, PACK>(a, op, c0, c1, from_slot, cur, tile, defs_s, Pint, Fint, TP, TF,
                                                                  pstride, tpstride, (size_t)T, (size_t)gtid, tid, x0, x1);
                 const bool m0 = !a.edge_mask || a.edge_mask[c0.edge];
                 const bool m1 = !a.edge_mask || a.edge_mask[c1.edge];
@@ -541,7 +558,7 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
                 continue;
             }
             double basev[4] = {1.0, 1.0, 1.0, 1.0};
-            if (op.code_row >= 0) f4_ld4(defs_s + tile[op.code_row * bd + tid] * 4, basev);
+            if (op.code_row >= 0) f4_ld4(defs_s + f4_code<BD, PACK>(tile, op.code_row, tid) * 4, basev);
             /* children descriptors and category-independent lookups */
             int kinds[F4_MAXD], mats[F4_MAXD], slots[F4_MAXD], edges[F4_MAXD], codes[F4_MAXD], bcs[F4_MAXD];
 #pragma unroll
@@ -550,7 +567,7 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
                 if (j < op.nchild) {
                     const F4Child ch = chs[op.first_child + j];
                     kinds[j] = ch.kind; mats[j] = ch.mat; slots[j] = ch.slot; edges[j] = ch.edge;
-                    if (ch.kind == F4_KIND_TIP) codes[j] = tile[ch.code_row * bd + tid];
+                    if (ch.kind == F4_KIND_TIP) codes[j] = f4_code<BD, PACK>(tile, ch.code_row, tid);
                     else bcs[j] = (a.scratchS[(size_t)ch.slot * T + gtid] >> 6) & 1;
                 }
             }

@@ -783,24 +783,24 @@ static int copy_site_matrix(plf_engine *e, const double *d_rows /*[R][cols]*/, i
 
 typedef void (*f4_kernel_t)(F4Args);
 
-template <int BD, int STAGED>
+template <int BD, int STAGED, bool PACK>
 static f4_kernel_t f4_select_c(int C, bool edge)
 {
     switch (C * 2 + (edge ? 1 : 0)) {
-    case 2: return fused4_kernel<1, false, BD, STAGED>;
-    case 3: return fused4_kernel<1, true, BD, STAGED>;
-    case 4: return fused4_kernel<2, false, BD, STAGED>;
-    case 5: return fused4_kernel<2, true, BD, STAGED>;
-    case 6: return fused4_kernel<3, false, BD, STAGED>;
-    case 7: return fused4_kernel<3, true, BD, STAGED>;
-    case 8: return fused4_kernel<4, false, BD, STAGED>;
-    case 9: return fused4_kernel<4, true, BD, STAGED>;
+    case 2: return fused4_kernel<1, false, BD, STAGED, PACK>;
+    case 3: return fused4_kernel<1, true, BD, STAGED, PACK>;
+    case 4: return fused4_kernel<2, false, BD, STAGED, PACK>;
+    case 5: return fused4_kernel<2, true, BD, STAGED, PACK>;
+    case 6: return fused4_kernel<3, false, BD, STAGED, PACK>;
+    case 7: return fused4_kernel<3, true, BD, STAGED, PACK>;
+    case 8: return fused4_kernel<4, false, BD, STAGED, PACK>;
+    case 9: return fused4_kernel<4, true, BD, STAGED, PACK>;
     }
     return nullptr;
 }
 
 /* mirrors the shared-memory carve-up at the top of fused4_kernel */
-static size_t f4_smem_bytes(const plf_engine *e, bool edge, int bd, int staged)
+static size_t f4_smem_bytes(const plf_engine *e, bool edge, int bd, int staged, bool pack = false)
 {
     const int C = e->C, Ei = (int)e->edge_of_int.size(), Et = (int)e->edge_of_tip.size();
     size_t off = 0;
@@ -810,7 +810,7 @@ static size_t f4_smem_bytes(const plf_engine *e, bool edge, int bd, int staged)
     off = f4_align16(off + (edge ? sizeof(double) * (bd / 32) * e->E : 0));
     off = f4_align16(off + (edge ? 0 : sizeof(double) * 4 * C * bd * e->stack_depth));
     off = f4_align16(off + (edge ? 0 : sizeof(int) * bd * e->stack_depth));
-    off = f4_align16(off + e->code_row_node.size() * bd);
+    off = f4_align16(off + (pack ? (e->code_row_node.size() + 1) / 2 : e->code_row_node.size()) * bd);
     off = f4_align16(off + e->K);
     off = f4_align16(off + sizeof(double) * 4 * e->K);
     const size_t nP = (size_t)C * Ei * 16 * sizeof(double), nT = (size_t)C * Et * e->K * 4 * sizeof(double);
@@ -852,20 +852,23 @@ static int run_fused(plf_engine *e, Query &q)
     size_t smem = 0;
     {
         /* candidate configurations, best first; PLF_F4_CONFIG=<index> forces one (tuning aid) */
-        struct Cand { int bd, staged; f4_kernel_t k; };
+        struct Cand { int bd, staged; bool pack; f4_kernel_t k; };
+        const bool can_pack = e->K <= 16;
         const Cand cands[] = {
-            {384, 1, f4_select_c<384, 1>(e->C, edge)},
-            {512, 1, f4_select_c<512, 1>(e->C, edge)},
-            {256, 2, f4_select_c<256, 2>(e->C, edge)},
-            {256, 1, f4_select_c<256, 1>(e->C, edge)},
-            {128, 2, f4_select_c<128, 2>(e->C, edge)},
-            {128, 0, f4_select_c<128, 0>(e->C, edge)},
+            {384, 2, true, can_pack ? f4_select_c<384, 2, true>(e->C, edge) : nullptr},
+            {384, 1, false, f4_select_c<384, 1, false>(e->C, edge)},
+            {512, 1, false, f4_select_c<512, 1, false>(e->C, edge)},
+            {256, 2, false, f4_select_c<256, 2, false>(e->C, edge)},
+            {256, 1, false, f4_select_c<256, 1, false>(e->C, edge)},
+            {128, 2, false, f4_select_c<128, 2, false>(e->C, edge)},
+            {128, 0, false, f4_select_c<128, 0, false>(e->C, edge)},
         };
         const int ncand = (int)(sizeof(cands) / sizeof(cands[0]));
         const char *force = edge ? getenv("PLF_F4_CONFIG") : nullptr;
         for (int i = 0; i < ncand; i++) {
             if (force && atoi(force) != i) continue;
-            smem = f4_smem_bytes(e, edge, cands[i].bd, cands[i].staged);
+            if (!cands[i].k) continue;
+            smem = f4_smem_bytes(e, edge, cands[i].bd, cands[i].staged, cands[i].pack);
             if (smem <= smem_cap) { kern = cands[i].k; bd = cands[i].bd; break; }
         }
         if (!kern) FAIL(e, "fused kernel needs %zu bytes of shared memory", smem);
