@@ -123,12 +123,16 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.lines = []          # (arrival time, text)
+        self.windows = []        # timed regions [t0, t1] (time.perf_counter)
+
+    def mark(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -137,7 +141,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if not self.proc:
@@ -147,9 +151,17 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        # samples that arrived inside a timed region; a region shorter than the sampling period may hold none,
+        # then every sample taken while the GPU was under load (warm-up to the last timed step) is used
+        inside = [ln for t, ln in self.lines if any(a <= t <= b + 0.02 for a, b in self.windows)]
+        window = "timed regions"
+        if not inside and self.windows:
+            lo, hi = self.windows[0][0] - 1.0, self.windows[-1][1] + 0.02
+            inside = [ln for t, ln in self.lines if lo <= t <= hi]
+            window = "warm-up + timed regions (timed regions shorter than the sampling period)"
+        sm, mx, reasons = [], None, set()
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -162,7 +174,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "window": window, "reasons": sorted(reasons)}
 
 
 def load_json(path):
@@ -259,20 +271,25 @@ def run_ours(args):
         eng.set_edge_rates(pb["edge_rates"])          # invalidates P, Q.P and the tip tables
         return eng.deriv(per_site=False)
 
+    sync_upload = bool(os.environ.get("PLF_BENCH_SYNC_UPLOAD"))
+
     def step_e2e():
-        eng.set_data_ptr(defs, pb["codes_t"].data_ptr(), S, 1)
-        eng.set_site_weights(pb["w_t"].numpy())
+        if sync_upload:
+            eng.set_data_ptr(defs, pb["codes_t"].data_ptr(), S, 1)
+            eng.set_site_weights(pb["w_t"].numpy())
+        else:       # chunked upload overlapped with the kernel
+            eng.set_data_async_ptr(defs, pb["codes_t"].data_ptr(), S, pb["w_t"].data_ptr(), 1)
         eng.set_edge_rates(pb["edge_rates"])
         return eng.deriv(per_site=False)
 
     # ---- device-resident measurement ----
     eng.set_data_ptr(defs, pb["codes_t"].data_ptr(), S, 1)
     eng.set_site_weights(pb["w_t"].numpy())
-    for _ in range(args.warmup):
-        res = step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        res = step_resident()
     barrier()
     eng.launch_count(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -286,20 +303,23 @@ def run_ours(args):
     e1.record(stream)
     barrier()
     wall = time.perf_counter() - t0
+    sampler.mark(t0, t0 + wall)
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count()
-    clocks = sampler.stop() if rank == 0 else None
     # ---- end-to-end measurement (host buffers) ----
-    e2e_steps = max(1, min(args.steps, 10))
+    e2e_steps = max(1, min(args.steps, 50))
     for _ in range(min(args.warmup, 3)):
         step_e2e()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t1 = time.perf_counter()
     f0.record(stream)
     for _ in range(e2e_steps):
         res2 = step_e2e()
     f1.record(stream)
     barrier()
+    sampler.mark(t1, time.perf_counter())
+    clocks = sampler.stop() if rank == 0 else None
     ms_e2e = f0.elapsed_time(f1)
     if world > 1:
         tt = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
@@ -351,7 +371,7 @@ def run_ours(args):
                    "cache": "inputs and scratch (%.0f MB) exceed the 126 MB L2; no explicit flush" % (S * N / 1e6 + 600)},
         "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(S * N + 8 * S + 8 * Eg),
                 "d2h_bytes_per_step": int(8 * (1 + Eg)), "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
-                "api": "plf_set_data + plf_set_site_weights + plf_set_edge_rates + plf_deriv (include/plf.h), pinned host buffers"},
+                "api": ("plf_set_data + plf_set_site_weights" if sync_upload else "plf_set_data_async") + " + plf_set_edge_rates + plf_deriv (include/plf.h), pinned host buffers"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
@@ -451,7 +471,7 @@ def main():
     os.dup2(2, 1)          # anything else that writes to fd 1 goes to stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sites", type=int, default=1000000)

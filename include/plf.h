@@ -87,6 +87,18 @@ int plf_set_edge_rates(plf_engine *e, const double *edge_rates /*[E]*/);
 int plf_set_data(plf_engine *e, int64_t site_count, int def_count,
                  const double *defs /*[K][n]*/, const void *codes /*[S][N]*/, int code_bytes);
 
+/*
+ * The same, without waiting for the copy: the codes (and, if given, the site
+ * weights) travel in chunks on a second stream and the next query starts on
+ * the first chunk while the later ones are still in flight (4-state fused
+ * path; other paths simply wait).  `codes` and `site_weights` must stay valid
+ * and unchanged until the next query or plf_synchronize returns; use pinned
+ * host memory, otherwise the copy is staged and nothing overlaps.
+ */
+int plf_set_data_async(plf_engine *e, int64_t site_count, int def_count,
+                       const double *defs /*[K][n]*/, const void *codes /*[S][N]*/, int code_bytes,
+                       const double *site_weights /*[S] or NULL*/);
+
 /* Per-site weights used by the *_sum outputs (NULL = all ones).  reduction.c:24-118. */
 int plf_set_site_weights(plf_engine *e, const double *w /*[S] or NULL*/);
 

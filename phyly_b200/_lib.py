@@ -38,6 +38,7 @@ def load():
     lib.plf_set_model.argtypes = [P, c.c_int, c.c_int, P, P, P, P, P, c.c_int, P]
     lib.plf_set_edge_rates.argtypes = [P, P]
     lib.plf_set_data.argtypes = [P, c.c_int64, c.c_int, P, P, c.c_int]
+    lib.plf_set_data_async.argtypes = [P, c.c_int64, c.c_int, P, P, c.c_int, P]
     lib.plf_set_site_weights.argtypes = [P, P]
     lib.plf_ll.argtypes = [P, P, P]
     lib.plf_deriv.argtypes = [P, P, P, P, P, P]
@@ -56,7 +57,7 @@ def load():
     lib.plf_stream.argtypes = [P]
     lib.plf_stream.restype = P
     lib.plf_synchronize.argtypes = [P]
-    for name in ("plf_set_path", "plf_set_tree", "plf_set_model", "plf_set_edge_rates", "plf_set_data",
+    for name in ("plf_set_path", "plf_set_tree", "plf_set_model", "plf_set_edge_rates", "plf_set_data", "plf_set_data_async",
                  "plf_set_site_weights", "plf_ll", "plf_deriv", "plf_marginal", "plf_edge_expect",
                  "plf_get_transition_matrices", "plf_get_derivative_matrices", "plf_get_frechet_matrices",
                  "plf_last_timing", "plf_comm_unique_id", "plf_comm_init", "plf_synchronize"):

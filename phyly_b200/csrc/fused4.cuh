@@ -85,6 +85,7 @@ struct F4Args {
     unsigned int *scratchS;          /* [nslots][T]: byte c = rescale count | const flag << 6 */
     double *site_ll;                 /* [S] or NULL */
     double *edge_site_out;           /* [E][S] or NULL */
+    int64_t s_begin, s_end;          /* this launch covers sites [s_begin, s_end) (a chunk of the data) */
     double *block_ll;                /* [grid] */
     double *block_edge;              /* [grid][E] */
     int *error_flag;
@@ -333,12 +334,12 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
     for (int c = 0; c < C; c++) prior[c] = a.cat_prior[c];
 
     double ll_acc = 0.0;
-    const int64_t ntiles = (a.S + bd - 1) / bd;
+    const int64_t ntiles = (a.s_end - a.s_begin + bd - 1) / bd;
 
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int64_t site_raw = t * bd + tid;
-        const bool valid = site_raw < a.S;
-        const int64_t site = valid ? site_raw : a.S - 1;
+        const int64_t site_raw = a.s_begin + t * bd + tid;
+        const bool valid = site_raw < a.s_end;
+        const int64_t site = valid ? site_raw : a.s_end - 1;
         const double w = valid ? (a.site_w ? a.site_w[site] : 1.0) : 0.0;
         /* stage this tile's character codes: each thread only ever reads its own column */
         if (PACK) {

@@ -103,6 +103,15 @@ struct plf_engine {
     bool have_w = false;
     std::vector<unsigned char> def_const_h;
 
+    /* data upload still in flight (plf_set_data_async): chunk k covers sites
+     * [bounds[k], bounds[k+1]) and is complete on the device when chunk_ev[k] fires */
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> chunk_ev;
+    std::vector<int64_t> pend_bounds;
+    bool pend_active = false;
+    int pend_in_bytes = 1;
+    unsigned char *flags_pinned = nullptr;
+
     /* fused program */
     std::vector<F4Op> ops;
     std::vector<F4Child> children;
@@ -139,16 +148,16 @@ struct plf_engine {
 
 /* codes_in[S][N] (1 or 4 bytes) -> codes[N][S] (1 or 4 bytes); also flags nodes that carry data */
 template <typename TIn, typename TOut>
-__global__ void transpose_codes_kernel(const TIn *in, TOut *out, int64_t S, int N,
+__global__ void transpose_codes_kernel(const TIn *in, TOut *out, int64_t s_begin, int64_t s_end, int64_t S, int N,
                                        const unsigned char *def_ones, int *node_flags)
 {
     __shared__ int tile[32][33];
-    const int64_t s0 = (int64_t)blockIdx.x * 32;
+    const int64_t s0 = s_begin + (int64_t)blockIdx.x * 32;
     const int n0 = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         int64_t s = s0 + r;
         int nd = n0 + threadIdx.x;
-        tile[r][threadIdx.x] = (s < S && nd < N) ? (int)in[(size_t)s * N + nd] : -1;
+        tile[r][threadIdx.x] = (s < s_end && nd < N) ? (int)in[(size_t)s * N + nd] : -1;
     }
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -156,7 +165,7 @@ __global__ void transpose_codes_kernel(const TIn *in, TOut *out, int64_t S, int 
         int64_t s = s0 + threadIdx.x;
         int code = tile[threadIdx.x][r];
         bool has = false;
-        if (nd < N && s < S) {
+        if (nd < N && s < s_end) {
             out[(size_t)nd * S + s] = (TOut)code;
             has = !def_ones[code];
         }
@@ -287,6 +296,9 @@ extern "C" void plf_destroy(plf_engine *e)
                       &e->g_cat_k, &e->g_site_m, &e->g_site_k, &e->g_edge_out, &e->g_marg_out, &e->g_tr};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
+    for (cudaEvent_t v : e->chunk_ev) cudaEventDestroy(v);
+    if (e->flags_pinned) cudaFreeHost(e->flags_pinned);
     cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -308,6 +320,7 @@ extern "C" int plf_synchronize(plf_engine *e)
     if (!e) return -1;
     CK(e, cudaSetDevice(e->device));
     CK(e, cudaStreamSynchronize(e->stream));
+    if (e->copy_stream) CK(e, cudaStreamSynchronize(e->copy_stream));   /* host buffers of an async upload are free again */
     return 0;
 }
 
@@ -594,7 +607,63 @@ static int upload_L(plf_engine *e, const double *l_hi, const double *l_lo)
 /* data                                                                */
 /* ------------------------------------------------------------------ */
 
-extern "C" int plf_set_data(plf_engine *e, int64_t S, int K, const double *defs, const void *codes, int code_bytes)
+/* site-major -> node-major for sites [s0, s1) on the engine's stream; accumulates the "node carries data" flags */
+static int launch_transpose(plf_engine *e, int64_t s0, int64_t s1, int in_bytes)
+{
+    const int N = e->N;
+    const int64_t S = e->S;
+    int *flags = e->d_err.as<int>() + 4;
+    dim3 blk(32, 8), grid((unsigned)((s1 - s0 + 31) / 32), (unsigned)((N + 31) / 32));
+    if (in_bytes == 1)
+        transpose_codes_kernel<unsigned char, unsigned char><<<grid, blk, 0, e->stream>>>(
+            e->d_codes_in.as<unsigned char>(), e->d_codes.as<unsigned char>(), s0, s1, S, N, e->d_def_ones.as<unsigned char>(), flags);
+    else if (e->code_bytes == 1)
+        transpose_codes_kernel<int, unsigned char><<<grid, blk, 0, e->stream>>>(
+            e->d_codes_in.as<int>(), e->d_codes.as<unsigned char>(), s0, s1, S, N, e->d_def_ones.as<unsigned char>(), flags);
+    else
+        transpose_codes_kernel<int, int><<<grid, blk, 0, e->stream>>>(
+            e->d_codes_in.as<int>(), e->d_codes.as<int>(), s0, s1, S, N, e->d_def_ones.as<unsigned char>(), flags);
+    KCHECK(e);
+    return 0;
+}
+
+/* after every chunk has been transposed: bring the node flags to the host (asynchronously) */
+static int launch_flags_readback(plf_engine *e)
+{
+    int *flags = e->d_err.as<int>() + 4;
+    flags_to_bytes_kernel<<<(e->N + 127) / 128, 128, 0, e->stream>>>(flags, e->d_node_has_data.as<unsigned char>(), e->N);
+    KCHECK(e);
+    CK(e, cudaMemcpyAsync(e->flags_pinned, e->d_node_has_data.p, e->N, cudaMemcpyDeviceToHost, e->stream));
+    return 0;
+}
+
+/* the stream has been synchronised: compare the flags with the ones the program was built for */
+static bool adopt_flags(plf_engine *e)
+{
+    std::vector<unsigned char> flags_h(e->flags_pinned, e->flags_pinned + e->N);
+    if (flags_h == e->node_has_data_h) return false;
+    e->node_has_data_h = flags_h;
+    e->program_dirty = true;
+    return true;
+}
+
+/* finish an upload started by plf_set_data_async without overlapping it with compute */
+static int resolve_pending(plf_engine *e)
+{
+    if (!e->pend_active) return 0;
+    for (size_t k = 0; k + 1 < e->pend_bounds.size(); k++) {
+        CK(e, cudaStreamWaitEvent(e->stream, e->chunk_ev[k], 0));
+        if (launch_transpose(e, e->pend_bounds[k], e->pend_bounds[k + 1], e->pend_in_bytes)) return -1;
+    }
+    if (launch_flags_readback(e)) return -1;
+    CK(e, cudaStreamSynchronize(e->stream));
+    adopt_flags(e);
+    e->pend_active = false;
+    return 0;
+}
+
+static int set_data_common(plf_engine *e, int64_t S, int K, const double *defs, const void *codes, int code_bytes,
+                           const double *w, bool async)
 {
     if (!e) return -1;
     if (e->N == 0 || e->n == 0) FAIL(e, "plf_set_data: set the tree and the model first");
@@ -613,6 +682,8 @@ extern "C" int plf_set_data(plf_engine *e, int64_t S, int K, const double *defs,
         }
         dconst[k] = c; dones[k] = o;
     }
+    /* an earlier asynchronous upload may still be writing the buffers that are about to be reused */
+    if (e->pend_active) { CK(e, cudaStreamSynchronize(e->copy_stream)); e->pend_active = false; }
     e->def_const_h = dconst;
     const int dev_bytes = (K <= 256) ? 1 : 4;
     ENSURE(e, e->d_defs, sizeof(double) * K * n);
@@ -622,37 +693,69 @@ extern "C" int plf_set_data(plf_engine *e, int64_t S, int K, const double *defs,
     ENSURE(e, e->d_codes, (size_t)S * N * dev_bytes);
     ENSURE(e, e->d_node_has_data, N);
     ENSURE(e, e->d_err, sizeof(int) * (N + 4));
-    CK(e, cudaMemcpyAsync(e->d_defs.p, defs, sizeof(double) * K * n, cudaMemcpyHostToDevice, e->stream));
-    CK(e, cudaMemcpyAsync(e->d_def_const.p, dconst.data(), K, cudaMemcpyHostToDevice, e->stream));
-    CK(e, cudaMemcpyAsync(e->d_def_ones.p, dones.data(), K, cudaMemcpyHostToDevice, e->stream));
-    CK(e, cudaMemcpyAsync(e->d_codes_in.p, codes, (size_t)S * N * code_bytes, cudaMemcpyHostToDevice, e->stream));
-    int *flags = e->d_err.as<int>() + 4;
-    CK(e, cudaMemsetAsync(e->d_err.p, 0, sizeof(int) * (N + 4), e->stream));
-    dim3 blk(32, 8), grid((unsigned)((S + 31) / 32), (unsigned)((N + 31) / 32));
-    if (code_bytes == 1)
-        transpose_codes_kernel<unsigned char, unsigned char><<<grid, blk, 0, e->stream>>>(
-            e->d_codes_in.as<unsigned char>(), e->d_codes.as<unsigned char>(), S, N, e->d_def_ones.as<unsigned char>(), flags);
-    else if (dev_bytes == 1)
-        transpose_codes_kernel<int, unsigned char><<<grid, blk, 0, e->stream>>>(
-            e->d_codes_in.as<int>(), e->d_codes.as<unsigned char>(), S, N, e->d_def_ones.as<unsigned char>(), flags);
-    else
-        transpose_codes_kernel<int, int><<<grid, blk, 0, e->stream>>>(
-            e->d_codes_in.as<int>(), e->d_codes.as<int>(), S, N, e->d_def_ones.as<unsigned char>(), flags);
-    KCHECK(e);
-    flags_to_bytes_kernel<<<(N + 127) / 128, 128, 0, e->stream>>>(flags, e->d_node_has_data.as<unsigned char>(), N);
-    KCHECK(e);
-    /* host-side range check of the codes would cost a pass over S*N bytes; the
-     * caller (the JSON front end) has already validated them (parsemodel.c:600-613). */
-    {
-        std::vector<unsigned char> flags_h(N);
-        CK(e, cudaMemcpyAsync(flags_h.data(), e->d_node_has_data.p, N, cudaMemcpyDeviceToHost, e->stream));
-        CK(e, cudaStreamSynchronize(e->stream));
-        if (flags_h != e->node_has_data_h) { e->node_has_data_h = flags_h; e->program_dirty = true; }
-    }
+    if (!e->flags_pinned) CK(e, cudaMallocHost((void **)&e->flags_pinned, 1 << 16));
+    if (N > (1 << 16)) FAIL(e, "plf_set_data: more than 65536 nodes");
     e->S = S; e->K = K; e->code_bytes = dev_bytes;
     e->TP_valid = false;
     e->have_w = false;
+    CK(e, cudaMemcpyAsync(e->d_defs.p, defs, sizeof(double) * K * n, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->d_def_const.p, dconst.data(), K, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->d_def_ones.p, dones.data(), K, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemsetAsync(e->d_err.p, 0, sizeof(int) * (N + 4), e->stream));
+    if (w) ENSURE(e, e->d_site_w, sizeof(double) * S);
+    const size_t row = (size_t)N * code_bytes;
+    if (!async) {
+        CK(e, cudaMemcpyAsync(e->d_codes_in.p, codes, (size_t)S * row, cudaMemcpyHostToDevice, e->stream));
+        if (w) { CK(e, cudaMemcpyAsync(e->d_site_w.p, w, sizeof(double) * S, cudaMemcpyHostToDevice, e->stream)); e->have_w = true; }
+        if (launch_transpose(e, 0, S, code_bytes)) return -1;
+        if (launch_flags_readback(e)) return -1;
+        /* a host-side range check of the codes would cost a pass over S*N bytes; the
+         * caller (the JSON front end) has already validated them (parsemodel.c:600-613). */
+        CK(e, cudaStreamSynchronize(e->stream));   /* dconst / dones are locals; the flags are needed now */
+        adopt_flags(e);
+        return 0;
+    }
+    /* asynchronous: chunks of whole waves of the fused kernel (sm_count CTAs x 384 sites), copied on a second
+     * stream; the queries wait chunk by chunk, so that the kernel runs while later chunks are still in flight */
+    if (!e->copy_stream) CK(e, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    const int64_t unit = (int64_t)e->sm_count * 384 * 2;
+    e->pend_bounds.clear();
+    for (int64_t s = 0; s < S; s += unit) e->pend_bounds.push_back(s);
+    if (e->pend_bounds.size() > 1 && S - e->pend_bounds.back() < unit / 4) e->pend_bounds.pop_back();   /* no tiny tail chunk */
+    e->pend_bounds.push_back(S);
+    const size_t nch = e->pend_bounds.size() - 1;
+    while (e->chunk_ev.size() < nch + 1) {
+        cudaEvent_t v;
+        CK(e, cudaEventCreateWithFlags(&v, cudaEventDisableTiming));
+        e->chunk_ev.push_back(v);
+    }
+    /* the copy stream must not overtake earlier work on the main stream that still reads the buffers */
+    CK(e, cudaEventRecord(e->chunk_ev[nch], e->stream));
+    CK(e, cudaStreamWaitEvent(e->copy_stream, e->chunk_ev[nch], 0));
+    for (size_t k = 0; k < nch; k++) {
+        const int64_t s0 = e->pend_bounds[k], s1 = e->pend_bounds[k + 1];
+        CK(e, cudaMemcpyAsync((char *)e->d_codes_in.p + (size_t)s0 * row, (const char *)codes + (size_t)s0 * row,
+                              (size_t)(s1 - s0) * row, cudaMemcpyHostToDevice, e->copy_stream));
+        if (w) CK(e, cudaMemcpyAsync(e->d_site_w.as<double>() + s0, w + s0, sizeof(double) * (s1 - s0),
+                                     cudaMemcpyHostToDevice, e->copy_stream));
+        CK(e, cudaEventRecord(e->chunk_ev[k], e->copy_stream));
+    }
+    if (w) e->have_w = true;
+    e->pend_in_bytes = code_bytes;
+    e->pend_active = true;
+    CK(e, cudaStreamSynchronize(e->stream));       /* dconst / dones are locals */
     return 0;
+}
+
+extern "C" int plf_set_data(plf_engine *e, int64_t S, int K, const double *defs, const void *codes, int code_bytes)
+{
+    return set_data_common(e, S, K, defs, codes, code_bytes, nullptr, false);
+}
+
+extern "C" int plf_set_data_async(plf_engine *e, int64_t S, int K, const double *defs, const void *codes, int code_bytes,
+                                  const double *site_weights)
+{
+    return set_data_common(e, S, K, defs, codes, code_bytes, site_weights, true);
 }
 
 extern "C" int plf_set_site_weights(plf_engine *e, const double *w)
@@ -878,11 +981,18 @@ static int run_fused(plf_engine *e, Query &q)
     int per_sm = 0;
     CK(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, bd, smem));
     if (per_sm < 1) FAIL(e, "fused kernel cannot be resident (smem %zu)", smem);
-    const int64_t ntiles = (e->S + bd - 1) / bd;
+    /* one launch per chunk of sites: a single chunk normally, the upload's chunks while it is still in flight */
+    const bool pipelined = e->pend_active;
+    std::vector<int64_t> bounds;
+    if (pipelined) bounds = e->pend_bounds; else { bounds.push_back(0); bounds.push_back(e->S); }
+    const size_t nchunk = bounds.size() - 1;
+    int64_t longest = 0;
+    for (size_t k = 0; k < nchunk; k++) longest = std::max(longest, bounds[k + 1] - bounds[k]);
+    const int64_t ntiles = (longest + bd - 1) / bd;
     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)per_sm * e->sm_count);
     const size_t T = (size_t)grid * bd;
 
-    ENSURE(e, e->d_block_ll, sizeof(double) * grid);
+    ENSURE(e, e->d_block_ll, sizeof(double) * grid * nchunk);
     ENSURE(e, e->d_sum, sizeof(double) * (1 + e->E + (size_t)e->N * e->n));
     ENSURE(e, e->d_err, sizeof(int) * (e->N + 4));
     CK(e, cudaMemsetAsync(e->d_err.p, 0, sizeof(int), e->stream));
@@ -892,7 +1002,7 @@ static int run_fused(plf_engine *e, Query &q)
     if (edge) {
         ENSURE(e, e->d_scratch, sizeof(double4) * (size_t)e->C * e->nslots * T);
         ENSURE(e, e->d_scratchS, sizeof(unsigned int) * (size_t)e->nslots * T);
-        ENSURE(e, e->d_block_edge, sizeof(double) * (size_t)grid * e->E);
+        ENSURE(e, e->d_block_edge, sizeof(double) * (size_t)grid * e->E * nchunk);
         a.scratch = e->d_scratch.as<double4>(); a.scratchS = e->d_scratchS.as<unsigned int>();
         a.block_edge = e->d_block_edge.as<double>();
         if (q.edge_mask_h) {
@@ -907,17 +1017,30 @@ static int run_fused(plf_engine *e, Query &q)
         }
     }
     CK(e, cudaEventRecord(e->ev[3], e->stream));
-    CK(e, cudaEventRecord(e->ev[3], e->stream));
-    kern<<<grid, bd, smem, e->stream>>>(a);
-    KCHECK(e);
+    for (size_t k = 0; k < nchunk; k++) {
+        a.s_begin = bounds[k]; a.s_end = bounds[k + 1];
+        a.block_ll = e->d_block_ll.as<double>() + k * (size_t)grid;
+        if (edge) a.block_edge = e->d_block_edge.as<double>() + k * (size_t)grid * e->E;
+        if (pipelined) {
+            /* this chunk's codes and weights have arrived; bring them into the node-major layout */
+            CK(e, cudaStreamWaitEvent(e->stream, e->chunk_ev[k], 0));
+            if (launch_transpose(e, a.s_begin, a.s_end, e->pend_in_bytes)) return -1;
+        }
+        kern<<<grid, bd, smem, e->stream>>>(a);
+        KCHECK(e);
+    }
     CK(e, cudaEventRecord(e->ev[4], e->stream));
     e->kernel_timed = true;
+    if (pipelined && launch_flags_readback(e)) return -1;
+    const int rows = grid * (int)nchunk;
+    a.block_ll = e->d_block_ll.as<double>();
+    if (edge) a.block_edge = e->d_block_edge.as<double>();
     double *dsum = e->d_sum.as<double>();
-    sum_rows_kernel<<<1, 32, 0, e->stream>>>(a.block_ll, grid, 1, dsum);
+    sum_rows_kernel<<<1, 32, 0, e->stream>>>(a.block_ll, rows, 1, dsum);
     KCHECK(e);
     size_t nsum = 1;
     if (edge && !q.site_edge) {
-        sum_rows_kernel<<<(e->E + 127) / 128, 128, 0, e->stream>>>(a.block_edge, grid, e->E, dsum + 1);
+        sum_rows_kernel<<<(e->E + 127) / 128, 128, 0, e->stream>>>(a.block_edge, rows, e->E, dsum + 1);
         KCHECK(e);
         nsum = 1 + e->E;
     }
@@ -936,6 +1059,11 @@ static int run_fused(plf_engine *e, Query &q)
     CK(e, cudaMemcpyAsync(&herr, e->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     if (q.site_ll) CK(e, cudaMemcpyAsync(q.site_ll, e->d_site_ll.p, sizeof(double) * e->S, cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
+    if (pipelined) {
+        e->pend_active = false;
+        /* the program was compiled for the previous data's pattern of data-carrying nodes: redo if that changed */
+        if (adopt_flags(e)) return 1;
+    }
     if (q.site_edge && copy_site_matrix(e, e->d_edge_site.as<double>(), e->E, e->S, q.site_edge)) return -1;
     if (herr && (q.sum_ll || q.sum_edge)) FAIL(e, "a site with non-zero weight has zero likelihood");
     if (q.sum_ll) *q.sum_ll = hs[0];
@@ -1099,17 +1227,20 @@ static int run_generic(plf_engine *e, Query &q)
     return 0;
 }
 
-/* common driver: matrices, path selection, timing */
-static int run_query(plf_engine *e, Query &q, bool need_D, const double *l_hi, const double *l_lo, int kind)
+/* common driver: matrices, path selection, timing.  Returns 1 when the query has to be repeated. */
+static int run_query_once(plf_engine *e, Query &q, bool need_D, const double *l_hi, const double *l_lo, int kind)
 {
     if (e->S == 0 || e->n == 0 || e->N == 0) FAIL(e, "engine is not fully configured (tree, model and data are required)");
     CK(e, cudaSetDevice(e->device));
     bool use_fused = fused_applicable(e) && !q.want_marg;
     if (e->path == PLF_PATH_GENERIC) use_fused = false;
+    /* an upload in flight is overlapped with the fused kernel only; it needs a program built for earlier data */
+    if (e->pend_active && !(use_fused && e->node_has_data_h.size() == (size_t)e->N) && resolve_pending(e)) return -1;
     if (use_fused) {
         if (ensure_program(e)) return -1;
         if (!fused_fits(e, q.want_edge)) use_fused = false;
     }
+    if (!use_fused && resolve_pending(e)) return -1;
     if (e->path == PLF_PATH_FUSED4 && !use_fused) FAIL(e, "the fused 4-state path does not apply to this query");
     CK(e, cudaEventRecord(e->ev[0], e->stream));
     if (ensure_matrices(e, need_D)) return -1;
@@ -1136,6 +1267,13 @@ static int run_query(plf_engine *e, Query &q, bool need_D, const double *l_hi, c
     e->ms_kernel = 0.f;
     if (e->kernel_timed) cudaEventElapsedTime(&e->ms_kernel, e->ev[3], e->ev[4]);
     return 0;
+}
+
+static int run_query(plf_engine *e, Query &q, bool need_D, const double *l_hi, const double *l_lo, int kind)
+{
+    int rc = run_query_once(e, q, need_D, l_hi, l_lo, kind);
+    if (rc == 1) rc = run_query_once(e, q, need_D, l_hi, l_lo, kind);
+    return rc;
 }
 
 extern "C" int plf_ll(plf_engine *e, double *site_ll, double *sum)

@@ -89,6 +89,27 @@ class Engine:
         self.S = S
         self._ck(self._lib.plf_set_data(self._h, S, defs.shape[0], _ptr(defs), ctypes.c_void_p(codes_ptr), code_bytes))
 
+    def set_data_async(self, defs, codes, weights=None):
+        """plf_set_data_async: the upload overlaps the next query.  The engine keeps references to the host
+        arrays until then (they must not be modified in between)."""
+        defs = _f64(defs)
+        if codes.dtype == np.uint8:
+            cb = 1
+        else:
+            codes = np.ascontiguousarray(codes, dtype=np.int32)
+            cb = 4
+        codes = np.ascontiguousarray(codes)
+        weights = None if weights is None else _f64(weights)
+        self._pending_host = (codes, weights)
+        self.S = codes.shape[0]
+        self._ck(self._lib.plf_set_data_async(self._h, self.S, defs.shape[0], _ptr(defs), _ptr(codes), cb, _ptr(weights)))
+
+    def set_data_async_ptr(self, defs, codes_ptr, S, weights_ptr=None, code_bytes=1):
+        defs = _f64(defs)
+        self.S = S
+        self._ck(self._lib.plf_set_data_async(self._h, S, defs.shape[0], _ptr(defs), ctypes.c_void_p(codes_ptr), code_bytes,
+                                              ctypes.c_void_p(weights_ptr) if weights_ptr else None))
+
     def set_site_weights(self, w):
         self._ck(self._lib.plf_set_site_weights(self._h, _ptr(_f64(w))))
 
