@@ -91,6 +91,24 @@ struct F4Args {
     int *error_flag;
 };
 
+/*
+ * Constant-memory variant (CM): the compact matrices of the internal-child edges live in __constant__
+ * memory and the tree program travels as a kernel parameter.  Everything the op loop decodes is then
+ * warp-uniform by construction (loop counters -> constant bank), so the compiler keeps it in uniform
+ * registers and the 4x4 matrices enter the DFMAs as uniform operands (LDCU) instead of costing one
+ * shared-memory wavefront per 16 bytes -- the kernel is bound by the LSU pipe, not by fp64 issue.
+ */
+#define F4_CM_MAXD 4000      /* doubles per matrix set: C * Ei * 16 <= 4000 (2 sets = 64000 of the 65536 bytes) */
+#define F4_CM_MAXOPS 64
+#define F4_CM_MAXCH 128
+__constant__ double f4_cP[F4_CM_MAXD];
+__constant__ double f4_cF[F4_CM_MAXD];
+
+struct F4Prog {
+    F4Op ops[F4_CM_MAXOPS];
+    F4Child ch[F4_CM_MAXCH];
+};
+
 __device__ __forceinline__ void f4_matvec(const double *__restrict__ M, const double v[4], double out[4])
 {
     const double2 *M2 = reinterpret_cast<const double2 *>(M);
@@ -118,6 +136,48 @@ __device__ __forceinline__ void f4_matvec_t(const double *__restrict__ M, const 
         out[1] = fma(a.y, v[i], out[1]);
         out[2] = fma(b.x, v[i], out[2]);
         out[3] = fma(b.y, v[i], out[3]);
+    }
+}
+
+/* out = M v with M = base[off..] (shared / global memory) or, for CM, the constant set WHICH (0 = P, 1 = F) */
+template <bool CM, int WHICH>
+__device__ __forceinline__ void f4_mv(const double *__restrict__ base, int off, const double v[4], double out[4])
+{
+    if (CM) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            double r;
+            if (WHICH) {
+                r = f4_cF[off + 4 * i] * v[0];
+                r = fma(f4_cF[off + 4 * i + 1], v[1], r);
+                r = fma(f4_cF[off + 4 * i + 2], v[2], r);
+                r = fma(f4_cF[off + 4 * i + 3], v[3], r);
+            } else {
+                r = f4_cP[off + 4 * i] * v[0];
+                r = fma(f4_cP[off + 4 * i + 1], v[1], r);
+                r = fma(f4_cP[off + 4 * i + 2], v[2], r);
+                r = fma(f4_cP[off + 4 * i + 3], v[3], r);
+            }
+            out[i] = r;
+        }
+    } else {
+        f4_matvec(base + off, v, out);
+    }
+}
+
+/* out = P^T v */
+template <bool CM>
+__device__ __forceinline__ void f4_mvt(const double *__restrict__ base, int off, const double v[4], double out[4])
+{
+    if (CM) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) out[j] = f4_cP[off + j] * v[0];
+#pragma unroll
+        for (int i = 1; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) out[j] = fma(f4_cP[off + 4 * i + j], v[i], out[j]);
+    } else {
+        f4_matvec_t(base + off, v, out);
     }
 }
 
@@ -184,7 +244,7 @@ __device__ __forceinline__ double f4_warp_sum2(double a, double b, int lane)
  * Outside step specialised for a node with exactly two children of kinds (K0, K1) in
  * {(CUR, TIP), (CUR, STACK), (TIP, TIP)}: straight-line code, no filler factors.
  */
-template <int C, int BD, int K0, int K1, bool PACK>
+template <int C, int BD, int K0, int K1, bool PACK, bool CM>
 __device__ __forceinline__ void f4_outside2(const F4Args &a, const F4Op &op, const F4Child &c0, const F4Child &c1,
                                             bool from_slot, double *cur, const unsigned char *tile, const double *defs_s,
                                             const double *Pint, const double *Fint, const double *TP, const double *TF,
@@ -199,7 +259,7 @@ __device__ __forceinline__ void f4_outside2(const F4Args &a, const F4Op &op, con
     if (K0 == F4_KIND_TIP) code0 = f4_code<BD, PACK>(tile, c0.code_row, tid); else bc0 = (a.scratchS[(size_t)c0.slot * T + gtid] >> 6) & 1;
     if (K1 == F4_KIND_TIP) code1 = f4_code<BD, PACK>(tile, c1.code_row, tid); else bc1 = (a.scratchS[(size_t)c1.slot * T + gtid] >> 6) & 1;
     x0 = 0.0; x1 = 0.0;
-#pragma unroll 2
+#pragma unroll (CM ? 1 : 2)
     for (int c = 0; c < C; c++) {
         /* loads of this category first */
         double l0[4], l1[4], fa[4];
@@ -233,8 +293,8 @@ __device__ __forceinline__ void f4_outside2(const F4Args &a, const F4Op &op, con
             f4_ld4(TP + c * tpstride + (c0.mat * a.K + code0) * 4, em0);
             f4_ld4(TF + c * tpstride + (c0.mat * a.K + code0) * 4, y0);
         } else {
-            f4_matvec(Pint + c * pstride + c0.mat * 16, l0, em0);
-            f4_matvec(Fint + c * pstride + c0.mat * 16, l0, y0);
+            f4_mv<CM, 0>(Pint, c * pstride + c0.mat * 16, l0, em0);
+            f4_mv<CM, 1>(Fint, c * pstride + c0.mat * 16, l0, y0);
             if (bc0) {
 #pragma unroll
                 for (int i = 0; i < 4; i++) { em0[i] = l0[i]; if (a.f_zero_rowsum) y0[i] = 0.0; }
@@ -244,8 +304,8 @@ __device__ __forceinline__ void f4_outside2(const F4Args &a, const F4Op &op, con
             f4_ld4(TP + c * tpstride + (c1.mat * a.K + code1) * 4, em1);
             f4_ld4(TF + c * tpstride + (c1.mat * a.K + code1) * 4, y1);
         } else {
-            f4_matvec(Pint + c * pstride + c1.mat * 16, l1, em1);
-            f4_matvec(Fint + c * pstride + c1.mat * 16, l1, y1);
+            f4_mv<CM, 0>(Pint, c * pstride + c1.mat * 16, l1, em1);
+            f4_mv<CM, 1>(Fint, c * pstride + c1.mat * 16, l1, y1);
             if (bc1) {
 #pragma unroll
                 for (int i = 0; i < 4; i++) { em1[i] = l1[i]; if (a.f_zero_rowsum) y1[i] = 0.0; }
@@ -262,7 +322,7 @@ __device__ __forceinline__ void f4_outside2(const F4Args &a, const F4Op &op, con
         x1 += xv;
         if (K0 != F4_KIND_TIP) {
             double fb[4];
-            f4_matvec_t(Pint + c * pstride + c0.mat * 16, fe0, fb);
+            f4_mvt<CM>(Pint, c * pstride + c0.mat * 16, fe0, fb);
             if (K0 == F4_KIND_CUR) {
 #pragma unroll
                 for (int i = 0; i < 4; i++) cur[(c * 4 + i) * BD + tid] = fb[i];
@@ -272,9 +332,179 @@ __device__ __forceinline__ void f4_outside2(const F4Args &a, const F4Op &op, con
         }
         if (K1 != F4_KIND_TIP) {
             double fb[4];
-            f4_matvec_t(Pint + c * pstride + c1.mat * 16, fe1, fb);
+            f4_mvt<CM>(Pint, c * pstride + c1.mat * 16, fe1, fb);
             /* the child's inside vector is dead after this op: its slot carries fn down */
             a.scratch[((size_t)c1.slot * C + c) * T + gtid] = make_double4(fb[0], fb[1], fb[2], fb[3]);
+        }
+    }
+}
+
+
+/* root of one site: likelihood of each category, combined over categories with their scale counts */
+template <int C, int BD>
+__device__ __forceinline__ void f4_root_site(const F4Args &a, const double *cur, int tid, int curf, const double *prior,
+                                             const int *ktot, int *kcat, double &site_m, int &site_k, bool &have)
+{
+    constexpr int bd = BD;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            double r[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) r[i] = cur[(c * 4 + i) * bd + tid];
+            double lh;
+            if (a.root_mode == PLF_ROOT_NONE) lh = (r[0] + r[1]) + (r[2] + r[3]);
+            else if (a.root_mode == PLF_ROOT_UNIFORM) lh = curf ? r[0] : ((r[0] + r[1]) + (r[2] + r[3])) * 0.25;
+            else if (a.root_mode == PLF_ROOT_EQUILIBRIUM && curf) lh = r[0];
+            else {
+                lh = a.root_vec[0] * r[0];
+                lh = fma(a.root_vec[1], r[1], lh);
+                lh = fma(a.root_vec[2], r[2], lh);
+                lh = fma(a.root_vec[3], r[3], lh);
+            }
+            const double v = prior[c] * lh;
+            kcat[c] = (v > 0.0) ? ktot[c] : INT_MIN;
+            if (v > 0.0) {
+                if (!have) { site_m = v; site_k = ktot[c]; have = true; }
+                else if (ktot[c] > site_k) { site_m = scalbn(site_m, PLF_SCALE_BITS * (site_k - ktot[c])) + v; site_k = ktot[c]; }
+                else if (ktot[c] == site_k) site_m += v;
+                else site_m += scalbn(v, PLF_SCALE_BITS * (ktot[c] - site_k));
+            }
+        }
+}
+
+/* The same, out of line.  CM kernels call this one: with the root code inlined into the tile loop the
+ * compiler stops treating the op loops as warp-uniform (observed with nvcc 12.9), and the uniform
+ * constant loads are the point of those kernels. */
+template <int C, int BD>
+__device__ __noinline__ void f4_root_site_ool(const F4Args &a, const double *cur, int tid, int curf, const double *prior,
+                                              const int *ktot, int *kcat, double &site_m, int &site_k, bool &have)
+{
+    f4_root_site<C, BD>(a, cur, tid, curf, prior, ktot, kcat, site_m, site_k, have);
+}
+
+/* values of the kernel's frame that the out-of-line outside step needs */
+struct F4Ctx {
+    double *cur, *accE;
+    const unsigned char *tile;
+    const double *defs_s, *Pint, *Fint, *TP, *TF;
+    const F4Child *chp;
+    int pstride, tpstride, tid, lane, warp;
+    size_t T, gtid;
+    int64_t site;
+    bool valid;
+};
+
+/*
+ * Outside step for a node with any number of children (1..F4_MAXD) of any kind (non-CM kernels only).
+ */
+template <int C, int BD, bool PACK, bool CM>
+__device__ __forceinline__ void f4_outside_general(const F4Args &a, const F4Op &op, bool from_slot, const F4Ctx &k)
+{
+    constexpr int bd = BD;
+    double *cur = k.cur, *accE = k.accE;
+    const unsigned char *tile = k.tile;
+    const double *defs_s = k.defs_s, *Pint = k.Pint, *Fint = k.Fint, *TP = k.TP, *TF = k.TF;
+    const F4Child *chp = k.chp;
+    const int pstride = k.pstride, tpstride = k.tpstride, tid = k.tid, lane = k.lane, warp = k.warp;
+    const size_t T = k.T, gtid = k.gtid;
+    const int64_t site = k.site;
+    const bool valid = k.valid;
+    double basev[4] = {1.0, 1.0, 1.0, 1.0};
+    if (op.code_row >= 0) f4_ld4(defs_s + f4_code<BD, PACK>(tile, op.code_row, tid) * 4, basev);
+    /* children descriptors and category-independent lookups */
+    int kinds[F4_MAXD], mats[F4_MAXD], slots[F4_MAXD], edges[F4_MAXD], codes[F4_MAXD], bcs[F4_MAXD];
+#pragma unroll
+    for (int j = 0; j < F4_MAXD; j++) {
+        kinds[j] = -1; mats[j] = 0; slots[j] = 0; edges[j] = 0; codes[j] = 0; bcs[j] = 0;
+        if (j < op.nchild) {
+            const F4Child ch = chp[op.first_child + j];
+            kinds[j] = ch.kind; mats[j] = ch.mat; slots[j] = ch.slot; edges[j] = ch.edge;
+            if (ch.kind == F4_KIND_TIP) codes[j] = f4_code<BD, PACK>(tile, ch.code_row, tid);
+            else bcs[j] = (a.scratchS[(size_t)ch.slot * T + gtid] >> 6) & 1;
+        }
+    }
+    double x[F4_MAXD] = {0.0, 0.0, 0.0};
+    const unsigned int sword_a = a.scratchS[(size_t)op.slot * T + gtid];
+#pragma unroll 1
+    for (int c = 0; c < C; c++) {
+        double fa[4];
+        const size_t so_a = ((size_t)op.slot * C + c) * T + gtid;
+        if (from_slot) {
+            double4 f4v = a.scratch[so_a];
+            fa[0] = f4v.x; fa[1] = f4v.y; fa[2] = f4v.z; fa[3] = f4v.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) fa[i] = cur[(c * 4 + i) * bd + tid];
+        }
+        const int sa = (sword_a >> (8 * c)) & 63;
+#pragma unroll
+        for (int i = 0; i < 4; i++) fa[i] *= basev[i];
+        if (sa) {
+            const double sc = __hiloint2double((1023 + PLF_SCALE_BITS * sa) << 20, 0);
+#pragma unroll
+            for (int i = 0; i < 4; i++) fa[i] *= sc;
+        }
+        double em[F4_MAXD][4], y[F4_MAXD][4];
+#pragma unroll
+        for (int j = 0; j < F4_MAXD; j++) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) { em[j][i] = 1.0; y[j][i] = 0.0; }
+            if (kinds[j] == F4_KIND_TIP) {
+                f4_ld4(TP + c * tpstride + (mats[j] * a.K + codes[j]) * 4, em[j]);
+                f4_ld4(TF + c * tpstride + (mats[j] * a.K + codes[j]) * 4, y[j]);
+            } else if (kinds[j] >= 0) {
+                double4 l4 = a.scratch[((size_t)slots[j] * C + c) * T + gtid];
+                double lv[4] = {l4.x, l4.y, l4.z, l4.w};
+                if (bcs[j]) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) em[j][i] = lv[i];
+                } else {
+                    f4_mv<CM, 0>(Pint, c * pstride + mats[j] * 16, lv, em[j]);
+                }
+                if (!(bcs[j] && a.f_zero_rowsum)) f4_mv<CM, 1>(Fint, c * pstride + mats[j] * 16, lv, y[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < F4_MAXD; j++) {
+            if (kinds[j] >= 0) {
+                double fe[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    double f = fa[i];
+#pragma unroll
+                    for (int j2 = 0; j2 < F4_MAXD; j2++) if (j2 != j) f *= em[j2][i];
+                    fe[i] = f;
+                }
+                double xv = fe[0] * y[j][0];
+                xv = fma(fe[1], y[j][1], xv);
+                xv = fma(fe[2], y[j][2], xv);
+                xv = fma(fe[3], y[j][3], xv);
+                x[j] += xv;
+                if (kinds[j] != F4_KIND_TIP) {
+                    double fb[4];
+                    f4_mvt<CM>(Pint, c * pstride + mats[j] * 16, fe, fb);
+                    if (kinds[j] == F4_KIND_CUR) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) cur[(c * 4 + i) * bd + tid] = fb[i];
+                    } else {
+                        /* the child's inside vector is dead after this op: its slot carries fn down */
+                        a.scratch[((size_t)slots[j] * C + c) * T + gtid] = make_double4(fb[0], fb[1], fb[2], fb[3]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < F4_MAXD; j++) {
+        if (kinds[j] >= 0) {
+            const int e = edges[j];
+            const bool me = !a.edge_mask || a.edge_mask[e];
+            if (a.edge_site_out) {
+                if (valid && me) a.edge_site_out[(size_t)e * a.S + site] = x[j];
+            } else {
+                double xs = f4_warp_sum(x[j]);
+                if (lane == 0 && me) accE[warp * a.E + e] += xs;
+            }
         }
     }
 }
@@ -285,9 +515,11 @@ __device__ __forceinline__ void f4_outside2(const F4Args &a, const F4Op &op, con
  * The dynamic shared memory layout below is mirrored on the host by f4_smem_bytes().
  */
 /* STAGED: 2 = all tables in shared memory, 1 = all but TF (read through L1), 0 = none.
- * PACK: the tile's character codes are stored two per byte (needs K <= 16). */
-template <int C, bool EDGE, int BD, int STAGED, bool PACK>
-__global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
+ * PACK: the tile's character codes are stored two per byte (needs K <= 16).
+ * CM: internal-edge matrices in constant memory and the program in `prog` (see above); STAGED then
+ *     only concerns the tip tables. */
+template <int C, bool EDGE, int BD, int STAGED, bool PACK, bool CM>
+__global__ void __launch_bounds__(BD) fused4_kernel(const F4Args a, const __grid_constant__ F4Prog prog)
 {
     extern __shared__ __align__(16) unsigned char f4_smem[];
     const int tid = threadIdx.x;
@@ -297,10 +529,19 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
     const int64_t T = (int64_t)gridDim.x * bd;
     const int64_t gtid = (int64_t)blockIdx.x * bd + tid;
 
+    /* pointers inside the argument struct are not assumed to be global memory by default */
+
+
+
+
+
+
     /* ---- carve shared memory ---- */
     size_t off = 0;
-    F4Op *ops = reinterpret_cast<F4Op *>(f4_smem + off); off = f4_align16(off + sizeof(F4Op) * a.nops);
-    F4Child *chs = reinterpret_cast<F4Child *>(f4_smem + off); off = f4_align16(off + sizeof(F4Child) * a.nchildren);
+    F4Op *ops_s = reinterpret_cast<F4Op *>(f4_smem + off); off = f4_align16(off + (CM ? 0 : sizeof(F4Op) * a.nops));
+    F4Child *chs_s = reinterpret_cast<F4Child *>(f4_smem + off); off = f4_align16(off + (CM ? 0 : sizeof(F4Child) * a.nchildren));
+#define F4_OP(i) (CM ? prog.ops[i] : ops_s[i])
+#define F4_CH(i) (CM ? prog.ch[i] : chs_s[i])
     double *cur = reinterpret_cast<double *>(f4_smem + off); off = f4_align16(off + sizeof(double) * 4 * C * bd);   /* [C][4][bd] */
     double *accE = reinterpret_cast<double *>(f4_smem + off); off = f4_align16(off + (EDGE ? sizeof(double) * nwarp * a.E : 0));
     double *stack = reinterpret_cast<double *>(f4_smem + off); off = f4_align16(off + (EDGE ? 0 : sizeof(double) * 4 * C * bd * a.stack_depth));
@@ -310,7 +551,7 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
     double *defs_s = reinterpret_cast<double *>(f4_smem + off); off = f4_align16(off + sizeof(double) * 4 * a.K);
     const double *Pint = a.Pint, *TP = a.TP, *Fint = a.Fint, *TF = a.TF;
     if (STAGED) {
-        const size_t nP = (size_t)C * a.Ei * 16, nT = (size_t)C * a.Et * a.K * 4;
+        const size_t nP = CM ? 0 : (size_t)C * a.Ei * 16, nT = (size_t)C * a.Et * a.K * 4;
         double *sP = reinterpret_cast<double *>(f4_smem + off); off += sizeof(double) * nP;
         double *sT = reinterpret_cast<double *>(f4_smem + off); off += sizeof(double) * nT;
         double *sF = reinterpret_cast<double *>(f4_smem + off); off += EDGE ? sizeof(double) * nP : 0;
@@ -320,8 +561,10 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
         Pint = sP; TP = sT; Fint = sF;
         if (STAGED == 2) TF = sTF;
     }
-    for (int i = tid; i < a.nops; i += bd) ops[i] = a.ops[i];
-    for (int i = tid; i < a.nchildren; i += bd) chs[i] = a.children[i];
+    if (!CM) {
+        for (int i = tid; i < a.nops; i += bd) ops_s[i] = a.ops[i];
+        for (int i = tid; i < a.nchildren; i += bd) chs_s[i] = a.children[i];
+    }
     for (int i = tid; i < a.K; i += bd) dconst[i] = a.def_const[i];
     for (int i = tid; i < 4 * a.K; i += bd) defs_s[i] = a.defs[i];
     if (EDGE) for (int i = tid; i < nwarp * a.E; i += bd) accE[i] = 0.0;
@@ -360,7 +603,7 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
         for (int c = 0; c < C; c++) ktot[c] = 0;
 #pragma unroll 1
         for (int o = 0; o < a.nops; o++) {
-            const F4Op op = ops[o];
+            const F4Op op = F4_OP(o);
             if (!EDGE && op.spill_before) {
 #pragma unroll
                 for (int c = 0; c < C; c++)
@@ -385,7 +628,7 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
             }
 #pragma unroll 1
             for (int j = 0; j < op.nchild; j++) {
-                const F4Child ch = chs[op.first_child + j];
+                const F4Child ch = F4_CH(op.first_child + j);
                 double em[C][4];
                 int bc;
                 if (ch.kind == F4_KIND_TIP) {
@@ -424,9 +667,8 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
 #pragma unroll
                             for (int i = 0; i < 4; i++) em[c][i] = v[c][i];
                     } else {
-                        const double *pm = Pint + ch.mat * 16;
 #pragma unroll
-                        for (int c = 0; c < C; c++) f4_matvec(pm + c * pstride, v[c], em[c]);
+                        for (int c = 0; c < C; c++) f4_mv<CM, 0>(Pint, ch.mat * 16 + c * pstride, v[c], em[c]);
                     }
                 }
                 if (first) {
@@ -465,30 +707,8 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
         int site_k = 0;
         bool have = false;
         int kcat[C];
-#pragma unroll
-        for (int c = 0; c < C; c++) {
-            double r[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) r[i] = cur[(c * 4 + i) * bd + tid];
-            double lh;
-            if (a.root_mode == PLF_ROOT_NONE) lh = (r[0] + r[1]) + (r[2] + r[3]);
-            else if (a.root_mode == PLF_ROOT_UNIFORM) lh = curf ? r[0] : ((r[0] + r[1]) + (r[2] + r[3])) * 0.25;
-            else if (a.root_mode == PLF_ROOT_EQUILIBRIUM && curf) lh = r[0];
-            else {
-                lh = a.root_vec[0] * r[0];
-                lh = fma(a.root_vec[1], r[1], lh);
-                lh = fma(a.root_vec[2], r[2], lh);
-                lh = fma(a.root_vec[3], r[3], lh);
-            }
-            const double v = prior[c] * lh;
-            kcat[c] = (v > 0.0) ? ktot[c] : INT_MIN;
-            if (v > 0.0) {
-                if (!have) { site_m = v; site_k = ktot[c]; have = true; }
-                else if (ktot[c] > site_k) { site_m = scalbn(site_m, PLF_SCALE_BITS * (site_k - ktot[c])) + v; site_k = ktot[c]; }
-                else if (ktot[c] == site_k) site_m += v;
-                else site_m += scalbn(v, PLF_SCALE_BITS * (ktot[c] - site_k));
-            }
-        }
+        if (CM) f4_root_site_ool<C, BD>(a, cur, tid, curf, prior, ktot, kcat, site_m, site_k, have);
+        else f4_root_site<C, BD>(a, cur, tid, curf, prior, ktot, kcat, site_m, site_k, have);
         {
             const double c_hi = 177.445678223346, c_lo = 5.936759843446527e-15;   /* 256 ln 2 */
             double ll = log(site_m);
@@ -520,14 +740,14 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
         }
 #pragma unroll 1
         for (int o = a.nops - 1; o >= 0; o--) {
-            const F4Op op = ops[o];
+            const F4Op op = F4_OP(o);
             /* fn_a comes from "cur" if this node was consumed from registers by its parent, else from its slot */
-            const bool from_slot = (o != a.nops - 1) && ops[o + 1].spill_before;
+            const bool from_slot = (o != a.nops - 1) && F4_OP(o + 1).spill_before;
             /* the next node (o-1) reads these slab lines: start fetching them */
             if (o > 0) {
-                const F4Op nx = ops[o - 1];
+                const F4Op nx = F4_OP(o - 1);
                 for (int j = 0; j < nx.nchild; j++) {
-                    const F4Child nc = chs[nx.first_child + j];
+                    const F4Child nc = F4_CH(nx.first_child + j);
                     if (nc.kind != F4_KIND_TIP) {
 #pragma unroll
                         for (int c = 0; c < C; c++) f4_prefetch(&a.scratch[((size_t)nc.slot * C + c) * T + gtid]);
@@ -535,127 +755,38 @@ __global__ void __launch_bounds__(BD) fused4_kernel(F4Args a)
                 }
             }
             if (op.nchild == 2) {
-                const F4Child c0 = chs[op.first_child], c1 = chs[op.first_child + 1];
+                const F4Child c0 = F4_CH(op.first_child), c1 = F4_CH(op.first_child + 1);
                 double x0, x1;
                 if (c0.kind == F4_KIND_CUR && c1.kind == F4_KIND_TIP)
-                    f4_outside2<C, BD, F4_KIND_CUR, F4_KIND_TIP, PACK>(a, op, c0, c1, from_slot, cur, tile, defs_s, Pint, Fint, TP, TF,
+                    f4_outside2<C, BD, F4_KIND_CUR, F4_KIND_TIP, PACK, CM>(a, op, c0, c1, from_slot, cur, tile, defs_s, Pint, Fint, TP, TF,
                                                                  pstride, tpstride, (size_t)T, (size_t)gtid, tid, x0, x1);
                 else if (c0.kind == F4_KIND_CUR)
-                    f4_outside2<C, BD, F4_KIND_CUR, F4_KIND_STACK, PACK>(a, op, c0, c1, from_slot, cur, tile, defs_s, Pint, Fint, TP, TF,
+                    f4_outside2<C, BD, F4_KIND_CUR, F4_KIND_STACK, PACK, CM>(a, op, c0, c1, from_slot, cur, tile, defs_s, Pint, Fint, TP, TF,
                                                                    pstride, tpstride, (size_t)T, (size_t)gtid, tid, x0, x1);
                 else
-                    f4_outside2<C, BD, F4_KIND_TIP, F4_KIND_TIP, PACK>(a, op, c0, c1, from_slot, cur, tile, defs_s, Pint, Fint, TP, TF,
+                    f4_outside2<C, BD, F4_KIND_TIP, F4_KIND_TIP, PACK, CM>(a, op, c0, c1, from_slot, cur, tile, defs_s, Pint, Fint, TP, TF,
                                                                  pstride, tpstride, (size_t)T, (size_t)gtid, tid, x0, x1);
                 const bool m0 = !a.edge_mask || a.edge_mask[c0.edge];
                 const bool m1 = !a.edge_mask || a.edge_mask[c1.edge];
                 if (a.edge_site_out) {
                     if (valid && m0) a.edge_site_out[(size_t)c0.edge * a.S + site] = x0;
                     if (valid && m1) a.edge_site_out[(size_t)c1.edge * a.S + site] = x1;
-                } else if (m0 || m1) {
+                } else {
+                    /* the butterfly runs unconditionally: a shuffle under a condition the compiler cannot prove
+                     * warp-uniform (the mask comes from memory) makes it treat the whole op loop as divergent */
                     const double r = f4_warp_sum2(m0 ? x0 : 0.0, m1 ? x1 : 0.0, lane);
                     if (lane == 0 && m0) accE[warp * a.E + c0.edge] += r;
                     if (lane == 16 && m1) accE[warp * a.E + c1.edge] += r;
                 }
                 continue;
             }
-            double basev[4] = {1.0, 1.0, 1.0, 1.0};
-            if (op.code_row >= 0) f4_ld4(defs_s + f4_code<BD, PACK>(tile, op.code_row, tid) * 4, basev);
-            /* children descriptors and category-independent lookups */
-            int kinds[F4_MAXD], mats[F4_MAXD], slots[F4_MAXD], edges[F4_MAXD], codes[F4_MAXD], bcs[F4_MAXD];
-#pragma unroll
-            for (int j = 0; j < F4_MAXD; j++) {
-                kinds[j] = -1; mats[j] = 0; slots[j] = 0; edges[j] = 0; codes[j] = 0; bcs[j] = 0;
-                if (j < op.nchild) {
-                    const F4Child ch = chs[op.first_child + j];
-                    kinds[j] = ch.kind; mats[j] = ch.mat; slots[j] = ch.slot; edges[j] = ch.edge;
-                    if (ch.kind == F4_KIND_TIP) codes[j] = f4_code<BD, PACK>(tile, ch.code_row, tid);
-                    else bcs[j] = (a.scratchS[(size_t)ch.slot * T + gtid] >> 6) & 1;
-                }
-            }
-            double x[F4_MAXD] = {0.0, 0.0, 0.0};
-            const unsigned int sword_a = a.scratchS[(size_t)op.slot * T + gtid];
-#pragma unroll 1
-            for (int c = 0; c < C; c++) {
-                double fa[4];
-                const size_t so_a = ((size_t)op.slot * C + c) * T + gtid;
-                if (from_slot) {
-                    double4 f4v = a.scratch[so_a];
-                    fa[0] = f4v.x; fa[1] = f4v.y; fa[2] = f4v.z; fa[3] = f4v.w;
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 4; i++) fa[i] = cur[(c * 4 + i) * bd + tid];
-                }
-                const int sa = (sword_a >> (8 * c)) & 63;
-#pragma unroll
-                for (int i = 0; i < 4; i++) fa[i] *= basev[i];
-                if (sa) {
-                    const double sc = __hiloint2double((1023 + PLF_SCALE_BITS * sa) << 20, 0);
-#pragma unroll
-                    for (int i = 0; i < 4; i++) fa[i] *= sc;
-                }
-                double em[F4_MAXD][4], y[F4_MAXD][4];
-#pragma unroll
-                for (int j = 0; j < F4_MAXD; j++) {
-#pragma unroll
-                    for (int i = 0; i < 4; i++) { em[j][i] = 1.0; y[j][i] = 0.0; }
-                    if (kinds[j] == F4_KIND_TIP) {
-                        f4_ld4(TP + c * tpstride + (mats[j] * a.K + codes[j]) * 4, em[j]);
-                        f4_ld4(TF + c * tpstride + (mats[j] * a.K + codes[j]) * 4, y[j]);
-                    } else if (kinds[j] >= 0) {
-                        double4 l4 = a.scratch[((size_t)slots[j] * C + c) * T + gtid];
-                        double lv[4] = {l4.x, l4.y, l4.z, l4.w};
-                        if (bcs[j]) {
-#pragma unroll
-                            for (int i = 0; i < 4; i++) em[j][i] = lv[i];
-                        } else {
-                            f4_matvec(Pint + c * pstride + mats[j] * 16, lv, em[j]);
-                        }
-                        if (!(bcs[j] && a.f_zero_rowsum)) f4_matvec(Fint + c * pstride + mats[j] * 16, lv, y[j]);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < F4_MAXD; j++) {
-                    if (kinds[j] >= 0) {
-                        double fe[4];
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            double f = fa[i];
-#pragma unroll
-                            for (int j2 = 0; j2 < F4_MAXD; j2++) if (j2 != j) f *= em[j2][i];
-                            fe[i] = f;
-                        }
-                        double xv = fe[0] * y[j][0];
-                        xv = fma(fe[1], y[j][1], xv);
-                        xv = fma(fe[2], y[j][2], xv);
-                        xv = fma(fe[3], y[j][3], xv);
-                        x[j] += xv;
-                        if (kinds[j] != F4_KIND_TIP) {
-                            double fb[4];
-                            f4_matvec_t(Pint + c * pstride + mats[j] * 16, fe, fb);
-                            if (kinds[j] == F4_KIND_CUR) {
-#pragma unroll
-                                for (int i = 0; i < 4; i++) cur[(c * 4 + i) * bd + tid] = fb[i];
-                            } else {
-                                /* the child's inside vector is dead after this op: its slot carries fn down */
-                                a.scratch[((size_t)slots[j] * C + c) * T + gtid] = make_double4(fb[0], fb[1], fb[2], fb[3]);
-                            }
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < F4_MAXD; j++) {
-                if (kinds[j] >= 0) {
-                    const int e = edges[j];
-                    if (!a.edge_mask || a.edge_mask[e]) {
-                        if (a.edge_site_out) {
-                            if (valid) a.edge_site_out[(size_t)e * a.S + site] = x[j];
-                        } else {
-                            double xs = f4_warp_sum(x[j]);
-                            if (lane == 0) accE[warp * a.E + e] += xs;
-                        }
-                    }
-                }
+            if (!CM) {      /* the host selects a CM kernel only for programs made of two-children nodes */
+                F4Ctx k;
+                k.cur = cur; k.accE = accE; k.tile = tile; k.defs_s = defs_s; k.Pint = Pint; k.Fint = Fint; k.TP = TP; k.TF = TF;
+                k.chp = CM ? prog.ch : chs_s;
+                k.pstride = pstride; k.tpstride = tpstride; k.tid = tid; k.lane = lane; k.warp = warp;
+                k.T = (size_t)T; k.gtid = (size_t)gtid; k.site = site; k.valid = valid;
+                f4_outside_general<C, BD, PACK, CM>(a, op, from_slot, k);
             }
         }
     }

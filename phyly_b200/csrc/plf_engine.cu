@@ -14,6 +14,7 @@
 #include <cstring>
 #include <cmath>
 #include <string>
+#include <mutex>
 #include <vector>
 #include <algorithm>
 #include <dlfcn.h>
@@ -120,6 +121,10 @@ struct plf_engine {
     std::vector<unsigned char> node_has_data_h;
     int stack_depth = 0, nslots = 0, max_degree = 0;
     bool TP_valid = false, program_dirty = true;
+    F4Prog prog_h;
+    uint64_t program_version = 0, f4_tuned_version = ~(uint64_t)0;
+    size_t f4_tuned_pick = 0;
+    int f4_tuned_C = 0, f4_tuned_K = 0;
 
     /* scratch */
     DevBuf d_scratch, d_scratchS, d_block_ll, d_block_edge, d_edge_site, d_sum, d_site_ll, d_err, d_mask;
@@ -809,6 +814,7 @@ static int ensure_program(plf_engine *e)
     CK(e, cudaMemcpyAsync(e->d_code_row_node.p, e->code_row_node.data(), sizeof(int) * e->code_row_node.size(), cudaMemcpyHostToDevice, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
     e->program_dirty = false;
+    e->program_version++;
     e->TP_valid = false;
     return 0;
 }
@@ -884,31 +890,36 @@ static int copy_site_matrix(plf_engine *e, const double *d_rows /*[R][cols]*/, i
     return 0;
 }
 
-typedef void (*f4_kernel_t)(F4Args);
+typedef void (*f4_kernel_t)(const F4Args, const F4Prog);
 
-template <int BD, int STAGED, bool PACK>
+template <int BD, int STAGED, bool PACK, bool CM = false>
 static f4_kernel_t f4_select_c(int C, bool edge)
 {
     switch (C * 2 + (edge ? 1 : 0)) {
-    case 2: return fused4_kernel<1, false, BD, STAGED, PACK>;
-    case 3: return fused4_kernel<1, true, BD, STAGED, PACK>;
-    case 4: return fused4_kernel<2, false, BD, STAGED, PACK>;
-    case 5: return fused4_kernel<2, true, BD, STAGED, PACK>;
-    case 6: return fused4_kernel<3, false, BD, STAGED, PACK>;
-    case 7: return fused4_kernel<3, true, BD, STAGED, PACK>;
-    case 8: return fused4_kernel<4, false, BD, STAGED, PACK>;
-    case 9: return fused4_kernel<4, true, BD, STAGED, PACK>;
+    case 2: return fused4_kernel<1, false, BD, STAGED, PACK, CM>;
+    case 3: return fused4_kernel<1, true, BD, STAGED, PACK, CM>;
+    case 4: return fused4_kernel<2, false, BD, STAGED, PACK, CM>;
+    case 5: return fused4_kernel<2, true, BD, STAGED, PACK, CM>;
+    case 6: return fused4_kernel<3, false, BD, STAGED, PACK, CM>;
+    case 7: return fused4_kernel<3, true, BD, STAGED, PACK, CM>;
+    case 8: return fused4_kernel<4, false, BD, STAGED, PACK, CM>;
+    case 9: return fused4_kernel<4, true, BD, STAGED, PACK, CM>;
     }
     return nullptr;
 }
 
+/* the constant-memory matrices are one per device and context: queries of different engines (different
+ * streams) that use them are ordered through this event */
+static std::mutex g_cm_mutex;
+static cudaEvent_t g_cm_done[64];
+
 /* mirrors the shared-memory carve-up at the top of fused4_kernel */
-static size_t f4_smem_bytes(const plf_engine *e, bool edge, int bd, int staged, bool pack = false)
+static size_t f4_smem_bytes(const plf_engine *e, bool edge, int bd, int staged, bool pack = false, bool cm = false)
 {
-    const int C = e->C, Ei = (int)e->edge_of_int.size(), Et = (int)e->edge_of_tip.size();
+    const int C = e->C, Ei = cm ? 0 : (int)e->edge_of_int.size(), Et = (int)e->edge_of_tip.size();
     size_t off = 0;
-    off = f4_align16(off + sizeof(F4Op) * e->ops.size());
-    off = f4_align16(off + sizeof(F4Child) * e->children.size());
+    off = f4_align16(off + (cm ? 0 : sizeof(F4Op) * e->ops.size()));
+    off = f4_align16(off + (cm ? 0 : sizeof(F4Child) * e->children.size()));
     off = f4_align16(off + sizeof(double) * 4 * C * bd);
     off = f4_align16(off + (edge ? sizeof(double) * (bd / 32) * e->E : 0));
     off = f4_align16(off + (edge ? 0 : sizeof(double) * 4 * C * bd * e->stack_depth));
@@ -948,39 +959,42 @@ static int run_fused(plf_engine *e, Query &q)
     a.site_w = e->have_w ? e->d_site_w.as<double>() : nullptr;
     a.stack_depth = e->stack_depth; a.nslots = e->nslots;
 
-    /* block size, and whether the matrices / tip tables live in shared memory: prefer everything on chip */
-    const size_t smem_cap = 227 * 1024;
-    int bd = 256;
-    f4_kernel_t kern = nullptr;
-    size_t smem = 0;
+    /* candidate configurations (block size, which tables are staged in shared memory, packed codes, matrices
+     * in constant memory), preferred first.  PLF_F4_CONFIG=<index> forces one (tuning aid, edge queries). */
+    struct Cand { int bd, staged; bool pack, cm; f4_kernel_t k; size_t smem; int per_sm; };
+    std::vector<Cand> viable;
     {
-        /* candidate configurations, best first; PLF_F4_CONFIG=<index> forces one (tuning aid) */
-        struct Cand { int bd, staged; bool pack; f4_kernel_t k; };
+        const size_t smem_cap = 227 * 1024;
         const bool can_pack = e->K <= 16;
+        bool can_cm = (size_t)e->C * e->edge_of_int.size() * 16 <= F4_CM_MAXD && e->ops.size() <= F4_CM_MAXOPS &&
+                      e->children.size() <= F4_CM_MAXCH && e->device < 64;
+        for (const F4Op &op : e->ops) if (op.nchild != 2) can_cm = false;     /* CM kernels carry the two-children step only */
+        if (!edge) can_cm = false;      /* the log-likelihood-only kernel is faster with the matrices in shared memory */
         const Cand cands[] = {
-            {384, 2, true, can_pack ? f4_select_c<384, 2, true>(e->C, edge) : nullptr},
-            {384, 1, false, f4_select_c<384, 1, false>(e->C, edge)},
-            {512, 1, false, f4_select_c<512, 1, false>(e->C, edge)},
-            {256, 2, false, f4_select_c<256, 2, false>(e->C, edge)},
-            {256, 1, false, f4_select_c<256, 1, false>(e->C, edge)},
-            {128, 2, false, f4_select_c<128, 2, false>(e->C, edge)},
-            {128, 0, false, f4_select_c<128, 0, false>(e->C, edge)},
+            {512, 2, true, true, (can_cm && can_pack) ? f4_select_c<512, 2, true, true>(e->C, edge) : nullptr, 0, 0},
+            {512, 2, false, true, can_cm ? f4_select_c<512, 2, false, true>(e->C, edge) : nullptr, 0, 0},
+            {384, 2, false, true, can_cm ? f4_select_c<384, 2, false, true>(e->C, edge) : nullptr, 0, 0},
+            {384, 2, true, false, can_pack ? f4_select_c<384, 2, true>(e->C, edge) : nullptr, 0, 0},
+            {384, 1, false, false, f4_select_c<384, 1, false>(e->C, edge), 0, 0},
+            {512, 1, false, false, f4_select_c<512, 1, false>(e->C, edge), 0, 0},
+            {256, 2, false, false, f4_select_c<256, 2, false>(e->C, edge), 0, 0},
+            {128, 0, false, false, f4_select_c<128, 0, false>(e->C, edge), 0, 0},
         };
         const int ncand = (int)(sizeof(cands) / sizeof(cands[0]));
         const char *force = edge ? getenv("PLF_F4_CONFIG") : nullptr;
+        size_t smem = 0;
         for (int i = 0; i < ncand; i++) {
             if (force && atoi(force) != i) continue;
             if (!cands[i].k) continue;
-            smem = f4_smem_bytes(e, edge, cands[i].bd, cands[i].staged, cands[i].pack);
-            if (smem <= smem_cap) { kern = cands[i].k; bd = cands[i].bd; break; }
+            Cand c = cands[i];
+            c.smem = smem = f4_smem_bytes(e, edge, c.bd, c.staged, c.pack, c.cm);
+            if (c.smem > smem_cap) continue;
+            CK(e, cudaFuncSetAttribute(c.k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+            CK(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.per_sm, c.k, c.bd, c.smem));
+            if (c.per_sm >= 1) viable.push_back(c);
         }
-        if (!kern) FAIL(e, "fused kernel needs %zu bytes of shared memory", smem);
+        if (viable.empty()) FAIL(e, "fused kernel: no configuration fits (C = %d, %zu bytes of shared memory)", e->C, smem);
     }
-    if (!kern) FAIL(e, "fused kernel: unsupported category count %d", e->C);
-    CK(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CK(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, bd, smem));
-    if (per_sm < 1) FAIL(e, "fused kernel cannot be resident (smem %zu)", smem);
     /* one launch per chunk of sites: a single chunk normally, the upload's chunks while it is still in flight */
     const bool pipelined = e->pend_active;
     std::vector<int64_t> bounds;
@@ -988,11 +1002,34 @@ static int run_fused(plf_engine *e, Query &q)
     const size_t nchunk = bounds.size() - 1;
     int64_t longest = 0;
     for (size_t k = 0; k < nchunk; k++) longest = std::max(longest, bounds[k + 1] - bounds[k]);
-    const int64_t ntiles = (longest + bd - 1) / bd;
-    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)per_sm * e->sm_count);
-    const size_t T = (size_t)grid * bd;
+    auto grid_of = [&](const Cand &c) {
+        return (int)std::min<int64_t>((longest + c.bd - 1) / c.bd, (int64_t)c.per_sm * e->sm_count);
+    };
+    /* Which candidate: the tuned one if this program has been tuned, else the first.  Whether the
+     * constant-memory kernels beat the shared-memory ones depends on what the compiler made of each
+     * instantiation (tools/check_cm_uniform.sh), so the first large query times the leading candidates
+     * on a sample of the sites and keeps the fastest. */
+    const int64_t tune_sites = (int64_t)e->sm_count * 512 * 2;
+    const bool can_tune = edge && viable.size() > 1 && viable[0].cm && e->S >= tune_sites / 2 && !getenv("PLF_F4_NOTUNE");
+    size_t pick = 0;
+    bool tune = false;
+    if (can_tune) {
+        if (e->f4_tuned_version == e->program_version && e->f4_tuned_C == e->C && e->f4_tuned_K == e->K &&
+            e->f4_tuned_pick < viable.size()) pick = e->f4_tuned_pick;
+        else if (!pipelined) tune = true;
+        else while (pick + 1 < viable.size() && viable[pick].cm) pick++;      /* untuned and data still in flight */
+    } else {
+        while (pick + 1 < viable.size() && viable[pick].cm) pick++;          /* small problems: no constant-memory kernels */
+    }
+    size_t Tmax = 0;
+    int gmax = 0;
+    for (size_t i = 0; i < viable.size(); i++) {
+        if (!tune && i != pick) continue;
+        Tmax = std::max(Tmax, (size_t)grid_of(viable[i]) * viable[i].bd);
+        gmax = std::max(gmax, grid_of(viable[i]));
+    }
 
-    ENSURE(e, e->d_block_ll, sizeof(double) * grid * nchunk);
+    ENSURE(e, e->d_block_ll, sizeof(double) * gmax * nchunk);
     ENSURE(e, e->d_sum, sizeof(double) * (1 + e->E + (size_t)e->N * e->n));
     ENSURE(e, e->d_err, sizeof(int) * (e->N + 4));
     CK(e, cudaMemsetAsync(e->d_err.p, 0, sizeof(int), e->stream));
@@ -1000,9 +1037,9 @@ static int run_fused(plf_engine *e, Query &q)
     a.error_flag = e->d_err.as<int>();
     if (q.site_ll) { ENSURE(e, e->d_site_ll, sizeof(double) * e->S); a.site_ll = e->d_site_ll.as<double>(); }
     if (edge) {
-        ENSURE(e, e->d_scratch, sizeof(double4) * (size_t)e->C * e->nslots * T);
-        ENSURE(e, e->d_scratchS, sizeof(unsigned int) * (size_t)e->nslots * T);
-        ENSURE(e, e->d_block_edge, sizeof(double) * (size_t)grid * e->E * nchunk);
+        ENSURE(e, e->d_scratch, sizeof(double4) * (size_t)e->C * e->nslots * Tmax);
+        ENSURE(e, e->d_scratchS, sizeof(unsigned int) * (size_t)e->nslots * Tmax);
+        ENSURE(e, e->d_block_edge, sizeof(double) * (size_t)gmax * e->E * nchunk);
         a.scratch = e->d_scratch.as<double4>(); a.scratchS = e->d_scratchS.as<unsigned int>();
         a.block_edge = e->d_block_edge.as<double>();
         if (q.edge_mask_h) {
@@ -1016,6 +1053,45 @@ static int run_fused(plf_engine *e, Query &q)
             a.edge_site_out = e->d_edge_site.as<double>();
         }
     }
+    bool any_cm = false;
+    for (size_t i = 0; i < viable.size(); i++) if ((tune || i == pick) && viable[i].cm) any_cm = true;
+    std::unique_lock<std::mutex> cm_lock(g_cm_mutex, std::defer_lock);
+    if (any_cm) {
+        /* program as a kernel parameter, matrices into the constant bank (ordered against other engines) */
+        memset(&e->prog_h, 0, sizeof(F4Prog));
+        memcpy(e->prog_h.ops, e->ops.data(), sizeof(F4Op) * e->ops.size());
+        memcpy(e->prog_h.ch, e->children.data(), sizeof(F4Child) * e->children.size());
+        cm_lock.lock();
+        if (!g_cm_done[e->device]) CK(e, cudaEventCreateWithFlags(&g_cm_done[e->device], cudaEventDisableTiming));
+        CK(e, cudaStreamWaitEvent(e->stream, g_cm_done[e->device], 0));
+        const size_t nP = sizeof(double) * (size_t)e->C * e->edge_of_int.size() * 16;
+        CK(e, cudaMemcpyToSymbolAsync(f4_cP, a.Pint, nP, 0, cudaMemcpyDeviceToDevice, e->stream));
+        if (edge) CK(e, cudaMemcpyToSymbolAsync(f4_cF, a.Fint, nP, 0, cudaMemcpyDeviceToDevice, e->stream));
+    }
+    if (tune) {
+        /* time each leading candidate on the first tune_sites sites (results are overwritten by the real run) */
+        float best = 0.f;
+        const size_t ntry = std::min<size_t>(viable.size(), 5);
+        a.s_begin = 0; a.s_end = std::min<int64_t>(e->S, tune_sites);
+        for (size_t i = 0; i < ntry; i++) {
+            const Cand &c = viable[i];
+            float ms = 0.f;
+            for (int rep = 0; rep < 2; rep++) {      /* the first launch of a kernel pays for loading its code */
+                CK(e, cudaEventRecord(e->ev[3], e->stream));
+                c.k<<<grid_of(c), c.bd, c.smem, e->stream>>>(a, e->prog_h);
+                KCHECK(e);
+                CK(e, cudaEventRecord(e->ev[4], e->stream));
+                CK(e, cudaEventSynchronize(e->ev[4]));
+                CK(e, cudaEventElapsedTime(&ms, e->ev[3], e->ev[4]));
+            }
+            if (i == 0 || ms < best) { best = ms; pick = i; }
+        }
+        e->f4_tuned_version = e->program_version; e->f4_tuned_C = e->C; e->f4_tuned_K = e->K;
+        e->f4_tuned_pick = pick;
+        CK(e, cudaMemsetAsync(e->d_err.p, 0, sizeof(int), e->stream));
+    }
+    const Cand &use = viable[pick];
+    const int grid = grid_of(use);
     CK(e, cudaEventRecord(e->ev[3], e->stream));
     for (size_t k = 0; k < nchunk; k++) {
         a.s_begin = bounds[k]; a.s_end = bounds[k + 1];
@@ -1026,10 +1102,14 @@ static int run_fused(plf_engine *e, Query &q)
             CK(e, cudaStreamWaitEvent(e->stream, e->chunk_ev[k], 0));
             if (launch_transpose(e, a.s_begin, a.s_end, e->pend_in_bytes)) return -1;
         }
-        kern<<<grid, bd, smem, e->stream>>>(a);
+        use.k<<<grid, use.bd, use.smem, e->stream>>>(a, e->prog_h);
         KCHECK(e);
     }
     CK(e, cudaEventRecord(e->ev[4], e->stream));
+    if (any_cm) {
+        CK(e, cudaEventRecord(g_cm_done[e->device], e->stream));
+        cm_lock.unlock();
+    }
     e->kernel_timed = true;
     if (pipelined && launch_flags_readback(e)) return -1;
     const int rows = grid * (int)nchunk;
