@@ -345,15 +345,18 @@ def run_ours(args):
     n_tip_edges = Eg - n_int_edges
     flops = float(S) * C * (n_int_edges * (36 + 108) + n_tip_edges * (4 + 14))
     roofline = {
-        "bound": "hbm", "kernel": "fused4_kernel<true>",
+        "bound": "hbm", "kernel": traffic.get("kernel", "fused4_kernel"),
         "achieved": alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms else None, "peak": hbm_peak, "unit": "GB/s",
         "frac": (alg_bytes / (k_ms * 1e-3) / 1e9) / hbm_peak if k_ms else None,
         "traffic": traffic.get("dram_bytes_per_launch"),
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes,
         "note": ("algorithmic bytes are SURVEY 8(d)'s streamed-partials figure (79.4 B/update); the fused kernel keeps "
-                 "partials on chip, so a fraction above 1 means it moves less than that formulation; its real "
-                 "bound is the fp64 pipe, see fp64"),
+                 "partials on chip, so a fraction above 1 means it moves less than that formulation (traffic = DRAM "
+                 "bytes per launch measured by ncu); ncu shows it bound by slab-load latency and LSU wavefronts, "
+                 "fp64 gives its flop rate against the measured DFMA peak"),
+        "measured_dram_gbs": (traffic["dram_bytes_per_launch"] / (k_ms * 1e-3) / 1e9
+                              if (k_ms and traffic.get("dram_bytes_per_launch")) else None),
         "fp64": {"achieved_tflops": flops / (k_ms * 1e-3) / 1e12 if k_ms else None,
                  "peak_tflops": fp64.get("dfma_tflops"),
                  "frac": (flops / (k_ms * 1e-3) / 1e12) / fp64["dfma_tflops"] if (k_ms and fp64.get("dfma_tflops")) else None,

@@ -723,10 +723,12 @@ static int set_data_common(plf_engine *e, int64_t S, int K, const double *defs, 
     /* asynchronous: chunks of whole waves of the fused kernel (sm_count CTAs x 384 sites), copied on a second
      * stream; the queries wait chunk by chunk, so that the kernel runs while later chunks are still in flight */
     if (!e->copy_stream) CK(e, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-    const int64_t unit = (int64_t)e->sm_count * 384 * 2;
+    /* whole waves for both the 384- and the 512-thread kernels; the remainder rides with the last chunk so
+     * that only one launch ends on a partial wave */
+    const int64_t unit = (int64_t)e->sm_count * 1536;
     e->pend_bounds.clear();
-    for (int64_t s = 0; s < S; s += unit) e->pend_bounds.push_back(s);
-    if (e->pend_bounds.size() > 1 && S - e->pend_bounds.back() < unit / 4) e->pend_bounds.pop_back();   /* no tiny tail chunk */
+    for (int64_t s = 0; s + unit <= S; s += unit) e->pend_bounds.push_back(s);
+    if (e->pend_bounds.empty()) e->pend_bounds.push_back(0);
     e->pend_bounds.push_back(S);
     const size_t nch = e->pend_bounds.size() - 1;
     while (e->chunk_ev.size() < nch + 1) {
