@@ -55,7 +55,8 @@ struct F4Child {
                             tip child: index into the compact tip tables */
     int code_row;        /* tip child: row of the codes tile */
     int edge;            /* csr idx (output position) */
-    int pad[3];
+    int node;            /* the child node (output position of its marginal) */
+    int pad[2];
 };
 
 struct F4Args {
@@ -71,7 +72,7 @@ struct F4Args {
     const unsigned char *def_const;  /* [K] */
     const double *Pint;              /* [C][Ei][16] */
     const double *TP;                /* [C][Et][K][4] */
-    const double *Fint;              /* [C][Ei][16] or NULL */
+    const double *Fint;              /* [C][Ei][16] or NULL; marginal mode: P of the tip edges, [C][Et][16] */
     const double *TF;                /* [C][Et][K][4] or NULL */
     int f_zero_rowsum;
     const double *cat_prior;
@@ -86,6 +87,9 @@ struct F4Args {
     double *site_ll;                 /* [S] or NULL */
     double *edge_site_out;           /* [E][S] or NULL */
     int64_t s_begin, s_end;          /* this launch covers sites [s_begin, s_end) (a chunk of the data) */
+    int N;                           /* nodes */
+    double *marg_site_out;           /* marginal mode: [N][4][S] or NULL */
+    double *block_marg;              /* marginal mode: [grid * warps][N][4], zeroed by the host, accumulated here */
     double *block_ll;                /* [grid] */
     double *block_edge;              /* [grid][E] */
     int *error_flag;
@@ -244,12 +248,12 @@ __device__ __forceinline__ double f4_warp_sum2(double a, double b, int lane)
  * Outside step specialised for a node with exactly two children of kinds (K0, K1) in
  * {(CUR, TIP), (CUR, STACK), (TIP, TIP)}: straight-line code, no filler factors.
  */
-template <int C, int BD, int K0, int K1, bool PACK, bool CM>
+template <int C, int BD, int K0, int K1, bool PACK, bool CM, bool MARG>
 __device__ __forceinline__ void f4_outside2(const F4Args &a, const F4Op &op, const F4Child &c0, const F4Child &c1,
                                             bool from_slot, double *cur, const unsigned char *tile, const double *defs_s,
                                             const double *Pint, const double *Fint, const double *TP, const double *TF,
                                             int pstride, int tpstride, size_t T, size_t gtid, int tid,
-                                            double &x0, double &x1)
+                                            double &x0, double &x1, double *mgo)
 {
     double basev[4] = {1.0, 1.0, 1.0, 1.0};
     const bool has_base = op.code_row >= 0;
@@ -259,6 +263,9 @@ __device__ __forceinline__ void f4_outside2(const F4Args &a, const F4Op &op, con
     if (K0 == F4_KIND_TIP) code0 = f4_code<BD, PACK>(tile, c0.code_row, tid); else bc0 = (a.scratchS[(size_t)c0.slot * T + gtid] >> 6) & 1;
     if (K1 == F4_KIND_TIP) code1 = f4_code<BD, PACK>(tile, c1.code_row, tid); else bc1 = (a.scratchS[(size_t)c1.slot * T + gtid] >> 6) & 1;
     x0 = 0.0; x1 = 0.0;
+    /* marginal mode: posterior state distribution of this node and of its tip children, summed over categories */
+    double mg[4] = {0.0, 0.0, 0.0, 0.0}, mt0[4] = {0.0, 0.0, 0.0, 0.0}, mt1[4] = {0.0, 0.0, 0.0, 0.0};
+    const int ptstride = a.Et * 16;
 #pragma unroll (CM ? 1 : 2)
     for (int c = 0; c < C; c++) {
         /* loads of this category first */
@@ -291,35 +298,53 @@ __device__ __forceinline__ void f4_outside2(const F4Args &a, const F4Op &op, con
         double em0[4], y0[4], em1[4], y1[4];
         if (K0 == F4_KIND_TIP) {
             f4_ld4(TP + c * tpstride + (c0.mat * a.K + code0) * 4, em0);
-            f4_ld4(TF + c * tpstride + (c0.mat * a.K + code0) * 4, y0);
+            if (!MARG) f4_ld4(TF + c * tpstride + (c0.mat * a.K + code0) * 4, y0);
         } else {
             f4_mv<CM, 0>(Pint, c * pstride + c0.mat * 16, l0, em0);
-            f4_mv<CM, 1>(Fint, c * pstride + c0.mat * 16, l0, y0);
+            if (!MARG) f4_mv<CM, 1>(Fint, c * pstride + c0.mat * 16, l0, y0);
             if (bc0) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) { em0[i] = l0[i]; if (a.f_zero_rowsum) y0[i] = 0.0; }
+                for (int i = 0; i < 4; i++) { em0[i] = l0[i]; if (!MARG && a.f_zero_rowsum) y0[i] = 0.0; }
             }
         }
         if (K1 == F4_KIND_TIP) {
             f4_ld4(TP + c * tpstride + (c1.mat * a.K + code1) * 4, em1);
-            f4_ld4(TF + c * tpstride + (c1.mat * a.K + code1) * 4, y1);
+            if (!MARG) f4_ld4(TF + c * tpstride + (c1.mat * a.K + code1) * 4, y1);
         } else {
             f4_mv<CM, 0>(Pint, c * pstride + c1.mat * 16, l1, em1);
-            f4_mv<CM, 1>(Fint, c * pstride + c1.mat * 16, l1, y1);
+            if (!MARG) f4_mv<CM, 1>(Fint, c * pstride + c1.mat * 16, l1, y1);
             if (bc1) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) { em1[i] = l1[i]; if (a.f_zero_rowsum) y1[i] = 0.0; }
+                for (int i = 0; i < 4; i++) { em1[i] = l1[i]; if (!MARG && a.f_zero_rowsum) y1[i] = 0.0; }
             }
         }
         double fe0[4], fe1[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) { fe0[i] = fa[i] * em1[i]; fe1[i] = fa[i] * em0[i]; }
-        double xv = fe0[0] * y0[0];
-        xv = fma(fe0[1], y0[1], xv); xv = fma(fe0[2], y0[2], xv); xv = fma(fe0[3], y0[3], xv);
-        x0 += xv;
-        xv = fe1[0] * y1[0];
-        xv = fma(fe1[1], y1[1], xv); xv = fma(fe1[2], y1[2], xv); xv = fma(fe1[3], y1[3], xv);
-        x1 += xv;
+        if (!MARG) {
+            double xv = fe0[0] * y0[0];
+            xv = fma(fe0[1], y0[1], xv); xv = fma(fe0[2], y0[2], xv); xv = fma(fe0[3], y0[3], xv);
+            x0 += xv;
+            xv = fe1[0] * y1[0];
+            xv = fma(fe1[1], y1[1], xv); xv = fma(fe1[2], y1[2], xv); xv = fma(fe1[3], y1[3], xv);
+            x1 += xv;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) mg[i] = fma(fe0[i], em0[i], mg[i]);
+            /* a tip's posterior is def .* (P^T fe); Fint holds P of the tip edges in this mode */
+            if (K0 == F4_KIND_TIP) {
+                double fb[4];
+                f4_matvec_t(Fint + c * ptstride + c0.mat * 16, fe0, fb);
+#pragma unroll
+                for (int i = 0; i < 4; i++) mt0[i] += fb[i];
+            }
+            if (K1 == F4_KIND_TIP) {
+                double fb[4];
+                f4_matvec_t(Fint + c * ptstride + c1.mat * 16, fe1, fb);
+#pragma unroll
+                for (int i = 0; i < 4; i++) mt1[i] += fb[i];
+            }
+        }
         if (K0 != F4_KIND_TIP) {
             double fb[4];
             f4_mvt<CM>(Pint, c * pstride + c0.mat * 16, fe0, fb);
@@ -336,6 +361,39 @@ __device__ __forceinline__ void f4_outside2(const F4Args &a, const F4Op &op, con
             /* the child's inside vector is dead after this op: its slot carries fn down */
             a.scratch[((size_t)c1.slot * C + c) * T + gtid] = make_double4(fb[0], fb[1], fb[2], fb[3]);
         }
+    }
+    if (MARG) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) mgo[i] = mg[i];
+        if (K0 == F4_KIND_TIP) {
+            double d[4];
+            f4_ld4(defs_s + code0 * 4, d);
+#pragma unroll
+            for (int i = 0; i < 4; i++) mgo[4 + i] = mt0[i] * d[i];
+        }
+        if (K1 == F4_KIND_TIP) {
+            double d[4];
+            f4_ld4(defs_s + code1 * 4, d);
+#pragma unroll
+            for (int i = 0; i < 4; i++) mgo[8 + i] = mt1[i] * d[i];
+        }
+    }
+}
+
+/* marginal mode: one node's four posterior values go to the per-site output or, summed over the warp's
+ * sites (they carry the site weight already), to this warp's row of accumulators in global memory */
+__device__ __forceinline__ void f4_marg_out(const F4Args &a, double *accM, int node, const double *m, bool valid,
+                                            int64_t site, int lane)
+{
+    if (a.marg_site_out) {
+        if (valid) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) a.marg_site_out[((size_t)node * 4 + i) * a.S + site] = m[i];
+        }
+    } else {
+        const double r01 = f4_warp_sum2(m[0], m[1], lane), r23 = f4_warp_sum2(m[2], m[3], lane);
+        if (lane == 0) { accM[node * 4 + 0] += r01; accM[node * 4 + 2] += r23; }
+        if (lane == 16) { accM[node * 4 + 1] += r01; accM[node * 4 + 3] += r23; }
     }
 }
 
@@ -384,7 +442,7 @@ __device__ __noinline__ void f4_root_site_ool(const F4Args &a, const double *cur
 
 /* values of the kernel's frame that the out-of-line outside step needs */
 struct F4Ctx {
-    double *cur, *accE;
+    double *cur, *accE, *accM;
     const unsigned char *tile;
     const double *defs_s, *Pint, *Fint, *TP, *TF;
     const F4Child *chp;
@@ -397,11 +455,11 @@ struct F4Ctx {
 /*
  * Outside step for a node with any number of children (1..F4_MAXD) of any kind (non-CM kernels only).
  */
-template <int C, int BD, bool PACK, bool CM>
+template <int C, int BD, bool PACK, bool CM, bool MARG>
 __device__ __forceinline__ void f4_outside_general(const F4Args &a, const F4Op &op, bool from_slot, const F4Ctx &k)
 {
     constexpr int bd = BD;
-    double *cur = k.cur, *accE = k.accE;
+    double *cur = k.cur, *accE = k.accE, *accM = k.accM;
     const unsigned char *tile = k.tile;
     const double *defs_s = k.defs_s, *Pint = k.Pint, *Fint = k.Fint, *TP = k.TP, *TF = k.TF;
     const F4Child *chp = k.chp;
@@ -412,13 +470,17 @@ __device__ __forceinline__ void f4_outside_general(const F4Args &a, const F4Op &
     double basev[4] = {1.0, 1.0, 1.0, 1.0};
     if (op.code_row >= 0) f4_ld4(defs_s + f4_code<BD, PACK>(tile, op.code_row, tid) * 4, basev);
     /* children descriptors and category-independent lookups */
-    int kinds[F4_MAXD], mats[F4_MAXD], slots[F4_MAXD], edges[F4_MAXD], codes[F4_MAXD], bcs[F4_MAXD];
+    int kinds[F4_MAXD], mats[F4_MAXD], slots[F4_MAXD], edges[F4_MAXD], codes[F4_MAXD], bcs[F4_MAXD], nodes[F4_MAXD];
+    double mg[4] = {0.0, 0.0, 0.0, 0.0}, mt[F4_MAXD][4];
+    const int ptstride = a.Et * 16;
 #pragma unroll
     for (int j = 0; j < F4_MAXD; j++) {
-        kinds[j] = -1; mats[j] = 0; slots[j] = 0; edges[j] = 0; codes[j] = 0; bcs[j] = 0;
+        kinds[j] = -1; mats[j] = 0; slots[j] = 0; edges[j] = 0; codes[j] = 0; bcs[j] = 0; nodes[j] = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) mt[j][i] = 0.0;
         if (j < op.nchild) {
             const F4Child ch = chp[op.first_child + j];
-            kinds[j] = ch.kind; mats[j] = ch.mat; slots[j] = ch.slot; edges[j] = ch.edge;
+            kinds[j] = ch.kind; mats[j] = ch.mat; slots[j] = ch.slot; edges[j] = ch.edge; nodes[j] = ch.node;
             if (ch.kind == F4_KIND_TIP) codes[j] = f4_code<BD, PACK>(tile, ch.code_row, tid);
             else bcs[j] = (a.scratchS[(size_t)ch.slot * T + gtid] >> 6) & 1;
         }
@@ -451,7 +513,7 @@ __device__ __forceinline__ void f4_outside_general(const F4Args &a, const F4Op &
             for (int i = 0; i < 4; i++) { em[j][i] = 1.0; y[j][i] = 0.0; }
             if (kinds[j] == F4_KIND_TIP) {
                 f4_ld4(TP + c * tpstride + (mats[j] * a.K + codes[j]) * 4, em[j]);
-                f4_ld4(TF + c * tpstride + (mats[j] * a.K + codes[j]) * 4, y[j]);
+                if (!MARG) f4_ld4(TF + c * tpstride + (mats[j] * a.K + codes[j]) * 4, y[j]);
             } else if (kinds[j] >= 0) {
                 double4 l4 = a.scratch[((size_t)slots[j] * C + c) * T + gtid];
                 double lv[4] = {l4.x, l4.y, l4.z, l4.w};
@@ -461,7 +523,7 @@ __device__ __forceinline__ void f4_outside_general(const F4Args &a, const F4Op &
                 } else {
                     f4_mv<CM, 0>(Pint, c * pstride + mats[j] * 16, lv, em[j]);
                 }
-                if (!(bcs[j] && a.f_zero_rowsum)) f4_mv<CM, 1>(Fint, c * pstride + mats[j] * 16, lv, y[j]);
+                if (!MARG && !(bcs[j] && a.f_zero_rowsum)) f4_mv<CM, 1>(Fint, c * pstride + mats[j] * 16, lv, y[j]);
             }
         }
 #pragma unroll
@@ -475,11 +537,24 @@ __device__ __forceinline__ void f4_outside_general(const F4Args &a, const F4Op &
                     for (int j2 = 0; j2 < F4_MAXD; j2++) if (j2 != j) f *= em[j2][i];
                     fe[i] = f;
                 }
-                double xv = fe[0] * y[j][0];
-                xv = fma(fe[1], y[j][1], xv);
-                xv = fma(fe[2], y[j][2], xv);
-                xv = fma(fe[3], y[j][3], xv);
-                x[j] += xv;
+                if (!MARG) {
+                    double xv = fe[0] * y[j][0];
+                    xv = fma(fe[1], y[j][1], xv);
+                    xv = fma(fe[2], y[j][2], xv);
+                    xv = fma(fe[3], y[j][3], xv);
+                    x[j] += xv;
+                } else {
+                    if (j == 0) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) mg[i] = fma(fe[i], em[0][i], mg[i]);
+                    }
+                    if (kinds[j] == F4_KIND_TIP) {
+                        double fb[4];
+                        f4_matvec_t(Fint + c * ptstride + mats[j] * 16, fe, fb);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) mt[j][i] += fb[i];
+                    }
+                }
                 if (kinds[j] != F4_KIND_TIP) {
                     double fb[4];
                     f4_mvt<CM>(Pint, c * pstride + mats[j] * 16, fe, fb);
@@ -493,6 +568,20 @@ __device__ __forceinline__ void f4_outside_general(const F4Args &a, const F4Op &
                 }
             }
         }
+    }
+    if (MARG) {
+        f4_marg_out(a, accM, op.node, mg, valid, site, lane);
+#pragma unroll
+        for (int j = 0; j < F4_MAXD; j++) {
+            if (kinds[j] == F4_KIND_TIP) {
+                double d[4];
+                f4_ld4(defs_s + codes[j] * 4, d);
+#pragma unroll
+                for (int i = 0; i < 4; i++) d[i] *= mt[j][i];
+                f4_marg_out(a, accM, nodes[j], d, valid, site, lane);
+            }
+        }
+        return;
     }
 #pragma unroll
     for (int j = 0; j < F4_MAXD; j++) {
@@ -511,16 +600,19 @@ __device__ __forceinline__ void f4_outside_general(const F4Args &a, const F4Op &
 
 /*
  * C     : number of rate categories (1..4)
- * EDGE  : false = log-likelihood only; true = log-likelihood + per-edge bilinear forms
+ * MODE  : 0 = log-likelihood only; 1 = log-likelihood + per-edge bilinear forms (deriv / dwell / trans);
+ *         2 = log-likelihood + posterior marginals of every node
  * The dynamic shared memory layout below is mirrored on the host by f4_smem_bytes().
  */
 /* STAGED: 2 = all tables in shared memory, 1 = all but TF (read through L1), 0 = none.
  * PACK: the tile's character codes are stored two per byte (needs K <= 16).
  * CM: internal-edge matrices in constant memory and the program in `prog` (see above); STAGED then
  *     only concerns the tip tables. */
-template <int C, bool EDGE, int BD, int STAGED, bool PACK, bool CM>
+template <int C, int MODE, int BD, int STAGED, bool PACK, bool CM>
 __global__ void __launch_bounds__(BD) fused4_kernel(const F4Args a, const __grid_constant__ F4Prog prog)
 {
+    constexpr bool EDGE = MODE != 0;     /* an outside pass runs */
+    constexpr bool MARG = MODE == 2;     /* ... and produces node marginals instead of per-edge forms */
     extern __shared__ __align__(16) unsigned char f4_smem[];
     const int tid = threadIdx.x;
     constexpr int bd = BD;
@@ -543,7 +635,7 @@ __global__ void __launch_bounds__(BD) fused4_kernel(const F4Args a, const __grid
 #define F4_OP(i) (CM ? prog.ops[i] : ops_s[i])
 #define F4_CH(i) (CM ? prog.ch[i] : chs_s[i])
     double *cur = reinterpret_cast<double *>(f4_smem + off); off = f4_align16(off + sizeof(double) * 4 * C * bd);   /* [C][4][bd] */
-    double *accE = reinterpret_cast<double *>(f4_smem + off); off = f4_align16(off + (EDGE ? sizeof(double) * nwarp * a.E : 0));
+    double *accE = reinterpret_cast<double *>(f4_smem + off); off = f4_align16(off + ((EDGE && !MARG) ? sizeof(double) * nwarp * a.E : 0));
     double *stack = reinterpret_cast<double *>(f4_smem + off); off = f4_align16(off + (EDGE ? 0 : sizeof(double) * 4 * C * bd * a.stack_depth));
     int *stackf = reinterpret_cast<int *>(f4_smem + off); off = f4_align16(off + (EDGE ? 0 : sizeof(int) * bd * a.stack_depth));
     unsigned char *tile = f4_smem + off; off = f4_align16(off + (size_t)(PACK ? (a.ncode_rows + 1) / 2 : a.ncode_rows) * bd);
@@ -552,14 +644,16 @@ __global__ void __launch_bounds__(BD) fused4_kernel(const F4Args a, const __grid
     const double *Pint = a.Pint, *TP = a.TP, *Fint = a.Fint, *TF = a.TF;
     if (STAGED) {
         const size_t nP = CM ? 0 : (size_t)C * a.Ei * 16, nT = (size_t)C * a.Et * a.K * 4;
+        const size_t nF = MARG ? (size_t)C * a.Et * 16 : nP;       /* marginal mode: P of the tip edges */
         double *sP = reinterpret_cast<double *>(f4_smem + off); off += sizeof(double) * nP;
         double *sT = reinterpret_cast<double *>(f4_smem + off); off += sizeof(double) * nT;
-        double *sF = reinterpret_cast<double *>(f4_smem + off); off += EDGE ? sizeof(double) * nP : 0;
-        double *sTF = reinterpret_cast<double *>(f4_smem + off); off += (EDGE && STAGED == 2) ? sizeof(double) * nT : 0;
-        for (size_t i = tid; i < nP; i += bd) { sP[i] = a.Pint[i]; if (EDGE) sF[i] = a.Fint[i]; }
-        for (size_t i = tid; i < nT; i += bd) { sT[i] = a.TP[i]; if (EDGE && STAGED == 2) sTF[i] = a.TF[i]; }
+        double *sF = reinterpret_cast<double *>(f4_smem + off); off += EDGE ? sizeof(double) * nF : 0;
+        double *sTF = reinterpret_cast<double *>(f4_smem + off); off += (EDGE && !MARG && STAGED == 2) ? sizeof(double) * nT : 0;
+        if (!CM) for (size_t i = tid; i < nP; i += bd) sP[i] = a.Pint[i];
+        if (EDGE) for (size_t i = tid; i < nF; i += bd) sF[i] = a.Fint[i];
+        for (size_t i = tid; i < nT; i += bd) { sT[i] = a.TP[i]; if (EDGE && !MARG && STAGED == 2) sTF[i] = a.TF[i]; }
         Pint = sP; TP = sT; Fint = sF;
-        if (STAGED == 2) TF = sTF;
+        if (STAGED == 2 && !MARG) TF = sTF;
     }
     if (!CM) {
         for (int i = tid; i < a.nops; i += bd) ops_s[i] = a.ops[i];
@@ -567,7 +661,8 @@ __global__ void __launch_bounds__(BD) fused4_kernel(const F4Args a, const __grid
     }
     for (int i = tid; i < a.K; i += bd) dconst[i] = a.def_const[i];
     for (int i = tid; i < 4 * a.K; i += bd) defs_s[i] = a.defs[i];
-    if (EDGE) for (int i = tid; i < nwarp * a.E; i += bd) accE[i] = 0.0;
+    if (EDGE && !MARG) for (int i = tid; i < nwarp * a.E; i += bd) accE[i] = 0.0;
+    double *accM = MARG ? a.block_marg + ((size_t)blockIdx.x * nwarp + warp) * ((size_t)a.N * 4) : nullptr;
     __syncthreads();
 
     const int tpstride = a.Et * a.K * 4;     /* doubles per category in the tip tables */
@@ -724,7 +819,8 @@ __global__ void __launch_bounds__(BD) fused4_kernel(const F4Args a, const __grid
         if (!EDGE) continue;
 
         /* ---------------- outside pass ---------------- */
-        const double inv_site = (have && w != 0.0) ? (a.edge_site_out ? 1.0 : w) / site_m : 0.0;
+        const bool per_site_out = MARG ? (a.marg_site_out != nullptr) : (a.edge_site_out != nullptr);
+        const double inv_site = (have && w != 0.0) ? (per_site_out ? 1.0 : w) / site_m : 0.0;
         /* fn_root = root prior vector * prior_c * w / site_L, scaled so that fn .* L is O(1) */
 #pragma unroll
         for (int c = 0; c < C; c++) {
@@ -756,16 +852,22 @@ __global__ void __launch_bounds__(BD) fused4_kernel(const F4Args a, const __grid
             }
             if (op.nchild == 2) {
                 const F4Child c0 = F4_CH(op.first_child), c1 = F4_CH(op.first_child + 1);
-                double x0, x1;
+                double x0, x1, mgo[12];
                 if (c0.kind == F4_KIND_CUR && c1.kind == F4_KIND_TIP)
-                    f4_outside2<C, BD, F4_KIND_CUR, F4_KIND_TIP, PACK, CM>(a, op, c0, c1, from_slot, cur, tile, defs_s, Pint, Fint, TP, TF,
-                                                                 pstride, tpstride, (size_t)T, (size_t)gtid, tid, x0, x1);
+                    f4_outside2<C, BD, F4_KIND_CUR, F4_KIND_TIP, PACK, CM, MARG>(a, op, c0, c1, from_slot, cur, tile, defs_s, Pint, Fint, TP, TF,
+                                                                 pstride, tpstride, (size_t)T, (size_t)gtid, tid, x0, x1, mgo);
                 else if (c0.kind == F4_KIND_CUR)
-                    f4_outside2<C, BD, F4_KIND_CUR, F4_KIND_STACK, PACK, CM>(a, op, c0, c1, from_slot, cur, tile, defs_s, Pint, Fint, TP, TF,
-                                                                   pstride, tpstride, (size_t)T, (size_t)gtid, tid, x0, x1);
+                    f4_outside2<C, BD, F4_KIND_CUR, F4_KIND_STACK, PACK, CM, MARG>(a, op, c0, c1, from_slot, cur, tile, defs_s, Pint, Fint, TP, TF,
+                                                                   pstride, tpstride, (size_t)T, (size_t)gtid, tid, x0, x1, mgo);
                 else
-                    f4_outside2<C, BD, F4_KIND_TIP, F4_KIND_TIP, PACK, CM>(a, op, c0, c1, from_slot, cur, tile, defs_s, Pint, Fint, TP, TF,
-                                                                 pstride, tpstride, (size_t)T, (size_t)gtid, tid, x0, x1);
+                    f4_outside2<C, BD, F4_KIND_TIP, F4_KIND_TIP, PACK, CM, MARG>(a, op, c0, c1, from_slot, cur, tile, defs_s, Pint, Fint, TP, TF,
+                                                                 pstride, tpstride, (size_t)T, (size_t)gtid, tid, x0, x1, mgo);
+                if (MARG) {
+                    f4_marg_out(a, accM, op.node, mgo, valid, site, lane);
+                    if (c0.kind == F4_KIND_TIP) f4_marg_out(a, accM, c0.node, mgo + 4, valid, site, lane);
+                    if (c1.kind == F4_KIND_TIP) f4_marg_out(a, accM, c1.node, mgo + 8, valid, site, lane);
+                    continue;
+                }
                 const bool m0 = !a.edge_mask || a.edge_mask[c0.edge];
                 const bool m1 = !a.edge_mask || a.edge_mask[c1.edge];
                 if (a.edge_site_out) {
@@ -782,11 +884,11 @@ __global__ void __launch_bounds__(BD) fused4_kernel(const F4Args a, const __grid
             }
             if (!CM) {      /* the host selects a CM kernel only for programs made of two-children nodes */
                 F4Ctx k;
-                k.cur = cur; k.accE = accE; k.tile = tile; k.defs_s = defs_s; k.Pint = Pint; k.Fint = Fint; k.TP = TP; k.TF = TF;
+                k.cur = cur; k.accE = accE; k.accM = accM; k.tile = tile; k.defs_s = defs_s; k.Pint = Pint; k.Fint = Fint; k.TP = TP; k.TF = TF;
                 k.chp = CM ? prog.ch : chs_s;
                 k.pstride = pstride; k.tpstride = tpstride; k.tid = tid; k.lane = lane; k.warp = warp;
                 k.T = (size_t)T; k.gtid = (size_t)gtid; k.site = site; k.valid = valid;
-                f4_outside_general<C, BD, PACK, CM>(a, op, from_slot, k);
+                f4_outside_general<C, BD, PACK, CM, MARG>(a, op, from_slot, k);
             }
         }
     }
@@ -802,7 +904,7 @@ __global__ void __launch_bounds__(BD) fused4_kernel(const F4Args a, const __grid
             for (int i = 0; i < nwarp; i++) s += red[i];
             a.block_ll[blockIdx.x] = s;
         }
-        if (EDGE && !a.edge_site_out) {
+        if (EDGE && !MARG && !a.edge_site_out) {
             for (int e = tid; e < a.E; e += bd) {
                 double s = 0.0;
                 for (int wv = 0; wv < nwarp; wv++) s += accE[wv * a.E + e];

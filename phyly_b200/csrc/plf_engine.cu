@@ -116,7 +116,7 @@ struct plf_engine {
     /* fused program */
     std::vector<F4Op> ops;
     std::vector<F4Child> children;
-    DevBuf d_ops, d_children, d_TP, d_TF, d_Pint, d_Fint, d_edge_of_int, d_edge_of_tip, d_code_row_node, d_tip_of_edge, d_TPg;
+    DevBuf d_ops, d_children, d_TP, d_TF, d_Pint, d_Fint, d_Ptip, d_block_marg, d_marg_site, d_edge_of_int, d_edge_of_tip, d_code_row_node, d_tip_of_edge, d_TPg;
     std::vector<int> edge_of_int, edge_of_tip, code_row_node;
     std::vector<unsigned char> node_has_data_h;
     int stack_depth = 0, nslots = 0, max_degree = 0;
@@ -295,7 +295,7 @@ extern "C" void plf_destroy(plf_engine *e)
     DevBuf *bufs[] = {&e->d_indptr, &e->d_indices, &e->d_preorder, &e->d_node_has_data, &e->d_qhi, &e->d_qlo,
                       &e->d_edge_rates, &e->d_cat_rates, &e->d_cat_prior, &e->d_root_vec, &e->d_P, &e->d_D, &e->d_F,
                       &e->d_lhi, &e->d_llo, &e->d_expm_ws, &e->d_codes_in, &e->d_codes, &e->d_defs, &e->d_def_const,
-                      &e->d_def_ones, &e->d_site_w, &e->d_ops, &e->d_children, &e->d_TP, &e->d_TF, &e->d_scratch,
+                      &e->d_def_ones, &e->d_site_w, &e->d_ops, &e->d_children, &e->d_TP, &e->d_TF, &e->d_Ptip, &e->d_block_marg, &e->d_marg_site, &e->d_scratch,
                       &e->d_scratchS, &e->d_block_ll, &e->d_block_edge, &e->d_edge_site, &e->d_sum, &e->d_site_ll,
                       &e->d_err, &e->d_mask, &e->g_Lg, &e->g_Kg, &e->g_Cg, &e->g_Eg, &e->g_Fg, &e->g_FK, &e->g_cat_lh,
                       &e->g_cat_k, &e->g_site_m, &e->g_site_k, &e->g_edge_out, &e->g_marg_out, &e->g_tr};
@@ -420,7 +420,7 @@ static int build_program(plf_engine *e)
         auto add_internal = [&](int idx, int b, int kind) {
             F4Child ch;
             memset(&ch, 0, sizeof(ch));
-            ch.kind = kind; ch.slot = slot[b]; ch.mat = (int)e->edge_of_int.size(); ch.code_row = -1; ch.edge = idx;
+            ch.kind = kind; ch.slot = slot[b]; ch.mat = (int)e->edge_of_int.size(); ch.code_row = -1; ch.edge = idx; ch.node = b;
             e->edge_of_int.push_back(idx);
             e->children.push_back(ch); op.nchild++;
         };
@@ -439,7 +439,7 @@ static int build_program(plf_engine *e)
             if (is_leaf(b)) {
                 F4Child ch;
                 memset(&ch, 0, sizeof(ch));
-                ch.kind = F4_KIND_TIP; ch.slot = -1; ch.mat = (int)e->edge_of_tip.size(); ch.code_row = row_of(b); ch.edge = idx;
+                ch.kind = F4_KIND_TIP; ch.slot = -1; ch.mat = (int)e->edge_of_tip.size(); ch.code_row = row_of(b); ch.edge = idx; ch.node = b;
                 e->edge_of_tip.push_back(idx);
                 e->children.push_back(ch); op.nchild++;
             }
@@ -822,12 +822,22 @@ static int ensure_program(plf_engine *e)
 }
 
 /* compact matrices of the internal-child edges and tip tables for the fused kernel */
-static int ensure_tip_tables(plf_engine *e, const double *Fm, int f_mode)
+static int ensure_tip_tables(plf_engine *e, const double *Fm, int f_mode, bool want_ptip = false)
 {
     if (ensure_program(e)) return -1;
     const int Ei = (int)e->edge_of_int.size(), Et = (int)e->edge_of_tip.size();
     const size_t cntT = (size_t)e->C * Et * e->K * e->n, cntP = (size_t)e->C * Ei * 16;
     const int threads = 256;
+    if (want_ptip) {
+        /* marginal mode: the transition matrices of the tip edges themselves (a tip's posterior needs P^T fe) */
+        const size_t cntPt = (size_t)e->C * Et * 16;
+        ENSURE(e, e->d_Ptip, sizeof(double) * (cntPt + 1));
+        if (cntPt) {
+            compact_matrices_kernel<<<(unsigned)((cntPt + threads - 1) / threads), threads, 0, e->stream>>>(
+                e->d_P.as<double>(), e->d_edge_of_tip.as<int>(), e->C, e->E, Et, e->d_Ptip.as<double>());
+            KCHECK(e);
+        }
+    }
     if (!e->TP_valid) {
         ENSURE(e, e->d_TP, sizeof(double) * (cntT + 1));
         ENSURE(e, e->d_Pint, sizeof(double) * (cntP + 1));
@@ -894,18 +904,31 @@ static int copy_site_matrix(plf_engine *e, const double *d_rows /*[R][cols]*/, i
 
 typedef void (*f4_kernel_t)(const F4Args, const F4Prog);
 
+/* marginal-mode kernels: fewer configurations (no constant-memory variants) */
+template <int BD, int STAGED, bool PACK>
+static f4_kernel_t f4_select_marg(int C)
+{
+    switch (C) {
+    case 1: return fused4_kernel<1, 2, BD, STAGED, PACK, false>;
+    case 2: return fused4_kernel<2, 2, BD, STAGED, PACK, false>;
+    case 3: return fused4_kernel<3, 2, BD, STAGED, PACK, false>;
+    case 4: return fused4_kernel<4, 2, BD, STAGED, PACK, false>;
+    }
+    return nullptr;
+}
+
 template <int BD, int STAGED, bool PACK, bool CM = false>
 static f4_kernel_t f4_select_c(int C, bool edge)
 {
     switch (C * 2 + (edge ? 1 : 0)) {
-    case 2: return fused4_kernel<1, false, BD, STAGED, PACK, CM>;
-    case 3: return fused4_kernel<1, true, BD, STAGED, PACK, CM>;
-    case 4: return fused4_kernel<2, false, BD, STAGED, PACK, CM>;
-    case 5: return fused4_kernel<2, true, BD, STAGED, PACK, CM>;
-    case 6: return fused4_kernel<3, false, BD, STAGED, PACK, CM>;
-    case 7: return fused4_kernel<3, true, BD, STAGED, PACK, CM>;
-    case 8: return fused4_kernel<4, false, BD, STAGED, PACK, CM>;
-    case 9: return fused4_kernel<4, true, BD, STAGED, PACK, CM>;
+    case 2: return fused4_kernel<1, 0, BD, STAGED, PACK, CM>;
+    case 3: return fused4_kernel<1, 1, BD, STAGED, PACK, CM>;
+    case 4: return fused4_kernel<2, 0, BD, STAGED, PACK, CM>;
+    case 5: return fused4_kernel<2, 1, BD, STAGED, PACK, CM>;
+    case 6: return fused4_kernel<3, 0, BD, STAGED, PACK, CM>;
+    case 7: return fused4_kernel<3, 1, BD, STAGED, PACK, CM>;
+    case 8: return fused4_kernel<4, 0, BD, STAGED, PACK, CM>;
+    case 9: return fused4_kernel<4, 1, BD, STAGED, PACK, CM>;
     }
     return nullptr;
 }
@@ -916,21 +939,23 @@ static std::mutex g_cm_mutex;
 static cudaEvent_t g_cm_done[64];
 
 /* mirrors the shared-memory carve-up at the top of fused4_kernel */
-static size_t f4_smem_bytes(const plf_engine *e, bool edge, int bd, int staged, bool pack = false, bool cm = false)
+static size_t f4_smem_bytes(const plf_engine *e, bool edge, int bd, int staged, bool pack = false, bool cm = false,
+                            bool marg = false)
 {
     const int C = e->C, Ei = cm ? 0 : (int)e->edge_of_int.size(), Et = (int)e->edge_of_tip.size();
     size_t off = 0;
     off = f4_align16(off + (cm ? 0 : sizeof(F4Op) * e->ops.size()));
     off = f4_align16(off + (cm ? 0 : sizeof(F4Child) * e->children.size()));
     off = f4_align16(off + sizeof(double) * 4 * C * bd);
-    off = f4_align16(off + (edge ? sizeof(double) * (bd / 32) * e->E : 0));
+    off = f4_align16(off + ((edge && !marg) ? sizeof(double) * (bd / 32) * e->E : 0));
     off = f4_align16(off + (edge ? 0 : sizeof(double) * 4 * C * bd * e->stack_depth));
     off = f4_align16(off + (edge ? 0 : sizeof(int) * bd * e->stack_depth));
     off = f4_align16(off + (pack ? (e->code_row_node.size() + 1) / 2 : e->code_row_node.size()) * bd);
     off = f4_align16(off + e->K);
     off = f4_align16(off + sizeof(double) * 4 * e->K);
     const size_t nP = (size_t)C * Ei * 16 * sizeof(double), nT = (size_t)C * Et * e->K * 4 * sizeof(double);
-    if (staged) off += nP + nT + (edge ? nP : 0) + ((edge && staged == 2) ? nT : 0);
+    const size_t nF = marg ? (size_t)C * Et * 16 * sizeof(double) : nP;
+    if (staged) off += nP + nT + (edge ? nF : 0) + ((edge && !marg && staged == 2) ? nT : 0);
     return off + 16;
 }
 
@@ -941,19 +966,21 @@ static bool fused_fits(const plf_engine *e, bool edge)
 
 static int run_fused(plf_engine *e, Query &q)
 {
-    const bool edge = q.want_edge;
+    const bool marg = q.want_marg;              /* outside pass producing node marginals */
+    const bool edge = q.want_edge || marg;      /* an outside pass runs (slab, no stack) */
     F4Args a;
     memset(&a, 0, sizeof(a));
     a.nops = (int)e->ops.size(); a.nchildren = (int)e->children.size();
     a.ops = e->d_ops.as<F4Op>(); a.children = e->d_children.as<F4Child>();
-    a.E = e->E; a.K = e->K; a.S = e->S;
+    a.E = e->E; a.K = e->K; a.S = e->S; a.N = e->N;
     a.Ei = (int)e->edge_of_int.size(); a.Et = (int)e->edge_of_tip.size();
     a.ncode_rows = (int)e->code_row_node.size();
     a.code_row_node = e->d_code_row_node.as<int>();
     a.codes = e->d_codes.as<unsigned char>();
     a.defs = e->d_defs.as<double>(); a.def_const = e->d_def_const.as<unsigned char>();
     a.Pint = e->d_Pint.as<double>(); a.TP = e->d_TP.as<double>();
-    a.Fint = edge ? e->d_Fint.as<double>() : nullptr; a.TF = edge ? e->d_TF.as<double>() : nullptr;
+    a.Fint = marg ? e->d_Ptip.as<double>() : (edge ? e->d_Fint.as<double>() : nullptr);
+    a.TF = (edge && !marg) ? e->d_TF.as<double>() : nullptr;
     a.f_zero_rowsum = q.f_zero_rowsum;
     a.cat_prior = e->d_cat_prior.as<double>();
     a.root_mode = e->root_mode;
@@ -972,7 +999,13 @@ static int run_fused(plf_engine *e, Query &q)
                       e->children.size() <= F4_CM_MAXCH && e->device < 64;
         for (const F4Op &op : e->ops) if (op.nchild != 2) can_cm = false;     /* CM kernels carry the two-children step only */
         if (!edge) can_cm = false;      /* the log-likelihood-only kernel is faster with the matrices in shared memory */
-        const Cand cands[] = {
+        const Cand mcands[] = {
+            {384, 1, true, false, can_pack ? f4_select_marg<384, 1, true>(e->C) : nullptr, 0, 0},
+            {384, 1, false, false, f4_select_marg<384, 1, false>(e->C), 0, 0},
+            {256, 1, false, false, f4_select_marg<256, 1, false>(e->C), 0, 0},
+            {128, 0, false, false, f4_select_marg<128, 0, false>(e->C), 0, 0},
+        };
+        const Cand ecands[] = {
             {512, 2, true, true, (can_cm && can_pack) ? f4_select_c<512, 2, true, true>(e->C, edge) : nullptr, 0, 0},
             {512, 2, false, true, can_cm ? f4_select_c<512, 2, false, true>(e->C, edge) : nullptr, 0, 0},
             {384, 2, false, true, can_cm ? f4_select_c<384, 2, false, true>(e->C, edge) : nullptr, 0, 0},
@@ -982,14 +1015,15 @@ static int run_fused(plf_engine *e, Query &q)
             {256, 2, false, false, f4_select_c<256, 2, false>(e->C, edge), 0, 0},
             {128, 0, false, false, f4_select_c<128, 0, false>(e->C, edge), 0, 0},
         };
-        const int ncand = (int)(sizeof(cands) / sizeof(cands[0]));
-        const char *force = edge ? getenv("PLF_F4_CONFIG") : nullptr;
+        const Cand *cands = marg ? mcands : ecands;
+        const int ncand = marg ? (int)(sizeof(mcands) / sizeof(mcands[0])) : (int)(sizeof(ecands) / sizeof(ecands[0]));
+        const char *force = (edge && !marg) ? getenv("PLF_F4_CONFIG") : nullptr;
         size_t smem = 0;
         for (int i = 0; i < ncand; i++) {
             if (force && atoi(force) != i) continue;
             if (!cands[i].k) continue;
             Cand c = cands[i];
-            c.smem = smem = f4_smem_bytes(e, edge, c.bd, c.staged, c.pack, c.cm);
+            c.smem = smem = f4_smem_bytes(e, edge, c.bd, c.staged, c.pack, c.cm, marg);
             if (c.smem > smem_cap) continue;
             CK(e, cudaFuncSetAttribute(c.k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
             CK(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.per_sm, c.k, c.bd, c.smem));
@@ -1012,7 +1046,7 @@ static int run_fused(plf_engine *e, Query &q)
      * instantiation (tools/check_cm_uniform.sh), so the first large query times the leading candidates
      * on a sample of the sites and keeps the fastest. */
     const int64_t tune_sites = (int64_t)e->sm_count * 512 * 2;
-    const bool can_tune = edge && viable.size() > 1 && viable[0].cm && e->S >= tune_sites / 2 && !getenv("PLF_F4_NOTUNE");
+    const bool can_tune = edge && !marg && viable.size() > 1 && viable[0].cm && e->S >= tune_sites / 2 && !getenv("PLF_F4_NOTUNE");
     size_t pick = 0;
     bool tune = false;
     if (can_tune) {
@@ -1041,9 +1075,20 @@ static int run_fused(plf_engine *e, Query &q)
     if (edge) {
         ENSURE(e, e->d_scratch, sizeof(double4) * (size_t)e->C * e->nslots * Tmax);
         ENSURE(e, e->d_scratchS, sizeof(unsigned int) * (size_t)e->nslots * Tmax);
-        ENSURE(e, e->d_block_edge, sizeof(double) * (size_t)gmax * e->E * nchunk);
+        if (!marg) ENSURE(e, e->d_block_edge, sizeof(double) * (size_t)gmax * e->E * nchunk);
         a.scratch = e->d_scratch.as<double4>(); a.scratchS = e->d_scratchS.as<unsigned int>();
         a.block_edge = e->d_block_edge.as<double>();
+        if (marg && q.site_marg) {
+            ENSURE(e, e->d_marg_site, sizeof(double) * (size_t)e->N * 4 * e->S);
+            CK(e, cudaMemsetAsync(e->d_marg_site.p, 0, sizeof(double) * (size_t)e->N * 4 * e->S, e->stream));
+            a.marg_site_out = e->d_marg_site.as<double>();
+        } else if (marg) {
+            /* one row of accumulators per warp of the grid; every launch of this query adds into them */
+            const size_t rows = (size_t)gmax * 16;
+            ENSURE(e, e->d_block_marg, sizeof(double) * rows * e->N * 4);
+            CK(e, cudaMemsetAsync(e->d_block_marg.p, 0, sizeof(double) * rows * e->N * 4, e->stream));
+            a.block_marg = e->d_block_marg.as<double>();
+        }
         if (q.edge_mask_h) {
             ENSURE(e, e->d_mask, e->E);
             CK(e, cudaMemcpyAsync(e->d_mask.p, q.edge_mask_h, e->E, cudaMemcpyHostToDevice, e->stream));
@@ -1098,7 +1143,7 @@ static int run_fused(plf_engine *e, Query &q)
     for (size_t k = 0; k < nchunk; k++) {
         a.s_begin = bounds[k]; a.s_end = bounds[k + 1];
         a.block_ll = e->d_block_ll.as<double>() + k * (size_t)grid;
-        if (edge) a.block_edge = e->d_block_edge.as<double>() + k * (size_t)grid * e->E;
+        if (edge && !marg) a.block_edge = e->d_block_edge.as<double>() + k * (size_t)grid * e->E;
         if (pipelined) {
             /* this chunk's codes and weights have arrived; bring them into the node-major layout */
             CK(e, cudaStreamWaitEvent(e->stream, e->chunk_ev[k], 0));
@@ -1121,12 +1166,27 @@ static int run_fused(plf_engine *e, Query &q)
     sum_rows_kernel<<<1, 32, 0, e->stream>>>(a.block_ll, rows, 1, dsum);
     KCHECK(e);
     size_t nsum = 1;
-    if (edge && !q.site_edge) {
+    if (marg) {
+        const int cols = e->N * 4;
+        CK(e, cudaMemsetAsync(dsum + 1, 0, sizeof(double) * e->E, e->stream));
+        if (q.site_marg) {
+            if (q.sum_marg) {
+                CK(e, cudaMemsetAsync(dsum + 1 + e->E, 0, sizeof(double) * cols, e->stream));
+                wsum_rows_kernel<<<cols, 256, 0, e->stream>>>(a.marg_site_out, a.site_w, 0, (int)e->S, dsum + 1 + e->E, a.error_flag, 0);
+                KCHECK(e);
+            }
+        } else {
+            sum_rows_kernel<<<(cols + 127) / 128, 128, 0, e->stream>>>(a.block_marg, grid * (use.bd / 32), cols, dsum + 1 + e->E);
+            KCHECK(e);
+        }
+        nsum = 1 + e->E + cols;
+    }
+    if (edge && !marg && !q.site_edge) {
         sum_rows_kernel<<<(e->E + 127) / 128, 128, 0, e->stream>>>(a.block_edge, rows, e->E, dsum + 1);
         KCHECK(e);
         nsum = 1 + e->E;
     }
-    if (edge && q.site_edge && q.sum_edge) {
+    if (edge && !marg && q.site_edge && q.sum_edge) {
         /* per-site outputs requested together with sums: reduce the per-site rows with the weights */
         CK(e, cudaMemsetAsync(dsum + 1, 0, sizeof(double) * e->E, e->stream));
         wsum_rows_kernel<<<e->E, 256, 0, e->stream>>>(a.edge_site_out, a.site_w, 0, (int)e->S, dsum + 1, a.error_flag, 0);
@@ -1147,9 +1207,11 @@ static int run_fused(plf_engine *e, Query &q)
         if (adopt_flags(e)) return 1;
     }
     if (q.site_edge && copy_site_matrix(e, e->d_edge_site.as<double>(), e->E, e->S, q.site_edge)) return -1;
-    if (herr && (q.sum_ll || q.sum_edge)) FAIL(e, "a site with non-zero weight has zero likelihood");
+    if (herr && (q.sum_ll || q.sum_edge || q.sum_marg)) FAIL(e, "a site with non-zero weight has zero likelihood");
     if (q.sum_ll) *q.sum_ll = hs[0];
-    if (q.sum_edge && nsum > 1) memcpy(q.sum_edge, hs.data() + 1, sizeof(double) * e->E);
+    if (q.sum_edge && !marg && nsum > 1) memcpy(q.sum_edge, hs.data() + 1, sizeof(double) * e->E);
+    if (marg && q.site_marg && copy_site_matrix(e, e->d_marg_site.as<double>(), e->N * 4, e->S, q.site_marg)) return -1;
+    if (marg && q.sum_marg) memcpy(q.sum_marg, hs.data() + 1 + e->E, sizeof(double) * e->N * 4);
     return 0;
 }
 
@@ -1314,13 +1376,15 @@ static int run_query_once(plf_engine *e, Query &q, bool need_D, const double *l_
 {
     if (e->S == 0 || e->n == 0 || e->N == 0) FAIL(e, "engine is not fully configured (tree, model and data are required)");
     CK(e, cudaSetDevice(e->device));
-    bool use_fused = fused_applicable(e) && !q.want_marg;
+    bool use_fused = fused_applicable(e);
+    /* per-site marginals of a huge alignment: the generic path works in chunks of sites */
+    if (q.want_marg && q.site_marg && (size_t)e->N * 4 * e->S * sizeof(double) > ((size_t)32 << 30)) use_fused = false;
     if (e->path == PLF_PATH_GENERIC) use_fused = false;
     /* an upload in flight is overlapped with the fused kernel only; it needs a program built for earlier data */
     if (e->pend_active && !(use_fused && e->node_has_data_h.size() == (size_t)e->N) && resolve_pending(e)) return -1;
     if (use_fused) {
         if (ensure_program(e)) return -1;
-        if (!fused_fits(e, q.want_edge)) use_fused = false;
+        if (!fused_fits(e, q.want_edge || q.want_marg)) use_fused = false;
     }
     if (!use_fused && resolve_pending(e)) return -1;
     if (e->path == PLF_PATH_FUSED4 && !use_fused) FAIL(e, "the fused 4-state path does not apply to this query");
@@ -1339,7 +1403,7 @@ static int run_query_once(plf_engine *e, Query &q, bool need_D, const double *l_
                      q.edge_mask_h ? e->d_mask.as<unsigned char>() : nullptr, e->d_lhi.as<double>(), e->d_llo.as<double>())) return -1;
         q.Fm = e->d_F.as<double>(); q.f_zero_rowsum = 0; f_mode = 2;
     }
-    if (use_fused && ensure_tip_tables(e, q.want_edge ? q.Fm : nullptr, f_mode)) return -1;
+    if (use_fused && ensure_tip_tables(e, q.want_edge ? q.Fm : nullptr, f_mode, q.want_marg)) return -1;
     CK(e, cudaEventRecord(e->ev[1], e->stream));
     e->kernel_timed = false;
     int rc = use_fused ? run_fused(e, q) : run_generic(e, q);

@@ -152,13 +152,23 @@ def test_ll_and_deriv(name, prob):
 def test_marginal(name, prob):
     m, ref, K = _setup(name, prob)
     want = ref["marg"]
-    eng = _engine()
-    H.fill_engine(eng, m)
-    sm, tot = eng.marginal()
-    _assert_close(sm, want, "%s marginal" % name, atol=1e-300)
-    assert np.all(sm[want == 0.0] == 0.0)      # structural zeros stay exact
-    _assert_close(tot, want.sum(axis=0), "%s marginal sums" % name, atol=1e-13 * m.site_count)
-    eng.close()
+    S = m.site_count
+    rng = np.random.default_rng(3)
+    w = rng.integers(0, 4, S).astype(np.float64) + rng.random(S)
+    for path in _paths(m, int(ref["C"]), K):       # generic kernels, and the fused 4-state kernel in marginal mode
+        eng = _engine()
+        H.fill_engine(eng, m)
+        eng.set_path(path)
+        sm, tot = eng.marginal()
+        _assert_close(sm, want, "%s marginal path%d" % (name, path), atol=1e-300)
+        assert np.all(sm[want == 0.0] == 0.0), (name, path)      # structural zeros stay exact
+        _assert_close(tot, want.sum(axis=0), "%s marginal sums path%d" % (name, path), atol=1e-13 * S)
+        # site-summed only (the warp-reduction route of the fused kernel), with weights
+        eng.set_site_weights(w)
+        _, tot_w = eng.marginal(per_site=False)
+        _assert_close(tot_w, (w[:, None, None] * want).sum(axis=0), "%s weighted marginal sums path%d" % (name, path),
+                      atol=1e-13 * w.sum())
+        eng.close()
 
 
 @pytest.mark.parametrize("name,prob", PROBLEMS, ids=IDS)

@@ -5,7 +5,7 @@
 # constant-bank-3 loads are uniform and how many fell back to per-thread LDC.
 lib=${1:-$(dirname "$0")/../phyly_b200/lib/libarbplf_b200.so}
 cuobjdump -sass "$lib" | awk '
-/Function : /{name=$3; cm=(name ~ /fused4_kernelILi[0-9]+ELb[01]ELi[0-9]+ELi[0-9]ELb[01]ELb1E/)}
+/Function : /{name=$3; cm=(name ~ /fused4_kernelILi[0-9]+ELi[0-9]ELi[0-9]+ELi[0-9]ELb[01]ELb1E/)}
 cm && /c\[0x3\]\[UR/ {u[name]++}
 cm && /c\[0x3\]\[R/ {v[name]++}
 cm {seen[name]=1}
