@@ -127,6 +127,12 @@ def test_cfg3_marginals_sum_to_one():
     obs = codes[:, leaf] < 4
     assert np.allclose(sm[obs, leaf, :].max(axis=1), 1.0, atol=1e-12)
     np.testing.assert_allclose(tot, sm.sum(axis=0), rtol=1e-11, atol=1e-9)
+    # the fused kernel (used above) against the independent generic kernels, per site
+    from phyly_b200 import engine as E
+    eng.set_path(E.PATH_GENERIC)
+    sm_g, tot_g = eng.marginal()
+    np.testing.assert_allclose(sm, sm_g, rtol=1e-11, atol=1e-14)
+    np.testing.assert_allclose(tot, tot_g, rtol=1e-11, atol=1e-9)
     eng.close()
 
 
