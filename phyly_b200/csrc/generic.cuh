@@ -63,6 +63,12 @@ struct GenericArgs {
     const double *TP;
     const int *tip_of_edge;
     int Et;
+    /* csr indices of the edges whose child goes through the GEMM, in the order tile_inside_kernel meets them */
+    const int *int_seq;
+    int n_int_seq;
+    /* tile_inside_kernel stages the tile's tip codes in shared memory (1-byte codes, Et * 64 bytes) */
+    int tip_stage;
+    const int *tip_edge_csr;      /* [Et] csr index of each tip edge */
 };
 
 __device__ __forceinline__ int plf_code_at(const void *codes, int code_bytes, int64_t S, int node, int64_t site)

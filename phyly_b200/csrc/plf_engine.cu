@@ -116,7 +116,7 @@ struct plf_engine {
     /* fused program */
     std::vector<F4Op> ops;
     std::vector<F4Child> children;
-    DevBuf d_ops, d_children, d_TP, d_TF, d_Pint, d_Fint, d_Ptip, d_block_marg, d_marg_site, d_edge_of_int, d_edge_of_tip, d_code_row_node, d_tip_of_edge, d_TPg;
+    DevBuf d_ops, d_children, d_TP, d_TF, d_Pint, d_Fint, d_Ptip, d_block_marg, d_marg_site, d_edge_of_int, d_edge_of_tip, d_code_row_node, d_tip_of_edge, d_TPg, d_int_seq;
     std::vector<int> edge_of_int, edge_of_tip, code_row_node;
     std::vector<unsigned char> node_has_data_h;
     int stack_depth = 0, nslots = 0, max_degree = 0;
@@ -1302,7 +1302,29 @@ static int run_generic(plf_engine *e, Query &q)
         }
         a.TP = e->d_TPg.as<double>(); a.tip_of_edge = e->d_tip_of_edge.as<int>(); a.Et = Et;
     }
-    const size_t smem_tile = sizeof(double) * (TL_NP * TL_PS + TL_NP * TL_LS + 8 * TL_TS + TL_TS) + sizeof(int) * 5 * TL_TS;
+    if (use_tile) {
+        /* GEMM edges in the order of the inside kernel's walk (reverse BFS, children in csr order) */
+        std::vector<int> toe(E, -1);
+        if (a.tip_of_edge) for (int te = 0; te < (int)e->edge_of_tip.size(); te++) toe[e->edge_of_tip[te]] = te;
+        std::vector<int> seq, pos(N, 0);
+        for (int u = 0; u < N; u++) pos[e->preorder[u]] = u;
+        for (int u = N - 1; u >= 0; u--) {
+            const int nd = e->preorder[u];
+            for (int idx = e->indptr[nd]; idx < e->indptr[nd + 1]; idx++) if (toe[idx] < 0) seq.push_back(idx);
+        }
+        const size_t nseq = seq.size();
+        for (size_t t = 0; t < nseq; t++) seq.push_back(pos[e->indices[seq[t]]]);    /* walk position of the child */
+        ENSURE(e, e->d_int_seq, sizeof(int) * (seq.size() + 1));
+        CK(e, cudaMemcpyAsync(e->d_int_seq.p, seq.data(), sizeof(int) * seq.size(), cudaMemcpyHostToDevice, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+        a.int_seq = e->d_int_seq.as<int>(); a.n_int_seq = (int)nseq;
+    }
+    if (use_tile && a.tip_of_edge && e->code_bytes == 1 && (size_t)a.Et * TL_TS <= 32 * 1024) {
+        a.tip_stage = 1;
+        a.tip_edge_csr = e->d_edge_of_tip.as<int>();
+    }
+    const size_t smem_tile = sizeof(double) * (2 * TL_NP * TL_LS + 8 * TL_TS + TL_TS) + sizeof(int) * 2 * TL_TS +
+                             (a.tip_stage ? (size_t)a.Et * TL_TS : 0) + 16;
     const size_t smem_tile_out = sizeof(double) * (TL_NP * TL_LS + 8 * TL_TS + 3 * TL_TS) + sizeof(int) * 6 * TL_TS;
     if (use_tile) {
         CK(e, cudaFuncSetAttribute(tile_inside_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile));

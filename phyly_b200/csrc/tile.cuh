@@ -32,19 +32,40 @@ __device__ __forceinline__ void tl_dmma(double &d0, double &d1, double a, double
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-/* grid = (site tiles, categories), 256 threads */
-__global__ void __launch_bounds__(256) tile_inside_kernel(GenericArgs a, int keep_edges)
+/* asynchronous global -> shared copies (LDGSTS); src_bytes < size zero-fills the remainder */
+__device__ __forceinline__ void tl_cp16(void *dst, const void *src, int src_bytes)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes));
+}
+__device__ __forceinline__ void tl_cp8(void *dst, const void *src, int src_bytes)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(src_bytes));
+}
+__device__ __forceinline__ void tl_cp_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void tl_cp_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+/*
+ * grid = (site tiles, categories), 256 threads.
+ *
+ * The child tiles of the GEMM edges are double-buffered: while the tensor pipe works on one child's
+ * [64 states x 64 sites] tile, cp.async brings in the tile of the next GEMM edge of the traversal
+ * (a.int_seq, compiled by the host: the kernel walks the tree in reverse BFS order, so a tile needed next
+ * was finished long ago and nothing in flight depends on the current node).  Tip children never enter a
+ * GEMM: each thread gathers its 16 entries of P_e def_k from the tip table.  Per-site bookkeeping (scale
+ * exponent, constant-column flag) lives in the registers of thread `site`; the column maxima for the
+ * rescale are taken after every second child and after the last one.
+ */
+__global__ void __launch_bounds__(256, 2) tile_inside_kernel(GenericArgs a, int keep_edges)
 {
     extern __shared__ __align__(16) double tl_sm[];
-    double *Psm = tl_sm;                              /* [64][TL_PS] */
-    double *Lsm = Psm + TL_NP * TL_PS;                /* [64][TL_LS] */
-    double *colmax = Lsm + TL_NP * TL_LS;             /* [8][64] */
+    double *Lbuf = tl_sm;                             /* [2][64][TL_LS] */
+    double *colmax = Lbuf + 2 * TL_NP * TL_LS;        /* [8][64] */
     double *scale = colmax + 8 * TL_TS;               /* [64] */
-    int *kacc = reinterpret_cast<int *>(scale + TL_TS);      /* [64] */
-    int *kb = kacc + TL_TS;                           /* [64] */
-    int *bcs = kb + TL_TS;                            /* [64] */
-    int *cst = bcs + TL_TS;                           /* [64] */
-    int *codes_s = cst + TL_TS;                       /* [64] */
+    int *colmax_i = reinterpret_cast<int *>(colmax);  /* the same storage, for the integer maxima of the rescale */
+    int *bcs_s = reinterpret_cast<int *>(scale + TL_TS);     /* [2][64] constant-column flag of the staged child */
+    unsigned char *tipc = reinterpret_cast<unsigned char *>(bcs_s + 2 * TL_TS);   /* [Et][64] codes of the tips (if staged) */
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;            /* fragment coordinates */
@@ -53,48 +74,110 @@ __global__ void __launch_bounds__(256) tile_inside_kernel(GenericArgs a, int kee
     const int s0 = blockIdx.x * TL_TS;
     const int row = warp * 8 + g;                     /* output row owned by this thread */
     const size_t cN = (size_t)c * a.t.N, cE = (size_t)c * a.t.E;
+    const bool site_thread = tid < TL_TS;
+    const bool site_in = site_thread && s0 + tid < Sc;
+    const bool al16 = (Sc & 1) == 0;                  /* rows of the [state][site] arrays are 16-byte aligned */
+
+    /* rows n..63 of both buffers stay zero (k padding of the GEMM) */
+    for (int i = tid; i < 2 * TL_NP * TL_LS; i += 256) Lbuf[i] = 0.0;
+    /* the tile's tip codes: one coalesced pass instead of dependent code -> table loads per tip edge */
+    if (a.tip_stage) {
+        const unsigned char *cd = (const unsigned char *)a.codes;
+        for (int i = tid; i < a.Et * TL_TS; i += 256) {
+            const int te = i >> 6, s = i & 63;
+            const int b = a.t.indices[a.tip_edge_csr[te]];
+            tipc[i] = (s0 + s < Sc) ? cd[(size_t)b * a.S + a.s0 + s0 + s] : 0;
+        }
+    }
+    __syncthreads();
+
+    /* exponent / flag of the staged child, one tile ahead, in the registers of the site threads */
+    int kb_nxt = 0, bc_nxt = 0;
+    auto prefetch = [&](int p) {
+        const int idx = a.int_seq[p];
+        const int b = a.t.indices[idx];
+        double *dst = Lbuf + (size_t)(p & 1) * TL_NP * TL_LS;
+        const double *Lb = a.Lg + ((cN + b) * n) * Sc;
+        if (al16) {
+            for (int i = tid; i < n * (TL_TS / 2); i += 256) {
+                const int k = i >> 5, s = (i & 31) * 2;
+                const int left = Sc - (s0 + s);
+                const int bytes = left >= 2 ? 16 : (left == 1 ? 8 : 0);
+                tl_cp16(dst + k * TL_LS + s, bytes ? (const void *)(Lb + (size_t)k * Sc + s0 + s) : (const void *)Lb, bytes);
+            }
+        } else {
+            for (int i = tid; i < n * TL_TS; i += 256) {
+                const int k = i >> 6, s = i & 63;
+                const int bytes = (s0 + s < Sc) ? 8 : 0;
+                tl_cp8(dst + k * TL_LS + s, bytes ? (const void *)(Lb + (size_t)k * Sc + s0 + s) : (const void *)Lb, bytes);
+            }
+        }
+        tl_cp_commit();
+        {
+            /* this thread's A-fragment row of the edge's matrix: 61 doubles = 4 lines */
+            const char *pr = reinterpret_cast<const char *>(a.P + (cE + idx) * n * n + (size_t)(row < n ? row : 0) * n);
+            if (q == 0) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pr));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pr + 128));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pr + 256));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pr + 384));
+            }
+        }
+        if (site_thread) {
+            kb_nxt = site_in ? a.Kg[(cN + b) * Sc + s0 + tid] : 0;
+            bc_nxt = site_in ? a.Cg[(cN + b) * Sc + s0 + tid] : 0;
+            bcs_s[(p & 1) * TL_TS + tid] = bc_nxt;
+        }
+    };
+    /* p = next GEMM edge to consume, issued = GEMM tiles requested so far (p <= issued <= p + 1).  A tile may be
+     * requested only when its node has been stored: seq_u[t] is the walk position at which that happens. */
+    int p = 0, issued = 0;
+    const int *seq_u = a.int_seq + a.n_int_seq;
 
     for (int u = a.t.N - 1; u >= 0; u--) {
         const int nd = a.t.preorder[u];
         const int start = a.t.indptr[nd], stop = a.t.indptr[nd + 1];
         if (start == stop) continue;                  /* leaves are written by generic_leaf_kernel */
         double acc[8][2];
-        bool first = true;
-        __syncthreads();
-        if (tid < TL_TS) {
-            kacc[tid] = 0;
-            int cf = 1, code = -1;
-            if (a.t.node_has_data[nd] && s0 + tid < Sc) {
-                code = plf_code_at(a.codes, a.code_bytes, a.S, nd, a.s0 + s0 + tid);
-                cf = a.def_const[code];
-            }
-            cst[tid] = cf;
-            codes_s[tid] = code;
+        int kacc = 0, cst = 1, own_code = -1;         /* meaningful in the site threads */
+        if (site_in && a.t.node_has_data[nd]) {
+            own_code = plf_code_at(a.codes, a.code_bytes, a.S, nd, a.s0 + s0 + tid);
+            cst = a.def_const[own_code];
         }
         for (int idx = start; idx < stop; idx++) {
             const int b = a.t.indices[idx];
-            __syncthreads();
             const int te = a.tip_of_edge ? a.tip_of_edge[idx] : -1;
             double em[8][2];
             if (te >= 0) {
-                /* tip child: no GEMM, gather the column from the tip table (P_e def_k) through L1 */
-                const double *Tt = a.TP + (((size_t)c * a.Et + te) * a.K) * n;
-                if (tid < TL_TS) {
-                    int code = 0;
-                    if (s0 + tid < Sc) code = plf_code_at(a.codes, a.code_bytes, a.S, b, a.s0 + s0 + tid);
-                    kb[tid] = code;                       /* reused as the code of this site */
-                    bcs[tid] = a.def_const[code];
+                /* tip child: no GEMM, gather P_e def_k for this thread's 16 sites through L1 */
+                const double *Tt = a.TP + (((size_t)c * a.Et + te) * a.K) * n + (row < n ? row : 0);
+                if (a.tip_stage) {
+                    const unsigned char *tc = tipc + te * TL_TS + q * 2;
+#pragma unroll
+                    for (int nb = 0; nb < 8; nb++) {
+                        const uchar2 cc = *reinterpret_cast<const uchar2 *>(tc + nb * 8);
+                        em[nb][0] = __ldg(Tt + (int)cc.x * n);
+                        em[nb][1] = __ldg(Tt + (int)cc.y * n);
+                    }
+                    if (row >= n) {
+#pragma unroll
+                        for (int nb = 0; nb < 8; nb++) { em[nb][0] = 0.0; em[nb][1] = 0.0; }
+                    }
+                    if (site_in) cst &= a.def_const[tipc[te * TL_TS + tid]];
+                } else {
+#pragma unroll
+                    for (int nb = 0; nb < 8; nb++)
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const int s = nb * 8 + q * 2 + h;
+                            const int code = (s0 + s < Sc) ? plf_code_at(a.codes, a.code_bytes, a.S, b, a.s0 + s0 + s) : 0;
+                            em[nb][h] = (row < n) ? __ldg(Tt + (size_t)code * n) : 0.0;
+                        }
+                    if (site_in) cst &= a.def_const[plf_code_at(a.codes, a.code_bytes, a.S, b, a.s0 + s0 + tid)];
                 }
-                __syncthreads();
-#pragma unroll
-                for (int nb = 0; nb < 8; nb++)
-#pragma unroll
-                    for (int h = 0; h < 2; h++)
-                        em[nb][h] = (row < n) ? __ldg(Tt + (size_t)kb[nb * 8 + q * 2 + h] * n + row) : 0.0;
-                __syncthreads();
-                if (tid < TL_TS) kb[tid] = 0;             /* a tip carries no exponent */
-                __syncthreads();
             } else {
+                const int buf = p & 1;
+                const double *Ls = Lbuf + (size_t)buf * TL_NP * TL_LS;
                 /* A fragments of P_e straight from global memory (hot in L1/L2, shared by all CTAs) */
                 const double *Pm = a.P + (cE + idx) * n * n;
                 double af[TL_NP / 4];
@@ -103,18 +186,11 @@ __global__ void __launch_bounds__(256) tile_inside_kernel(GenericArgs a, int kee
                     const int k = kk * 4 + q;
                     af[kk] = (row < n && k < n) ? __ldg(Pm + row * n + k) : 0.0;
                 }
-                /* stage the child's tile [state][site] */
-                const double *Lb = a.Lg + ((cN + b) * n) * Sc;
-                for (int i = tid; i < TL_NP * TL_TS; i += 256) {
-                    const int k = i >> 6, s = i & 63;
-                    Lsm[k * TL_LS + s] = (k < n && s0 + s < Sc) ? Lb[(size_t)k * Sc + s0 + s] : 0.0;
-                }
-                if (tid < TL_TS) {
-                    const bool in = s0 + tid < Sc;
-                    kb[tid] = in ? a.Kg[(cN + b) * Sc + s0 + tid] : 0;
-                    bcs[tid] = in ? a.Cg[(cN + b) * Sc + s0 + tid] : 0;
-                }
-                __syncthreads();
+                if (issued == p) { prefetch(p); issued++; }      /* not requested ahead of time: fetch it now */
+                tl_cp_wait();
+                __syncthreads();          /* tile p has landed; every warp is done with tile p-1 (other buffer) */
+                const int kb_cur = kb_nxt, bc_cur = bc_nxt;
+                if (p + 1 < a.n_int_seq && seq_u[p + 1] > u) { prefetch(p + 1); issued++; }
                 /* em = P_e . L_b on the FP64 tensor pipe */
 #pragma unroll
                 for (int nb = 0; nb < 8; nb++) { em[nb][0] = 0.0; em[nb][1] = 0.0; }
@@ -122,66 +198,65 @@ __global__ void __launch_bounds__(256) tile_inside_kernel(GenericArgs a, int kee
                 for (int kk = 0; kk < TL_NP / 4; kk++) {
 #pragma unroll
                     for (int nb = 0; nb < 8; nb++) {
-                        const double bf = Lsm[(kk * 4 + q) * TL_LS + nb * 8 + g];
+                        const double bf = Ls[(kk * 4 + q) * TL_LS + nb * 8 + g];
                         tl_dmma(em[nb][0], em[nb][1], af[kk], bf);
                     }
                 }
-            }
-            /* constant column maps to itself (arb_mat_extras.c:84-91); keep edge vectors; multiply in */
-#pragma unroll
-            for (int nb = 0; nb < 8; nb++) {
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int s = nb * 8 + q * 2 + h;
-                    if (te < 0 && bcs[s] && row < n) em[nb][h] = Lsm[s];   /* row 0 of the child tile */
-                }
-                if (keep_edges && row < n) {
-                    const int s = nb * 8 + q * 2;
-                    double *Eo = a.Eg + ((cE + idx) * n + row) * Sc + s0 + s;
-                    if (s0 + s + 1 < Sc && (((size_t)(Eo - a.Eg)) & 1) == 0) *reinterpret_cast<double2 *>(Eo) = make_double2(em[nb][0], em[nb][1]);
-                    else { if (s0 + s < Sc) Eo[0] = em[nb][0]; if (s0 + s + 1 < Sc) Eo[1] = em[nb][1]; }
-                }
-                if (first) { acc[nb][0] = em[nb][0]; acc[nb][1] = em[nb][1]; }
-                else { acc[nb][0] *= em[nb][0]; acc[nb][1] *= em[nb][1]; }
-            }
-            first = false;
-            /* per-site max over all rows -> rescale (exponents in units of 2^256) */
-            {
-                double mx[8][2];
+                /* a constant column maps to itself (arb_mat_extras.c:84-91): row 0 of the child tile */
 #pragma unroll
                 for (int nb = 0; nb < 8; nb++)
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
-                        double m = acc[nb][h];
-                        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 4));
-                        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 8));
-                        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 16));
-                        mx[nb][h] = m;
+                        const int s = nb * 8 + q * 2 + h;
+                        if (bcs_s[buf * TL_TS + s] && row < n) em[nb][h] = Ls[s];
                     }
-                if (g == 0) {
-#pragma unroll
-                    for (int nb = 0; nb < 8; nb++) {
-                        colmax[warp * TL_TS + nb * 8 + q * 2] = mx[nb][0];
-                        colmax[warp * TL_TS + nb * 8 + q * 2 + 1] = mx[nb][1];
-                    }
-                }
+                kacc += kb_cur;
+                cst &= bc_cur;
+                p++;
             }
-            __syncthreads();
-            if (tid < TL_TS) {
-                double m = 0.0;
-                for (int w = 0; w < 8; w++) m = fmax(m, colmax[w * TL_TS + tid]);
-                int k = kacc[tid] + kb[tid];
-                double sc = 1.0;
-                while (m > 0.0 && m < PLF_TWO_M256) { m *= PLF_TWO_P256; sc *= PLF_TWO_P256; k -= 1; }
-                kacc[tid] = k;
-                scale[tid] = sc;
-                cst[tid] &= bcs[tid];
-            }
-            __syncthreads();
+            /* keep the edge vectors for the outside pass; multiply in */
 #pragma unroll
             for (int nb = 0; nb < 8; nb++) {
-                acc[nb][0] *= scale[nb * 8 + q * 2];
-                acc[nb][1] *= scale[nb * 8 + q * 2 + 1];
+                if (keep_edges && row < n) {
+                    const int s = nb * 8 + q * 2;
+                    double *Eo = a.Eg + ((cE + idx) * n + row) * Sc + s0 + s;
+                    if (s0 + s + 1 < Sc && al16) *reinterpret_cast<double2 *>(Eo) = make_double2(em[nb][0], em[nb][1]);
+                    else { if (s0 + s < Sc) Eo[0] = em[nb][0]; if (s0 + s + 1 < Sc) Eo[1] = em[nb][1]; }
+                }
+                if (idx == start) { acc[nb][0] = em[nb][0]; acc[nb][1] = em[nb][1]; }
+                else { acc[nb][0] *= em[nb][0]; acc[nb][1] *= em[nb][1]; }
+            }
+            /* per-site max over all rows -> rescale (exponents in units of 2^256), every second child */
+            if (((idx - start) & 1) || idx == stop - 1) {
+#pragma unroll
+                for (int nb = 0; nb < 8; nb++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        /* non-negative doubles order like their high words: the column maximum only decides
+                         * whether (and how often) to multiply by 2^256, so 32 bits of it are enough */
+                        int m = __double2hiint(acc[nb][h]);
+                        m = max(m, __shfl_xor_sync(0xffffffffu, m, 4));
+                        m = max(m, __shfl_xor_sync(0xffffffffu, m, 8));
+                        m = max(m, __shfl_xor_sync(0xffffffffu, m, 16));
+                        if (g == 0) colmax_i[warp * TL_TS + nb * 8 + q * 2 + h] = m;
+                    }
+                __syncthreads();
+                if (site_thread) {
+                    int m = 0;
+#pragma unroll
+                    for (int w = 0; w < 8; w++) m = max(m, colmax_i[w * TL_TS + tid]);
+                    /* high word of 2^-256 is 0x2FF00000; one step of 2^256 adds 0x10000000 to it.  A column
+                     * whose high word is 0 (zero, or below 2^-1042) is left alone. */
+                    double sc = 1.0;
+                    while (m > 0 && m < 0x2FF00000) { m += 0x10000000; sc *= PLF_TWO_P256; kacc -= 1; }
+                    scale[tid] = sc;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int nb = 0; nb < 8; nb++) {
+                    acc[nb][0] *= scale[nb * 8 + q * 2];
+                    acc[nb][1] *= scale[nb * 8 + q * 2 + 1];
+                }
             }
         }
         /* base vector of a node that carries data (rare) */
@@ -190,8 +265,11 @@ __global__ void __launch_bounds__(256) tile_inside_kernel(GenericArgs a, int kee
             for (int nb = 0; nb < 8; nb++)
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    const int code = codes_s[nb * 8 + q * 2 + h];
-                    if (code >= 0 && row < n) acc[nb][h] *= a.defs[(size_t)code * n + row];
+                    const int s = nb * 8 + q * 2 + h;
+                    if (s0 + s < Sc && row < n) {
+                        const int code = plf_code_at(a.codes, a.code_bytes, a.S, nd, a.s0 + s0 + s);
+                        acc[nb][h] *= a.defs[(size_t)code * n + row];
+                    }
                 }
         }
         /* store the node's partials, exponents and flags */
@@ -200,17 +278,24 @@ __global__ void __launch_bounds__(256) tile_inside_kernel(GenericArgs a, int kee
 #pragma unroll
             for (int nb = 0; nb < 8; nb++) {
                 const int s = nb * 8 + q * 2;
-                if (s0 + s < Sc) La[s] = acc[nb][0];
-                if (s0 + s + 1 < Sc) La[s + 1] = acc[nb][1];
+                if (s0 + s + 1 < Sc && al16) *reinterpret_cast<double2 *>(La + s) = make_double2(acc[nb][0], acc[nb][1]);
+                else { if (s0 + s < Sc) La[s] = acc[nb][0]; if (s0 + s + 1 < Sc) La[s + 1] = acc[nb][1]; }
             }
         }
-        if (tid < TL_TS && s0 + tid < Sc) {
-            a.Kg[(cN + nd) * Sc + s0 + tid] = kacc[tid];
-            a.Cg[(cN + nd) * Sc + s0 + tid] = (unsigned char)cst[tid];
+        if (site_in) {
+            a.Kg[(cN + nd) * Sc + s0 + tid] = kacc;
+            a.Cg[(cN + nd) * Sc + s0 + tid] = (unsigned char)cst;
+        }
+        if (issued == p && p < a.n_int_seq && seq_u[p] >= u) {
+            /* the next GEMM tile is this node or an earlier one (a node without GEMM children, e.g. a cherry,
+             * is not followed by a request of its own): request it now, behind this node's stores */
+            __syncthreads();
+            prefetch(p);
+            issued++;
         }
         if (nd == a.t.root) {
             /* root_prior_expectation (model.c:282-350): weighted column sums */
-            double part[8][2];
+            __syncthreads();
 #pragma unroll
             for (int nb = 0; nb < 8; nb++)
 #pragma unroll
@@ -225,28 +310,20 @@ __global__ void __launch_bounds__(256) tile_inside_kernel(GenericArgs a, int kee
                     v += __shfl_xor_sync(0xffffffffu, v, 4);
                     v += __shfl_xor_sync(0xffffffffu, v, 8);
                     v += __shfl_xor_sync(0xffffffffu, v, 16);
-                    part[nb][h] = v;
+                    if (g == 0) colmax[warp * TL_TS + nb * 8 + q * 2 + h] = v;
                 }
-            __syncthreads();
-            if (g == 0) {
-#pragma unroll
-                for (int nb = 0; nb < 8; nb++) {
-                    colmax[warp * TL_TS + nb * 8 + q * 2] = part[nb][0];
-                    colmax[warp * TL_TS + nb * 8 + q * 2 + 1] = part[nb][1];
-                }
-            }
             /* acc row 0 for the constant-column shortcut of the uniform / equilibrium priors */
             if (warp == 0 && g == 0) {
 #pragma unroll
                 for (int nb = 0; nb < 8; nb++) { scale[nb * 8 + q * 2] = acc[nb][0]; scale[nb * 8 + q * 2 + 1] = acc[nb][1]; }
             }
             __syncthreads();
-            if (tid < TL_TS && s0 + tid < Sc) {
+            if (site_in) {
                 double lh = 0.0;
                 for (int w = 0; w < 8; w++) lh += colmax[w * TL_TS + tid];
-                if (cst[tid] && (a.root_mode == PLF_ROOT_UNIFORM || a.root_mode == PLF_ROOT_EQUILIBRIUM)) lh = scale[tid];
+                if (cst && (a.root_mode == PLF_ROOT_UNIFORM || a.root_mode == PLF_ROOT_EQUILIBRIUM)) lh = scale[tid];
                 a.cat_lh[(size_t)c * Sc + s0 + tid] = lh;
-                a.cat_k[(size_t)c * Sc + s0 + tid] = kacc[tid];
+                a.cat_k[(size_t)c * Sc + s0 + tid] = kacc;
             }
         }
     }
