@@ -61,6 +61,7 @@ struct GenericArgs {
     int want_edge, want_marg;
     /* tip tables for the tile kernel: TP[c][tip edge][k][i] = (P_e def_k)_i, tip_of_edge[csr idx] = tip edge or -1 */
     const double *TP;
+    const double *TF;             /* the same with the edge-form matrices (F_e def_k), or NULL */
     const int *tip_of_edge;
     int Et;
     /* csr indices of the edges whose child goes through the GEMM, in the order tile_inside_kernel meets them */

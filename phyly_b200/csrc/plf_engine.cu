@@ -47,6 +47,10 @@ struct DevBuf {
         return 0;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    ~DevBuf() { release(); }          /* plf_destroy deletes the engine with its device current */
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
@@ -116,7 +120,7 @@ struct plf_engine {
     /* fused program */
     std::vector<F4Op> ops;
     std::vector<F4Child> children;
-    DevBuf d_ops, d_children, d_TP, d_TF, d_Pint, d_Fint, d_Ptip, d_block_marg, d_marg_site, d_edge_of_int, d_edge_of_tip, d_code_row_node, d_tip_of_edge, d_TPg, d_int_seq;
+    DevBuf d_ops, d_children, d_TP, d_TF, d_Pint, d_Fint, d_Ptip, d_block_marg, d_marg_site, d_edge_of_int, d_edge_of_tip, d_code_row_node, d_tip_of_edge, d_TPg, d_TFg, d_int_seq;
     std::vector<int> edge_of_int, edge_of_tip, code_row_node;
     std::vector<unsigned char> node_has_data_h;
     int stack_depth = 0, nslots = 0, max_degree = 0;
@@ -1301,6 +1305,15 @@ static int run_generic(plf_engine *e, Query &q)
             KCHECK(e);
         }
         a.TP = e->d_TPg.as<double>(); a.tip_of_edge = e->d_tip_of_edge.as<int>(); a.Et = Et;
+        if (q.want_edge && a.Fm && cnt) {
+            /* the same for the edge forms, so that tip edges need no GEMM in the outside pass either */
+            ENSURE(e, e->d_TFg, sizeof(double) * (cnt + 1));
+            tip_table_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, e->stream>>>(
+                a.Fm, e->d_defs.as<double>(), e->d_def_const.as<unsigned char>(),
+                e->d_edge_of_tip.as<int>(), C, E, Et, e->K, n, a.f_zero_rowsum ? 1 : 2, e->d_TFg.as<double>());
+            KCHECK(e);
+            a.TF = e->d_TFg.as<double>();
+        }
     }
     if (use_tile) {
         /* GEMM edges in the order of the inside kernel's walk (reverse BFS, children in csr order) */
@@ -1335,8 +1348,11 @@ static int run_generic(plf_engine *e, Query &q)
         a.s0 = s0; a.Sc = (int)std::min<int64_t>(Sc, e->S - s0);
         const unsigned gx = (unsigned)((a.Sc + PLF_TS - 1) / PLF_TS);
         if (use_tile) {
-            generic_leaf_kernel<<<dim3((a.Sc + 255) / 256, C), 256, 0, e->stream>>>(a);
-            KCHECK(e);
+            /* leaf vectors are only read by the outside pass, or by the GEMMs when there are no tip tables */
+            if (q.want_marg || !a.tip_of_edge || (q.want_edge && !a.TF)) {
+                generic_leaf_kernel<<<dim3((a.Sc + 255) / 256, C), 256, 0, e->stream>>>(a);
+                KCHECK(e);
+            }
             tile_inside_kernel<<<dim3((a.Sc + TL_TS - 1) / TL_TS, C), 256, smem_tile, e->stream>>>(a, outside ? 1 : 0);
             KCHECK(e);
         } else {

@@ -473,72 +473,81 @@ __global__ void __launch_bounds__(256, 2) tile_outside_kernel(GenericArgs a)
                 const bool want_x = a.want_edge && (!a.edge_mask || a.edge_mask[idx]);
                 const bool want_fn = !b_leaf || a.want_marg;
                 if (!want_x && !want_fn) continue;
-                /* fe = fa .* prod_{sib != idx} Em_sib ; exponent kfe = ka + sum K_sib */
+                /* fe = fa .* prod_{sib != idx} Em_sib ; exponent kfe = ka + sum K_sib.  Every factor has a column
+                 * maximum of at least 2^-256 p_min, so two of them cannot underflow: the mantissas are pulled
+                 * back into range after every second sibling only (the GEMM result is rescaled anyway). */
                 double fe[8][2];
                 TL_FOR_FRAG(nb, h) fe[nb][h] = fa[nb][h];
-                __syncthreads();
-                if (tid < TL_TS) kfe[tid] = ka[tid];
+                int kfe_r = 0, nsib = 0;                 /* site threads: exponent of fe (on top of ka) */
                 for (int idx2 = start; idx2 < stop; idx2++) {
                     if (idx2 == idx) continue;
                     double es[8][2];
                     tl_load_frag(es, a.Eg + (cE + idx2) * n * Sc, row, n, Sc, s0, q);
                     TL_FOR_FRAG(nb, h) fe[nb][h] *= es[nb][h];
-                    __syncthreads();
-                    if (site_in) kfe[tid] += a.Kg[(cN + a.t.indices[idx2]) * Sc + s0 + tid];
-                    /* keep the mantissas in range */
-                    tl_col_reduce<true>(fe, colbuf, colres, warp, g, q, tid);
-                    if (tid < TL_TS) {
-                        double m = colres[tid], sc = 1.0;
-                        int k = kfe[tid];
-                        while (m > 0.0 && m < PLF_TWO_M256) { m *= PLF_TWO_P256; sc *= PLF_TWO_P256; k -= 1; }
-                        while (m > PLF_TWO_P256) { m *= PLF_TWO_M256; sc *= PLF_TWO_M256; k += 1; }
-                        kfe[tid] = k; scl[tid] = sc;
+                    if (site_in) kfe_r += a.Kg[(cN + a.t.indices[idx2]) * Sc + s0 + tid];
+                    if ((++nsib & 1) == 0) {
+                        tl_col_reduce<true>(fe, colbuf, colres, warp, g, q, tid);
+                        if (tid < TL_TS) {
+                            double m = colres[tid], sc = 1.0;
+                            while (m > 0.0 && m < PLF_TWO_M256) { m *= PLF_TWO_P256; sc *= PLF_TWO_P256; kfe_r -= 1; }
+                            while (m > PLF_TWO_P256) { m *= PLF_TWO_M256; sc *= PLF_TWO_M256; kfe_r += 1; }
+                            scl[tid] = sc;
+                        }
+                        __syncthreads();
+                        TL_FOR_FRAG(nb, h) fe[nb][h] *= scl[nb * 8 + q * 2 + h];
                     }
-                    __syncthreads();
-                    TL_FOR_FRAG(nb, h) fe[nb][h] *= scl[nb * 8 + q * 2 + h];
                 }
+                /* site threads: exponent and flags of the child */
+                int kb_r = 0, bc_r = 0;
+                if (site_in) {
+                    kfe_r += ka[tid];
+                    kb_r = a.Kg[(cN + b) * Sc + s0 + tid];
+                    bc_r = a.Cg[(cN + b) * Sc + s0 + tid];
+                }
+                const int te = (b_leaf && a.TF && a.tip_of_edge) ? a.tip_of_edge[idx] : -1;
+                if (want_x && te >= 0) {
+                    /* tip child: x_e = fe . (F_e def_k) from the tip table, no GEMM */
+                    const double *Tt = a.TF + (((size_t)c * a.Et + te) * a.K) * n + (row < n ? row : 0);
+                    double y[8][2];
+                    TL_FOR_FRAG(nb, h) {
+                        const int s = nb * 8 + q * 2 + h;
+                        const int code = (s0 + s < Sc) ? plf_code_at(a.codes, a.code_bytes, a.S, b, a.s0 + s0 + s) : 0;
+                        y[nb][h] = (row < n) ? __ldg(Tt + (size_t)code * n) * fe[nb][h] : 0.0;
+                    }
+                    tl_col_reduce<false>(y, colbuf, colres, warp, g, q, tid);
+                    if (site_in && coef[tid] != 0.0)
+                        a.edge_out[(size_t)idx * Sc + s0 + tid] += scalbn(colres[tid] * coef[tid], PLF_SCALE_BITS * (kfe_r + kb_r - sitek[tid]));
+                    if (!want_fn) continue;
+                }
+                /* fe is the B operand of both products: z = F_e^T fe (then x_e = z . L_b) and fn_b = P_e^T fe */
                 __syncthreads();
-                /* the child's partial: tile as B operand (internal child) or code (tip) */
-                if (tid < TL_TS) {
-                    kbv[tid] = site_in ? a.Kg[(cN + b) * Sc + s0 + tid] : 0;
-                    bcv[tid] = site_in ? a.Cg[(cN + b) * Sc + s0 + tid] : 0;
-                    codev[tid] = (site_in && b_leaf && a.t.node_has_data[b]) ? plf_code_at(a.codes, a.code_bytes, a.S, b, a.s0 + s0 + tid) : -1;
-                }
-                if (want_x) {
-                    /* x_e = fe^T (F_e L_b)  (evaluate_site_frechet.c:18-39) */
-                    const double *Lb = a.Lg + ((cN + b) * n) * Sc;
-                    for (int i = tid; i < TL_NP * TL_TS; i += 256) {
-                        const int k = i >> 6, s = i & 63;
-                        Bsm[k * TL_LS + s] = (k < n && s0 + s < Sc) ? Lb[(size_t)k * Sc + s0 + s] : 0.0;
-                    }
+                if (row < TL_NP) TL_FOR_FRAG(nb, h) Bsm[row * TL_LS + nb * 8 + q * 2 + h] = fe[nb][h];
+                __syncthreads();
+                if (want_x && te < 0) {
+                    /* x_e = fe^T (F_e L_b) = (F_e^T fe)^T L_b  (evaluate_site_frechet.c:18-39) */
                     const double *Fm = a.Fm + (cE + idx) * n * n;
                     double af[TL_NP / 4];
 #pragma unroll
                     for (int kk = 0; kk < TL_NP / 4; kk++) {
                         const int k = kk * 4 + q;
-                        af[kk] = (row < n && k < n) ? __ldg(Fm + row * n + k) : 0.0;
+                        af[kk] = (row < n && k < n) ? __ldg(Fm + k * n + row) : 0.0;     /* A = F^T */
                     }
-                    __syncthreads();
-                    double y[8][2];
-                    TL_FOR_FRAG(nb, h) y[nb][h] = 0.0;
+                    double lb[8][2];
+                    tl_load_frag(lb, a.Lg + (cN + b) * n * Sc, row, n, Sc, s0, q);
+                    double z[8][2];
+                    TL_FOR_FRAG(nb, h) z[nb][h] = 0.0;
 #pragma unroll
                     for (int kk = 0; kk < TL_NP / 4; kk++) {
 #pragma unroll
-                        for (int nb = 0; nb < 8; nb++) tl_dmma(y[nb][0], y[nb][1], af[kk], Bsm[(kk * 4 + q) * TL_LS + nb * 8 + g]);
+                        for (int nb = 0; nb < 8; nb++) tl_dmma(z[nb][0], z[nb][1], af[kk], Bsm[(kk * 4 + q) * TL_LS + nb * 8 + g]);
                     }
-                    TL_FOR_FRAG(nb, h) {
-                        const int s = nb * 8 + q * 2 + h;
-                        y[nb][h] = (a.f_zero_rowsum && bcv[s]) ? 0.0 : y[nb][h] * fe[nb][h];
-                    }
-                    tl_col_reduce<false>(y, colbuf, colres, warp, g, q, tid);
-                    if (site_in && coef[tid] != 0.0)
-                        a.edge_out[(size_t)idx * Sc + s0 + tid] += scalbn(colres[tid] * coef[tid], PLF_SCALE_BITS * (kfe[tid] + kbv[tid] - sitek[tid]));
-                    __syncthreads();
+                    TL_FOR_FRAG(nb, h) z[nb][h] *= lb[nb][h];
+                    tl_col_reduce<false>(z, colbuf, colres, warp, g, q, tid);
+                    if (site_in && coef[tid] != 0.0 && !(a.f_zero_rowsum && bc_r))
+                        a.edge_out[(size_t)idx * Sc + s0 + tid] += scalbn(colres[tid] * coef[tid], PLF_SCALE_BITS * (kfe_r + kb_r - sitek[tid]));
                 }
                 if (want_fn) {
-                    /* fn_b = P_e^T fe  (util.c:464-498): fe becomes the B operand */
-                    __syncthreads();
-                    TL_FOR_FRAG(nb, h) Bsm[row * TL_LS + nb * 8 + q * 2 + h] = fe[nb][h];
+                    /* fn_b = P_e^T fe  (util.c:464-498) */
                     const double *Pm = a.P + (cE + idx) * n * n;
                     double af[TL_NP / 4];
 #pragma unroll
@@ -546,7 +555,6 @@ __global__ void __launch_bounds__(256, 2) tile_outside_kernel(GenericArgs a)
                         const int k = kk * 4 + q;
                         af[kk] = (row < n && k < n) ? __ldg(Pm + k * n + row) : 0.0;     /* A = P^T */
                     }
-                    __syncthreads();
                     double fb[8][2];
                     TL_FOR_FRAG(nb, h) fb[nb][h] = 0.0;
 #pragma unroll
@@ -557,7 +565,7 @@ __global__ void __launch_bounds__(256, 2) tile_outside_kernel(GenericArgs a)
                     tl_col_reduce<true>(fb, colbuf, colres, warp, g, q, tid);
                     if (tid < TL_TS) {
                         double m = colres[tid], sc = 1.0;
-                        int k = kfe[tid];
+                        int k = kfe_r;
                         while (m > PLF_TWO_P256) { m *= PLF_TWO_M256; sc *= PLF_TWO_M256; k += 1; }
                         while (m > 0.0 && m < PLF_TWO_M256) { m *= PLF_TWO_P256; sc *= PLF_TWO_P256; k -= 1; }
                         scl[tid] = sc;
@@ -571,7 +579,6 @@ __global__ void __launch_bounds__(256, 2) tile_outside_kernel(GenericArgs a)
                             if (s0 + s < Sc) Fb[s] = fb[nb][h] * scl[s];
                         }
                     }
-                    __syncthreads();
                 }
             }
         }
