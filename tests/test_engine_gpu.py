@@ -221,3 +221,52 @@ def test_zero_likelihood_is_an_error():
     with pytest.raises(EngineError):
         eng.ll()
     eng.close()
+
+
+def _cm_applicable(m, C, K):
+    """The constant-memory kernels take binary internal nodes, <= 64 of them, and C * internal edges <= 250."""
+    t = m.tree
+    deg = [t.indptr[i + 1] - t.indptr[i] for i in range(t.node_count)]
+    internal = [i for i in range(t.node_count) if deg[i] > 0]
+    n_int_edges = sum(1 for i in range(t.node_count) for j in range(t.indptr[i], t.indptr[i + 1]) if deg[t.indices[j]] > 0)
+    return (m.n == 4 and C <= 4 and K <= 16 and all(deg[i] == 2 for i in internal) and len(internal) <= 64
+            and C * n_int_edges <= 250)
+
+
+@pytest.mark.parametrize("config", [0, 1, 2])
+@pytest.mark.parametrize("name,prob", PROBLEMS, ids=IDS)
+def test_constant_memory_kernels(name, prob, config, monkeypatch):
+    """The production choice at bench size (matrices in __constant__ memory, program as kernel parameter, 512 or
+    384 threads) is forced onto the small problems so that it meets the oracle too: per-site and summed
+    derivatives, edge masks, and a Frechet (trans) query."""
+    m, ref, K = _setup(name, prob)
+    C = int(ref["C"])
+    if not _cm_applicable(m, C, K):
+        pytest.skip("not a binary 4-state problem")
+    from phyly_b200 import engine as E
+    monkeypatch.setenv("PLF_F4_CONFIG", str(config))
+    ll_w, D_w = ref["ll"], ref["D"]
+    S = m.site_count
+    eng = _engine()
+    cs = H.fill_engine(eng, m)
+    eng.set_path(E.PATH_FUSED4)
+    r = eng.deriv(per_site=True, per_site_ll=True)
+    _assert_close(r["site_ll"], ll_w, "%s cm%d ll" % (name, config), atol=LL_ATOL)
+    _assert_close(r["site_deriv"], D_w, "%s cm%d deriv" % (name, config), atol=CANCEL * ref["Dabs"] + 1e-300)
+    assert np.all(r["site_deriv"][D_w == 0.0] == 0.0)
+    rng = np.random.default_rng(5)
+    w = rng.integers(0, 4, S).astype(np.float64) + rng.random(S)
+    eng.set_site_weights(w)
+    mask = np.zeros(D_w.shape[1], dtype=np.uint8)
+    mask[1::2] = 1
+    r2 = eng.deriv(edge_mask=mask, per_site=False)
+    want = (w[:, None] * D_w).sum(axis=0)
+    mag = (np.abs(w[:, None] * D_w)).sum(axis=0).max()
+    _assert_close(r2["sum_deriv"][mask == 1], want[mask == 1], "%s cm%d masked sums" % (name, config), atol=1e-13 * mag)
+    assert np.all(r2["sum_deriv"][mask == 0] == 0.0)
+    assert H.close(r2["sum_ll"], float((w * ll_w).sum()), 1e-11, 1e-13)
+    eng.set_site_weights(np.ones(S))
+    Ld, Lt, Lt_hi, Lt_lo, Lg = H.frechet_directions(m, cs)
+    xt, _ = eng.edge_expect(E.KIND_TRANS, Lt_hi, Lt_lo)
+    _assert_close(xt, ref["Xt"], "%s cm%d trans" % (name, config), atol=1e-300)
+    eng.close()
