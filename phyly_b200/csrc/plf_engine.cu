@@ -731,8 +731,10 @@ static int set_data_common(plf_engine *e, int64_t S, int K, const double *defs, 
      * that only one launch ends on a partial wave */
     const int64_t unit = (int64_t)e->sm_count * 1536;
     e->pend_bounds.clear();
-    for (int64_t s = 0; s + unit <= S; s += unit) e->pend_bounds.push_back(s);
-    if (e->pend_bounds.empty()) e->pend_bounds.push_back(0);
+    e->pend_bounds.push_back(0);
+    /* a short first chunk (one wave of 512-thread CTAs) so that the kernel starts early */
+    int64_t s = (S >= 2 * unit) ? (int64_t)e->sm_count * 512 : unit;
+    for (; s + unit <= S; s += unit) e->pend_bounds.push_back(s);
     e->pend_bounds.push_back(S);
     const size_t nch = e->pend_bounds.size() - 1;
     while (e->chunk_ev.size() < nch + 1) {
