@@ -313,8 +313,9 @@ __global__ void __launch_bounds__(PLF_TS) generic_outside_kernel(GenericArgs a)
 }
 
 /* leaves: write their base vectors as "inside" vectors once per chunk (so that
- * parents read every child the same way). blockIdx.y = category. */
-__global__ void generic_leaf_kernel(GenericArgs a)
+ * parents read every child the same way). blockIdx.y = category.  write_vectors = 0 writes the
+ * exponents and constant flags only (the tile kernels take the vectors of tips from tip tables). */
+__global__ void generic_leaf_kernel(GenericArgs a, int write_vectors)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const int c = blockIdx.y;
@@ -327,9 +328,9 @@ __global__ void generic_leaf_kernel(GenericArgs a)
         int cst = 1;
         if (a.t.node_has_data[nd]) {
             int code = plf_code_at(a.codes, a.code_bytes, a.S, nd, a.s0 + s);
-            for (int i = 0; i < n; i++) La[(size_t)i * Sc] = a.defs[(size_t)code * n + i];
+            if (write_vectors) for (int i = 0; i < n; i++) La[(size_t)i * Sc] = a.defs[(size_t)code * n + i];
             cst = a.def_const[code];
-        } else {
+        } else if (write_vectors) {
             for (int i = 0; i < n; i++) La[(size_t)i * Sc] = 1.0;
         }
         a.Kg[(cN + nd) * Sc + s] = 0;

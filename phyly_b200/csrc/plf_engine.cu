@@ -44,6 +44,9 @@ struct DevBuf {
             want = bytes;
         }
         cap = want;
+        /* debugging aid: fresh device memory is usually zero, which hides reads of cells nobody wrote */
+        static const bool poison = getenv("PLF_POISON") != nullptr;
+        if (poison) cudaMemset(p, 0xFF, want);
         return 0;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -1350,11 +1353,10 @@ static int run_generic(plf_engine *e, Query &q)
         a.s0 = s0; a.Sc = (int)std::min<int64_t>(Sc, e->S - s0);
         const unsigned gx = (unsigned)((a.Sc + PLF_TS - 1) / PLF_TS);
         if (use_tile) {
-            /* leaf vectors are only read by the outside pass, or by the GEMMs when there are no tip tables */
-            if (q.want_marg || !a.tip_of_edge || (q.want_edge && !a.TF)) {
-                generic_leaf_kernel<<<dim3((a.Sc + 255) / 256, C), 256, 0, e->stream>>>(a);
-                KCHECK(e);
-            }
+            /* leaf vectors are only read when there are no tip tables, or by the marginal pass */
+            generic_leaf_kernel<<<dim3((a.Sc + 255) / 256, C), 256, 0, e->stream>>>(
+                a, (q.want_marg || !a.tip_of_edge || (q.want_edge && !a.TF)) ? 1 : 0);
+            KCHECK(e);
             tile_inside_kernel<<<dim3((a.Sc + TL_TS - 1) / TL_TS, C), 256, smem_tile, e->stream>>>(a, outside ? 1 : 0);
             KCHECK(e);
         } else {

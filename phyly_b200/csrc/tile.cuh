@@ -498,13 +498,15 @@ __global__ void __launch_bounds__(256, 2) tile_outside_kernel(GenericArgs a)
                     }
                 }
                 /* site threads: exponent and flags of the child */
+                const int te = (b_leaf && a.TF && a.tip_of_edge) ? a.tip_of_edge[idx] : -1;
                 int kb_r = 0, bc_r = 0;
                 if (site_in) {
                     kfe_r += ka[tid];
-                    kb_r = a.Kg[(cN + b) * Sc + s0 + tid];
-                    bc_r = a.Cg[(cN + b) * Sc + s0 + tid];
+                    if (te < 0) {       /* a tip handled through the tip table has no stored vector (exponent 0) */
+                        kb_r = a.Kg[(cN + b) * Sc + s0 + tid];
+                        bc_r = a.Cg[(cN + b) * Sc + s0 + tid];
+                    }
                 }
-                const int te = (b_leaf && a.TF && a.tip_of_edge) ? a.tip_of_edge[idx] : -1;
                 if (want_x && te >= 0) {
                     /* tip child: x_e = fe . (F_e def_k) from the tip table, no GEMM */
                     const double *Tt = a.TF + (((size_t)c * a.Et + te) * a.K) * n + (row < n ? row : 0);
