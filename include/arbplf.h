@@ -13,15 +13,17 @@
  *   arbplf_marginal  <- arbplf_marginal_run  (arbplfmarginal.c:404-446)
  *   arbplf_dwell     <- arbplf_dwell_run     (arbplfdwell.c:570-610)
  *   arbplf_trans     <- arbplf_trans_run     (arbplftrans.c:612-660)
+ *   arbplf_em_update <- arbplf_em_update_run (arbplfem.c:540-588): two trans-type passes
+ *                       (exit rates on the diagonal / rates off the diagonal) and their ratio
  *
  * Contract (same as runjson.c:10-66): the returned string is malloc'd and
  * owned by the caller (free()); on failure NULL is returned, *retcode is
  * non-zero and a message has been written to stderr.  The input is borrowed.
  * The functions are not re-entrant (one shared engine handle per process).
  *
- * The second-order programs of the reference (hess, inv-hess, newton-*,
- * em-update) are outside this build's hot path; their entry points exist so
- * that a binding can link, and fail with retcode -1.
+ * The second-order programs of the reference (hess, inv-hess, newton-*) are
+ * outside this build's hot path; their entry points exist so that a binding
+ * can link, and fail with retcode -1.
  */
 #ifndef ARBPLF_B200_H
 #define ARBPLF_B200_H
@@ -35,13 +37,13 @@ char *arbplf_deriv(const char *json_in, int *retcode);
 char *arbplf_marginal(const char *json_in, int *retcode);
 char *arbplf_dwell(const char *json_in, int *retcode);
 char *arbplf_trans(const char *json_in, int *retcode);
+char *arbplf_em_update(const char *json_in, int *retcode);
 
 char *arbplf_hess(const char *json_in, int *retcode);
 char *arbplf_inv_hess(const char *json_in, int *retcode);
 char *arbplf_newton_delta(const char *json_in, int *retcode);
 char *arbplf_newton_update(const char *json_in, int *retcode);
 char *arbplf_newton_refine(const char *json_in, int *retcode);
-char *arbplf_em_update(const char *json_in, int *retcode);
 
 /* run_string_script of runjson.c:117-147: stdin -> f -> stdout, returns the exit status */
 int arbplf_run_stdio(char *(*f)(const char *, int *));

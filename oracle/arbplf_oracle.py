@@ -1376,12 +1376,83 @@ def per_site_edge_expect(m: Model, be, sites: Sequence[int], L, trans: bool, req
     return _edge_expectations(m, cs, be, base, F, requested_csr, trans=trans), cs
 
 
+def run_em_update(root, mode="mp"):
+    """
+    One EM update of the edge rate coefficients (arbplfem.c): per edge, the conditionally expected number of
+    transitions over the conditionally expected exit-rate-weighted dwell time, times the current coefficient.
+    Frechet directions arbplfem.c:116-128 (L_dwell = diag(-Q_ii), L_trans = offdiag(Q)), accumulation
+    :232-379 (every category weighted by prior_c * rate_c, categories of exactly zero likelihood skipped,
+    sites weighted by w_s / divisor / site_L), final ratio :434-458, output in user edge order :475-490.
+    """
+    be = get_backend(mode)
+    m = _top(root, ["site_reduction"], "arbplf-em-update")
+    t = m.tree
+    n = m.n
+    E = t.edge_count
+    r_site = parse_column_reduction(root.get("site_reduction"), m.site_count, "site")
+    if r_site.agg_mode == AGG_NONE:
+        raise OracleError("aggregation over sites is required")       # arbplfem.c:566-571
+    cs = cross_site(m, be)
+    L_dwell = be.zeros(n, n)
+    L_trans = be.zeros(n, n)
+    for a in range(n):
+        L_dwell[a, a] = -cs.Q[a, a]
+        for b in range(n):
+            if a != b:
+                L_trans[a, b] = cs.Q[a, b]
+    req = [True] * E
+    Fd = frechet_matrices(cs, be, L_dwell, req)
+    Ft = frechet_matrices(cs, be, L_trans, req)
+    w, div = agg_weights(r_site, m.site_count, be)
+    dwell_accum = be.zeros(E)
+    trans_accum = be.zeros(E)
+    sites = _requested_sites(r_site, m.site_count)
+    if sites:
+        base = _base_vectors(m, be, sites)
+        S = base.shape[0]
+        site_L = be.zeros(S)
+        dwell_site = be.zeros(S, E)
+        trans_site = be.zeros(S, E)
+        for c in range(cs.C):
+            lh, node, nconst, edge = site_lhood(m, cs, be, base, c, keep_edges=True)
+            cat_L = cs.prior[c] * lh
+            site_L = site_L + cat_L
+            live = np.array([bool(x != 0) for x in cat_L])             # arbplfem.c:322
+            fn, fe = site_forward(m, cs, be, base, c, edge)
+            wgt = cs.prior[c] * cs.rates[c]                              # arbplfem.c:351
+            for idx in range(E):
+                b = t.indices[idx]
+                xd = (_matvec(Fd[c, idx], node[b]) * fe[idx]).sum(axis=1)
+                xt = (_matvec(Ft[c, idx], node[b]) * fe[idx]).sum(axis=1)
+                dwell_site[:, idx] = dwell_site[:, idx] + np.where(live, xd * wgt, be.num(0))
+                trans_site[:, idx] = trans_site[:, idx] + np.where(live, xt * wgt, be.num(0))
+        for k, s in enumerate(sites):
+            if not (site_L[k] > 0):
+                raise OracleError("site %d has zero likelihood" % s)
+            f = w[s] / div / site_L[k]
+            dwell_accum = dwell_accum + dwell_site[k] * f
+            trans_accum = trans_accum + trans_site[k] * f
+    rows = []
+    for e in range(E):
+        idx = t.order[e]
+        v = be.num(0)
+        if trans_accum[idx] != 0:
+            v = trans_accum[idx] / dwell_accum[idx]
+        v = v * cs.edge_rates[idx]
+        d = be.to_float(v)
+        if d == 0.0:
+            d = 0.0
+        rows.append([e, d])
+    return {"columns": ["edge", "value"], "data": rows}
+
+
 PROGRAMS = {
     "ll": run_ll,
     "deriv": run_deriv,
     "marginal": run_marginal,
     "dwell": run_dwell,
     "trans": run_trans,
+    "em_update": run_em_update,
 }
 
 

@@ -423,6 +423,72 @@ done:
 }
 
 /* ------------------------------------------------------------------ */
+/* arbplf-em-update                                                    */
+/* ------------------------------------------------------------------ */
+
+/*
+ * One EM update of the edge rate coefficients (arbplfem.c).  The reference accumulates, per edge,
+ *   trans = sum_s w_s/L_s sum_c prior_c rate_c fe^T Frechet(offdiag Q) L_b     (arbplfem.c:122-128,351-353)
+ *   dwell = sum_s w_s/L_s sum_c prior_c rate_c fe^T Frechet(diag -Q_ii) L_b     (arbplfem.c:117-120)
+ * and returns t_e * trans / dwell (0 when trans is exactly 0, :434-458).  Both sums are what the device
+ * seam's PLF_KIND_TRANS query returns for those two directions up to a common factor t_e, which cancels in
+ * the ratio.  Site aggregation is required (:566-571); all edges are reported in the user's order.
+ */
+char *arbplf_em_update(const char *json_in, int *retcode)
+{
+    static const char *const keys[] = {"model_and_data", "?site_reduction", NULL};
+    const jv *v[2];
+    ctx c;
+    reduction r_site, r_edge;
+    reduction_init(&r_site); reduction_init(&r_edge);
+    axis ax_site, ax_edge;
+    memset(&ax_site, 0, sizeof ax_site); memset(&ax_edge, 0, sizeof ax_edge);
+    double *val = NULL, *Lh = NULL, *Ll = NULL, *sum_d = NULL, *sum_t = NULL;
+    char *out = NULL;
+    int rc = -1;
+    if (ctx_parse(&c, json_in, keys, v)) goto done;
+    const int n = c.m.n, E = c.m.E;
+    const int64_t S = c.m.S;
+    if (reduction_parse(&r_site, (int)S, "site", v[1])) goto done;
+    if (reduction_parse(&r_edge, E, "edge", NULL)) goto done;
+    if (axis_init(&ax_site, "site", (int)S, &r_site) || axis_init(&ax_edge, "edge", E, &r_edge)) goto done;
+    if (!ax_site.aggregated) { fprintf(stderr, "error: aggregation over sites is required\n"); goto done; }
+    val = calloc(E > 0 ? E : 1, sizeof(double));
+    if (S > 0 && E > 0) {
+        if (ctx_load(&c)) goto done;
+        Lh = calloc((size_t)n * n, sizeof(double));
+        Ll = calloc((size_t)n * n, sizeof(double));
+        sum_d = calloc(E, sizeof(double));
+        sum_t = calloc(E, sizeof(double));
+        if (plf_set_site_weights(c.e, ax_site.w)) { fprintf(stderr, "error: %s\n", plf_last_error(c.e)); goto done; }
+        /* exit rates on the diagonal */
+        for (int i = 0; i < n; i++) { Lh[i * n + i] = -c.d.q_hi[i * n + i]; Ll[i * n + i] = -c.d.q_lo[i * n + i]; }
+        if (plf_edge_expect(c.e, PLF_KIND_TRANS, Lh, Ll, NULL, NULL, sum_d)) { fprintf(stderr, "error: %s\n", plf_last_error(c.e)); goto done; }
+        /* rates off the diagonal */
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) {
+                Lh[i * n + j] = (i == j) ? 0.0 : c.d.q_hi[i * n + j];
+                Ll[i * n + j] = (i == j) ? 0.0 : c.d.q_lo[i * n + j];
+            }
+        if (plf_edge_expect(c.e, PLF_KIND_TRANS, Lh, Ll, NULL, NULL, sum_t)) { fprintf(stderr, "error: %s\n", plf_last_error(c.e)); goto done; }
+        for (int e = 0; e < E; e++) {
+            const int idx = c.m.order[e];
+            double x = 0.0;
+            if (sum_t[idx] != 0.0) x = sum_t[idx] / sum_d[idx] * c.d.edge_rates_csr[idx];
+            if (!isfinite(x)) { fprintf(stderr, "error: the EM update of edge %d is not finite\n", e); goto done; }
+            val[e] = x;
+        }
+    }
+    out = table_to_json(&ax_edge, 1, val);
+    rc = 0;
+done:
+    free(val); free(Lh); free(Ll); free(sum_d); free(sum_t);
+    axis_clear(&ax_site); axis_clear(&ax_edge);
+    reduction_clear(&r_site); reduction_clear(&r_edge);
+    return finish(&c, out, rc, retcode);
+}
+
+/* ------------------------------------------------------------------ */
 /* model summary, unsupported programs, stdio shell                    */
 /* ------------------------------------------------------------------ */
 
@@ -491,7 +557,6 @@ char *arbplf_inv_hess(const char *j, int *rc) { (void)j; return unsupported("arb
 char *arbplf_newton_delta(const char *j, int *rc) { (void)j; return unsupported("arbplf-newton-delta", rc); }
 char *arbplf_newton_update(const char *j, int *rc) { (void)j; return unsupported("arbplf-newton-update", rc); }
 char *arbplf_newton_refine(const char *j, int *rc) { (void)j; return unsupported("arbplf-newton-refine", rc); }
-char *arbplf_em_update(const char *j, int *rc) { (void)j; return unsupported("arbplf-em-update", rc); }
 
 /* runjson.c:88-147 */
 int arbplf_run_stdio(char *(*f)(const char *, int *))

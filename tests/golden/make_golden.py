@@ -69,6 +69,9 @@ CASES = [
     # GeLL.test.likelihood/README.md:29-31, GeLL.driver.DNA/README.md:30-32
     ("gell_test", "ll", "GeLL.test.likelihood/in.json", {"columns": ["value"], "data": [[-2616.073919844292]]}),
     ("gell_driver", "ll", "GeLL.driver.DNA/in.json", {"columns": ["value"], "data": [[-2616.0735881244163]]}),
+    ("fels_em_full", "em_update", "Felsenstein.2004.fig.16.4/em-update/with.full.data/in.json", "Felsenstein.2004.fig.16.4/em-update/with.full.data/out.json"),
+    ("fels_em_leaf", "em_update", "Felsenstein.2004.fig.16.4/em-update/with.leaf.data/in.json", "Felsenstein.2004.fig.16.4/em-update/with.leaf.data/out.json"),
+    ("fels_em_none", "em_update", "Felsenstein.2004.fig.16.4/em-update/with.no.data/in.json", "Felsenstein.2004.fig.16.4/em-update/with.no.data/out.json"),
 ]
 
 

@@ -205,9 +205,19 @@ def test_malformed_json_is_rejected():
 def test_unsupported_programs_fail_cleanly():
     import phyly_b200.arbplf as A
     for f in (A.arbplf_hess, A.arbplf_inv_hess, A.arbplf_newton_delta, A.arbplf_newton_update,
-              A.arbplf_newton_refine, A.arbplf_em_update):
+              A.arbplf_newton_refine):
         with pytest.raises(RuntimeError):
             f(json.dumps(GOOD))
+
+
+def test_em_update_requires_site_aggregation():
+    # arbplfem.c:566-571: rejected while parsing, before any device work
+    import phyly_b200.arbplf as A
+    no_agg = {k: v for k, v in GOOD.items() if k != "site_reduction"}
+    with pytest.raises(RuntimeError):
+        A.arbplf_em_update(json.dumps(no_agg))
+    with pytest.raises(RuntimeError):       # edge reduction is not part of the schema (strict unpack, arbplfem.c:517-523)
+        A.arbplf_em_update(json.dumps(dict(GOOD, edge_reduction={"aggregation": "sum"})))
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -24,7 +24,7 @@ pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CASES = H.manifest()
-SUPPORTED = {"ll", "deriv", "marginal", "dwell", "trans"}
+SUPPORTED = {"ll", "deriv", "marginal", "dwell", "trans", "em_update"}
 
 # Absolute floors, only where the reference's exact arithmetic cancels to a
 # value far below the magnitude of the terms (see tests/test_engine_gpu.py):
@@ -184,3 +184,21 @@ def test_edge_permutation_equivariance():
     vb = {perm[r[0]]: r[1] for r in b["data"]}
     for e in range(E):
         assert abs(va[e] - vb[e]) <= 1e-12 * abs(va[e]) + 1e-14
+
+
+def test_em_update_against_oracle_with_mixture_and_weights():
+    """arbplf-em-update beyond the reference's three goldens: a gamma + invariant mixture (one category of rate
+    0, skipped per site when its likelihood is exactly 0), weighted site aggregation, a selection with
+    duplicates."""
+    from oracle import arbplf_oracle as O
+    doc = copy.deepcopy(H.golden_in("beast_gtrgi"))
+    S = len(doc["model_and_data"]["character_data"]) if "character_data" in doc["model_and_data"] else \
+        len(doc["model_and_data"]["probability_array"])
+    rng = np.random.default_rng(8)
+    sel = [int(x) for x in rng.integers(0, S, 12)]
+    for red in ({"aggregation": "sum"}, {"aggregation": "avg", "selection": sel},
+                {"selection": sel, "aggregation": [float(x) for x in rng.random(len(sel)) + 0.1]}):
+        doc["site_reduction"] = red
+        want = O.run("em_update", doc, mode="mp")
+        got = _run("em_update", doc)
+        _check(got, want, "em_update %s" % json.dumps(red)[:40])
