@@ -320,11 +320,30 @@ def run_ours(args):
     barrier()
     sampler.mark(t1, time.perf_counter())
     clocks = sampler.stop() if rank == 0 else None
+    # ---- supplementary: log-likelihood only (the metric's other half), device-resident, same timing rules ----
+    ll_steps = max(1, min(args.steps, 50))
+
+    def step_ll():
+        eng.set_edge_rates(pb["edge_rates"])
+        return eng.ll(per_site=False)
+
+    for _ in range(3):
+        step_ll()
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ll_kern = []
+    g0.record(stream)
+    for _ in range(ll_steps):
+        step_ll()
+        ll_kern.append(eng.last_kernel_ms())
+    g1.record(stream)
+    barrier()
+    ms_ll = g0.elapsed_time(g1)
     ms_e2e = f0.elapsed_time(f1)
     if world > 1:
-        tt = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([ms, ms_e2e, ms_ll], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(tt[0]), float(tt[1])
+        ms, ms_e2e, ms_ll = float(tt[0]), float(tt[1]), float(tt[2])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -378,6 +397,11 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
+        "ll_only": {"metric": "site-edge-category updates/s (ll)", "value": updates_per_step * ll_steps / (ms_ll * 1e-3),
+                    "unit": "updates/s", "steps": ll_steps, "ms_per_step": ms_ll / ll_steps,
+                    "kernel_ms": float(np.mean(ll_kern)),
+                    "roofline_frac_hbm": (BYTES_PER_UPDATE_LL * float(S) * Eg * C / (float(np.mean(ll_kern)) * 1e-3) / 1e9) / hbm_peak,
+                    "note": "supplementary; algorithmic bytes 31.9 B/update (SURVEY 8d); no slab, partials never leave the SM"},
         "result_check": {"sum_ll": res["sum_ll"], "sum_ll_e2e": res2["sum_ll"], "wall_s": wall},
     }
     if world == 1 and not args.no_cpu_baseline:
