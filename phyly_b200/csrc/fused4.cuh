@@ -398,12 +398,15 @@ __device__ __forceinline__ void f4_marg_out(const F4Args &a, double *accM, int n
 }
 
 
-/* root of one site: likelihood of each category, combined over categories with their scale counts */
+/* root of one site: likelihood of each category, combined over categories with their scale counts.
+ * Kept free of data-dependent branches: with branches here nvcc 12.9 stops treating the op loops of the
+ * constant-memory kernels as warp-uniform (tools/check_cm_uniform.sh). */
 template <int C, int BD>
 __device__ __forceinline__ void f4_root_site(const F4Args &a, const double *cur, int tid, int curf, const double *prior,
                                              const int *ktot, int *kcat, double &site_m, int &site_k, bool &have)
 {
     constexpr int bd = BD;
+    double vv[C];
 #pragma unroll
         for (int c = 0; c < C; c++) {
             double r[4];
@@ -419,25 +422,22 @@ __device__ __forceinline__ void f4_root_site(const F4Args &a, const double *cur,
                 lh = fma(a.root_vec[2], r[2], lh);
                 lh = fma(a.root_vec[3], r[3], lh);
             }
-            const double v = prior[c] * lh;
-            kcat[c] = (v > 0.0) ? ktot[c] : INT_MIN;
-            if (v > 0.0) {
-                if (!have) { site_m = v; site_k = ktot[c]; have = true; }
-                else if (ktot[c] > site_k) { site_m = scalbn(site_m, PLF_SCALE_BITS * (site_k - ktot[c])) + v; site_k = ktot[c]; }
-                else if (ktot[c] == site_k) site_m += v;
-                else site_m += scalbn(v, PLF_SCALE_BITS * (ktot[c] - site_k));
-            }
+            vv[c] = prior[c] * lh;
+            kcat[c] = (vv[c] > 0.0) ? ktot[c] : INT_MIN;
         }
-}
-
-/* The same, out of line.  CM kernels call this one: with the root code inlined into the tile loop the
- * compiler stops treating the op loops as warp-uniform (observed with nvcc 12.9), and the uniform
- * constant loads are the point of those kernels. */
-template <int C, int BD>
-__device__ __noinline__ void f4_root_site_ool(const F4Args &a, const double *cur, int tid, int curf, const double *prior,
-                                              const int *ktot, int *kcat, double &site_m, int &site_k, bool &have)
-{
-    f4_root_site<C, BD>(a, cur, tid, curf, prior, ktot, kcat, site_m, site_k, have);
+        /* branch-free combination: largest exponent first, then every live category scaled onto it */
+        int km = INT_MIN;
+#pragma unroll
+        for (int c = 0; c < C; c++) km = max(km, kcat[c]);
+        have = km != INT_MIN;
+        site_k = have ? km : 0;
+        site_m = 0.0;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const int dk = (kcat[c] == INT_MIN) ? 0 : kcat[c] - site_k;          /* <= 0 */
+            const double sc = (dk < -3) ? 0.0 : __hiloint2double((1023 + PLF_SCALE_BITS * dk) << 20, 0);
+            site_m += (kcat[c] == INT_MIN) ? 0.0 : vv[c] * sc;
+        }
 }
 
 /* values of the kernel's frame that the out-of-line outside step needs */
@@ -802,8 +802,7 @@ __global__ void __launch_bounds__(BD) fused4_kernel(const F4Args a, const __grid
         int site_k = 0;
         bool have = false;
         int kcat[C];
-        if (CM) f4_root_site_ool<C, BD>(a, cur, tid, curf, prior, ktot, kcat, site_m, site_k, have);
-        else f4_root_site<C, BD>(a, cur, tid, curf, prior, ktot, kcat, site_m, site_k, have);
+        f4_root_site<C, BD>(a, cur, tid, curf, prior, ktot, kcat, site_m, site_k, have);
         {
             const double c_hi = 177.445678223346, c_lo = 5.936759843446527e-15;   /* 256 ln 2 */
             double ll = log(site_m);

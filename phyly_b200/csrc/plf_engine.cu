@@ -129,9 +129,9 @@ struct plf_engine {
     int stack_depth = 0, nslots = 0, max_degree = 0;
     bool TP_valid = false, program_dirty = true;
     F4Prog prog_h;
-    uint64_t program_version = 0, f4_tuned_version = ~(uint64_t)0;
-    size_t f4_tuned_pick = 0;
-    int f4_tuned_C = 0, f4_tuned_K = 0;
+    uint64_t program_version = 0, f4_tuned_version[2] = {~(uint64_t)0, ~(uint64_t)0};     /* [0] ll, [1] edge queries */
+    size_t f4_tuned_pick[2] = {0, 0};
+    int f4_tuned_C[2] = {0, 0}, f4_tuned_K[2] = {0, 0};
 
     /* scratch */
     DevBuf d_scratch, d_scratchS, d_block_ll, d_block_edge, d_edge_site, d_sum, d_site_ll, d_err, d_mask;
@@ -1007,7 +1007,6 @@ static int run_fused(plf_engine *e, Query &q)
         bool can_cm = (size_t)e->C * e->edge_of_int.size() * 16 <= F4_CM_MAXD && e->ops.size() <= F4_CM_MAXOPS &&
                       e->children.size() <= F4_CM_MAXCH && e->device < 64;
         for (const F4Op &op : e->ops) if (op.nchild != 2) can_cm = false;     /* CM kernels carry the two-children step only */
-        if (!edge) can_cm = false;      /* the log-likelihood-only kernel is faster with the matrices in shared memory */
         const Cand mcands[] = {
             {384, 1, true, false, can_pack ? f4_select_marg<384, 1, true>(e->C) : nullptr, 0, 0},
             {384, 1, false, false, f4_select_marg<384, 1, false>(e->C), 0, 0},
@@ -1026,7 +1025,7 @@ static int run_fused(plf_engine *e, Query &q)
         };
         const Cand *cands = marg ? mcands : ecands;
         const int ncand = marg ? (int)(sizeof(mcands) / sizeof(mcands[0])) : (int)(sizeof(ecands) / sizeof(ecands[0]));
-        const char *force = (edge && !marg) ? getenv("PLF_F4_CONFIG") : nullptr;
+        const char *force = marg ? nullptr : getenv(edge ? "PLF_F4_CONFIG" : "PLF_F4_CONFIG_LL");
         size_t smem = 0;
         for (int i = 0; i < ncand; i++) {
             if (force && atoi(force) != i) continue;
@@ -1055,12 +1054,12 @@ static int run_fused(plf_engine *e, Query &q)
      * instantiation (tools/check_cm_uniform.sh), so the first large query times the leading candidates
      * on a sample of the sites and keeps the fastest. */
     const int64_t tune_sites = (int64_t)e->sm_count * 512 * 2;
-    const bool can_tune = edge && !marg && viable.size() > 1 && viable[0].cm && e->S >= tune_sites / 2 && !getenv("PLF_F4_NOTUNE");
+    const bool can_tune = !marg && viable.size() > 1 && viable[0].cm && e->S >= tune_sites / 2 && !getenv("PLF_F4_NOTUNE");
     size_t pick = 0;
     bool tune = false;
     if (can_tune) {
-        if (e->f4_tuned_version == e->program_version && e->f4_tuned_C == e->C && e->f4_tuned_K == e->K &&
-            e->f4_tuned_pick < viable.size()) pick = e->f4_tuned_pick;
+        if (e->f4_tuned_version[edge] == e->program_version && e->f4_tuned_C[edge] == e->C && e->f4_tuned_K[edge] == e->K &&
+            e->f4_tuned_pick[edge] < viable.size()) pick = e->f4_tuned_pick[edge];
         else if (!pipelined) tune = true;
         else while (pick + 1 < viable.size() && viable[pick].cm) pick++;      /* untuned and data still in flight */
     } else {
@@ -1142,8 +1141,8 @@ static int run_fused(plf_engine *e, Query &q)
             }
             if (i == 0 || ms < best) { best = ms; pick = i; }
         }
-        e->f4_tuned_version = e->program_version; e->f4_tuned_C = e->C; e->f4_tuned_K = e->K;
-        e->f4_tuned_pick = pick;
+        e->f4_tuned_version[edge] = e->program_version; e->f4_tuned_C[edge] = e->C; e->f4_tuned_K[edge] = e->K;
+        e->f4_tuned_pick[edge] = pick;
         CK(e, cudaMemsetAsync(e->d_err.p, 0, sizeof(int), e->stream));
     }
     const Cand &use = viable[pick];
