@@ -80,7 +80,8 @@ struct F4Args {
     double root_vec[4];
     const double *site_w;            /* [S] or NULL */
     const unsigned char *edge_mask;  /* [E] or NULL */
-    int stack_depth;                 /* ll-only mode: shared-memory stack entries */
+    int stack_depth;                 /* ll-only mode: shared-memory stack entries (0 when the stack is global) */
+    int gstack;                      /* ll-only mode: pending partials go to scratch / scratchS (L2-resident) */
     int nslots;
     double4 *scratch;                /* [nslots][C][T] */
     unsigned int *scratchS;          /* [nslots][T]: byte c = rescale count | const flag << 6 */
@@ -700,11 +701,21 @@ __global__ void __launch_bounds__(BD) fused4_kernel(const F4Args a, const __grid
         for (int o = 0; o < a.nops; o++) {
             const F4Op op = F4_OP(o);
             if (!EDGE && op.spill_before) {
+                if (a.gstack) {
+                    /* a few hundred bytes per thread that come back within the tile: they stay in L2 */
 #pragma unroll
-                for (int c = 0; c < C; c++)
+                    for (int c = 0; c < C; c++)
+                        a.scratch[((size_t)sp * C + c) * T + gtid] =
+                            make_double4(cur[(c * 4 + 0) * bd + tid], cur[(c * 4 + 1) * bd + tid],
+                                         cur[(c * 4 + 2) * bd + tid], cur[(c * 4 + 3) * bd + tid]);
+                    a.scratchS[(size_t)sp * T + gtid] = (unsigned int)curf;
+                } else {
 #pragma unroll
-                    for (int i = 0; i < 4; i++) stack[((sp * C + c) * 4 + i) * bd + tid] = cur[(c * 4 + i) * bd + tid];
-                stackf[sp * bd + tid] = curf;
+                    for (int c = 0; c < C; c++)
+#pragma unroll
+                        for (int i = 0; i < 4; i++) stack[((sp * C + c) * 4 + i) * bd + tid] = cur[(c * 4 + i) * bd + tid];
+                    stackf[sp * bd + tid] = curf;
+                }
                 sp++;
             }
             double acc[C][4];
@@ -750,11 +761,20 @@ __global__ void __launch_bounds__(BD) fused4_kernel(const F4Args a, const __grid
                         }
                     } else {
                         sp--;
-                        bc = stackf[sp * bd + tid];
+                        if (a.gstack) {
+                            bc = (int)a.scratchS[(size_t)sp * T + gtid];
 #pragma unroll
-                        for (int c = 0; c < C; c++)
+                            for (int c = 0; c < C; c++) {
+                                const double4 l4 = a.scratch[((size_t)sp * C + c) * T + gtid];
+                                v[c][0] = l4.x; v[c][1] = l4.y; v[c][2] = l4.z; v[c][3] = l4.w;
+                            }
+                        } else {
+                            bc = stackf[sp * bd + tid];
 #pragma unroll
-                            for (int i = 0; i < 4; i++) v[c][i] = stack[((sp * C + c) * 4 + i) * bd + tid];
+                            for (int c = 0; c < C; c++)
+#pragma unroll
+                                for (int i = 0; i < 4; i++) v[c][i] = stack[((sp * C + c) * 4 + i) * bd + tid];
+                        }
                     }
                     if (bc) {
 #pragma unroll

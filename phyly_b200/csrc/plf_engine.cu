@@ -949,16 +949,17 @@ static cudaEvent_t g_cm_done[64];
 
 /* mirrors the shared-memory carve-up at the top of fused4_kernel */
 static size_t f4_smem_bytes(const plf_engine *e, bool edge, int bd, int staged, bool pack = false, bool cm = false,
-                            bool marg = false)
+                            bool marg = false, bool gstack = false)
 {
+    const int sdepth = gstack ? 0 : e->stack_depth;
     const int C = e->C, Ei = cm ? 0 : (int)e->edge_of_int.size(), Et = (int)e->edge_of_tip.size();
     size_t off = 0;
     off = f4_align16(off + (cm ? 0 : sizeof(F4Op) * e->ops.size()));
     off = f4_align16(off + (cm ? 0 : sizeof(F4Child) * e->children.size()));
     off = f4_align16(off + sizeof(double) * 4 * C * bd);
     off = f4_align16(off + ((edge && !marg) ? sizeof(double) * (bd / 32) * e->E : 0));
-    off = f4_align16(off + (edge ? 0 : sizeof(double) * 4 * C * bd * e->stack_depth));
-    off = f4_align16(off + (edge ? 0 : sizeof(int) * bd * e->stack_depth));
+    off = f4_align16(off + (edge ? 0 : sizeof(double) * 4 * C * bd * sdepth));
+    off = f4_align16(off + (edge ? 0 : sizeof(int) * bd * sdepth));
     off = f4_align16(off + (pack ? (e->code_row_node.size() + 1) / 2 : e->code_row_node.size()) * bd);
     off = f4_align16(off + e->K);
     off = f4_align16(off + sizeof(double) * 4 * e->K);
@@ -999,7 +1000,7 @@ static int run_fused(plf_engine *e, Query &q)
 
     /* candidate configurations (block size, which tables are staged in shared memory, packed codes, matrices
      * in constant memory), preferred first.  PLF_F4_CONFIG=<index> forces one (tuning aid, edge queries). */
-    struct Cand { int bd, staged; bool pack, cm; f4_kernel_t k; size_t smem; int per_sm; };
+    struct Cand { int bd, staged; bool pack, cm; f4_kernel_t k; size_t smem; int per_sm; bool gstack; };
     std::vector<Cand> viable;
     {
         const size_t smem_cap = 227 * 1024;
@@ -1023,15 +1024,29 @@ static int run_fused(plf_engine *e, Query &q)
             {256, 2, false, false, f4_select_c<256, 2, false>(e->C, edge), 0, 0},
             {128, 0, false, false, f4_select_c<128, 0, false>(e->C, edge), 0, 0},
         };
-        const Cand *cands = marg ? mcands : ecands;
-        const int ncand = marg ? (int)(sizeof(mcands) / sizeof(mcands[0])) : (int)(sizeof(ecands) / sizeof(ecands[0]));
+        /* log-likelihood only: no slab; the pending partials of the post-order walk either sit in shared
+         * memory (which limits the CTA to 256 threads at depth 3) or in a small L2-resident global stack */
+        const Cand lcands[] = {
+            {512, 2, true, true, (can_cm && can_pack) ? f4_select_c<512, 2, true, true>(e->C, false) : nullptr, 0, 0, true},
+            {512, 2, true, false, can_pack ? f4_select_c<512, 2, true, false>(e->C, false) : nullptr, 0, 0, true},
+            {512, 2, false, true, can_cm ? f4_select_c<512, 2, false, true>(e->C, false) : nullptr, 0, 0, true},
+            {384, 2, true, false, can_pack ? f4_select_c<384, 2, true>(e->C, false) : nullptr, 0, 0, true},
+            {384, 2, true, false, can_pack ? f4_select_c<384, 2, true>(e->C, false) : nullptr, 0, 0, false},
+            {384, 1, false, false, f4_select_c<384, 1, false>(e->C, false), 0, 0, false},
+            {256, 2, false, false, f4_select_c<256, 2, false>(e->C, false), 0, 0, false},
+            {256, 2, false, false, f4_select_c<256, 2, false>(e->C, false), 0, 0, true},
+            {128, 0, false, false, f4_select_c<128, 0, false>(e->C, false), 0, 0, false},
+        };
+        const Cand *cands = marg ? mcands : (edge ? ecands : lcands);
+        const int ncand = marg ? (int)(sizeof(mcands) / sizeof(mcands[0]))
+                               : (edge ? (int)(sizeof(ecands) / sizeof(ecands[0])) : (int)(sizeof(lcands) / sizeof(lcands[0])));
         const char *force = marg ? nullptr : getenv(edge ? "PLF_F4_CONFIG" : "PLF_F4_CONFIG_LL");
         size_t smem = 0;
         for (int i = 0; i < ncand; i++) {
             if (force && atoi(force) != i) continue;
             if (!cands[i].k) continue;
             Cand c = cands[i];
-            c.smem = smem = f4_smem_bytes(e, edge, c.bd, c.staged, c.pack, c.cm, marg);
+            c.smem = smem = f4_smem_bytes(e, edge, c.bd, c.staged, c.pack, c.cm, marg, c.gstack);
             if (c.smem > smem_cap) continue;
             CK(e, cudaFuncSetAttribute(c.k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
             CK(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.per_sm, c.k, c.bd, c.smem));
@@ -1108,8 +1123,17 @@ static int run_fused(plf_engine *e, Query &q)
             a.edge_site_out = e->d_edge_site.as<double>();
         }
     }
-    bool any_cm = false;
-    for (size_t i = 0; i < viable.size(); i++) if ((tune || i == pick) && viable[i].cm) any_cm = true;
+    bool any_cm = false, any_gstack = false;
+    for (size_t i = 0; i < viable.size(); i++) {
+        if (!(tune || i == pick)) continue;
+        if (viable[i].cm) any_cm = true;
+        if (viable[i].gstack) any_gstack = true;
+    }
+    if (!edge && any_gstack && e->stack_depth > 0) {
+        ENSURE(e, e->d_scratch, sizeof(double4) * (size_t)e->C * e->stack_depth * Tmax);
+        ENSURE(e, e->d_scratchS, sizeof(unsigned int) * (size_t)e->stack_depth * Tmax);
+        a.scratch = e->d_scratch.as<double4>(); a.scratchS = e->d_scratchS.as<unsigned int>();
+    }
     std::unique_lock<std::mutex> cm_lock(g_cm_mutex, std::defer_lock);
     if (any_cm) {
         /* program as a kernel parameter, matrices into the constant bank (ordered against other engines) */
@@ -1130,6 +1154,9 @@ static int run_fused(plf_engine *e, Query &q)
         a.s_begin = 0; a.s_end = std::min<int64_t>(e->S, tune_sites);
         for (size_t i = 0; i < ntry; i++) {
             const Cand &c = viable[i];
+            a.gstack = c.gstack ? 1 : 0; a.stack_depth = c.gstack ? 0 : e->stack_depth;
+            /* candidates may share a kernel function with different amounts of dynamic shared memory */
+            CK(e, cudaFuncSetAttribute(c.k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
             float ms = 0.f;
             for (int rep = 0; rep < 2; rep++) {      /* the first launch of a kernel pays for loading its code */
                 CK(e, cudaEventRecord(e->ev[3], e->stream));
@@ -1147,6 +1174,8 @@ static int run_fused(plf_engine *e, Query &q)
     }
     const Cand &use = viable[pick];
     const int grid = grid_of(use);
+    a.gstack = use.gstack ? 1 : 0; a.stack_depth = use.gstack ? 0 : e->stack_depth;
+    CK(e, cudaFuncSetAttribute(use.k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)use.smem));
     CK(e, cudaEventRecord(e->ev[3], e->stream));
     for (size_t k = 0; k < nchunk; k++) {
         a.s_begin = bounds[k]; a.s_end = bounds[k + 1];

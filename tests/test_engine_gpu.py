@@ -245,11 +245,15 @@ def test_constant_memory_kernels(name, prob, config, monkeypatch):
         pytest.skip("not a binary 4-state problem")
     from phyly_b200 import engine as E
     monkeypatch.setenv("PLF_F4_CONFIG", str(config))
+    monkeypatch.setenv("PLF_F4_CONFIG_LL", "0" if config == 0 else "2")     # the ll-only constant-memory kernels
     ll_w, D_w = ref["ll"], ref["D"]
     S = m.site_count
     eng = _engine()
     cs = H.fill_engine(eng, m)
     eng.set_path(E.PATH_FUSED4)
+    site_ll, tot = eng.ll()
+    _assert_close(site_ll, ll_w, "%s cm%d ll-only" % (name, config), atol=LL_ATOL)
+    assert H.close(tot, float(np.sum(ll_w)), 1e-11, 1e-13)
     r = eng.deriv(per_site=True, per_site_ll=True)
     _assert_close(r["site_ll"], ll_w, "%s cm%d ll" % (name, config), atol=LL_ATOL)
     _assert_close(r["site_deriv"], D_w, "%s cm%d deriv" % (name, config), atol=CANCEL * ref["Dabs"] + 1e-300)
