@@ -1,8 +1,10 @@
 import csv, re, collections, sys
 raw, src = sys.argv[1], sys.argv[2]
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0      # which captured launch
 rows=list(csv.reader(open(raw)))
-hdr=rows[0]; units=rows[1]; r=rows[2]
-want=['gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum','gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed','launch__registers_per_thread','launch__grid_size','launch__block_size','smsp__inst_executed.sum','sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active','sm__warps_active.avg.pct_of_peak_sustained_active','smsp__issue_active.avg.pct_of_peak_sustained_active','l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed','launch__shared_mem_per_block_dynamic','l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum','l1tex__data_pipe_lsu_wavefronts_mem_shared.sum','lts__t_sector_hit_rate.pct','l1tex__t_sector_hit_rate.pct','sm__inst_executed_pipe_lsu.sum.pct_of_peak_sustained_active']
+hdr=rows[0]; units=rows[1]; r=rows[2 + which]
+print('kernel:', r[hdr.index('Kernel Name')])
+want=['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active','gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum','gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed','launch__registers_per_thread','launch__grid_size','launch__block_size','smsp__inst_executed.sum','sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active','sm__warps_active.avg.pct_of_peak_sustained_active','smsp__issue_active.avg.pct_of_peak_sustained_active','l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed','launch__shared_mem_per_block_dynamic','l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum','l1tex__data_pipe_lsu_wavefronts_mem_shared.sum','lts__t_sector_hit_rate.pct','l1tex__t_sector_hit_rate.pct','sm__inst_executed_pipe_lsu.sum.pct_of_peak_sustained_active']
 for i,h in enumerate(hdr):
     if h in want: print('  %-75s %s %s'%(h, r[i], units[i]))
 rows=list(csv.reader(open(src)))
@@ -12,7 +14,8 @@ for rr in rows:
     if cur is None: continue
     if cur['hdr'] is None: cur['hdr']=rr; continue
     cur['rows'].append(rr)
-sec=sections[0]; hdr=sec['hdr']; ix={h:i for i,h in enumerate(hdr)}
+nlaunch=max(1,len(list(csv.reader(open(raw))))-2)
+sec=sections[which*max(1,len(sections)//nlaunch)]; hdr=sec['hdr']; ix={h:i for i,h in enumerate(hdr)}
 def f(x):
     try: return float(x)
     except: return 0.0
