@@ -234,6 +234,32 @@ __device__ __forceinline__ void f4_prefetch(const void *p)
 }
 
 
+/*
+ * Unstaged kernels (trees whose tables exceed shared memory): fetch what the coming node will read into L1 --
+ * the 4x4 matrices of its internal-child edges (one 128-byte line per category, lanes 0..C-1 of each warp)
+ * and, per thread, the tip-table rows its own character codes select.
+ */
+template <int C, int BD, bool PACK, bool WITH_F>
+__device__ __forceinline__ void f4_prefetch_tables(const F4Args &a, const F4Child &nc, const unsigned char *tile,
+                                                   const double *Pint, const double *Fint, const double *TP, const double *TF,
+                                                   int pstride, int tpstride, int tid, int lane)
+{
+    if (nc.kind == F4_KIND_TIP) {
+        const int code = f4_code<BD, PACK>(tile, nc.code_row, tid);
+        const double *tp = TP + (nc.mat * a.K + code) * 4;
+#pragma unroll
+        for (int c = 0; c < C; c++) f4_prefetch(tp + c * tpstride);
+        if (WITH_F) {
+            const double *tf = TF + (nc.mat * a.K + code) * 4;
+#pragma unroll
+            for (int c = 0; c < C; c++) f4_prefetch(tf + c * tpstride);
+        }
+    } else if (lane < C) {
+        f4_prefetch(Pint + lane * pstride + nc.mat * 16);
+        if (WITH_F) f4_prefetch(Fint + lane * pstride + nc.mat * 16);
+    }
+}
+
 /* sums of two values over the warp in one butterfly: sum(a) lands in lanes < 16, sum(b) in lanes >= 16 */
 __device__ __forceinline__ double f4_warp_sum2(double a, double b, int lane)
 {
@@ -700,6 +726,11 @@ __global__ void __launch_bounds__(BD) fused4_kernel(const F4Args a, const __grid
 #pragma unroll 1
         for (int o = 0; o < a.nops; o++) {
             const F4Op op = F4_OP(o);
+            if (STAGED == 0 && !CM && o + 1 < a.nops) {
+                const F4Op nx = F4_OP(o + 1);
+                for (int j = 0; j < nx.nchild; j++)
+                    f4_prefetch_tables<C, BD, PACK, false>(a, F4_CH(nx.first_child + j), tile, Pint, Fint, TP, TF, pstride, tpstride, tid, lane);
+            }
             if (!EDGE && op.spill_before) {
                 if (a.gstack) {
                     /* a few hundred bytes per thread that come back within the tile: they stay in L2 */
@@ -867,6 +898,8 @@ __global__ void __launch_bounds__(BD) fused4_kernel(const F4Args a, const __grid
 #pragma unroll
                         for (int c = 0; c < C; c++) f4_prefetch(&a.scratch[((size_t)nc.slot * C + c) * T + gtid]);
                     }
+                    if (STAGED == 0 && !CM)
+                        f4_prefetch_tables<C, BD, PACK, !MARG>(a, nc, tile, Pint, Fint, TP, TF, pstride, tpstride, tid, lane);
                 }
             }
             if (op.nchild == 2) {

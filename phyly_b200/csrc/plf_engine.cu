@@ -46,7 +46,7 @@ struct DevBuf {
         cap = want;
         /* debugging aid: fresh device memory is usually zero, which hides reads of cells nobody wrote */
         static const bool poison = getenv("PLF_POISON") != nullptr;
-        if (poison) cudaMemset(p, 0xFF, want);
+        if (poison) { cudaMemset(p, 0xFF, want); cudaDeviceSynchronize(); }   /* also against non-blocking streams */
         return 0;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -129,9 +129,9 @@ struct plf_engine {
     int stack_depth = 0, nslots = 0, max_degree = 0;
     bool TP_valid = false, program_dirty = true;
     F4Prog prog_h;
-    uint64_t program_version = 0, f4_tuned_version[2] = {~(uint64_t)0, ~(uint64_t)0};     /* [0] ll, [1] edge queries */
-    size_t f4_tuned_pick[2] = {0, 0};
-    int f4_tuned_C[2] = {0, 0}, f4_tuned_K[2] = {0, 0};
+    uint64_t program_version = 0, f4_tuned_version[3] = {~(uint64_t)0, ~(uint64_t)0, ~(uint64_t)0};   /* ll, edge forms, marginals */
+    size_t f4_tuned_pick[3] = {0, 0, 0};
+    int f4_tuned_C[3] = {0, 0, 0}, f4_tuned_K[3] = {0, 0, 0};
 
     /* scratch */
     DevBuf d_scratch, d_scratchS, d_block_ll, d_block_edge, d_edge_site, d_sum, d_site_ll, d_err, d_mask;
@@ -1012,6 +1012,10 @@ static int run_fused(plf_engine *e, Query &q)
             {384, 1, true, false, can_pack ? f4_select_marg<384, 1, true>(e->C) : nullptr, 0, 0},
             {384, 1, false, false, f4_select_marg<384, 1, false>(e->C), 0, 0},
             {256, 1, false, false, f4_select_marg<256, 1, false>(e->C), 0, 0},
+            /* larger trees: tables through L1 / L2, CTAs stay large */
+            {384, 0, true, false, can_pack ? f4_select_marg<384, 0, true>(e->C) : nullptr, 0, 0},
+            {384, 0, false, false, f4_select_marg<384, 0, false>(e->C), 0, 0},
+            {256, 0, false, false, f4_select_marg<256, 0, false>(e->C), 0, 0},
             {128, 0, false, false, f4_select_marg<128, 0, false>(e->C), 0, 0},
         };
         const Cand ecands[] = {
@@ -1022,6 +1026,11 @@ static int run_fused(plf_engine *e, Query &q)
             {384, 1, false, false, f4_select_c<384, 1, false>(e->C, edge), 0, 0},
             {512, 1, false, false, f4_select_c<512, 1, false>(e->C, edge), 0, 0},
             {256, 2, false, false, f4_select_c<256, 2, false>(e->C, edge), 0, 0},
+            /* larger trees (the tables no longer fit shared memory): tables through L1 / L2, CTAs stay large */
+            {512, 0, true, false, can_pack ? f4_select_c<512, 0, true>(e->C, edge) : nullptr, 0, 0},
+            {384, 0, true, false, can_pack ? f4_select_c<384, 0, true>(e->C, edge) : nullptr, 0, 0},
+            {384, 0, false, false, f4_select_c<384, 0, false>(e->C, edge), 0, 0},
+            {256, 0, false, false, f4_select_c<256, 0, false>(e->C, edge), 0, 0},
             {128, 0, false, false, f4_select_c<128, 0, false>(e->C, edge), 0, 0},
         };
         /* log-likelihood only: no slab; the pending partials of the post-order walk either sit in shared
@@ -1035,6 +1044,11 @@ static int run_fused(plf_engine *e, Query &q)
             {384, 1, false, false, f4_select_c<384, 1, false>(e->C, false), 0, 0, false},
             {256, 2, false, false, f4_select_c<256, 2, false>(e->C, false), 0, 0, false},
             {256, 2, false, false, f4_select_c<256, 2, false>(e->C, false), 0, 0, true},
+            {512, 0, true, false, can_pack ? f4_select_c<512, 0, true>(e->C, false) : nullptr, 0, 0, true},
+            {384, 0, true, false, can_pack ? f4_select_c<384, 0, true>(e->C, false) : nullptr, 0, 0, true},
+            {384, 0, false, false, f4_select_c<384, 0, false>(e->C, false), 0, 0, true},
+            {256, 0, false, false, f4_select_c<256, 0, false>(e->C, false), 0, 0, true},
+            {128, 0, false, false, f4_select_c<128, 0, false>(e->C, false), 0, 0, true},
             {128, 0, false, false, f4_select_c<128, 0, false>(e->C, false), 0, 0, false},
         };
         const Cand *cands = marg ? mcands : (edge ? ecands : lcands);
@@ -1069,12 +1083,13 @@ static int run_fused(plf_engine *e, Query &q)
      * instantiation (tools/check_cm_uniform.sh), so the first large query times the leading candidates
      * on a sample of the sites and keeps the fastest. */
     const int64_t tune_sites = (int64_t)e->sm_count * 512 * 2;
-    const bool can_tune = !marg && viable.size() > 1 && viable[0].cm && e->S >= tune_sites / 2 && !getenv("PLF_F4_NOTUNE");
+    const bool can_tune = viable.size() > 1 && e->S >= tune_sites / 2 && !getenv("PLF_F4_NOTUNE");
+    const int tm = marg ? 2 : (edge ? 1 : 0);      /* tuning slot: ll, edge forms, marginals */
     size_t pick = 0;
     bool tune = false;
     if (can_tune) {
-        if (e->f4_tuned_version[edge] == e->program_version && e->f4_tuned_C[edge] == e->C && e->f4_tuned_K[edge] == e->K &&
-            e->f4_tuned_pick[edge] < viable.size()) pick = e->f4_tuned_pick[edge];
+        if (e->f4_tuned_version[tm] == e->program_version && e->f4_tuned_C[tm] == e->C && e->f4_tuned_K[tm] == e->K &&
+            e->f4_tuned_pick[tm] < viable.size()) pick = e->f4_tuned_pick[tm];
         else if (!pipelined) tune = true;
         else while (pick + 1 < viable.size() && viable[pick].cm) pick++;      /* untuned and data still in flight */
     } else {
@@ -1168,9 +1183,12 @@ static int run_fused(plf_engine *e, Query &q)
             }
             if (i == 0 || ms < best) { best = ms; pick = i; }
         }
-        e->f4_tuned_version[edge] = e->program_version; e->f4_tuned_C[edge] = e->C; e->f4_tuned_K[edge] = e->K;
-        e->f4_tuned_pick[edge] = pick;
+        e->f4_tuned_version[tm] = e->program_version; e->f4_tuned_C[tm] = e->C; e->f4_tuned_K[tm] = e->K;
+        e->f4_tuned_pick[tm] = pick;
         CK(e, cudaMemsetAsync(e->d_err.p, 0, sizeof(int), e->stream));
+        /* the marginal accumulators are added to by every launch: forget what the timing runs left there */
+        if (marg && a.block_marg)
+            CK(e, cudaMemsetAsync(e->d_block_marg.p, 0, sizeof(double) * (size_t)gmax * 16 * e->N * 4, e->stream));
     }
     const Cand &use = viable[pick];
     const int grid = grid_of(use);
