@@ -28,6 +28,12 @@
  *     is usable plf_create fails.
  *   - a handle is not thread safe; use one handle per host thread / per GPU.
  */
+/*
+ * Threading and sharing: an engine handle is to be used from one host thread at a time; different
+ * handles (also on the same device) may be used from different threads -- the one device-wide resource,
+ * the constant bank that holds the matrices of the small-tree kernels, is serialised inside the library.
+ * Queries are synchronous: when a plf_* query returns, its host outputs are final.
+ */
 #ifndef PLF_H
 #define PLF_H
 
