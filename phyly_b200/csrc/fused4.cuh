@@ -103,9 +103,9 @@ struct F4Args {
  * registers and the 4x4 matrices enter the DFMAs as uniform operands (LDCU) instead of costing one
  * shared-memory wavefront per 16 bytes -- the kernel is bound by the LSU pipe, not by fp64 issue.
  */
-#define F4_CM_MAXD 4000      /* doubles per matrix set: C * Ei * 16 <= 4000 (2 sets = 64000 of the 65536 bytes) */
-#define F4_CM_MAXOPS 64
-#define F4_CM_MAXCH 128
+#define F4_CM_MAXD 4064      /* doubles per matrix set: C * Ei * 16 <= 4064 (2 sets = 65024 of the 65536 bytes) */
+#define F4_CM_MAXOPS 128
+#define F4_CM_MAXCH 256
 __constant__ double f4_cP[F4_CM_MAXD];
 __constant__ double f4_cF[F4_CM_MAXD];
 

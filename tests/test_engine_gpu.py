@@ -224,13 +224,13 @@ def test_zero_likelihood_is_an_error():
 
 
 def _cm_applicable(m, C, K):
-    """The constant-memory kernels take binary internal nodes, <= 64 of them, and C * internal edges <= 250."""
+    """The constant-memory kernels take binary internal nodes, <= 128 of them, and C * internal edges <= 254."""
     t = m.tree
     deg = [t.indptr[i + 1] - t.indptr[i] for i in range(t.node_count)]
     internal = [i for i in range(t.node_count) if deg[i] > 0]
     n_int_edges = sum(1 for i in range(t.node_count) for j in range(t.indptr[i], t.indptr[i + 1]) if deg[t.indices[j]] > 0)
-    return (m.n == 4 and C <= 4 and K <= 16 and all(deg[i] == 2 for i in internal) and len(internal) <= 64
-            and C * n_int_edges <= 250)
+    return (m.n == 4 and C <= 4 and K <= 16 and all(deg[i] == 2 for i in internal) and len(internal) <= 128
+            and C * n_int_edges <= 254)
 
 
 @pytest.mark.parametrize("config", [0, 1, 2])
