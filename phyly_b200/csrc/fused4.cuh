@@ -260,6 +260,21 @@ __device__ __forceinline__ void f4_prefetch_tables(const F4Args &a, const F4Chil
     }
 }
 
+/* slab accesses: every line is written once and read once, so they are marked streaming (evict-first) and do
+ * not displace the tables and prefetched lines in L1 / L2 */
+__device__ __forceinline__ double4 f4_slab_ld(const double4 *p)
+{
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    const double2 a = __ldcs(q), b = __ldcs(q + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void f4_slab_st(double4 *p, double x, double y, double z, double w)
+{
+    double2 *q = reinterpret_cast<double2 *>(p);
+    __stcs(q, make_double2(x, y));
+    __stcs(q + 1, make_double2(z, w));
+}
+
 /* sums of two values over the warp in one butterfly: sum(a) lands in lanes < 16, sum(b) in lanes >= 16 */
 __device__ __forceinline__ double f4_warp_sum2(double a, double b, int lane)
 {
@@ -298,15 +313,15 @@ __device__ __forceinline__ void f4_outside2(const F4Args &a, const F4Op &op, con
         /* loads of this category first */
         double l0[4], l1[4], fa[4];
         if (K0 != F4_KIND_TIP) {
-            double4 v = a.scratch[((size_t)c0.slot * C + c) * T + gtid];
+            double4 v = f4_slab_ld(&a.scratch[((size_t)c0.slot * C + c) * T + gtid]);
             l0[0] = v.x; l0[1] = v.y; l0[2] = v.z; l0[3] = v.w;
         }
         if (K1 != F4_KIND_TIP) {
-            double4 v = a.scratch[((size_t)c1.slot * C + c) * T + gtid];
+            double4 v = f4_slab_ld(&a.scratch[((size_t)c1.slot * C + c) * T + gtid]);
             l1[0] = v.x; l1[1] = v.y; l1[2] = v.z; l1[3] = v.w;
         }
         if (from_slot) {
-            double4 v = a.scratch[((size_t)op.slot * C + c) * T + gtid];
+            double4 v = f4_slab_ld(&a.scratch[((size_t)op.slot * C + c) * T + gtid]);
             fa[0] = v.x; fa[1] = v.y; fa[2] = v.z; fa[3] = v.w;
         } else {
 #pragma unroll
@@ -379,14 +394,14 @@ __device__ __forceinline__ void f4_outside2(const F4Args &a, const F4Op &op, con
 #pragma unroll
                 for (int i = 0; i < 4; i++) cur[(c * 4 + i) * BD + tid] = fb[i];
             } else {
-                a.scratch[((size_t)c0.slot * C + c) * T + gtid] = make_double4(fb[0], fb[1], fb[2], fb[3]);
+                f4_slab_st(&a.scratch[((size_t)c0.slot * C + c) * T + gtid], fb[0], fb[1], fb[2], fb[3]);
             }
         }
         if (K1 != F4_KIND_TIP) {
             double fb[4];
             f4_mvt<CM>(Pint, c * pstride + c1.mat * 16, fe1, fb);
             /* the child's inside vector is dead after this op: its slot carries fn down */
-            a.scratch[((size_t)c1.slot * C + c) * T + gtid] = make_double4(fb[0], fb[1], fb[2], fb[3]);
+            f4_slab_st(&a.scratch[((size_t)c1.slot * C + c) * T + gtid], fb[0], fb[1], fb[2], fb[3]);
         }
     }
     if (MARG) {
@@ -519,7 +534,7 @@ __device__ __forceinline__ void f4_outside_general(const F4Args &a, const F4Op &
         double fa[4];
         const size_t so_a = ((size_t)op.slot * C + c) * T + gtid;
         if (from_slot) {
-            double4 f4v = a.scratch[so_a];
+            double4 f4v = f4_slab_ld(&a.scratch[so_a]);
             fa[0] = f4v.x; fa[1] = f4v.y; fa[2] = f4v.z; fa[3] = f4v.w;
         } else {
 #pragma unroll
@@ -542,7 +557,7 @@ __device__ __forceinline__ void f4_outside_general(const F4Args &a, const F4Op &
                 f4_ld4(TP + c * tpstride + (mats[j] * a.K + codes[j]) * 4, em[j]);
                 if (!MARG) f4_ld4(TF + c * tpstride + (mats[j] * a.K + codes[j]) * 4, y[j]);
             } else if (kinds[j] >= 0) {
-                double4 l4 = a.scratch[((size_t)slots[j] * C + c) * T + gtid];
+                double4 l4 = f4_slab_ld(&a.scratch[((size_t)slots[j] * C + c) * T + gtid]);
                 double lv[4] = {l4.x, l4.y, l4.z, l4.w};
                 if (bcs[j]) {
 #pragma unroll
@@ -590,7 +605,7 @@ __device__ __forceinline__ void f4_outside_general(const F4Args &a, const F4Op &
                         for (int i = 0; i < 4; i++) cur[(c * 4 + i) * bd + tid] = fb[i];
                     } else {
                         /* the child's inside vector is dead after this op: its slot carries fn down */
-                        a.scratch[((size_t)slots[j] * C + c) * T + gtid] = make_double4(fb[0], fb[1], fb[2], fb[3]);
+                        f4_slab_st(&a.scratch[((size_t)slots[j] * C + c) * T + gtid], fb[0], fb[1], fb[2], fb[3]);
                     }
                 }
             }
@@ -787,7 +802,7 @@ __global__ void __launch_bounds__(BD) fused4_kernel(const F4Args a, const __grid
                         bc = (a.scratchS[(size_t)ch.slot * T + gtid] >> 6) & 1;
 #pragma unroll
                         for (int c = 0; c < C; c++) {
-                            double4 l4 = a.scratch[so + (size_t)c * T];
+                            double4 l4 = f4_slab_ld(&a.scratch[so + (size_t)c * T]);
                             v[c][0] = l4.x; v[c][1] = l4.y; v[c][2] = l4.z; v[c][3] = l4.w;
                         }
                     } else {
@@ -842,7 +857,7 @@ __global__ void __launch_bounds__(BD) fused4_kernel(const F4Args a, const __grid
                 for (int i = 0; i < 4; i++) cur[(c * 4 + i) * bd + tid] = acc[c][i];
                 if (EDGE) {
                     const size_t so = ((size_t)op.slot * C + c) * T + gtid;
-                    a.scratch[so] = make_double4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+                    f4_slab_st(&a.scratch[so], acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
                 }
             }
             if (EDGE) a.scratchS[(size_t)op.slot * T + gtid] = sword;
