@@ -732,12 +732,16 @@ static int set_data_common(plf_engine *e, int64_t S, int K, const double *defs, 
     if (!e->copy_stream) CK(e, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
     /* whole waves for both the 384- and the 512-thread kernels; the remainder rides with the last chunk so
      * that only one launch ends on a partial wave */
-    const int64_t unit = (int64_t)e->sm_count * 1536;
+    /* Chunks are whole waves of 512-thread CTAs and double in size: the copy runs about twice as fast as the
+     * kernel, so chunk k+1 (twice chunk k) lands just before kernel k ends; the remainder rides with the last
+     * chunk so that only one launch ends on a partial wave. */
+    const int64_t wave = (int64_t)e->sm_count * 512;
     e->pend_bounds.clear();
     e->pend_bounds.push_back(0);
-    /* a short first chunk (one wave of 512-thread CTAs) so that the kernel starts early */
-    int64_t s = (S >= 2 * unit) ? (int64_t)e->sm_count * 512 : unit;
-    for (; s + unit <= S; s += unit) e->pend_bounds.push_back(s);
+    {
+        int64_t s = 0, len = wave;
+        while (S - s - len >= len && e->pend_bounds.size() < 8) { s += len; e->pend_bounds.push_back(s); len *= 2; }
+    }
     e->pend_bounds.push_back(S);
     const size_t nch = e->pend_bounds.size() - 1;
     while (e->chunk_ev.size() < nch + 1) {
