@@ -161,7 +161,7 @@ struct plf_engine {
 /* codes_in[S][N] (1 or 4 bytes) -> codes[N][S] (1 or 4 bytes); also flags nodes that carry data */
 template <typename TIn, typename TOut>
 __global__ void transpose_codes_kernel(const TIn *in, TOut *out, int64_t s_begin, int64_t s_end, int64_t S, int N,
-                                       const unsigned char *def_ones, int *node_flags)
+                                       const unsigned char *def_ones, int *node_flags, int K, int *bad_code)
 {
     __shared__ int tile[32][33];
     const int64_t s0 = s_begin + (int64_t)blockIdx.x * 32;
@@ -177,6 +177,7 @@ __global__ void transpose_codes_kernel(const TIn *in, TOut *out, int64_t s_begin
         int64_t s = s0 + threadIdx.x;
         int code = tile[threadIdx.x][r];
         bool has = false;
+        if (nd < N && s < s_end && (unsigned)code >= (unsigned)K) { *bad_code = 1; code = 0; }   /* reported by the host */
         if (nd < N && s < s_end) {
             out[(size_t)nd * S + s] = (TOut)code;
             has = !def_ones[code];
@@ -625,16 +626,17 @@ static int launch_transpose(plf_engine *e, int64_t s0, int64_t s1, int in_bytes)
     const int N = e->N;
     const int64_t S = e->S;
     int *flags = e->d_err.as<int>() + 4;
+    int *bad = e->d_err.as<int>() + 1;          /* set when a code is not a row of the definition table */
     dim3 blk(32, 8), grid((unsigned)((s1 - s0 + 31) / 32), (unsigned)((N + 31) / 32));
     if (in_bytes == 1)
         transpose_codes_kernel<unsigned char, unsigned char><<<grid, blk, 0, e->stream>>>(
-            e->d_codes_in.as<unsigned char>(), e->d_codes.as<unsigned char>(), s0, s1, S, N, e->d_def_ones.as<unsigned char>(), flags);
+            e->d_codes_in.as<unsigned char>(), e->d_codes.as<unsigned char>(), s0, s1, S, N, e->d_def_ones.as<unsigned char>(), flags, e->K, bad);
     else if (e->code_bytes == 1)
         transpose_codes_kernel<int, unsigned char><<<grid, blk, 0, e->stream>>>(
-            e->d_codes_in.as<int>(), e->d_codes.as<unsigned char>(), s0, s1, S, N, e->d_def_ones.as<unsigned char>(), flags);
+            e->d_codes_in.as<int>(), e->d_codes.as<unsigned char>(), s0, s1, S, N, e->d_def_ones.as<unsigned char>(), flags, e->K, bad);
     else
         transpose_codes_kernel<int, int><<<grid, blk, 0, e->stream>>>(
-            e->d_codes_in.as<int>(), e->d_codes.as<int>(), s0, s1, S, N, e->d_def_ones.as<unsigned char>(), flags);
+            e->d_codes_in.as<int>(), e->d_codes.as<int>(), s0, s1, S, N, e->d_def_ones.as<unsigned char>(), flags, e->K, bad);
     KCHECK(e);
     return 0;
 }
@@ -646,7 +648,16 @@ static int launch_flags_readback(plf_engine *e)
     flags_to_bytes_kernel<<<(e->N + 127) / 128, 128, 0, e->stream>>>(flags, e->d_node_has_data.as<unsigned char>(), e->N);
     KCHECK(e);
     CK(e, cudaMemcpyAsync(e->flags_pinned, e->d_node_has_data.p, e->N, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaMemcpyAsync(e->flags_pinned + e->N, e->d_err.as<int>() + 1, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     return 0;
+}
+
+/* after the readback has completed: did the transposition meet a code outside the definition table? */
+static bool data_has_bad_code(const plf_engine *e)
+{
+    int bad = 0;
+    memcpy(&bad, e->flags_pinned + e->N, sizeof(int));
+    return bad != 0;
 }
 
 /* the stream has been synchronised: compare the flags with the ones the program was built for */
@@ -671,6 +682,7 @@ static int resolve_pending(plf_engine *e)
     CK(e, cudaStreamSynchronize(e->stream));
     adopt_flags(e);
     e->pend_active = false;
+    if (data_has_bad_code(e)) { e->S = 0; FAIL(e, "plf_set_data_async: a character code is not a row of the definition table"); }
     return 0;
 }
 
@@ -706,7 +718,7 @@ static int set_data_common(plf_engine *e, int64_t S, int K, const double *defs, 
     ENSURE(e, e->d_node_has_data, N);
     ENSURE(e, e->d_err, sizeof(int) * (N + 4));
     if (!e->flags_pinned) CK(e, cudaMallocHost((void **)&e->flags_pinned, 1 << 16));
-    if (N > (1 << 16)) FAIL(e, "plf_set_data: more than 65536 nodes");
+    if (N > (1 << 16) - 8) FAIL(e, "plf_set_data: more than 65528 nodes");
     e->S = S; e->K = K; e->code_bytes = dev_bytes;
     e->TP_valid = false;
     e->have_w = false;
@@ -725,6 +737,7 @@ static int set_data_common(plf_engine *e, int64_t S, int K, const double *defs, 
          * caller (the JSON front end) has already validated them (parsemodel.c:600-613). */
         CK(e, cudaStreamSynchronize(e->stream));   /* dconst / dones are locals; the flags are needed now */
         adopt_flags(e);
+        if (data_has_bad_code(e)) { e->S = 0; FAIL(e, "plf_set_data: a character code is not a row of the definition table"); }
         return 0;
     }
     /* asynchronous: chunks of whole waves of the fused kernel (sm_count CTAs x 384 sites), copied on a second
@@ -1262,6 +1275,7 @@ static int run_fused(plf_engine *e, Query &q)
     CK(e, cudaStreamSynchronize(e->stream));
     if (pipelined) {
         e->pend_active = false;
+        if (data_has_bad_code(e)) { e->S = 0; FAIL(e, "plf_set_data_async: a character code is not a row of the definition table"); }
         /* the program was compiled for the previous data's pattern of data-carrying nodes: redo if that changed */
         if (adopt_flags(e)) return 1;
     }

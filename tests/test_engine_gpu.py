@@ -274,3 +274,29 @@ def test_constant_memory_kernels(name, prob, config, monkeypatch):
     xt, _ = eng.edge_expect(E.KIND_TRANS, Lt_hi, Lt_lo)
     _assert_close(xt, ref["Xt"], "%s cm%d trans" % (name, config), atol=1e-300)
     eng.close()
+
+
+def test_out_of_range_character_code_is_an_error():
+    """A code that is not a row of the definition table is caught on the device while the data is transposed
+    (the JSON front end validates codes itself, parsemodel.c:600-613; the binary seam must not trust them)."""
+    from phyly_b200.engine import EngineError
+    prob = H.random_problem(31, ntips=6, n=4, S=50, ncat=2)
+    m = O.parse_model(prob["model_and_data"])
+    defs, codes = H.dedupe_rows(m.dense_pmat())
+    for use_async in (False, True):
+        eng = _engine()
+        H.fill_engine(eng, m)
+        bad = np.ascontiguousarray(codes.astype(np.uint8))
+        bad[17, 3] = defs.shape[0]              # first invalid code
+        if use_async:
+            eng.set_data_async(defs, bad)
+            with pytest.raises(EngineError):
+                eng.ll()
+        else:
+            with pytest.raises(EngineError):
+                eng.set_data(defs, bad)
+        with pytest.raises(EngineError):        # no data is installed afterwards
+            eng.ll()
+        eng.set_data(defs, np.ascontiguousarray(codes.astype(np.uint8)))
+        eng.ll()
+        eng.close()
