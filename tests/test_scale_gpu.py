@@ -255,3 +255,44 @@ def test_async_upload_matches_synchronous_upload():
     eng.set_data_async(defs, codes, w)
     tot = eng.marginal(per_site=False)[1]
     assert np.allclose(tot.sum(axis=1), w.sum(), rtol=1e-11)
+
+
+def test_every_fused_configuration_agrees(monkeypatch):
+    """Each candidate configuration of the fused kernel (block size, staged / unstaged tables with prefetch,
+    packed codes, constant-memory matrices, shared / global stack) is forced in turn on one problem and must
+    reproduce the sums of the default choice; the same for a tree too large for the constant-memory kernels."""
+    from phyly_b200.engine import EngineError
+    for taxa, sites in ((24, 30000), (160, 6000)):
+        b, pb = _problem(sites, taxa)
+        eng = pb["eng"]
+        defs = np.array(b.DEFS, dtype=np.float64)
+        eng.set_data(defs, pb["codes"])
+        rng = np.random.default_rng(5)
+        w = 1.0 + rng.poisson(2.0, pb["S"]).astype(np.float64)
+        eng.set_site_weights(w)
+        monkeypatch.delenv("PLF_F4_CONFIG", raising=False)
+        monkeypatch.delenv("PLF_F4_CONFIG_LL", raising=False)
+        want = eng.deriv(per_site=False)
+        want_ll = eng.ll(per_site=False)[1]
+        scale = np.abs(want["sum_deriv"]).max()
+        ran_edge = ran_ll = 0
+        for i in range(16):
+            monkeypatch.setenv("PLF_F4_CONFIG", str(i))
+            monkeypatch.setenv("PLF_F4_CONFIG_LL", str(i))
+            try:
+                got = eng.deriv(per_site=False)
+            except EngineError as ex:
+                assert "no configuration fits" in str(ex), ex
+            else:
+                ran_edge += 1
+                assert abs(got["sum_ll"] - want["sum_ll"]) <= 1e-12 * abs(want["sum_ll"]), (taxa, i)
+                assert np.all(np.abs(got["sum_deriv"] - want["sum_deriv"]) <= 1e-11 * np.abs(want["sum_deriv"]) + 1e-12 * scale), (taxa, i)
+            try:
+                got_ll = eng.ll(per_site=False)[1]
+            except EngineError as ex:
+                assert "no configuration fits" in str(ex), ex
+            else:
+                ran_ll += 1
+                assert abs(got_ll - want_ll) <= 1e-12 * abs(want_ll), (taxa, i)
+        assert ran_edge >= 3 and ran_ll >= 3, (taxa, ran_edge, ran_ll)
+        eng.close()
