@@ -1071,7 +1071,7 @@ static int run_fused(plf_engine *e, Query &q)
         const Cand *cands = marg ? mcands : (edge ? ecands : lcands);
         const int ncand = marg ? (int)(sizeof(mcands) / sizeof(mcands[0]))
                                : (edge ? (int)(sizeof(ecands) / sizeof(ecands[0])) : (int)(sizeof(lcands) / sizeof(lcands[0])));
-        const char *force = marg ? nullptr : getenv(edge ? "PLF_F4_CONFIG" : "PLF_F4_CONFIG_LL");
+        const char *force = getenv(marg ? "PLF_F4_CONFIG_MARG" : (edge ? "PLF_F4_CONFIG" : "PLF_F4_CONFIG_LL"));
         size_t smem = 0;
         for (int i = 0; i < ncand; i++) {
             if (force && atoi(force) != i) continue;

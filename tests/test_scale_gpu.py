@@ -272,13 +272,23 @@ def test_every_fused_configuration_agrees(monkeypatch):
         eng.set_site_weights(w)
         monkeypatch.delenv("PLF_F4_CONFIG", raising=False)
         monkeypatch.delenv("PLF_F4_CONFIG_LL", raising=False)
+        monkeypatch.delenv("PLF_F4_CONFIG_MARG", raising=False)
         want = eng.deriv(per_site=False)
         want_ll = eng.ll(per_site=False)[1]
+        want_mg = eng.marginal(per_site=False)[1]
         scale = np.abs(want["sum_deriv"]).max()
-        ran_edge = ran_ll = 0
+        ran_edge = ran_ll = ran_mg = 0
         for i in range(16):
             monkeypatch.setenv("PLF_F4_CONFIG", str(i))
             monkeypatch.setenv("PLF_F4_CONFIG_LL", str(i))
+            monkeypatch.setenv("PLF_F4_CONFIG_MARG", str(i))
+            try:
+                got_mg = eng.marginal(per_site=False)[1]
+            except EngineError as ex:
+                assert "no configuration fits" in str(ex), ex
+            else:
+                ran_mg += 1
+                assert np.allclose(got_mg, want_mg, rtol=1e-11, atol=1e-12 * np.abs(want_mg).max()), (taxa, i)
             try:
                 got = eng.deriv(per_site=False)
             except EngineError as ex:
@@ -294,5 +304,5 @@ def test_every_fused_configuration_agrees(monkeypatch):
             else:
                 ran_ll += 1
                 assert abs(got_ll - want_ll) <= 1e-12 * abs(want_ll), (taxa, i)
-        assert ran_edge >= 3 and ran_ll >= 3, (taxa, ran_edge, ran_ll)
+        assert ran_edge >= 3 and ran_ll >= 3 and ran_mg >= 2, (taxa, ran_edge, ran_ll, ran_mg)
         eng.close()
