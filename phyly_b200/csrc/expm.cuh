@@ -178,9 +178,7 @@ __global__ void __launch_bounds__(256) expm_dd_kernel(ExpmArgs a)
     const size_t off = ((size_t)c * a.E + e) * nn;
     if (a.P) for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) a.P[off + idx] = dd_to_d(SX[idx]);
     if (want_f) {
-        double fs = (a.f_scale_mode == 1) ? r * t : 1.0;
         dd_t fsd = (a.f_scale_mode == 1) ? rt : dd_make(1.0, 0.0);
-        (void)fs;
         for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) a.F[off + idx] = dd_to_d(dd_mul(SY[idx], fsd));
     }
     if (a.D) {

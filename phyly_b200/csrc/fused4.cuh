@@ -623,10 +623,9 @@ __device__ __forceinline__ void f4_outside_general(const F4Args &a, const F4Op &
                 f4_marg_out(a, accM, nodes[j], d, valid, site, lane);
             }
         }
-        return;
     }
 #pragma unroll
-    for (int j = 0; j < F4_MAXD; j++) {
+    for (int j = 0; j < (MARG ? 0 : F4_MAXD); j++) {
         if (kinds[j] >= 0) {
             const int e = edges[j];
             const bool me = !a.edge_mask || a.edge_mask[e];
@@ -691,8 +690,9 @@ __global__ void __launch_bounds__(BD) fused4_kernel(const F4Args a, const __grid
         double *sT = reinterpret_cast<double *>(f4_smem + off); off += sizeof(double) * nT;
         double *sF = reinterpret_cast<double *>(f4_smem + off); off += EDGE ? sizeof(double) * nF : 0;
         double *sTF = reinterpret_cast<double *>(f4_smem + off); off += (EDGE && !MARG && STAGED == 2) ? sizeof(double) * nT : 0;
-        if (!CM) for (size_t i = tid; i < nP; i += bd) sP[i] = a.Pint[i];
-        if (EDGE) for (size_t i = tid; i < nF; i += bd) sF[i] = a.Fint[i];
+        /* (counts as int: a compile-time zero count would make the loop test an unsigned comparison with 0) */
+        for (int i = tid; i < (int)nP; i += bd) sP[i] = a.Pint[i];
+        for (int i = tid; i < (EDGE ? (int)nF : 0); i += bd) sF[i] = a.Fint[i];
         for (size_t i = tid; i < nT; i += bd) { sT[i] = a.TP[i]; if (EDGE && !MARG && STAGED == 2) sTF[i] = a.TF[i]; }
         Pint = sP; TP = sT; Fint = sF;
         if (STAGED == 2 && !MARG) TF = sTF;
