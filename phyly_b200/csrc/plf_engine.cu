@@ -1405,12 +1405,16 @@ static int run_generic(plf_engine *e, Query &q)
         a.tip_stage = 1;
         a.tip_edge_csr = e->d_edge_of_tip.as<int>();
     }
-    const size_t smem_tile = sizeof(double) * (2 * TL_NP * TL_LS + 8 * TL_TS + TL_TS) + sizeof(int) * 2 * TL_TS +
+    /* padded state count of the tile kernels: 32 for amino-acid-sized models, 64 for codon-sized ones */
+    const int tnp = (n <= 32 && !getenv("PLF_TILE_NP64")) ? 32 : 64, tnw = tnp / 8;
+    const size_t smem_tile = sizeof(double) * (2 * tnp * TL_LS + tnw * TL_TS + TL_TS) + sizeof(int) * 2 * TL_TS +
                              (a.tip_stage ? (size_t)a.Et * TL_TS : 0) + 16;
-    const size_t smem_tile_out = sizeof(double) * (TL_NP * TL_LS + 8 * TL_TS + 3 * TL_TS) + sizeof(int) * 6 * TL_TS;
+    const size_t smem_tile_out = sizeof(double) * (tnp * TL_LS + tnw * TL_TS + 3 * TL_TS) + sizeof(int) * 6 * TL_TS;
     if (use_tile) {
-        CK(e, cudaFuncSetAttribute(tile_inside_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile));
-        CK(e, cudaFuncSetAttribute(tile_outside_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile_out));
+        CK(e, cudaFuncSetAttribute(tile_inside_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile));
+        CK(e, cudaFuncSetAttribute(tile_outside_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile_out));
+        CK(e, cudaFuncSetAttribute(tile_inside_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile));
+        CK(e, cudaFuncSetAttribute(tile_outside_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile_out));
     }
 
     for (int64_t s0 = 0; s0 < e->S; s0 += Sc) {
@@ -1421,7 +1425,8 @@ static int run_generic(plf_engine *e, Query &q)
             generic_leaf_kernel<<<dim3((a.Sc + 255) / 256, C), 256, 0, e->stream>>>(
                 a, (q.want_marg || !a.tip_of_edge || (q.want_edge && !a.TF)) ? 1 : 0);
             KCHECK(e);
-            tile_inside_kernel<<<dim3((a.Sc + TL_TS - 1) / TL_TS, C), 256, smem_tile, e->stream>>>(a, outside ? 1 : 0);
+            if (tnp == 32) tile_inside_kernel<32><<<dim3((a.Sc + TL_TS - 1) / TL_TS, C), 128, smem_tile, e->stream>>>(a, outside ? 1 : 0);
+            else tile_inside_kernel<64><<<dim3((a.Sc + TL_TS - 1) / TL_TS, C), 256, smem_tile, e->stream>>>(a, outside ? 1 : 0);
             KCHECK(e);
         } else {
             generic_inside_kernel<<<dim3(gx, C), PLF_TS, smem_in, e->stream>>>(a);
@@ -1437,7 +1442,8 @@ static int run_generic(plf_engine *e, Query &q)
             if (q.want_edge) CK(e, cudaMemsetAsync(a.edge_out, 0, sizeof(double) * (size_t)E * a.Sc, e->stream));
             if (q.want_marg) CK(e, cudaMemsetAsync(a.marg_out, 0, sizeof(double) * (size_t)N * n * a.Sc, e->stream));
             if (use_tile) {
-                tile_outside_kernel<<<(a.Sc + TL_TS - 1) / TL_TS, 256, smem_tile_out, e->stream>>>(a);
+                if (tnp == 32) tile_outside_kernel<32><<<(a.Sc + TL_TS - 1) / TL_TS, 128, smem_tile_out, e->stream>>>(a);
+                else tile_outside_kernel<64><<<(a.Sc + TL_TS - 1) / TL_TS, 256, smem_tile_out, e->stream>>>(a);
                 KCHECK(e);
             } else {
                 generic_outside_kernel<<<gx, PLF_TS, smem_out, e->stream>>>(a);

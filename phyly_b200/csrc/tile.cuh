@@ -57,12 +57,15 @@ __device__ __forceinline__ void tl_cp_wait() { asm volatile("cp.async.wait_group
  * exponent, constant-column flag) lives in the registers of thread `site`; the column maxima for the
  * rescale are taken after every second child and after the last one.
  */
-__global__ void __launch_bounds__(256, 2) tile_inside_kernel(GenericArgs a, int keep_edges)
+template <int NP>
+__global__ void __launch_bounds__(NP * 4, (NP == 64 ? 2 : 4)) tile_inside_kernel(GenericArgs a, int keep_edges)
 {
+    constexpr int NT = NP * 4;                        /* threads: one warp per 8 output rows */
+    constexpr int NW = NP / 8;
     extern __shared__ __align__(16) double tl_sm[];
     double *Lbuf = tl_sm;                             /* [2][64][TL_LS] */
-    double *colmax = Lbuf + 2 * TL_NP * TL_LS;        /* [8][64] */
-    double *scale = colmax + 8 * TL_TS;               /* [64] */
+    double *colmax = Lbuf + 2 * NP * TL_LS;        /* [8][64] */
+    double *scale = colmax + NW * TL_TS;               /* [64] */
     int *colmax_i = reinterpret_cast<int *>(colmax);  /* the same storage, for the integer maxima of the rescale */
     int *bcs_s = reinterpret_cast<int *>(scale + TL_TS);     /* [2][64] constant-column flag of the staged child */
     unsigned char *tipc = reinterpret_cast<unsigned char *>(bcs_s + 2 * TL_TS);   /* [Et][64] codes of the tips (if staged) */
@@ -79,11 +82,11 @@ __global__ void __launch_bounds__(256, 2) tile_inside_kernel(GenericArgs a, int 
     const bool al16 = (Sc & 1) == 0;                  /* rows of the [state][site] arrays are 16-byte aligned */
 
     /* rows n..63 of both buffers stay zero (k padding of the GEMM) */
-    for (int i = tid; i < 2 * TL_NP * TL_LS; i += 256) Lbuf[i] = 0.0;
+    for (int i = tid; i < 2 * NP * TL_LS; i += NT) Lbuf[i] = 0.0;
     /* the tile's tip codes: one coalesced pass instead of dependent code -> table loads per tip edge */
     if (a.tip_stage) {
         const unsigned char *cd = (const unsigned char *)a.codes;
-        for (int i = tid; i < a.Et * TL_TS; i += 256) {
+        for (int i = tid; i < a.Et * TL_TS; i += NT) {
             const int te = i >> 6, s = i & 63;
             const int b = a.t.indices[a.tip_edge_csr[te]];
             tipc[i] = (s0 + s < Sc) ? cd[(size_t)b * a.S + a.s0 + s0 + s] : 0;
@@ -96,17 +99,17 @@ __global__ void __launch_bounds__(256, 2) tile_inside_kernel(GenericArgs a, int 
     auto prefetch = [&](int p) {
         const int idx = a.int_seq[p];
         const int b = a.t.indices[idx];
-        double *dst = Lbuf + (size_t)(p & 1) * TL_NP * TL_LS;
+        double *dst = Lbuf + (size_t)(p & 1) * NP * TL_LS;
         const double *Lb = a.Lg + ((cN + b) * n) * Sc;
         if (al16) {
-            for (int i = tid; i < n * (TL_TS / 2); i += 256) {
+            for (int i = tid; i < n * (TL_TS / 2); i += NT) {
                 const int k = i >> 5, s = (i & 31) * 2;
                 const int left = Sc - (s0 + s);
                 const int bytes = left >= 2 ? 16 : (left == 1 ? 8 : 0);
                 tl_cp16(dst + k * TL_LS + s, bytes ? (const void *)(Lb + (size_t)k * Sc + s0 + s) : (const void *)Lb, bytes);
             }
         } else {
-            for (int i = tid; i < n * TL_TS; i += 256) {
+            for (int i = tid; i < n * TL_TS; i += NT) {
                 const int k = i >> 6, s = i & 63;
                 const int bytes = (s0 + s < Sc) ? 8 : 0;
                 tl_cp8(dst + k * TL_LS + s, bytes ? (const void *)(Lb + (size_t)k * Sc + s0 + s) : (const void *)Lb, bytes);
@@ -117,10 +120,7 @@ __global__ void __launch_bounds__(256, 2) tile_inside_kernel(GenericArgs a, int 
             /* this thread's A-fragment row of the edge's matrix: 61 doubles = 4 lines */
             const char *pr = reinterpret_cast<const char *>(a.P + (cE + idx) * n * n + (size_t)(row < n ? row : 0) * n);
             if (q == 0) {
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(pr));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(pr + 128));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(pr + 256));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(pr + 384));
+                for (int o = 0; o < n * 8; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(pr + o));
             }
         }
         if (site_thread) {
@@ -177,12 +177,12 @@ __global__ void __launch_bounds__(256, 2) tile_inside_kernel(GenericArgs a, int 
                 }
             } else {
                 const int buf = p & 1;
-                const double *Ls = Lbuf + (size_t)buf * TL_NP * TL_LS;
+                const double *Ls = Lbuf + (size_t)buf * NP * TL_LS;
                 /* A fragments of P_e straight from global memory (hot in L1/L2, shared by all CTAs) */
                 const double *Pm = a.P + (cE + idx) * n * n;
-                double af[TL_NP / 4];
+                double af[NP / 4];
 #pragma unroll
-                for (int kk = 0; kk < TL_NP / 4; kk++) {
+                for (int kk = 0; kk < NP / 4; kk++) {
                     const int k = kk * 4 + q;
                     af[kk] = (row < n && k < n) ? __ldg(Pm + row * n + k) : 0.0;
                 }
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256, 2) tile_inside_kernel(GenericArgs a, int 
 #pragma unroll
                 for (int nb = 0; nb < 8; nb++) { em[nb][0] = 0.0; em[nb][1] = 0.0; }
 #pragma unroll
-                for (int kk = 0; kk < TL_NP / 4; kk++) {
+                for (int kk = 0; kk < NP / 4; kk++) {
 #pragma unroll
                     for (int nb = 0; nb < 8; nb++) {
                         const double bf = Ls[(kk * 4 + q) * TL_LS + nb * 8 + g];
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(256, 2) tile_inside_kernel(GenericArgs a, int 
                 if (site_thread) {
                     int m = 0;
 #pragma unroll
-                    for (int w = 0; w < 8; w++) m = max(m, colmax_i[w * TL_TS + tid]);
+                    for (int w = 0; w < NW; w++) m = max(m, colmax_i[w * TL_TS + tid]);
                     /* high word of 2^-256 is 0x2FF00000; one step of 2^256 adds 0x10000000 to it.  A column
                      * whose high word is 0 (zero, or below 2^-1042) is left alone. */
                     double sc = 1.0;
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(256, 2) tile_inside_kernel(GenericArgs a, int 
             __syncthreads();
             if (site_in) {
                 double lh = 0.0;
-                for (int w = 0; w < 8; w++) lh += colmax[w * TL_TS + tid];
+                for (int w = 0; w < NW; w++) lh += colmax[w * TL_TS + tid];
                 if (cst && (a.root_mode == PLF_ROOT_UNIFORM || a.root_mode == PLF_ROOT_EQUILIBRIUM)) lh = scale[tid];
                 a.cat_lh[(size_t)c * Sc + s0 + tid] = lh;
                 a.cat_k[(size_t)c * Sc + s0 + tid] = kacc;
@@ -346,7 +346,7 @@ __device__ __forceinline__ void tl_load_frag(double (&f)[8][2], const double *ro
 }
 
 /* per-site (column) reduction over all 64 rows: result[s] for s = tid < 64, valid after the call */
-template <bool IS_MAX>
+template <bool IS_MAX, int NW>
 __device__ __forceinline__ void tl_col_reduce(const double (&f)[8][2], double *colbuf, double *out, int warp, int g, int q, int tid)
 {
     double r[8][2];
@@ -370,7 +370,7 @@ __device__ __forceinline__ void tl_col_reduce(const double (&f)[8][2], double *c
     __syncthreads();
     if (tid < TL_TS) {
         double m = 0.0;
-        for (int w = 0; w < 8; w++) m = IS_MAX ? fmax(m, colbuf[w * TL_TS + tid]) : m + colbuf[w * TL_TS + tid];
+        for (int w = 0; w < NW; w++) m = IS_MAX ? fmax(m, colbuf[w * TL_TS + tid]) : m + colbuf[w * TL_TS + tid];
         out[tid] = m;
     }
     __syncthreads();
@@ -383,12 +383,14 @@ __device__ __forceinline__ void tl_col_reduce(const double (&f)[8][2], double *c
  * siblings' edge vectors (kept by the inside pass), y = F_e L_b and fn_b = P_e^T fe on DMMA.
  * grid = (site tiles), 256 threads.
  */
-__global__ void __launch_bounds__(256, 2) tile_outside_kernel(GenericArgs a)
+template <int NP>
+__global__ void __launch_bounds__(NP * 4, (NP == 64 ? 2 : 4)) tile_outside_kernel(GenericArgs a)
 {
+    constexpr int NW = NP / 8;                        /* NP * 4 threads: one warp per 8 rows */
     extern __shared__ __align__(16) double tl_sm[];
     double *Bsm = tl_sm;                              /* [64][TL_LS] B operand: child partials or fe */
-    double *colbuf = Bsm + TL_NP * TL_LS;             /* [8][64] */
-    double *colres = colbuf + 8 * TL_TS;              /* [64] */
+    double *colbuf = Bsm + NP * TL_LS;             /* [8][64] */
+    double *colres = colbuf + NW * TL_TS;              /* [64] */
     double *coef = colres + TL_TS;                    /* [64] prior_c / site likelihood (0 if the category is dead) */
     double *scl = coef + TL_TS;                       /* [64] */
     int *ka = reinterpret_cast<int *>(scl + TL_TS);   /* [64] exponent of fn_a */
@@ -486,7 +488,7 @@ __global__ void __launch_bounds__(256, 2) tile_outside_kernel(GenericArgs a)
                     TL_FOR_FRAG(nb, h) fe[nb][h] *= es[nb][h];
                     if (site_in) kfe_r += a.Kg[(cN + a.t.indices[idx2]) * Sc + s0 + tid];
                     if ((++nsib & 1) == 0) {
-                        tl_col_reduce<true>(fe, colbuf, colres, warp, g, q, tid);
+                        tl_col_reduce<true, NW>(fe, colbuf, colres, warp, g, q, tid);
                         if (tid < TL_TS) {
                             double m = colres[tid], sc = 1.0;
                             while (m > 0.0 && m < PLF_TWO_M256) { m *= PLF_TWO_P256; sc *= PLF_TWO_P256; kfe_r -= 1; }
@@ -516,21 +518,21 @@ __global__ void __launch_bounds__(256, 2) tile_outside_kernel(GenericArgs a)
                         const int code = (s0 + s < Sc) ? plf_code_at(a.codes, a.code_bytes, a.S, b, a.s0 + s0 + s) : 0;
                         y[nb][h] = (row < n) ? __ldg(Tt + (size_t)code * n) * fe[nb][h] : 0.0;
                     }
-                    tl_col_reduce<false>(y, colbuf, colres, warp, g, q, tid);
+                    tl_col_reduce<false, NW>(y, colbuf, colres, warp, g, q, tid);
                     if (site_in && coef[tid] != 0.0)
                         a.edge_out[(size_t)idx * Sc + s0 + tid] += scalbn(colres[tid] * coef[tid], PLF_SCALE_BITS * (kfe_r + kb_r - sitek[tid]));
                     if (!want_fn) continue;
                 }
                 /* fe is the B operand of both products: z = F_e^T fe (then x_e = z . L_b) and fn_b = P_e^T fe */
                 __syncthreads();
-                if (row < TL_NP) TL_FOR_FRAG(nb, h) Bsm[row * TL_LS + nb * 8 + q * 2 + h] = fe[nb][h];
+                TL_FOR_FRAG(nb, h) Bsm[row * TL_LS + nb * 8 + q * 2 + h] = fe[nb][h];
                 __syncthreads();
                 if (want_x && te < 0) {
                     /* x_e = fe^T (F_e L_b) = (F_e^T fe)^T L_b  (evaluate_site_frechet.c:18-39) */
                     const double *Fm = a.Fm + (cE + idx) * n * n;
-                    double af[TL_NP / 4];
+                    double af[NP / 4];
 #pragma unroll
-                    for (int kk = 0; kk < TL_NP / 4; kk++) {
+                    for (int kk = 0; kk < NP / 4; kk++) {
                         const int k = kk * 4 + q;
                         af[kk] = (row < n && k < n) ? __ldg(Fm + k * n + row) : 0.0;     /* A = F^T */
                     }
@@ -539,32 +541,32 @@ __global__ void __launch_bounds__(256, 2) tile_outside_kernel(GenericArgs a)
                     double z[8][2];
                     TL_FOR_FRAG(nb, h) z[nb][h] = 0.0;
 #pragma unroll
-                    for (int kk = 0; kk < TL_NP / 4; kk++) {
+                    for (int kk = 0; kk < NP / 4; kk++) {
 #pragma unroll
                         for (int nb = 0; nb < 8; nb++) tl_dmma(z[nb][0], z[nb][1], af[kk], Bsm[(kk * 4 + q) * TL_LS + nb * 8 + g]);
                     }
                     TL_FOR_FRAG(nb, h) z[nb][h] *= lb[nb][h];
-                    tl_col_reduce<false>(z, colbuf, colres, warp, g, q, tid);
+                    tl_col_reduce<false, NW>(z, colbuf, colres, warp, g, q, tid);
                     if (site_in && coef[tid] != 0.0 && !(a.f_zero_rowsum && bc_r))
                         a.edge_out[(size_t)idx * Sc + s0 + tid] += scalbn(colres[tid] * coef[tid], PLF_SCALE_BITS * (kfe_r + kb_r - sitek[tid]));
                 }
                 if (want_fn) {
                     /* fn_b = P_e^T fe  (util.c:464-498) */
                     const double *Pm = a.P + (cE + idx) * n * n;
-                    double af[TL_NP / 4];
+                    double af[NP / 4];
 #pragma unroll
-                    for (int kk = 0; kk < TL_NP / 4; kk++) {
+                    for (int kk = 0; kk < NP / 4; kk++) {
                         const int k = kk * 4 + q;
                         af[kk] = (row < n && k < n) ? __ldg(Pm + k * n + row) : 0.0;     /* A = P^T */
                     }
                     double fb[8][2];
                     TL_FOR_FRAG(nb, h) fb[nb][h] = 0.0;
 #pragma unroll
-                    for (int kk = 0; kk < TL_NP / 4; kk++) {
+                    for (int kk = 0; kk < NP / 4; kk++) {
 #pragma unroll
                         for (int nb = 0; nb < 8; nb++) tl_dmma(fb[nb][0], fb[nb][1], af[kk], Bsm[(kk * 4 + q) * TL_LS + nb * 8 + g]);
                     }
-                    tl_col_reduce<true>(fb, colbuf, colres, warp, g, q, tid);
+                    tl_col_reduce<true, NW>(fb, colbuf, colres, warp, g, q, tid);
                     if (tid < TL_TS) {
                         double m = colres[tid], sc = 1.0;
                         int k = kfe_r;

@@ -8,6 +8,7 @@ Parity at BASELINE.json's sizes, where the 320-bit oracle
         fused path vs generic path (independent kernels) for a weighted trans direction.
 """
 import json
+import os
 
 import numpy as np
 import pytest
@@ -211,6 +212,64 @@ def test_cfg4_codon_generic_path_against_c_port():
     np.testing.assert_allclose(site_ll, ref_ll, rtol=1e-11)
     assert abs(r["sum_ll"] - sum_ll) <= 1e-11 * abs(sum_ll)
     np.testing.assert_allclose(r["sum_deriv"], sum_d, rtol=1e-10, atol=1e-10 * np.abs(sum_d).max())
+    eng.close()
+
+
+def test_amino_acid_sized_model_against_c_port():
+    """A 20-state reversible model (the 32-row instantiation of the DMMA tile kernels): ll, ll+deriv and
+    marginals on a 40-taxon tree against the C restatement / the independent scalar kernels."""
+    import phyly_b200.arbplf as A
+    from oracle import c_port
+    from phyly_b200.engine import Engine
+    b = _bench()
+    rng = np.random.default_rng(77)
+    n = 20
+    pi = rng.dirichlet(np.ones(n) * 4)
+    R = rng.random((n, n)) + 0.05
+    R = (R + R.T) / 2
+    Q = R * pi[None, :]
+    np.fill_diagonal(Q, 0.0)
+    edges, N = b.yule_tree(40, seed=5)
+    defs = np.vstack([np.eye(n), np.ones((1, n))])
+    md = {"edges": edges, "edge_rate_coefficients": [float(x) for x in rng.exponential(0.15, len(edges))],
+          "rate_matrix": Q.tolist(), "root_prior": "equilibrium_distribution", "rate_divisor": "equilibrium_exit_rate",
+          "rate_mixture": {"rates": [0.3, 1.7], "prior": [0.4, 0.6]},
+          "character_definitions": defs.tolist(), "character_data": [[n] * N]}
+    s = json.loads(A.arbplf_model_summary(json.dumps({"model_and_data": md})))
+    eng = Engine(0)
+    eng.set_tree(s["indptr"], s["indices"], s["preorder"])
+    eng.set_model(np.array(s["q_hi"]).reshape(n, n), np.array(s["q_lo"]).reshape(n, n), s["edge_rates_csr"], s["cat_rates"],
+                  s["cat_prior"], s["root_mode"], s["root_vec"])
+    P = eng.transition_matrices()
+    D = eng.derivative_matrices()
+    S = 1000 + 37                                   # ragged last tile
+    codes = np.full((S, N), n, dtype=np.uint8)
+    for a in range(N):
+        if s["indptr"][a] == s["indptr"][a + 1]:
+            col = rng.integers(0, n, S)
+            col[rng.random(S) < 0.05] = n
+            codes[:, a] = col
+    eng.set_data(defs, codes)
+    w = rng.random(S) + 0.5
+    eng.set_site_weights(w)
+    r = eng.deriv(per_site=False)
+    site_ll, _ = eng.ll()
+    ref_ll, sum_ll, sum_d = c_port.ll_deriv(s["indptr"], s["indices"], s["preorder"], P, D, np.array(s["cat_prior"]),
+                                            s["root_mode"], np.array(s["root_vec"]), codes, defs, w=w)
+    np.testing.assert_allclose(site_ll, ref_ll, rtol=1e-11)
+    assert abs(r["sum_ll"] - sum_ll) <= 1e-11 * abs(sum_ll)
+    np.testing.assert_allclose(r["sum_deriv"], sum_d, rtol=1e-10, atol=1e-10 * np.abs(sum_d).max())
+    # marginals: tile kernels against the scalar generic kernels (PLF_NO_TILE is read per query)
+    sm, tot = eng.marginal()
+    np.testing.assert_allclose(sm.sum(axis=2), 1.0, rtol=0, atol=1e-12)
+    os.environ["PLF_NO_TILE"] = "1"
+    try:
+        sm_g, tot_g = eng.marginal()
+        r_g = eng.deriv(per_site=False)
+    finally:
+        del os.environ["PLF_NO_TILE"]
+    np.testing.assert_allclose(sm, sm_g, rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(r["sum_deriv"], r_g["sum_deriv"], rtol=1e-10, atol=1e-10 * np.abs(sum_d).max())
     eng.close()
 
 
