@@ -376,6 +376,8 @@ def run_ours(args):
                  "fp64 gives its flop rate against the measured DFMA peak"),
         "measured_dram_gbs": (traffic["dram_bytes_per_launch"] / (k_ms * 1e-3) / 1e9
                               if (k_ms and traffic.get("dram_bytes_per_launch")) else None),
+        "measured_dram_frac": (traffic["dram_bytes_per_launch"] / (k_ms * 1e-3) / 1e9 / hbm_peak
+                               if (k_ms and traffic.get("dram_bytes_per_launch")) else None),
         "fp64": {"achieved_tflops": flops / (k_ms * 1e-3) / 1e12 if k_ms else None,
                  "peak_tflops": fp64.get("dfma_tflops"),
                  "frac": (flops / (k_ms * 1e-3) / 1e12) / fp64["dfma_tflops"] if (k_ms and fp64.get("dfma_tflops")) else None,
