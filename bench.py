@@ -419,12 +419,21 @@ def cpu_port_problem(pb):
                 root_mode=pb["summary"]["root_mode"], root_vec=np.array(pb["summary"]["root_vec"]))
 
 
+def host_threads():
+    """All host cores this process may use.  Not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to
+    its workers, which would silently turn the reference arm into a one-thread run for N > 1."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(pb, target_seconds=15.0, sample=None):
     """Time oracle/c (the 'port' of the reference algorithm) on a bounded sample, all host threads."""
     from oracle import c_port
     cp = cpu_port_problem(pb)
     s = pb["summary"]
-    threads = c_port.max_threads()
+    threads = host_threads()
     defs = np.array(DEFS, dtype=np.float64)
 
     def run(nsites):
@@ -450,7 +459,7 @@ def run_reference(args):
         return
     pb = build_problem(args, 0, 0, use_engine=False)
     from oracle import c_port
-    threads = c_port.max_threads()
+    threads = host_threads()
     # size each step so that the whole run ends within a few minutes
     first = cpu_baseline(pb, target_seconds=2.0)
     rate = first["value"] / (pb["E"] * pb["C"])               # sites per second
