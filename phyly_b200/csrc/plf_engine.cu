@@ -25,6 +25,7 @@
 #include "generic.cuh"
 #include "fused4.cuh"
 #include "tile.cuh"
+#include "dmma.h"
 
 /* ------------------------------------------------------------------ */
 /* small utilities                                                     */
@@ -128,6 +129,9 @@ struct plf_engine {
     std::vector<unsigned char> node_has_data_h;
     int stack_depth = 0, nslots = 0, max_degree = 0;
     bool TP_valid = false, program_dirty = true;
+    bool dm_valid = false;       /* packed matrices / tip tables of the DMMA kernels (dmma.cuh) */
+    DevBuf d_dmPf, d_dmTPf, d_dmTFf, d_dm_defsf, d_dm_rootf, d_dm_stack, d_dm_stackmeta, d_dm_slab, d_dm_slabmeta, d_dm_Of, d_dm_oidx, d_dm_otr;
+    int dm_out_depth = 0;
     F4Prog prog_h;
     uint64_t program_version = 0, f4_tuned_version[3] = {~(uint64_t)0, ~(uint64_t)0, ~(uint64_t)0};   /* ll, edge forms, marginals */
     size_t f4_tuned_pick[3] = {0, 0, 0};
@@ -500,7 +504,7 @@ extern "C" int plf_set_tree(plf_engine *e, int node_count, const int *indptr, co
     CK(e, cudaMemcpyAsync(e->d_indices.p, indices, sizeof(int) * E, cudaMemcpyHostToDevice, e->stream));
     CK(e, cudaMemcpyAsync(e->d_preorder.p, preorder, sizeof(int) * N, cudaMemcpyHostToDevice, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
-    e->P_valid = e->D_valid = e->TP_valid = false;
+    e->P_valid = e->D_valid = e->TP_valid = e->dm_valid = false;
     e->S = 0;   /* data must be (re)set after the tree */
     return 0;
 }
@@ -547,7 +551,7 @@ extern "C" int plf_set_model(plf_engine *e, int n, int C, const double *q_hi, co
     CK(e, cudaMemcpyAsync(e->d_cat_prior.p, e->cat_prior.data(), sizeof(double) * C, cudaMemcpyHostToDevice, e->stream));
     CK(e, cudaMemcpyAsync(e->d_root_vec.p, e->root_vec.data(), sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
-    e->P_valid = e->D_valid = e->TP_valid = false;
+    e->P_valid = e->D_valid = e->TP_valid = e->dm_valid = false;
     return 0;
 }
 
@@ -561,7 +565,7 @@ extern "C" int plf_set_edge_rates(plf_engine *e, const double *edge_rates)
     CK(e, cudaSetDevice(e->device));
     CK(e, cudaMemcpyAsync(e->d_edge_rates.p, e->edge_rates.data(), sizeof(double) * e->E, cudaMemcpyHostToDevice, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
-    e->P_valid = e->D_valid = e->TP_valid = false;
+    e->P_valid = e->D_valid = e->TP_valid = e->dm_valid = false;
     return 0;
 }
 
@@ -599,7 +603,7 @@ static int ensure_matrices(plf_engine *e, bool need_D)
     if (run_expm(e, e->d_P.as<double>(), need_D ? e->d_D.as<double>() : nullptr, nullptr, 0, nullptr, nullptr, nullptr)) return -1;
     e->P_valid = true;
     if (need_D) e->D_valid = true;
-    e->TP_valid = false;
+    e->TP_valid = e->dm_valid = false;
     return 0;
 }
 
@@ -720,7 +724,7 @@ static int set_data_common(plf_engine *e, int64_t S, int K, const double *defs, 
     if (!e->flags_pinned) CK(e, cudaMallocHost((void **)&e->flags_pinned, 1 << 16));
     if (N > (1 << 16) - 8) FAIL(e, "plf_set_data: more than 65528 nodes");
     e->S = S; e->K = K; e->code_bytes = dev_bytes;
-    e->TP_valid = false;
+    e->TP_valid = e->dm_valid = false;
     e->have_w = false;
     CK(e, cudaMemcpyAsync(e->d_defs.p, defs, sizeof(double) * K * n, cudaMemcpyHostToDevice, e->stream));
     CK(e, cudaMemcpyAsync(e->d_def_const.p, dconst.data(), K, cudaMemcpyHostToDevice, e->stream));
@@ -843,7 +847,7 @@ static int ensure_program(plf_engine *e)
     CK(e, cudaStreamSynchronize(e->stream));
     e->program_dirty = false;
     e->program_version++;
-    e->TP_valid = false;
+    e->TP_valid = e->dm_valid = false;
     return 0;
 }
 
@@ -1485,6 +1489,208 @@ static int run_generic(plf_engine *e, Query &q)
     return 0;
 }
 
+/*
+ * 16 < n <= 64 (amino-acid, codon models), ll and edge-form queries: the FP64 tensor-pipe kernels of dmma.cu.
+ * Marginals of such models stay on the tile / generic kernels.
+ */
+static bool dmma_applicable(const plf_engine *e, const Query &q)
+{
+    return dm_blocks_for(e->n) != 0 && !q.want_marg && e->code_bytes == 1 && e->K <= 256 && !getenv("PLF_NO_DMMA");
+}
+
+static int ensure_dm_tables(plf_engine *e, int NB, const double *Fm, int f_zero_rowsum)
+{
+    if (ensure_program(e)) return -1;
+    const int n = e->n, C = e->C, E = e->E, K = e->K;
+    const int Ei = (int)e->edge_of_int.size(), Et = (int)e->edge_of_tip.size();
+    const size_t slot = dm_slot_doubles_host(NB), W = 8 * (size_t)NB;
+    if (!e->dm_valid) {
+        ENSURE(e, e->d_dmPf, sizeof(double) * ((size_t)C * Ei * slot + 1));
+        ENSURE(e, e->d_dmTPf, sizeof(double) * ((size_t)C * Et * K * W + 1));
+        ENSURE(e, e->d_dm_defsf, sizeof(double) * ((size_t)K * W + 1));
+        ENSURE(e, e->d_dm_rootf, sizeof(double) * W);
+        /* matrices of the outside pass in its consumption order: ops backwards, internal children last to first,
+         * P_e then F_e (negative index = second source), all transposed */
+        std::vector<int> oidx, otr;
+        int depth = 0, sp = 0;
+        for (int o = (int)e->ops.size() - 1; o >= 0; o--) {
+            const F4Op &op = e->ops[o];
+            if (o != (int)e->ops.size() - 1) sp--;
+            for (int j = op.nchild - 1; j >= 0; j--) {
+                const F4Child &ch = e->children[op.first_child + j];
+                if (ch.kind == F4_KIND_TIP) continue;
+                oidx.push_back(ch.edge); oidx.push_back(-(ch.edge + 1));
+                otr.push_back(1); otr.push_back(1);
+                sp++;
+                depth = std::max(depth, sp);
+            }
+        }
+        e->dm_out_depth = std::max(depth, 1);
+        ENSURE(e, e->d_dm_oidx, sizeof(int) * (oidx.size() + 1));
+        ENSURE(e, e->d_dm_otr, sizeof(int) * (otr.size() + 1));
+        std::vector<double> rootf(W, 0.0);
+        for (int pos = 0; pos < (int)W; pos++) {
+            const int qq = pos / (2 * NB), rem = pos % (2 * NB);
+            const int i = 8 * (rem >> 1) + 2 * qq + (rem & 1);
+            if (i >= n) continue;
+            if (e->root_mode == PLF_ROOT_NONE) rootf[pos] = 1.0;
+            else if (e->root_mode == PLF_ROOT_UNIFORM) rootf[pos] = 1.0 / (double)n;
+            else rootf[pos] = e->root_vec[i];
+        }
+        CK(e, cudaMemcpyAsync(e->d_dm_oidx.p, oidx.data(), sizeof(int) * oidx.size(), cudaMemcpyHostToDevice, e->stream));
+        CK(e, cudaMemcpyAsync(e->d_dm_otr.p, otr.data(), sizeof(int) * otr.size(), cudaMemcpyHostToDevice, e->stream));
+        CK(e, cudaMemcpyAsync(e->d_dm_rootf.p, rootf.data(), sizeof(double) * W, cudaMemcpyHostToDevice, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+        CK(e, dm_pack(e->d_P.as<double>(), nullptr, e->d_edge_of_int.as<int>(), nullptr, Ei, C, E, n, NB, e->d_dmPf.as<double>(), e->stream));
+        e->launches++;
+        CK(e, dm_tip_table(e->d_P.as<double>(), e->d_defs.as<double>(), e->d_def_const.as<unsigned char>(), e->d_edge_of_tip.as<int>(),
+                           C, E, Et, K, n, NB, 0, e->d_dmTPf.as<double>(), e->stream));
+        e->launches++;
+        CK(e, dm_tip_table(nullptr, e->d_defs.as<double>(), e->d_def_const.as<unsigned char>(), nullptr,
+                           1, E, 1, K, n, NB, 0, e->d_dm_defsf.as<double>(), e->stream));
+        e->launches++;
+        e->dm_valid = true;
+    }
+    if (Fm) {
+        ENSURE(e, e->d_dm_Of, sizeof(double) * ((size_t)C * 2 * Ei * slot + 1));
+        ENSURE(e, e->d_dmTFf, sizeof(double) * ((size_t)C * Et * K * W + 1));
+        CK(e, dm_pack(e->d_P.as<double>(), Fm, e->d_dm_oidx.as<int>(), e->d_dm_otr.as<int>(), 2 * Ei, C, E, n, NB, e->d_dm_Of.as<double>(), e->stream));
+        e->launches++;
+        CK(e, dm_tip_table(Fm, e->d_defs.as<double>(), e->d_def_const.as<unsigned char>(), e->d_edge_of_tip.as<int>(),
+                           C, E, Et, K, n, NB, f_zero_rowsum ? 1 : 2, e->d_dmTFf.as<double>(), e->stream));
+        e->launches++;
+    }
+    return 0;
+}
+
+static int run_dmma(plf_engine *e, Query &q)
+{
+    const int n = e->n, C = e->C, N = e->N, E = e->E;
+    const int NB = dm_blocks_for(n);
+    if (ensure_dm_tables(e, NB, q.want_edge ? q.Fm : nullptr, q.f_zero_rowsum)) return -1;
+    const int Ei = (int)e->edge_of_int.size(), Et = (int)e->edge_of_tip.size();
+    const int nrows = (int)e->code_row_node.size();
+
+    /* ring slots that fit beside the warps' code tiles */
+    int R = DM_MAX_R;
+    while (R > 2 && dm_smem_bytes(NB, R, nrows) > 227 * 1024) R--;
+    if (dm_smem_bytes(NB, R, nrows) > 227 * 1024) FAIL(e, "tree too large for the tensor-pipe kernels (%d code rows)", nrows);
+    if (const char *s = getenv("PLF_DM_R")) R = std::max(2, std::min(R, atoi(s)));
+
+    /* chunk of sites: the slab of edge vectors (keep mode) is the only large buffer */
+    const size_t per_group = q.want_edge ? (size_t)C * Ei * ((size_t)NB * 32 * 16 + 32 * 4) + (size_t)E * 64 : 0;
+    size_t free_b = 0, total_b = 0;
+    CK(e, cudaMemGetInfo(&free_b, &total_b));
+    int64_t Sc = e->S;
+    if (per_group) {
+        const size_t have = e->d_dm_slab.cap + e->d_dm_slabmeta.cap + e->g_edge_out.cap;
+        const size_t budget = std::min<size_t>((size_t)32 << 30, (free_b + have) / 2);
+        const int64_t groups = std::max<int64_t>(DM_TILE / 8, (int64_t)(budget / per_group));
+        Sc = std::min<int64_t>(e->S, groups * 8 / DM_TILE * DM_TILE);
+    }
+    Sc = std::min<int64_t>(Sc, (int64_t)1 << 24);
+    if (const char *s = getenv("PLF_DM_CHUNK")) Sc = std::min<int64_t>(Sc, std::max<int64_t>(DM_TILE, atoll(s) / DM_TILE * DM_TILE));
+    const int64_t ngroups_max = (Sc + 7) / 8;
+
+    const int grid_max = e->sm_count;
+    ENSURE(e, e->d_dm_stack, sizeof(double2) * (size_t)grid_max * DM_NW * std::max(1, std::max(e->stack_depth, q.want_edge ? 2 * e->dm_out_depth : 0)) * NB * 32);
+    ENSURE(e, e->d_dm_stackmeta, sizeof(int) * (size_t)grid_max * DM_NW * std::max(1, std::max(e->stack_depth, q.want_edge ? 4 * e->dm_out_depth : 0)) * 32);
+    ENSURE(e, e->g_cat_lh, sizeof(double) * (size_t)C * Sc);
+    ENSURE(e, e->g_cat_k, sizeof(int) * (size_t)C * Sc);
+    ENSURE(e, e->g_site_m, sizeof(double) * Sc);
+    ENSURE(e, e->g_site_k, sizeof(int) * Sc);
+    ENSURE(e, e->d_site_ll, sizeof(double) * e->S);
+    ENSURE(e, e->d_sum, sizeof(double) * (1 + E));
+    ENSURE(e, e->d_err, sizeof(int) * (N + 4));
+    if (q.want_edge) {
+        ENSURE(e, e->d_dm_slab, sizeof(double2) * (size_t)C * Ei * ngroups_max * NB * 32 + 16);
+        ENSURE(e, e->d_dm_slabmeta, sizeof(int) * (size_t)C * Ei * ngroups_max * 32 + 16);
+        ENSURE(e, e->g_edge_out, sizeof(double) * (size_t)E * Sc);
+    }
+    if (q.edge_mask_h) {
+        ENSURE(e, e->d_mask, E);
+        CK(e, cudaMemcpyAsync(e->d_mask.p, q.edge_mask_h, E, cudaMemcpyHostToDevice, e->stream));
+    }
+    double *dsum = e->d_sum.as<double>();
+    CK(e, cudaMemsetAsync(dsum, 0, sizeof(double) * (1 + E), e->stream));
+    CK(e, cudaMemsetAsync(e->d_err.p, 0, sizeof(int), e->stream));
+
+    DmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.C = C; a.K = e->K;
+    a.nops = (int)e->ops.size(); a.ops = e->d_ops.as<F4Op>(); a.children = e->d_children.as<F4Child>();
+    a.Ei = Ei; a.Et = Et; a.nrows = nrows; a.code_row_node = e->d_code_row_node.as<int>();
+    a.codes = e->d_codes.as<unsigned char>(); a.S = e->S;
+    a.def_const = e->d_def_const.as<unsigned char>(); a.defsf = e->d_dm_defsf.as<double>();
+    a.Pf = e->d_dmPf.as<double>(); a.TPf = e->d_dmTPf.as<double>(); a.rootf = e->d_dm_rootf.as<double>();
+    a.root_const_ok = (e->root_mode == PLF_ROOT_UNIFORM || e->root_mode == PLF_ROOT_EQUILIBRIUM) ? 1 : 0;
+    a.cat_lh = e->g_cat_lh.as<double>(); a.cat_k = e->g_cat_k.as<int>();
+    a.R = R;
+    a.stack = e->d_dm_stack.as<double2>(); a.stack_meta = e->d_dm_stackmeta.as<int>();
+    a.Of = e->d_dm_Of.as<double>(); a.TFf = e->d_dmTFf.as<double>();
+    a.cat_prior = e->d_cat_prior.as<double>();
+    a.site_m = e->g_site_m.as<double>(); a.site_k = e->g_site_k.as<int>();
+    a.edge_mask = q.edge_mask_h ? e->d_mask.as<unsigned char>() : nullptr;
+    a.f_zero_rowsum = q.f_zero_rowsum;
+    a.edge_out = q.want_edge ? e->g_edge_out.as<double>() : nullptr;
+
+    /* generic_site_kernel combines the categories */
+    GenericArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.C = C; ga.cat_prior = a.cat_prior; ga.cat_lh = a.cat_lh; ga.cat_k = a.cat_k;
+    ga.site_m = e->g_site_m.as<double>(); ga.site_k = e->g_site_k.as<int>(); ga.site_ll = e->d_site_ll.as<double>();
+
+    const double *w = e->have_w ? e->d_site_w.as<double>() : nullptr;
+    CK(e, cudaEventRecord(e->ev[3], e->stream));
+    for (int64_t s0 = 0; s0 < e->S; s0 += Sc) {
+        a.s0 = s0; a.Sc = (int)std::min<int64_t>(Sc, e->S - s0);
+        a.ntiles = (a.Sc + DM_TILE - 1) / DM_TILE;
+        a.ngroups = (a.Sc + 7) / 8;
+        a.slab = q.want_edge ? e->d_dm_slab.as<double2>() : nullptr;
+        a.slab_meta = q.want_edge ? e->d_dm_slabmeta.as<int>() : nullptr;
+        a.stack_depth = std::max(1, e->stack_depth);
+        const long long items = (long long)a.ntiles * C;
+        CK(e, dm_launch_inside(a, NB, (int)std::min<long long>(grid_max, items), e->stream));
+        e->launches++;
+        ga.s0 = s0; ga.Sc = a.Sc;
+        generic_site_kernel<<<(a.Sc + 255) / 256, 256, 0, e->stream>>>(ga);
+        KCHECK(e);
+        if (q.sum_ll) {
+            wsum_rows_kernel<<<1, 256, 0, e->stream>>>(ga.site_ll + s0, w, s0, a.Sc, dsum, e->d_err.as<int>(), 1);
+            KCHECK(e);
+        }
+        if (q.want_edge) {
+            CK(e, cudaMemsetAsync(a.edge_out, 0, sizeof(double) * (size_t)E * a.Sc, e->stream));
+            a.stack_depth = e->dm_out_depth;
+            CK(e, dm_launch_outside(a, NB, std::min(grid_max, a.ntiles), e->stream));
+            e->launches++;
+            if (q.sum_edge) {
+                wsum_rows_kernel<<<E, 256, 0, e->stream>>>(a.edge_out, w, s0, a.Sc, dsum + 1, e->d_err.as<int>(), 0);
+                KCHECK(e);
+            }
+            if (q.site_edge) {
+                CK(e, cudaStreamSynchronize(e->stream));
+                if (copy_site_matrix(e, a.edge_out, E, a.Sc, q.site_edge + (size_t)s0 * E)) return -1;
+            }
+        }
+    }
+    CK(e, cudaEventRecord(e->ev[4], e->stream));
+    e->kernel_timed = true;
+    const size_t nsum = 1 + E;
+    if (finish_sums(e, dsum, nsum)) return -1;
+    CK(e, cudaEventRecord(e->ev[2], e->stream));
+    std::vector<double> hs(nsum);
+    int herr = 0;
+    CK(e, cudaMemcpyAsync(hs.data(), dsum, sizeof(double) * nsum, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaMemcpyAsync(&herr, e->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    if (q.site_ll) CK(e, cudaMemcpyAsync(q.site_ll, e->d_site_ll.p, sizeof(double) * e->S, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    if (herr && q.sum_ll) FAIL(e, "a site with non-zero weight has zero likelihood");
+    if (q.sum_ll) *q.sum_ll = hs[0];
+    if (q.sum_edge) memcpy(q.sum_edge, hs.data() + 1, sizeof(double) * E);
+    return 0;
+}
+
 /* common driver: matrices, path selection, timing.  Returns 1 when the query has to be repeated. */
 static int run_query_once(plf_engine *e, Query &q, bool need_D, const double *l_hi, const double *l_lo, int kind)
 {
@@ -1520,7 +1726,7 @@ static int run_query_once(plf_engine *e, Query &q, bool need_D, const double *l_
     if (use_fused && ensure_tip_tables(e, q.want_edge ? q.Fm : nullptr, f_mode, q.want_marg)) return -1;
     CK(e, cudaEventRecord(e->ev[1], e->stream));
     e->kernel_timed = false;
-    int rc = use_fused ? run_fused(e, q) : run_generic(e, q);
+    int rc = use_fused ? run_fused(e, q) : (e->path != PLF_PATH_GENERIC && dmma_applicable(e, q)) ? run_dmma(e, q) : run_generic(e, q);
     if (rc) return rc;
     cudaEventElapsedTime(&e->ms_mat, e->ev[0], e->ev[1]);
     cudaEventElapsedTime(&e->ms_sites, e->ev[1], e->ev[2]);
