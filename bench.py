@@ -23,8 +23,13 @@ algorithm: the C restatement in oracle/c (the Arb reference itself cannot be
 built in this image), all host threads, on a bounded sample of the same
 workload.
 
-N > 1: one process per GPU (torchrun), each rank owns S site patterns of its
-own (weak scaling), results are summed with one in-stream ncclAllReduce.
+N > 1: one process per GPU (torchrun); the SAME alignment is sharded over the
+ranks in contiguous blocks of sites (strong scaling, BASELINE.json configs[1]:
+"sharded 1/2/4/8"), results are summed with one in-stream ncclAllReduce; a
+weak-scaling measurement (a whole alignment per GPU) is reported beside it.
+
+At N = 1 the line also carries "cfg4" (61-state codon model on the FP64 tensor
+pipe) and "json_e2e" (the cfg2 document through the arbplf-deriv drop-in).
 """
 import argparse
 import ctypes
@@ -88,31 +93,32 @@ def model_document(taxa):
     return {"model_and_data": md}, N
 
 
-def simulate_codes(summary, P, S, seed, out):
-    """Simulate S columns down the tree under the model; leaves observed (1% missing), internal nodes unobserved."""
+def simulate_codes(summary, P, S, seed, out, pi=None, missing=0.01):
+    """Simulate S columns down the tree under the model; leaves observed (1% missing), internal nodes unobserved.
+    Any state count: the code of state i is i, the missing-data code is n."""
     rng = np.random.default_rng(seed)
     indptr, indices, preorder = summary["indptr"], summary["indices"], summary["preorder"]
     N = len(preorder)
-    C = P.shape[0]
+    C, n = P.shape[0], P.shape[-1]
     cum = np.cumsum(P, axis=3)
     cat = rng.integers(0, C, S)
-    state = np.empty((N, S), dtype=np.int8)
+    state = np.empty((N, S), dtype=np.int16)
     root = preorder[0]
-    state[root] = np.searchsorted(np.cumsum(PI), rng.random(S)).clip(0, 3)
+    state[root] = np.searchsorted(np.cumsum(PI if pi is None else pi), rng.random(S)).clip(0, n - 1)
     for a in preorder:
         for idx in range(indptr[a], indptr[a + 1]):
             b = indices[idx]
-            rows = cum[cat, idx, state[a].astype(np.int64)]          # [S,4]
+            rows = cum[cat, idx, state[a].astype(np.int64)]          # [S,n]
             u = rng.random(S)
-            state[b] = (u[:, None] > rows).sum(axis=1).clip(0, 3)
+            state[b] = (u[:, None] > rows).sum(axis=1).clip(0, n - 1)
     for a in range(N):
         if indptr[a] == indptr[a + 1]:
             col = state[a].astype(np.uint8)
-            miss = rng.random(S) < 0.01
-            col[miss] = 4
+            miss = rng.random(S) < missing
+            col[miss] = n
             out[:, a] = col
         else:
-            out[:, a] = 4
+            out[:, a] = n
 
 
 class ClockSampler:
@@ -216,7 +222,8 @@ def host_matrices(summary):
 
 
 def build_problem(args, local, rank, use_engine=True):
-    """Host-side setup through the product's own C host layer (no oracle involved)."""
+    """Host-side setup through the product's own C host layer (no oracle involved).  Every rank simulates the same
+    alignment of args.sites columns (seed 3); sharding happens in run_ours."""
     import phyly_b200.arbplf as A
     doc, N = model_document(args.taxa)
     summary = json.loads(A.arbplf_model_summary(json.dumps(doc)))
@@ -240,9 +247,153 @@ def build_problem(args, local, rank, use_engine=True):
     else:
         codes_t, w_t = None, None
         codes = np.empty((S, N), dtype=np.uint8)
-    simulate_codes(summary, P, S, seed=3 + rank, out=codes)
+    simulate_codes(summary, P, S, seed=3, out=codes)
     return dict(eng=eng, summary=summary, N=N, E=N - 1, n=n, C=C, S=S, codes_t=codes_t, codes=codes, w_t=w_t,
-                edge_rates=edge_rates, P=P, D=D)
+                edge_rates=edge_rates, P=P, D=D, doc=doc)
+
+
+def codon_model(kappa=2.0, omega=0.5, seed=4):
+    """GY94-style 61-state rate matrix with F3x4 frequencies."""
+    rng = np.random.default_rng(seed)
+    code = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"
+    codons = [(a, b_, c) for a in range(4) for b_ in range(4) for c in range(4)]
+    aa = {cd: code[16 * cd[0] + 4 * cd[1] + cd[2]] for cd in codons}
+    sense = [cd for cd in codons if aa[cd] != "*"]
+    f = rng.dirichlet(np.ones(4) * 5, size=3)
+    pi = np.array([f[0][cd[0]] * f[1][cd[1]] * f[2][cd[2]] for cd in sense])
+    pi /= pi.sum()
+    n = len(sense)
+    Q = np.zeros((n, n))
+    transitions = {(0, 1), (1, 0), (2, 3), (3, 2)}       # T<->C, A<->G
+    for i, ci in enumerate(sense):
+        for j, cj in enumerate(sense):
+            diff = [k for k in range(3) if ci[k] != cj[k]]
+            if len(diff) != 1:
+                continue
+            k = diff[0]
+            r = pi[j]
+            if (ci[k], cj[k]) in transitions:
+                r *= kappa
+            if aa[ci] != aa[cj]:
+                r *= omega
+            Q[i, j] = r
+    return Q, pi
+
+
+def bench_cfg4(local, peaks_fp64, taxa=256, sites=100000, steps=10):
+    """BASELINE.json configs[3] (cfg4): 61-state GY94 codon model, 256 taxa x 100 000 codon sites, ll and ll + deriv on
+    the FP64 tensor-pipe kernels (dmma.cu).  Timed on the device, data resident."""
+    import torch
+    import phyly_b200.arbplf as A
+    from phyly_b200.engine import Engine
+    Q, pi = codon_model()
+    n = Q.shape[0]
+    edges, N = yule_tree(taxa, seed=21)
+    rng = np.random.default_rng(22)
+    defs = np.vstack([np.eye(n), np.ones((1, n))])
+    md = {"edges": edges, "edge_rate_coefficients": [float(x) for x in rng.exponential(0.05, len(edges))],
+          "rate_matrix": Q.tolist(), "root_prior": "equilibrium_distribution", "rate_divisor": "equilibrium_exit_rate",
+          "character_definitions": defs.tolist(), "character_data": [[n] * N]}
+    s = json.loads(A.arbplf_model_summary(json.dumps({"model_and_data": md})))
+    eng = Engine(local)
+    eng.set_tree(s["indptr"], s["indices"], s["preorder"])
+    eng.set_model(np.array(s["q_hi"]).reshape(n, n), np.array(s["q_lo"]).reshape(n, n), s["edge_rates_csr"], s["cat_rates"],
+                  s["cat_prior"], s["root_mode"], s["root_vec"])
+    P = eng.transition_matrices()
+    base = np.full((sites // 4, N), n, dtype=np.uint8)
+    simulate_codes(s, P, sites // 4, seed=24, out=base, pi=np.array(s["equilibrium"]))
+    codes = np.tile(base, (4, 1))
+    eng.set_data(defs, codes)
+    S, E = codes.shape[0], N - 1
+    Ei = sum(1 for b in s["indices"] if s["indptr"][b] != s["indptr"][b + 1])
+    stream = torch.cuda.ExternalStream(eng.stream(), device=local)
+    out = {"workload": "cfg4: GY94 61-state codon model (kappa 2, omega 0.5, F3x4) x %d-taxon Yule tree x %d codon sites, "
+                       "C = 1, data resident" % (taxa, S), "taxa": taxa, "sites": S, "states": n, "edges": E,
+           "flop_convention": "2 n^2 flops per contraction on the true state count n = 61 (the kernels work on 64 padded states) "
+                              "plus n per edge for the Hadamard products: ll = Ei (2 n^2) + E n per site (SURVEY 8d: 1.92e11 per "
+                              "evaluation); ll+deriv = 3 Ei (2 n^2) + 4 E n (two more contractions per internal-child edge in "
+                              "the outside pass: P^T fe and F^T fe)",
+           "peak_tflops": peaks_fp64.get("dmma_m8n8k4_tflops"), "peak_source": "profiles/fp64_peak.json (tools/fp64_peak.cu, this GPU model)"}
+    for kind in ("ll", "ll_deriv"):
+        fn = (lambda: eng.ll(per_site=False)) if kind == "ll" else (lambda: eng.deriv(per_site=False))
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        km = []
+        e0.record(stream)
+        for _ in range(steps):
+            r = fn()
+            km.append(eng.last_kernel_ms())
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        k_ms = float(np.mean(km))
+        flops = float(S) * ((1 if kind == "ll" else 3) * Ei * 2.0 * n * n + (1 if kind == "ll" else 4) * E * n)
+        tf = flops / (k_ms * 1e-3) / 1e12
+        out[kind] = {"ms_per_step": ms, "kernels_ms": k_ms, "updates_per_s": float(S) * E / (ms * 1e-3),
+                     "kernel": eng.last_kernel_name(), "flops_per_step": flops,
+                     "roofline": {"bound": "tensor", "achieved": tf, "peak": out["peak_tflops"], "unit": "TFLOP/s",
+                                  "frac": tf / out["peak_tflops"] if out["peak_tflops"] else None},
+                     "sum_ll": (r[1] if kind == "ll" else r["sum_ll"])}
+    eng.close()
+    return out
+
+
+def json_document_bytes(doc, codes):
+    """The arbplf JSON document of the workload with its character_data, built without a Python-level loop."""
+    S, N = codes.shape
+    row = np.empty((S, 2 * N + 2), dtype=np.uint8)
+    row[:, 0] = ord("[")
+    row[:, 1:2 * N:2] = codes + ord("0")
+    row[:, 2:2 * N:2] = ord(",")
+    row[:, 2 * N] = ord("]")
+    row[:, 2 * N + 1] = ord(",")
+    data = row.tobytes()[:-1]
+    md = dict(doc["model_and_data"])
+    md["character_data"] = "@@DATA@@"
+    top = {"model_and_data": md, "site_reduction": {"aggregation": "sum"}}
+    head, tail = json.dumps(top).split('"@@DATA@@"')
+    return head.encode() + b"[" + data + b"]" + tail.encode()
+
+
+def bench_json_e2e(pb, max_sites):
+    """The drop-in path at size: the cfg2 document (character_data for every site) through arbplf_deriv of the C ABI in
+    this process and through the arbplf-deriv executable (stdin -> stdout), with the host layer's own phase timings."""
+    import ctypes as c
+    from phyly_b200 import _lib
+    S = min(pb["S"], max_sites)
+    t0 = time.perf_counter()
+    text = json_document_bytes(pb["doc"], pb["codes"][:S])
+    t_build = time.perf_counter() - t0
+    lib = _lib.load()
+    lib.arbplf_deriv.restype = c.c_void_p
+    lib.arbplf_deriv.argtypes = [c.c_char_p, c.POINTER(c.c_int)]
+    lib.arbplf_last_timing.argtypes = [c.POINTER(c.c_double)]
+    libc = c.CDLL(None)
+    libc.free.argtypes = [c.c_void_p]
+    out = {"sites": S, "document_bytes": len(text), "build_document_s": t_build}
+    for rep in range(2):            # the second call has the engine, its buffers and the tuned kernel choice
+        rc = c.c_int(0)
+        t0 = time.perf_counter()
+        res = lib.arbplf_deriv(text, c.byref(rc))
+        wall = time.perf_counter() - t0
+        if not res or rc.value != 0:
+            return {"error": "arbplf_deriv failed with retcode %d" % rc.value}
+        first = c.string_at(res)[:200].decode()
+        libc.free(res)
+        ph = (c.c_double * 4)()
+        lib.arbplf_last_timing(ph)
+        out["in_process_call_%d" % (rep + 1)] = {"wall_s": wall, "parse_s": ph[0], "model_and_upload_s": ph[1], "compute_s": ph[2],
+                                                 "emit_s": ph[3], "updates_per_s": float(S) * pb["E"] * pb["C"] / wall}
+    out["output_head"] = first[:120]
+    exe = os.path.join(ROOT, "phyly_b200", "bin", "arbplf-deriv")
+    if os.path.exists(exe):
+        t0 = time.perf_counter()
+        pr = subprocess.run([exe], input=text, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        out["cli"] = {"wall_s": time.perf_counter() - t0, "retcode": pr.returncode,
+                      "note": "process start, CUDA context and first-query kernel tuning included"}
+    return out
 
 
 def run_ours(args):
@@ -253,13 +404,14 @@ def run_ours(args):
     torch.cuda.set_device(local)
     pb = build_problem(args, local, rank)
     eng = pb["eng"]
-    S, Eg, C, N = pb["S"], pb["E"], pb["C"], pb["N"]
+    S_total, Eg, C, N = pb["S"], pb["E"], pb["C"], pb["N"]
     defs = np.array(DEFS, dtype=np.float64)
     if world > 1:
         uid = [E.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         eng.comm_init(world, rank, uid[0])
     stream = torch.cuda.ExternalStream(eng.stream(), device=local)
+    sync_upload = bool(os.environ.get("PLF_BENCH_SYNC_UPLOAD"))
 
     def barrier():
         torch.cuda.synchronize()
@@ -267,147 +419,217 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        eng.set_edge_rates(pb["edge_rates"])          # invalidates P, Q.P and the tip tables
-        return eng.deriv(per_site=False)
+    def measure(lo, hi, steps, want_e2e, want_ll):
+        """Times the step on the site patterns [lo, hi) of the alignment: resident, end to end, ll only."""
+        S = hi - lo
+        codes_ptr = pb["codes_t"].data_ptr() + lo * N
+        w_ptr = pb["w_t"].data_ptr() + 8 * lo
+        w_np = pb["w_t"].numpy()[lo:hi]
 
-    sync_upload = bool(os.environ.get("PLF_BENCH_SYNC_UPLOAD"))
+        def step_resident():
+            eng.set_edge_rates(pb["edge_rates"])          # invalidates P, Q.P and the tip tables
+            return eng.deriv(per_site=False)
 
-    def step_e2e():
-        if sync_upload:
-            eng.set_data_ptr(defs, pb["codes_t"].data_ptr(), S, 1)
-            eng.set_site_weights(pb["w_t"].numpy())
-        else:       # chunked upload overlapped with the kernel
-            eng.set_data_async_ptr(defs, pb["codes_t"].data_ptr(), S, pb["w_t"].data_ptr(), 1)
-        eng.set_edge_rates(pb["edge_rates"])
-        return eng.deriv(per_site=False)
+        def step_e2e():
+            if sync_upload:
+                eng.set_data_ptr(defs, codes_ptr, S, 1)
+                eng.set_site_weights(w_np)
+            else:       # chunked upload overlapped with the kernel
+                eng.set_data_async_ptr(defs, codes_ptr, S, w_ptr, 1)
+            eng.set_edge_rates(pb["edge_rates"])
+            return eng.deriv(per_site=False)
 
-    # ---- device-resident measurement ----
-    eng.set_data_ptr(defs, pb["codes_t"].data_ptr(), S, 1)
-    eng.set_site_weights(pb["w_t"].numpy())
+        def step_ll():
+            eng.set_edge_rates(pb["edge_rates"])
+            return eng.ll(per_site=False)
+
+        eng.set_data_ptr(defs, codes_ptr, S, 1)
+        eng.set_site_weights(w_np)
+        for _ in range(args.warmup):
+            res = step_resident()
+        barrier()
+        eng.launch_count(reset=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kern_ms, mat_ms, site_ms = [], [], []
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            res = step_resident()
+            kern_ms.append(eng.last_kernel_ms())
+            tm = eng.last_timing()
+            mat_ms.append(tm[0]); site_ms.append(tm[1])
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        out = dict(S=S, steps=steps, ms=e0.elapsed_time(e1), wall=wall, t0=t0, launches=eng.launch_count(), res=res,
+                   kern_ms=float(np.mean(kern_ms)), mat_ms=float(np.mean(mat_ms)), site_ms=float(np.mean(site_ms)),
+                   kernel=eng.last_kernel_name())
+        if want_e2e:
+            e2e_steps = max(1, min(steps, 50))
+            for _ in range(min(args.warmup, 3)):
+                step_e2e()
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t1 = time.perf_counter()
+            f0.record(stream)
+            for _ in range(e2e_steps):
+                res2 = step_e2e()
+            f1.record(stream)
+            barrier()
+            out.update(e2e_steps=e2e_steps, ms_e2e=f0.elapsed_time(f1), t1=t1, t1_end=time.perf_counter(), res2=res2)
+        if want_ll:
+            ll_steps = max(1, min(steps, 50))
+            for _ in range(3):
+                step_ll()
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ll_kern = []
+            g0.record(stream)
+            for _ in range(ll_steps):
+                step_ll()
+                ll_kern.append(eng.last_kernel_ms())
+            g1.record(stream)
+            barrier()
+            out.update(ll_steps=ll_steps, ms_ll=g0.elapsed_time(g1), ll_kern=float(np.mean(ll_kern)), ll_kernel=eng.last_kernel_name())
+        return out
+
+    def max_over_ranks(vals):
+        if world == 1:
+            return [float(v) for v in vals]
+        tt = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return [float(x) for x in tt]
+
+    # ---- headline: the SAME alignment sharded over the ranks (strong scaling; at N = 1 the whole of it) ----
+    lo, hi = rank * S_total // world, (rank + 1) * S_total // world
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(args.warmup):
-        res = step_resident()
-    barrier()
-    eng.launch_count(reset=True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kern_ms, mat_ms = [], []
-    t0 = time.perf_counter()
-    e0.record(stream)
-    for _ in range(args.steps):
-        res = step_resident()
-        kern_ms.append(eng.last_kernel_ms())
-        mat_ms.append(eng.last_timing()[0])
-    e1.record(stream)
-    barrier()
-    wall = time.perf_counter() - t0
-    sampler.mark(t0, t0 + wall)
-    ms = e0.elapsed_time(e1)
-    launches = eng.launch_count()
-    # ---- end-to-end measurement (host buffers) ----
-    e2e_steps = max(1, min(args.steps, 50))
-    for _ in range(min(args.warmup, 3)):
-        step_e2e()
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t1 = time.perf_counter()
-    f0.record(stream)
-    for _ in range(e2e_steps):
-        res2 = step_e2e()
-    f1.record(stream)
-    barrier()
-    sampler.mark(t1, time.perf_counter())
+    m = measure(lo, hi, args.steps, True, True)
+    if rank == 0:
+        sampler.mark(m["t0"], m["t0"] + m["wall"])
+        sampler.mark(m["t1"], m["t1_end"])
     clocks = sampler.stop() if rank == 0 else None
-    # ---- supplementary: log-likelihood only (the metric's other half), device-resident, same timing rules ----
-    ll_steps = max(1, min(args.steps, 50))
-
-    def step_ll():
-        eng.set_edge_rates(pb["edge_rates"])
-        return eng.ll(per_site=False)
-
-    for _ in range(3):
-        step_ll()
-    barrier()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ll_kern = []
-    g0.record(stream)
-    for _ in range(ll_steps):
-        step_ll()
-        ll_kern.append(eng.last_kernel_ms())
-    g1.record(stream)
-    barrier()
-    ms_ll = g0.elapsed_time(g1)
-    ms_e2e = f0.elapsed_time(f1)
+    ms, ms_e2e, ms_ll = max_over_ranks([m["ms"], m["ms_e2e"], m["ms_ll"]])
+    # ---- the collective checked against its inputs: local sums gathered over gloo vs the all-reduced vector ----
+    allreduce_check = None
     if world > 1:
-        tt = torch.tensor([ms, ms_e2e, ms_ll], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, ms_ll = float(tt[0]), float(tt[1]), float(tt[2])
+        eng.comm_pause(True)
+        loc = eng.deriv(per_site=False)
+        eng.comm_pause(False)
+        glob = eng.deriv(per_site=False)
+        mine = np.concatenate([[loc["sum_ll"]], loc["sum_deriv"]])
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        want = np.sum(np.stack(gathered), axis=0)
+        got = np.concatenate([[glob["sum_ll"]], glob["sum_deriv"]])
+        err = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-300)))
+        allreduce_check = {"values": int(got.size), "max_rel_diff_vs_sum_of_local": err, "ok": bool(err <= 1e-13),
+                           "sum_ll_all_ranks": float(got[0]), "local_sum_ll": [float(g[0]) for g in gathered]}
+        assert allreduce_check["ok"], allreduce_check
+    # ---- weak scaling beside it (N > 1 only): every rank owns a whole alignment of args.sites patterns ----
+    weak = None
+    if world > 1:
+        mw = measure(0, S_total, max(3, min(args.steps, 20)), False, False)
+        (ms_w,) = max_over_ranks([mw["ms"]])
+        weak = {"scaling": "weak", "sites_per_gpu": S_total, "steps": mw["steps"], "ms_per_step": ms_w / mw["steps"],
+                "value": float(S_total) * Eg * C * world * mw["steps"] / (ms_w * 1e-3), "unit": "updates/s",
+                "kernel_ms": mw["kern_ms"]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    updates_per_step = float(S) * Eg * C * world
+    S = m["S"]
+    updates_per_step = float(S_total) * Eg * C
     value = updates_per_step * args.steps / (ms * 1e-3)
-    e2e_value = updates_per_step * e2e_steps / (ms_e2e * 1e-3)
+    e2e_value = updates_per_step * m["e2e_steps"] / (ms_e2e * 1e-3)
     peaks = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"))
     hbm_peak = peaks["hbm_gbs"] if peaks and "hbm_gbs" in peaks else 6650.0
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     fp64 = load_json(os.path.join(ROOT, "profiles", "fp64_peak.json")) or {}
-    traffic = load_json(os.path.join(ROOT, "profiles", "ncu_traffic.json")) or {}
-    k_ms = float(np.mean(kern_ms)) if kern_ms else None
-    alg_bytes = BYTES_PER_UPDATE_LL_DERIV * float(S) * Eg * C
-    # fp64 work of the fused kernel per (site, category): see DESIGN.md section 5
-    n_int_edges = sum(1 for b in pb["summary"]["indices"]
-                      if pb["summary"]["indptr"][b] != pb["summary"]["indptr"][b + 1])
+    traffic_db = (load_json(os.path.join(ROOT, "profiles", "ncu_traffic.json")) or {}).get("kernels", {})
+    k_ms = m["kern_ms"]
+    # ---- roofline of the dominant kernel (rank 0's shard of S sites) ----
+    summary = pb["summary"]
+    n_int_edges = sum(1 for b in summary["indices"] if summary["indptr"][b] != summary["indptr"][b + 1])
     n_tip_edges = Eg - n_int_edges
+    n_internal = n_int_edges + 1
+    tr = traffic_db.get(m["kernel"])
+    traffic = tr["dram_bytes_per_launch"] * (float(S) / tr["sites"]) if tr else None
+    # bytes the kernel is written to move (fused4.cuh): every internal node's partial goes once to the slab and comes back
+    # once (double4 + 1 byte per category), the codes of the tips once, weights in, site log-likelihoods out
+    own_bytes = float(S) * (2.0 * 33.0 * n_internal * C + (n_tip_edges) + 8 + 8)
+    streamed_bytes = BYTES_PER_UPDATE_LL_DERIV * float(S) * Eg * C
+    compulsory = float(S) * (n_tip_edges + 8)
+    moved = traffic if traffic else own_bytes
     flops = float(S) * C * (n_int_edges * (36 + 108) + n_tip_edges * (4 + 14))
     roofline = {
-        "bound": "hbm", "kernel": traffic.get("kernel", "fused4_kernel"),
-        "achieved": alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms else None, "peak": hbm_peak, "unit": "GB/s",
-        "frac": (alg_bytes / (k_ms * 1e-3) / 1e9) / hbm_peak if k_ms else None,
-        "traffic": traffic.get("dram_bytes_per_launch"),
+        "bound": "hbm", "kernel": m["kernel"],
+        "achieved": moved / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+        "frac": moved / (k_ms * 1e-3) / 1e9 / hbm_peak,
+        "traffic": traffic,
+        "bytes_basis": ("DRAM bytes per launch measured by ncu for exactly this instantiation (profiles/ncu_traffic.json), scaled "
+                        "to this launch's sites" if traffic else "the kernel's own byte model (no ncu capture of this instantiation)"),
         "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": alg_bytes,
-        "note": ("algorithmic bytes are SURVEY 8(d)'s streamed-partials figure (79.4 B/update); the fused kernel keeps "
-                 "partials on chip, so a fraction above 1 means it moves less than that formulation (traffic = DRAM "
-                 "bytes per launch measured by ncu); ncu shows it bound by slab-load latency and LSU wavefronts, "
-                 "fp64 gives its flop rate against the measured DFMA peak"),
-        "measured_dram_gbs": (traffic["dram_bytes_per_launch"] / (k_ms * 1e-3) / 1e9
-                              if (k_ms and traffic.get("dram_bytes_per_launch")) else None),
-        "measured_dram_frac": (traffic["dram_bytes_per_launch"] / (k_ms * 1e-3) / 1e9 / hbm_peak
-                               if (k_ms and traffic.get("dram_bytes_per_launch")) else None),
-        "fp64": {"achieved_tflops": flops / (k_ms * 1e-3) / 1e12 if k_ms else None,
-                 "peak_tflops": fp64.get("dfma_tflops"),
-                 "frac": (flops / (k_ms * 1e-3) / 1e12) / fp64["dfma_tflops"] if (k_ms and fp64.get("dfma_tflops")) else None,
+        "own_model_bytes_per_launch": own_bytes,
+        "frac_own_model": own_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
+        "streamed_model_bytes_per_launch": streamed_bytes,
+        "frac_streamed_model": streamed_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
+        "compulsory_bytes_per_launch": compulsory,
+        "compulsory_bound_ms": compulsory / (hbm_peak * 1e9) * 1e3,
+        "note": ("frac = bytes this kernel really moves / its time / measured HBM copy peak.  frac_streamed_model is SURVEY "
+                 "8(d)'s figure for a formulation that streams every partial (79.4 B/update), which this kernel does not follow "
+                 "(its value above 1 only says the kernel moves fewer bytes than that); compulsory = tip codes + weights, the "
+                 "bound of a traversal that kept every partial on chip"),
+        "fp64": {"achieved_tflops": flops / (k_ms * 1e-3) / 1e12, "peak_tflops": fp64.get("dfma_tflops"),
+                 "frac": (flops / (k_ms * 1e-3) / 1e12) / fp64["dfma_tflops"] if fp64.get("dfma_tflops") else None,
                  "flops_per_launch": flops},
-        "kernel_ms": k_ms, "matrix_kernels_ms": float(np.mean(mat_ms)) if mat_ms else None,
+        "kernel_ms": k_ms,
     }
+    step_ms = ms / args.steps
     line = {
         "metric": "site-edge-category updates/s (ll+deriv)", "value": value, "unit": "updates/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg2: GTR+Gamma4 (examples/BEAST.GTRG model) x %d-taxon Yule tree x %d site patterns per GPU, "
-                               "arbplf-ll + arbplf-deriv, site axis summed" % (args.taxa, S),
-                   "sites_per_gpu": S, "taxa": args.taxa, "edges": Eg, "categories": C, "states": pb["n"],
-                   "sharding": "sites across GPUs, one ncclAllReduce of %d doubles" % (1 + Eg),
-                   "cache": "inputs and scratch (%.0f MB) exceed the 126 MB L2; no explicit flush" % (S * N / 1e6 + 600)},
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg2: GTR+Gamma4 (examples/BEAST.GTRG model) x %d-taxon Yule tree x %d site patterns in total, "
+                               "sharded over the GPUs, arbplf-ll + arbplf-deriv, site axis summed" % (args.taxa, S_total),
+                   "sites_total": S_total, "sites_per_gpu": S, "taxa": args.taxa, "edges": Eg, "categories": C, "states": pb["n"],
+                   "sharding": "contiguous blocks of sites, one ncclAllReduce of %d doubles per step" % (1 + Eg),
+                   "cache": "inputs and scratch (%.0f MB per GPU) exceed the 126 MB L2; no explicit flush" % (S * N / 1e6 + 600)},
+        "step_breakdown_ms": {"matrices_and_tables": m["mat_ms"], "fused_kernel": k_ms,
+                              "reduction_allreduce_readback": max(0.0, m["site_ms"] - k_ms),
+                              "host_gaps": max(0.0, step_ms - m["mat_ms"] - m["site_ms"]),
+                              "note": "CUDA events of rank 0 inside the step; host_gaps = step time not covered by them"},
         "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(S * N + 8 * S + 8 * Eg),
-                "d2h_bytes_per_step": int(8 * (1 + Eg)), "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
-                "api": ("plf_set_data + plf_set_site_weights" if sync_upload else "plf_set_data_async") + " + plf_set_edge_rates + plf_deriv (include/plf.h), pinned host buffers"},
-        "gpu_launches": int(launches),
+                "d2h_bytes_per_step": int(8 * (1 + Eg)), "steps": m["e2e_steps"], "ms_per_step": ms_e2e / m["e2e_steps"],
+                "api": ("plf_set_data + plf_set_site_weights" if sync_upload else "plf_set_data_async") + " + plf_set_edge_rates + plf_deriv (include/plf.h), pinned host buffers; bytes are per GPU"},
+        "gpu_launches": int(m["launches"]),
         "clocks": clocks,
         "roofline": roofline,
-        "ll_only": {"metric": "site-edge-category updates/s (ll)", "value": updates_per_step * ll_steps / (ms_ll * 1e-3),
-                    "unit": "updates/s", "steps": ll_steps, "ms_per_step": ms_ll / ll_steps,
-                    "kernel_ms": float(np.mean(ll_kern)),
-                    "roofline_frac_hbm": (BYTES_PER_UPDATE_LL * float(S) * Eg * C / (float(np.mean(ll_kern)) * 1e-3) / 1e9) / hbm_peak,
-                    "note": "supplementary; algorithmic bytes 31.9 B/update (SURVEY 8d); no slab, partials never leave the SM"},
-        "result_check": {"sum_ll": res["sum_ll"], "sum_ll_e2e": res2["sum_ll"], "wall_s": wall},
+        "ll_only": {"metric": "site-edge-category updates/s (ll)", "value": updates_per_step * m["ll_steps"] / (ms_ll * 1e-3),
+                    "unit": "updates/s", "steps": m["ll_steps"], "ms_per_step": ms_ll / m["ll_steps"],
+                    "kernel_ms": m["ll_kern"], "kernel": m["ll_kernel"],
+                    "compulsory_bound_ms": compulsory / (hbm_peak * 1e9) * 1e3,
+                    "frac_streamed_model": (BYTES_PER_UPDATE_LL * float(S) * Eg * C / (m["ll_kern"] * 1e-3) / 1e9) / hbm_peak,
+                    "note": "supplementary; no slab, partials never leave the SM: HBM traffic is the tip codes, the kernel is bound by issue / LSU, not DRAM"},
+        "result_check": {"sum_ll": m["res"]["sum_ll"], "sum_ll_e2e": m["res2"]["sum_ll"], "wall_s": m["wall"]},
     }
+    if allreduce_check:
+        line["allreduce_check"] = allreduce_check
+    if weak:
+        line["weak"] = weak
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(pb, target_seconds=args.cpu_seconds)
+    if world == 1 and not args.no_extras:
+        eng.close()
+        try:
+            line["cfg4"] = bench_cfg4(local, fp64)
+        except Exception as ex:       # a supplementary measurement must not lose the headline
+            line["cfg4"] = {"error": repr(ex)}
+        try:
+            line["json_e2e"] = bench_json_e2e(pb, args.json_sites)
+        except Exception as ex:
+            line["json_e2e"] = {"error": repr(ex)}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -516,6 +738,8 @@ def main():
     ap.add_argument("--taxa", type=int, default=64)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cfg4 and JSON drop-in measurements (N = 1)")
+    ap.add_argument("--json-sites", type=int, default=1000000)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

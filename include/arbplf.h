@@ -59,6 +59,10 @@ int arbplf_run_stdio(char *(*f)(const char *, int *));
  */
 char *arbplf_model_summary(const char *json_in, int *retcode);
 
+/* Wall-clock seconds of the phases of the most recent arbplf_* call: JSON parse + schema validation, derived model
+ * quantities + upload, device compute + reductions, output formatting (bench.py reports them as json_e2e). */
+void arbplf_last_timing(double out[4]);
+
 /* GPU ordinal used by the JSON entry points (default 0, or env ARBPLF_DEVICE). */
 void arbplf_set_device(int device);
 

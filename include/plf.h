@@ -119,6 +119,14 @@ int plf_ll(plf_engine *e, double *site_ll, double *sum);
 int plf_deriv(plf_engine *e, const unsigned char *edge_mask,
               double *site_ll, double *sum_ll, double *site_deriv, double *sum_deriv);
 
+/*
+ * Second order (arbplfhess.c:502-829): sum_ll = sum_s w_s log L_s, sum_deriv[E] its gradient and sum_hess[E][E] its
+ * Hessian with respect to the edge rate coefficients (csr edge order, full symmetric matrix).  sum_ll and sum_deriv
+ * may be NULL.  A rate category with a non-zero rate and zero likelihood at a weighted site is an error
+ * ("infeasible", arbplfhess.c:640-660).
+ */
+int plf_hess(plf_engine *e, double *sum_ll, double *sum_deriv /*[E]*/, double *sum_hess /*[E][E]*/);
+
 /* posterior marginals: site_marg [S][N][n], sum_marg [N][n] = sum_s w_s marg. */
 int plf_marginal(plf_engine *e, double *site_marg, double *sum_marg);
 
@@ -149,6 +157,10 @@ int plf_last_timing(plf_engine *e, float *ms_matrices, float *ms_sites);
 /* duration of the dominant per-site kernel alone (the fused 4-state kernel), 0 if it did not run */
 int plf_last_kernel_ms(plf_engine *e, float *ms_kernel);
 int64_t plf_launch_count(plf_engine *e, int reset);
+/* which instantiation ran as the dominant per-site kernel of the most recent query, spelled as the profiler spells it
+ * (e.g. "fused4_kernel<4,1,512,2,1,1>": categories, mode, block size, staging, packed codes, constant-memory matrices;
+ * the fused kernel's configuration is picked by timing, so this is the only way to know) */
+const char *plf_last_kernel_name(const plf_engine *e);
 
 /*
  * Multi-GPU: one engine per rank, sites sharded by the caller.  After
@@ -157,6 +169,8 @@ int64_t plf_launch_count(plf_engine *e, int reset);
  */
 int plf_comm_unique_id(char id[128]);
 int plf_comm_init(plf_engine *e, int nranks, int rank, const char id[128]);
+/* paused != 0: the *_sum outputs stay local (this rank's sites only) until resumed; for cross-checks of the collective */
+int plf_comm_pause(plf_engine *e, int paused);
 
 /* The CUDA stream the engine launches on (cudaStream_t as void*), for event timing. */
 void *plf_stream(plf_engine *e);

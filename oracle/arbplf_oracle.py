@@ -1446,6 +1446,176 @@ def run_em_update(root, mode="mp"):
     return {"columns": ["edge", "value"], "data": rows}
 
 
+
+# --------------------------------------------------------------------------
+# second order programs: hess, inv-hess, newton-delta, newton-update
+# (arbplfhess.c)
+# --------------------------------------------------------------------------
+
+def _site_lhood_subst(m: Model, cs: CrossSite, be, base, cat: int, subst: Dict[int, int]):
+    """
+    The site likelihood with the transition matrix of edge idx replaced by
+    Q^k P_idx for every (idx: k) in subst.  The likelihood is multilinear in
+    the per-edge matrices, so this is what evaluate_site_derivatives of
+    arbplfhess.c:343-443 computes through its "indirect plane": one
+    substitution for a first derivative, two (or Q^2 on one edge) for a second
+    one (arbplfhess.c:683-716).
+    """
+    t = m.tree
+    node = {}
+    for a in reversed(t.preorder):
+        v = base[:, a, :].copy()
+        for idx in range(t.indptr[a], t.indptr[a + 1]):
+            em = _matvec(cs.P[cat, idx], node[t.indices[idx]])
+            for _ in range(subst.get(idx, 0)):
+                em = _matvec(cs.Q, em)
+            v = v * em
+        node[a] = v
+    rootv = node[t.root]
+    if m.root_mode == ROOT_NONE:
+        return rootv.sum(axis=1)
+    return rootv @ root_prior_vector(m, cs, be)
+
+
+def second_order(m: Model, be, r_site: Reduction, want_h=True):
+    """
+    _recompute_second_order (arbplfhess.c:502-829): log likelihood, its
+    gradient and its Hessian with respect to the edge rate coefficients,
+    aggregated over the selected sites.  Everything in csr edge order.
+    Returns (x, ll, grad[E], hess[E, E]).
+    """
+    cs = cross_site(m, be)
+    t = m.tree
+    E = t.edge_count
+    w, div = agg_weights(r_site, m.site_count, be)
+    sites = _requested_sites(r_site, m.site_count)
+    ll = be.num(0)
+    grad = be.zeros(E)
+    hess = be.zeros(E, E)
+    x = [cs.edge_rates[i] for i in range(E)]
+    if not sites:
+        return x, ll, grad, hess
+    base = _base_vectors(m, be, sites)
+    S = base.shape[0]
+    site_l = be.zeros(S)
+    site_g = be.zeros(S, E)
+    site_h = be.zeros(S, E, E)
+    for c in range(cs.C):
+        lh = _site_lhood_subst(m, cs, be, base, c, {}) * cs.prior[c]
+        rate = cs.rates[c]
+        for k in range(S):
+            if lh[k] == 0 and rate != 0:
+                # arbplfhess.c:640-660
+                raise OracleError("error: infeasible")
+        if rate == 0:
+            # a zero-rate category has zero derivatives; its likelihood still counts
+            site_l = site_l + lh
+            continue
+        site_l = site_l + lh
+        for i in range(E):
+            gi = _site_lhood_subst(m, cs, be, base, c, {i: 1})
+            site_g[:, i] = site_g[:, i] + cs.prior[c] * rate * gi
+            if want_h:
+                for j in range(i + 1):
+                    sub = {i: 2} if i == j else {i: 1, j: 1}
+                    hij = _site_lhood_subst(m, cs, be, base, c, sub)
+                    site_h[:, i, j] = site_h[:, i, j] + cs.prior[c] * rate * rate * hij
+    for k, s_ in enumerate(sites):
+        L = site_l[k]
+        ws = w[s_] / div
+        ll = ll + ws * be.log(L)
+        for i in range(E):
+            grad[i] = grad[i] + ws * site_g[k, i] / L
+            if want_h:
+                for j in range(i + 1):
+                    # _lhood_hess_to_ll_hess, arbplfhess.c:455-495
+                    v = (site_h[k, i, j] - site_g[k, i] * site_g[k, j] / L) / L
+                    hess[i, j] = hess[i, j] + ws * v
+    for i in range(E):
+        for j in range(i):
+            hess[j, i] = hess[i, j]
+    return x, ll, grad, hess
+
+
+def _parse_second_order(root, what):
+    """_parse_second_order, arbplfhess.c:1162-1207: the site reduction is required and must aggregate."""
+    if not isinstance(root, dict):
+        raise OracleError("%s: expected an object" % what)
+    _strict_keys(root, ["model_and_data", "site_reduction"], [], what)
+    m = parse_model(root["model_and_data"])
+    r_site = parse_column_reduction(root["site_reduction"], m.site_count, "site")
+    if r_site.agg_mode == AGG_NONE:
+        raise OracleError("error: aggregation over sites is required")
+    return m, r_site
+
+
+def _edge_pair_table(m: Model, be, M):
+    t = m.tree
+    E = t.edge_count
+    data = []
+    for first in range(E):
+        for second in range(E):
+            i, j = t.order[first], t.order[second]
+            v = M[i, j] if j < i else M[j, i]
+            data.append([first, second, be.to_float(v)])
+    return {"columns": ["first_edge", "second_edge", "value"], "data": data}
+
+
+def _edge_table(m: Model, be, v):
+    t = m.tree
+    return {"columns": ["edge", "value"], "data": [[i, be.to_float(v[t.order[i]])] for i in range(t.edge_count)]}
+
+
+def _mat_inverse(be, A):
+    n = A.shape[0]
+    out = be.zeros(n, n)
+    for k in range(n):
+        e = [be.num(1 if i == k else 0) for i in range(n)]
+        col = be.solve(A, e)
+        for i in range(n):
+            out[i, k] = col[i]
+    return out
+
+
+def run_hess(root, mode="mp"):
+    """hess_query, arbplfhess.c:1279-1343."""
+    be = get_backend(mode)
+    m, r_site = _parse_second_order(root, "arbplf-hess")
+    _, _, _, H = second_order(m, be, r_site)
+    return _edge_pair_table(m, be, H)
+
+
+def run_inv_hess(root, mode="mp"):
+    """inv_hess_query, arbplfhess.c:1208-1277."""
+    be = get_backend(mode)
+    m, r_site = _parse_second_order(root, "arbplf-inv-hess")
+    _, _, _, H = second_order(m, be, r_site)
+    return _edge_pair_table(m, be, _mat_inverse(be, H))
+
+
+def newton_delta(be, g, H):
+    """so_get_newton_delta, arbplfhess.c:203-234: -inv(hess) grad."""
+    u = be.solve(H, list(g))
+    return [-x for x in u]
+
+
+def run_newton_delta(root, mode="mp"):
+    """newton_delta_query, arbplfhess.c:1345-1398."""
+    be = get_backend(mode)
+    m, r_site = _parse_second_order(root, "arbplf-newton-delta")
+    _, _, g, H = second_order(m, be, r_site)
+    return _edge_table(m, be, newton_delta(be, g, H))
+
+
+def run_newton_update(root, mode="mp"):
+    """newton_point_query, arbplfhess.c:1400-1452: x + delta."""
+    be = get_backend(mode)
+    m, r_site = _parse_second_order(root, "arbplf-newton-update")
+    x, _, g, H = second_order(m, be, r_site)
+    d = newton_delta(be, g, H)
+    return _edge_table(m, be, [x[i] + d[i] for i in range(len(d))])
+
+
 PROGRAMS = {
     "ll": run_ll,
     "deriv": run_deriv,
@@ -1453,6 +1623,10 @@ PROGRAMS = {
     "dwell": run_dwell,
     "trans": run_trans,
     "em_update": run_em_update,
+    "hess": run_hess,
+    "inv_hess": run_inv_hess,
+    "newton_delta": run_newton_delta,
+    "newton_update": run_newton_update,
 }
 
 

@@ -52,6 +52,10 @@ def load():
     lib.plf_last_kernel_ms.restype = c.c_int
     lib.plf_launch_count.argtypes = [P, c.c_int]
     lib.plf_launch_count.restype = c.c_int64
+    lib.plf_last_kernel_name.argtypes = [P]
+    lib.plf_last_kernel_name.restype = c.c_char_p
+    lib.plf_comm_pause.argtypes = [P, c.c_int]
+    lib.plf_comm_pause.restype = c.c_int
     lib.plf_comm_unique_id.argtypes = [c.c_char_p]
     lib.plf_comm_init.argtypes = [P, c.c_int, c.c_int, c.c_char_p]
     lib.plf_stream.argtypes = [P]

@@ -150,13 +150,16 @@ __global__ void dm_tip_table_kernel(const double *M, const double *defs, const u
     out[idx] = v;
 }
 
-/* four n-blocks (two packed pairs, chunk pc) of one contraction: em[i][h] = sum_k A[k] B[k][8 (4 pc + i) + ...] */
-template <int NB>
-__device__ __forceinline__ void dm_gemm_chunk(const double (&A)[2 * NB], const double2 *sl, int pc, double (&em)[4][2])
+/* four n-blocks (two packed pairs, chunk pc) of one contraction for the SG site groups of a warp:
+ * em[r][i][h] = sum_k A[r][k] B[k][8 (4 pc + i) + ...]; every B fragment read from shared memory feeds 2 SG DMMAs */
+template <int NB, int SG>
+__device__ __forceinline__ void dm_gemm_chunk(const double (&A)[SG][2 * NB], const double2 *sl, int pc, double (&em)[SG][4][2])
 {
     constexpr int NBP = (NB + 1) / 2;
 #pragma unroll
-    for (int i = 0; i < 4; i++) { em[i][0] = 0.0; em[i][1] = 0.0; }
+    for (int r = 0; r < SG; r++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) { em[r][i][0] = 0.0; em[r][i][1] = 0.0; }
 #pragma unroll
     for (int kk = 0; kk < 2 * NB; kk++) {
 #pragma unroll
@@ -164,20 +167,23 @@ __device__ __forceinline__ void dm_gemm_chunk(const double (&A)[2 * NB], const d
             const int nbp = 2 * pc + p;
             if (nbp < NBP) {
                 const double2 b = sl[(kk * NBP + nbp) * 32];
-                dm_dmma(em[2 * p][0], em[2 * p][1], A[kk], b.x);
-                if (2 * nbp + 1 < NB) dm_dmma(em[2 * p + 1][0], em[2 * p + 1][1], A[kk], b.y);
+#pragma unroll
+                for (int r = 0; r < SG; r++) {
+                    dm_dmma(em[r][2 * p][0], em[r][2 * p][1], A[r][kk], b.x);
+                    if (2 * nbp + 1 < NB) dm_dmma(em[r][2 * p + 1][0], em[r][2 * p + 1][1], A[r][kk], b.y);
+                }
             }
         }
     }
 }
 
 /* The ring of packed matrices.  Contraction number G of this CTA uses slot G % R in phase (G / R) & 1. */
-template <int NB, int NW>
+template <int NB>
 struct DmRing {
     static constexpr int SLOT = dm_slot_doubles(NB);
     double *slots;          /* [R][SLOT] */
     uint64_t *full;         /* [R] */
-    int *done;              /* [R] warps that have finished the slot's current matrix (running count) */
+    int *done;              /* [R] warps that have finished the slot's current matrix */
     const double *src;      /* packed matrices [C][nmat][SLOT] */
     int nmat, C, R;
     int cat_inner;          /* 0: sequence number -> item -> category = item % C;  1: category = sequence % C */
@@ -201,18 +207,21 @@ struct DmRing {
         dm_mbar_wait(&full[s], (unsigned)((G / R) & 1));
         return reinterpret_cast<const double2 *>(slots + (size_t)s * SLOT) + lane;
     }
-    /* the warp is done with the matrix of contraction G; the last warp refills the slot */
-    __device__ __forceinline__ void release(long long G, int lane)
+    /* the warp is done with the matrix of contraction G; the last of the nact warps working on it refills the slot */
+    __device__ __forceinline__ void release(long long G, int lane, int nact)
     {
         __syncwarp();
         if (lane == 0) {
             const int s = (int)(G % R);
             __threadfence_block();
             const int old = atomicAdd(&done[s], 1);
-            if ((old & (NW - 1)) == NW - 1 && G + R < total) {
-                __threadfence_block();
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue(G + R);
+            if (old == nact - 1) {
+                atomicExch(&done[s], 0);
+                if (G + R < total) {
+                    __threadfence_block();
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(G + R);
+                }
             }
         }
     }
@@ -232,22 +241,54 @@ struct DmRing {
     __device__ __forceinline__ unsigned char *after() const { return reinterpret_cast<unsigned char *>(done + DM_MAX_R); }
 };
 
-/* the warp's character codes of one tile: dst[row][8 sites] */
+/* the tree program in shared memory: ops {first_child, nchild, code_row, spill_before}, children {kind, mat, code_row, edge} */
+struct DmProg {
+    const int4 *ops, *ch;
+    unsigned char *after;
+};
+__device__ __forceinline__ DmProg dm_stage_program(const DmArgs &a, unsigned char *smem, int tid, int nthreads)
+{
+    DmProg p;
+    int4 *o = reinterpret_cast<int4 *>(smem + ((16 - (reinterpret_cast<uintptr_t>(smem) & 15)) & 15));
+    int4 *c = o + a.nops;
+    for (int i = tid; i < a.nops; i += nthreads) o[i] = a.ops4[i];
+    for (int i = tid; i < a.nchildren; i += nthreads) c[i] = a.ch4[i];
+    __syncthreads();
+    p.ops = o; p.ch = c; p.after = reinterpret_cast<unsigned char *>(c + a.nchildren);
+    return p;
+}
+struct DmOpV { int first_child, nchild, code_row, spill_before; };
+struct DmChV { int kind, mat, code_row, edge; };
+__device__ __forceinline__ DmOpV dm_op(const DmProg &p, int o) { const int4 v = p.ops[o]; return DmOpV{v.x, v.y, v.z, v.w}; }
+__device__ __forceinline__ DmChV dm_ch(const DmProg &p, int j) { const int4 v = p.ch[j]; return DmChV{v.x, v.y, v.z, v.w}; }
+
+/* tile t of the chunk: 8-site groups [g0, g0 + cnt); the tiles of the last wave are smaller so that it is spread evenly */
+__device__ __forceinline__ void dm_tile(const DmArgs &a, int t, int &g0, int &cnt)
+{
+    if (t < a.tiles_full) { g0 = t * DM_GROUPS; cnt = DM_GROUPS; }
+    else { g0 = a.tiles_full * DM_GROUPS + (t - a.tiles_full) * a.tail_gs; cnt = min(a.tail_gs, a.ngroups - g0); }
+}
+
+/* pull the table row of a tip child (this thread's 16 NB bytes of it) into L1 ahead of its use */
+__device__ __forceinline__ void dm_prefetch(const void *p)
+{
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+/* the warp's character codes of one tile: dst[row][8 SG sites] (site group r of the warp at bytes 8r..8r+7) */
+template <int SG>
 __device__ __forceinline__ void dm_stage_codes(const DmArgs &a, unsigned char *my_codes, int sw, int lane)
 {
     __syncwarp();
     for (int r = lane; r < a.nrows; r += 32) {
         const unsigned char *src = a.codes + (size_t)a.code_row_node[r] * a.S + a.s0 + sw;
-        unsigned char *dst = my_codes + r * 8;
-        if (sw + 8 <= a.Sc && ((reinterpret_cast<uintptr_t>(src) & 7) == 0)) {
-            *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(src);
+        unsigned char *dst = my_codes + r * (8 * SG);
+        if (sw + 8 * SG <= a.Sc && ((reinterpret_cast<uintptr_t>(src) & 7) == 0)) {
+#pragma unroll
+            for (int i = 0; i < SG; i++) reinterpret_cast<uint2 *>(dst)[i] = reinterpret_cast<const uint2 *>(src)[i];
         } else {
             /* ragged end of the chunk: sites beyond it repeat the chunk's last site (their results are not written) */
-            for (int s = 0; s < 8; s++) {
-                int off = s;
-                if (sw + s >= a.Sc) off = (sw < a.Sc) ? (a.Sc - 1 - sw) : (a.Sc - 1 - sw);
-                dst[s] = src[off];
-            }
+            for (int s = 0; s < 8 * SG; s++) dst[s] = src[(sw + s < a.Sc) ? s : (a.Sc - 1 - sw)];
         }
     }
     __syncwarp();
@@ -276,10 +317,10 @@ __device__ __forceinline__ int dm_site_max_hi(const double (&v)[2 * NB])
 }
 
 /*
- * Inside pass.  grid = persistent CTAs (work item i = blockIdx.x + k gridDim.x -> tile i / C,
- * category i % C), NW warps of 8 sites each.  NW must be a power of two.
+ * Inside pass.  grid = persistent CTAs (work item i = blockIdx.x + k gridDim.x -> tile i / C, category i % C),
+ * NW warps of SG site groups (8 SG sites) each; NW SG = DM_GROUPS.
  */
-template <int NB, int NW>
+template <int NB, int NW, int SG>
 __global__ void __launch_bounds__(NW * 32, 1) dm_inside_kernel(const DmArgs a)
 {
     extern __shared__ __align__(128) unsigned char dm_smem[];
@@ -290,163 +331,227 @@ __global__ void __launch_bounds__(NW * 32, 1) dm_inside_kernel(const DmArgs a)
 
     const long long nitems = (long long)a.ntiles * a.C;
     const long long my_items = (nitems > blockIdx.x) ? (nitems - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    DmRing<NB, NW> ring;
+    DmRing<NB> ring;
     ring.src = a.Pf; ring.nmat = a.Ei; ring.C = a.C; ring.R = a.R; ring.cat_inner = 0;
     ring.total = my_items * a.Ei;
     ring.setup(dm_smem, tid);
-    unsigned char *my_codes = ring.after() + (size_t)warp * a.nrows * 8;
+    const DmProg prog = dm_stage_program(a, ring.after(), tid, NW * 32);
+    unsigned char *my_codes = prog.after + (size_t)warp * a.nrows * (8 * SG);
+    /* The warps of a scheduler run the same program and would stay in lock-step (all in a contraction, then all
+     * outside one, leaving the tensor pipe idle): start them a fraction of an op apart. */
+    if (a.stagger > 0) {
+        const long long t0 = clock64(), wait = (long long)(warp >> 2) * a.stagger;
+        while (clock64() - t0 < wait) { }
+    }
 
-    double2 *my_stack = a.stack + ((size_t)blockIdx.x * NW + warp) * a.stack_depth * (NB * 32);
-    int *my_stack_meta = a.stack_meta + ((size_t)blockIdx.x * NW + warp) * a.stack_depth * 32;
+    double2 *my_stack = a.stack + ((size_t)blockIdx.x * NW + warp) * a.stack_depth * (SG * NB * 32);
+    int *my_stack_meta = a.stack_meta + ((size_t)blockIdx.x * NW + warp) * a.stack_depth * (SG * 32);
     long long G = 0;
 
     for (long long it = 0; it < my_items; it++) {
         const long long item = (long long)blockIdx.x + it * gridDim.x;
         const int tile = (int)(item / a.C), c = (int)(item % a.C);
-        const int sw = tile * (NW * 8) + warp * 8;          /* first site of this warp (within the chunk) */
-        const int site = sw + g;
-        const bool valid = site < a.Sc;
-        dm_stage_codes(a, my_codes, sw, lane);
+        int g0, cnt;
+        dm_tile(a, tile, g0, cnt);
+        const int nact = (cnt + SG - 1) / SG;
+        if (warp >= nact) {
+            /* a short tile of the last wave: this warp has no sites; nothing after such a tile may overtake it */
+            G += a.Ei;
+            __syncthreads();
+            continue;
+        }
+        const int gw = g0 + warp * SG;                      /* first 8-site group of this warp (within the chunk) */
+        const int sw = gw * 8;
+        dm_stage_codes<SG>(a, my_codes, sw, lane);
 
         const double *TPc = a.TPf + (size_t)c * a.Et * a.K * W + q * 2 * NB;
-        double cur[2 * NB];
-        int curk = 0, curc = 1, sp = 0;
+        double cur[SG][2 * NB];
+        int curk[SG], curc[SG], sp = 0;
 #pragma unroll
-        for (int i = 0; i < 2 * NB; i++) cur[i] = 0.0;
+        for (int r = 0; r < SG; r++) {
+            curk[r] = 0; curc[r] = 1;
+#pragma unroll
+            for (int i = 0; i < 2 * NB; i++) cur[r][i] = 0.0;
+        }
 
 #pragma unroll 1
         for (int o = 0; o < a.nops; o++) {
-            const F4Op op = a.ops[o];
-            if (op.spill_before) {
-                double2 *st = my_stack + (size_t)sp * (NB * 32) + lane;
+            const DmOpV op = dm_op(prog, o);
+            /* the rows this op and the next one will take from the tip table */
+#pragma unroll 1
+            for (int oo = (o == 0 ? 0 : o + 1); oo <= o + 1 && oo < a.nops; oo++) {
+                const DmOpV opn = dm_op(prog, oo);
+                for (int j = 0; j < opn.nchild; j++) {
+                    const DmChV ch = dm_ch(prog, opn.first_child + j);
+                    if (ch.kind == F4_KIND_TIP) {
 #pragma unroll
-                for (int nb = 0; nb < NB; nb++) __stcg(st + nb * 32, make_double2(cur[2 * nb], cur[2 * nb + 1]));
-                my_stack_meta[sp * 32 + lane] = curk * 2 + curc;
+                        for (int r = 0; r < SG; r++) dm_prefetch(TPc + ((size_t)ch.mat * a.K + my_codes[ch.code_row * (8 * SG) + 8 * r + g]) * W);
+                    }
+                }
+            }
+            if (op.spill_before) {
+                double2 *st = my_stack + (size_t)sp * (SG * NB * 32) + lane;
+#pragma unroll
+                for (int r = 0; r < SG; r++) {
+#pragma unroll
+                    for (int nb = 0; nb < NB; nb++) __stcg(st + (r * NB + nb) * 32, make_double2(cur[r][2 * nb], cur[r][2 * nb + 1]));
+                    my_stack_meta[(sp * SG + r) * 32 + lane] = curk[r] * 2 + curc[r];
+                }
                 sp++;
             }
-            double acc[2 * NB];
-            int kacc = 0, cst = 1;
-            if (op.code_row >= 0) {
-                /* the node itself carries data (rare) */
-                const int code = my_codes[op.code_row * 8 + g];
-                const double2 *dp = reinterpret_cast<const double2 *>(a.defsf + (size_t)code * W + q * 2 * NB);
+            double acc[SG][2 * NB];
+            int kacc[SG], cst[SG];
 #pragma unroll
-                for (int nb = 0; nb < NB; nb++) { const double2 v = __ldg(dp + nb); acc[2 * nb] = v.x; acc[2 * nb + 1] = v.y; }
-                cst = a.def_const[code];
-            } else {
+            for (int r = 0; r < SG; r++) {
+                kacc[r] = 0; cst[r] = 1;
+                if (op.code_row >= 0) {
+                    /* the node itself carries data (rare) */
+                    const int code = my_codes[op.code_row * (8 * SG) + 8 * r + g];
+                    const double2 *dp = reinterpret_cast<const double2 *>(a.defsf + (size_t)code * W + q * 2 * NB);
 #pragma unroll
-                for (int i = 0; i < 2 * NB; i++) acc[i] = 1.0;
+                    for (int nb = 0; nb < NB; nb++) { const double2 v = __ldg(dp + nb); acc[r][2 * nb] = v.x; acc[r][2 * nb + 1] = v.y; }
+                    cst[r] = a.def_const[code];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 2 * NB; i++) acc[r][i] = 1.0;
+                }
             }
 #pragma unroll 1
             for (int j = 0; j < op.nchild; j++) {
-                const F4Child ch = a.children[op.first_child + j];
-                int bc;
+                const DmChV ch = dm_ch(prog, op.first_child + j);
+                int bc[SG];
                 if (ch.kind == F4_KIND_TIP) {
-                    const int code = my_codes[ch.code_row * 8 + g];
-                    bc = a.def_const[code];
-                    const double2 *tp = reinterpret_cast<const double2 *>(TPc + ((size_t)ch.mat * a.K + code) * W);
 #pragma unroll
-                    for (int nb = 0; nb < NB; nb++) { const double2 v = __ldg(tp + nb); acc[2 * nb] *= v.x; acc[2 * nb + 1] *= v.y; }
+                    for (int r = 0; r < SG; r++) {
+                        const int code = my_codes[ch.code_row * (8 * SG) + 8 * r + g];
+                        bc[r] = a.def_const[code];
+                        const double2 *tp = reinterpret_cast<const double2 *>(TPc + ((size_t)ch.mat * a.K + code) * W);
+#pragma unroll
+                        for (int nb = 0; nb < NB; nb++) { const double2 v = __ldg(tp + nb); acc[r][2 * nb] *= v.x; acc[r][2 * nb + 1] *= v.y; }
+                    }
                 } else {
-                    int kb;
+                    int kb[SG];
                     if (ch.kind == F4_KIND_STACK) {
                         sp--;
-                        const double2 *st = my_stack + (size_t)sp * (NB * 32) + lane;
+                        const double2 *st = my_stack + (size_t)sp * (SG * NB * 32) + lane;
 #pragma unroll
-                        for (int nb = 0; nb < NB; nb++) { const double2 v = __ldcg(st + nb * 32); cur[2 * nb] = v.x; cur[2 * nb + 1] = v.y; }
-                        const int meta = my_stack_meta[sp * 32 + lane];
-                        kb = meta >> 1; bc = meta & 1;
+                        for (int r = 0; r < SG; r++) {
+#pragma unroll
+                            for (int nb = 0; nb < NB; nb++) { const double2 v = __ldcg(st + (r * NB + nb) * 32); cur[r][2 * nb] = v.x; cur[r][2 * nb + 1] = v.y; }
+                            const int meta = my_stack_meta[(sp * SG + r) * 32 + lane];
+                            kb[r] = meta >> 1; bc[r] = meta & 1;
+                        }
                     } else {
-                        kb = curk; bc = curc;
+#pragma unroll
+                        for (int r = 0; r < SG; r++) { kb[r] = curk[r]; bc[r] = curc[r]; }
                     }
                     /* a constant column maps to itself under a stochastic matrix (arb_mat_extras.c:84-91) */
-                    const double v0 = __shfl_sync(0xffffffffu, cur[0], lane & ~3);
+                    double v0[SG];
+#pragma unroll
+                    for (int r = 0; r < SG; r++) v0[r] = __shfl_sync(0xffffffffu, cur[r][0], lane & ~3);
                     const double2 *sl = ring.acquire(G, lane);
                     double2 *slab = nullptr;
                     if (a.slab) {
-                        const size_t cell = ((size_t)c * a.Ei + ch.mat) * a.ngroups + (size_t)(sw >> 3);
+                        const size_t cell = ((size_t)c * a.Ei + ch.mat) * a.ngroups + (size_t)gw;
                         slab = a.slab + cell * (NB * 32) + lane;
-                        if (sw < a.Sc) a.slab_meta[cell * 32 + lane] = kb * 2 + bc;
+#pragma unroll
+                        for (int r = 0; r < SG; r++)
+                            if (gw + r < a.ngroups) a.slab_meta[(cell + r) * 32 + lane] = kb[r] * 2 + bc[r];
                     }
 #pragma unroll
                     for (int pc = 0; pc < NCH; pc++) {
-                        double em[4][2];
-                        dm_gemm_chunk<NB>(cur, sl, pc, em);
+                        double em[SG][4][2];
+                        dm_gemm_chunk<NB, SG>(cur, sl, pc, em);
 #pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            const int nb = 4 * pc + i;
-                            if (nb < NB) {
-                                if (bc) {
-                                    em[i][0] = (8 * nb + 2 * q < a.n) ? v0 : 0.0;
-                                    em[i][1] = (8 * nb + 2 * q + 1 < a.n) ? v0 : 0.0;
+                        for (int r = 0; r < SG; r++) {
+#pragma unroll
+                            for (int i = 0; i < 4; i++) {
+                                const int nb = 4 * pc + i;
+                                if (nb < NB) {
+                                    if (bc[r]) {
+                                        em[r][i][0] = (8 * nb + 2 * q < a.n) ? v0[r] : 0.0;
+                                        em[r][i][1] = (8 * nb + 2 * q + 1 < a.n) ? v0[r] : 0.0;
+                                    }
+                                    if (slab && gw + r < a.ngroups) __stcs(slab + (r * NB + nb) * 32, make_double2(em[r][i][0], em[r][i][1]));
+                                    acc[r][2 * nb] *= em[r][i][0]; acc[r][2 * nb + 1] *= em[r][i][1];
                                 }
-                                if (slab && sw < a.Sc) __stcs(slab + nb * 32, make_double2(em[i][0], em[i][1]));
-                                acc[2 * nb] *= em[i][0]; acc[2 * nb + 1] *= em[i][1];
                             }
                         }
                     }
-                    ring.release(G, lane);
+                    ring.release(G, lane, nact);
                     G++;
-                    kacc += kb;
-                }
-                cst &= bc;
-                /* per-site rescale after every second factor (non-negative doubles order like their high words) */
-                if ((j & 1) || j == op.nchild - 1) {
-                    const double sc = dm_scale_up(dm_site_max_hi<NB>(acc), kacc);
-                    if (sc != 1.0) {
 #pragma unroll
-                        for (int i = 0; i < 2 * NB; i++) acc[i] *= sc;
+                    for (int r = 0; r < SG; r++) kacc[r] += kb[r];
+                }
+                /* per-site rescale after every second factor (non-negative doubles order like their high words) */
+                const bool resc = (j & 1) || j == op.nchild - 1;
+#pragma unroll
+                for (int r = 0; r < SG; r++) {
+                    cst[r] &= bc[r];
+                    if (resc) {
+                        const double sc = dm_scale_up(dm_site_max_hi<NB>(acc[r]), kacc[r]);
+                        if (sc != 1.0) {
+#pragma unroll
+                            for (int i = 0; i < 2 * NB; i++) acc[r][i] *= sc;
+                        }
                     }
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 2 * NB; i++) cur[i] = acc[i];
-            curk = kacc; curc = cst;
+            for (int r = 0; r < SG; r++) {
+#pragma unroll
+                for (int i = 0; i < 2 * NB; i++) cur[r][i] = acc[r][i];
+                curk[r] = kacc[r]; curc[r] = cst[r];
+            }
         }
         /* root_prior_expectation (model.c:282-350) */
-        {
+#pragma unroll
+        for (int r = 0; r < SG; r++) {
             const double2 *rp = reinterpret_cast<const double2 *>(a.rootf + q * 2 * NB);
             double lh = 0.0;
 #pragma unroll
-            for (int nb = 0; nb < NB; nb++) { const double2 r = __ldg(rp + nb); lh = fma(r.x, cur[2 * nb], lh); lh = fma(r.y, cur[2 * nb + 1], lh); }
+            for (int nb = 0; nb < NB; nb++) { const double2 rv = __ldg(rp + nb); lh = fma(rv.x, cur[r][2 * nb], lh); lh = fma(rv.y, cur[r][2 * nb + 1], lh); }
             lh += __shfl_xor_sync(0xffffffffu, lh, 1);
             lh += __shfl_xor_sync(0xffffffffu, lh, 2);
-            const double v0 = __shfl_sync(0xffffffffu, cur[0], lane & ~3);
-            if (curc && a.root_const_ok) lh = v0;
-            if (valid && q == 0) {
+            const double v0 = __shfl_sync(0xffffffffu, cur[r][0], lane & ~3);
+            if (curc[r] && a.root_const_ok) lh = v0;
+            const int site = sw + 8 * r + g;
+            if (site < a.Sc && q == 0) {
                 a.cat_lh[(size_t)c * a.Sc + site] = lh;
-                a.cat_k[(size_t)c * a.Sc + site] = curk;
+                a.cat_k[(size_t)c * a.Sc + site] = curk[r];
             }
         }
+        if (nact < NW) __syncthreads();
     }
 }
 
-/* edge vector of child ch at this warp's sites: block nb of em (tip table or slab), its exponent and constant flag */
+/* edge vector of a child at one site group of this warp: block nb of em (tip table or slab), its exponent and constant flag */
 struct DmChildRef {
     const double2 *p;       /* + nb * stride */
     int stride;
     int k, bc;
 };
 
-template <int NB>
-__device__ __forceinline__ DmChildRef dm_child_ref(const DmArgs &a, const F4Child &ch, int c, int sw, int lane, int g, int q,
+template <int NB, int SG>
+__device__ __forceinline__ DmChildRef dm_child_ref(const DmArgs &a, const DmChV &ch, int c, int gw, int r, int lane, int g, int q,
                                                    const unsigned char *my_codes)
 {
-    DmChildRef r;
+    DmChildRef ref;
     const int W = 8 * NB;
     if (ch.kind == F4_KIND_TIP) {
-        const int code = my_codes[ch.code_row * 8 + g];
-        r.p = reinterpret_cast<const double2 *>(a.TPf + (((size_t)c * a.Et + ch.mat) * a.K + code) * W + q * 2 * NB);
-        r.stride = 1;
-        r.k = 0; r.bc = a.def_const[code];
+        const int code = my_codes[ch.code_row * (8 * SG) + 8 * r + g];
+        ref.p = reinterpret_cast<const double2 *>(a.TPf + (((size_t)c * a.Et + ch.mat) * a.K + code) * W + q * 2 * NB);
+        ref.stride = 1;
+        ref.k = 0; ref.bc = a.def_const[code];
     } else {
-        const size_t cell = ((size_t)c * a.Ei + ch.mat) * a.ngroups + (size_t)(sw >> 3);
-        r.p = a.slab + cell * (NB * 32) + lane;
-        r.stride = 32;
+        /* groups beyond the chunk read the chunk's last group (their results are not written) */
+        const size_t cell = ((size_t)c * a.Ei + ch.mat) * a.ngroups + (size_t)min(gw + r, a.ngroups - 1);
+        ref.p = a.slab + cell * (NB * 32) + lane;
+        ref.stride = 32;
         const int meta = a.slab_meta[cell * 32 + lane];
-        r.k = meta >> 1; r.bc = meta & 1;
+        ref.k = meta >> 1; ref.bc = meta & 1;
     }
-    return r;
+    return ref;
 }
 
 /* bring a non-negative site vector into [2^-256, 2^256] both ways */
@@ -464,12 +569,10 @@ __device__ __forceinline__ void dm_rescale_both(double (&v)[2 * NB], int &k)
     }
 }
 
-__device__ __forceinline__ double dm_pow256(int k)
+__device__ __forceinline__ double dm_scale256(double x, int k)
 {
-    /* 2^(256 k), flushing to 0 / saturating outside the double range */
-    if (k < -5) return 0.0;
-    if (k > 3) k = 4;
-    return scalbn(1.0, 256 * k);
+    /* x 2^(256 k) without overflowing the exponent argument */
+    return scalbn(x, 256 * max(-16, min(16, k)));
 }
 
 /*
@@ -477,9 +580,9 @@ __device__ __forceinline__ double dm_pow256(int k)
  * that each (edge, site) output cell is accumulated by one thread.  Needs the slab of a keep-mode inside pass and
  * the combined site likelihoods (site_m, site_k).
  *
- * Per-warp stack entry: [fn | z][NB][32] double2 and int4 meta {exponent, high word of max fn, csr edge, -}.
+ * Per-warp stack entry: [SG][fn | z][NB][32] double2 and int4 meta [SG][32] {exponent, high word of max fn, csr edge, -}.
  */
-template <int NB, int NW>
+template <int NB, int NW, int SG>
 __global__ void __launch_bounds__(NW * 32, 1) dm_outside_kernel(const DmArgs a)
 {
     extern __shared__ __align__(128) unsigned char dm_smem[];
@@ -489,169 +592,216 @@ __global__ void __launch_bounds__(NW * 32, 1) dm_outside_kernel(const DmArgs a)
     const int W = 8 * NB;
 
     const long long my_items = (a.ntiles > (int)blockIdx.x) ? (a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    DmRing<NB, NW> ring;
+    DmRing<NB> ring;
     ring.src = a.Of; ring.nmat = 2 * a.Ei; ring.C = a.C; ring.R = a.R; ring.cat_inner = 1;
     ring.total = my_items * a.C * 2 * a.Ei;
     ring.setup(dm_smem, tid);
-    unsigned char *my_codes = ring.after() + (size_t)warp * a.nrows * 8;
+    const DmProg prog = dm_stage_program(a, ring.after(), tid, NW * 32);
+    unsigned char *my_codes = prog.after + (size_t)warp * a.nrows * (8 * SG);
+    /* The warps of a scheduler run the same program and would stay in lock-step (all in a contraction, then all
+     * outside one, leaving the tensor pipe idle): start them a fraction of an op apart. */
+    if (a.stagger > 0) {
+        const long long t0 = clock64(), wait = (long long)(warp >> 2) * a.stagger;
+        while (clock64() - t0 < wait) { }
+    }
 
-    double2 *my_stack = a.stack + ((size_t)blockIdx.x * NW + warp) * a.stack_depth * (2 * NB * 32);
-    int4 *my_stack_meta = reinterpret_cast<int4 *>(a.stack_meta) + ((size_t)blockIdx.x * NW + warp) * a.stack_depth * 32;
+    double2 *my_stack = a.stack + ((size_t)blockIdx.x * NW + warp) * a.stack_depth * (SG * 2 * NB * 32);
+    int4 *my_stack_meta = reinterpret_cast<int4 *>(a.stack_meta) + ((size_t)blockIdx.x * NW + warp) * a.stack_depth * (SG * 32);
     long long G = 0;
 
     for (long long it = 0; it < my_items; it++) {
         const int tile = (int)(blockIdx.x + it * gridDim.x);
-        const int sw = tile * (NW * 8) + warp * 8;
-        const int site = sw + g;
-        const bool valid = site < a.Sc;
-        dm_stage_codes(a, my_codes, sw, lane);
-        const double sm = valid ? a.site_m[site] : 0.0;
-        const int sk = valid ? a.site_k[site] : 0;
+        int g0, cnt;
+        dm_tile(a, tile, g0, cnt);
+        const int nact = (cnt + SG - 1) / SG;
+        if (warp >= nact) {
+            G += (long long)a.C * 2 * a.Ei;
+            __syncthreads();
+            continue;
+        }
+        const int gw = g0 + warp * SG;
+        const int sw = gw * 8;
+        dm_stage_codes<SG>(a, my_codes, sw, lane);
+        double sm[SG];
+        int sk[SG];
+        bool valid[SG];
+#pragma unroll
+        for (int r = 0; r < SG; r++) {
+            const int site = sw + 8 * r + g;
+            valid[r] = site < a.Sc;
+            sm[r] = valid[r] ? a.site_m[site] : 0.0;
+            sk[r] = valid[r] ? a.site_k[site] : 0;
+        }
 
 #pragma unroll 1
         for (int c = 0; c < a.C; c++) {
             const double *TFc = a.TFf + (size_t)c * a.Et * a.K * W + q * 2 * NB;
-            /* arbplfmarginal.c:184-191 / arbplfderiv.c:300-310: categories (and sites) of zero likelihood contribute nothing */
-            double coef = 0.0;
-            if (valid) {
-                const double prior = a.cat_prior[c];
-                if (prior * a.cat_lh[(size_t)c * a.Sc + site] > 0.0 && sm > 0.0) coef = prior / sm;
-            }
             int sp = 0;
-            double fn[2 * NB];
-            int kf = -sk;
-            {
+            double fn[SG][2 * NB];
+            int kf[SG];
+#pragma unroll
+            for (int r = 0; r < SG; r++) {
+                /* arbplfmarginal.c:184-191 / arbplfderiv.c:300-310: categories (and sites) of zero likelihood contribute nothing */
+                double coef = 0.0;
+                if (valid[r]) {
+                    const double prior = a.cat_prior[c];
+                    if (prior * a.cat_lh[(size_t)c * a.Sc + sw + 8 * r + g] > 0.0 && sm[r] > 0.0) coef = prior / sm[r];
+                }
+                kf[r] = -sk[r];
                 const double2 *rp = reinterpret_cast<const double2 *>(a.rootf + q * 2 * NB);
 #pragma unroll
-                for (int nb = 0; nb < NB; nb++) { const double2 r = __ldg(rp + nb); fn[2 * nb] = r.x * coef; fn[2 * nb + 1] = r.y * coef; }
+                for (int nb = 0; nb < NB; nb++) { const double2 rv = __ldg(rp + nb); fn[r][2 * nb] = rv.x * coef; fn[r][2 * nb + 1] = rv.y * coef; }
             }
 #pragma unroll 1
             for (int o = a.nops - 1; o >= 0; o--) {
-                const F4Op op = a.ops[o];
-                int in_edge = -1;
-                const double2 *zp = nullptr;
+                const DmOpV op = dm_op(prog, o);
                 if (o != a.nops - 1) {
                     sp--;
-                    const double2 *st = my_stack + (size_t)sp * (2 * NB * 32) + lane;
-                    const int4 meta = my_stack_meta[sp * 32 + lane];
-                    kf = meta.x; in_edge = meta.z;
-                    int m = meta.y;
-                    double sc = 1.0;
-                    if (m > 0) {
-                        while (m < DM_HI_M256) { m += 0x10000000; sc *= DM_TWO_P256; kf -= 1; }
-                        while (m >= DM_HI_P256) { m -= 0x10000000; sc *= DM_TWO_M256; kf += 1; }
-                    }
 #pragma unroll
-                    for (int nb = 0; nb < NB; nb++) { const double2 v = __ldcg(st + nb * 32); fn[2 * nb] = v.x * sc; fn[2 * nb + 1] = v.y * sc; }
-                    zp = st + NB * 32;
-                    /* z keeps the exponent it was computed with */
-                    const int kz = meta.x;
-                    /* L_a from the children's edge vectors, then x_e = z . L_a (evaluate_site_frechet.c:18-39) */
-                    double La[2 * NB];
-                    int kL = 0, cstL = 1;
-                    if (op.code_row >= 0) {
-                        const int code = my_codes[op.code_row * 8 + g];
-                        const double2 *dp = reinterpret_cast<const double2 *>(a.defsf + (size_t)code * W + q * 2 * NB);
+                    for (int r = 0; r < SG; r++) {
+                        const double2 *st = my_stack + ((size_t)sp * SG + r) * (2 * NB * 32) + lane;
+                        const int4 meta = my_stack_meta[(sp * SG + r) * 32 + lane];
+                        const int in_edge = meta.z, kz = meta.x;         /* z keeps the exponent it was computed with */
+                        kf[r] = meta.x;
+                        int m = meta.y;
+                        double sc = 1.0;
+                        if (m > 0) {
+                            while (m < DM_HI_M256) { m += 0x10000000; sc *= DM_TWO_P256; kf[r] -= 1; }
+                            while (m >= DM_HI_P256) { m -= 0x10000000; sc *= DM_TWO_M256; kf[r] += 1; }
+                        }
 #pragma unroll
-                        for (int nb = 0; nb < NB; nb++) { const double2 v = __ldg(dp + nb); La[2 * nb] = v.x; La[2 * nb + 1] = v.y; }
-                        cstL = a.def_const[code];
-                    } else {
+                        for (int nb = 0; nb < NB; nb++) { const double2 v = __ldcg(st + nb * 32); fn[r][2 * nb] = v.x * sc; fn[r][2 * nb + 1] = v.y * sc; }
+                        const double2 *zp = st + NB * 32;
+                        /* L_a from the children's edge vectors, then x_e = z . L_a (evaluate_site_frechet.c:18-39) */
+                        double La[2 * NB];
+                        int kL = 0, cstL = 1;
+                        if (op.code_row >= 0) {
+                            const int code = my_codes[op.code_row * (8 * SG) + 8 * r + g];
+                            const double2 *dp = reinterpret_cast<const double2 *>(a.defsf + (size_t)code * W + q * 2 * NB);
 #pragma unroll
-                        for (int i = 0; i < 2 * NB; i++) La[i] = 1.0;
-                    }
+                            for (int nb = 0; nb < NB; nb++) { const double2 v = __ldg(dp + nb); La[2 * nb] = v.x; La[2 * nb + 1] = v.y; }
+                            cstL = a.def_const[code];
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 2 * NB; i++) La[i] = 1.0;
+                        }
 #pragma unroll 1
-                    for (int j = 0; j < op.nchild; j++) {
-                        const F4Child ch = a.children[op.first_child + j];
-                        const DmChildRef r = dm_child_ref<NB>(a, ch, c, sw, lane, g, q, my_codes);
+                        for (int j = 0; j < op.nchild; j++) {
+                            const DmChildRef ref = dm_child_ref<NB, SG>(a, dm_ch(prog, op.first_child + j), c, gw, r, lane, g, q, my_codes);
 #pragma unroll
-                        for (int nb = 0; nb < NB; nb++) { const double2 v = r.p[nb * r.stride]; La[2 * nb] *= v.x; La[2 * nb + 1] *= v.y; }
-                        kL += r.k; cstL &= r.bc;
-                        if ((j & 1) || j == op.nchild - 1) {
-                            const double sc2 = dm_scale_up(dm_site_max_hi<NB>(La), kL);
-                            if (sc2 != 1.0) {
+                            for (int nb = 0; nb < NB; nb++) { const double2 v = ref.p[nb * ref.stride]; La[2 * nb] *= v.x; La[2 * nb + 1] *= v.y; }
+                            kL += ref.k; cstL &= ref.bc;
+                            if ((j & 1) || j == op.nchild - 1) {
+                                const double sc2 = dm_scale_up(dm_site_max_hi<NB>(La), kL);
+                                if (sc2 != 1.0) {
 #pragma unroll
-                                for (int i = 0; i < 2 * NB; i++) La[i] *= sc2;
+                                    for (int i = 0; i < 2 * NB; i++) La[i] *= sc2;
+                                }
                             }
                         }
-                    }
-                    double x = 0.0;
+                        double x = 0.0;
 #pragma unroll
-                    for (int nb = 0; nb < NB; nb++) { const double2 v = __ldcg(zp + nb * 32); x = fma(v.x, La[2 * nb], x); x = fma(v.y, La[2 * nb + 1], x); }
-                    x += __shfl_xor_sync(0xffffffffu, x, 1);
-                    x += __shfl_xor_sync(0xffffffffu, x, 2);
-                    if (a.f_zero_rowsum && cstL) x = 0.0;
-                    if (valid && q == 0 && x != 0.0 && (!a.edge_mask || a.edge_mask[in_edge]))
-                        a.edge_out[(size_t)in_edge * a.Sc + site] += x * dm_pow256(kz + kL);
+                        for (int nb = 0; nb < NB; nb++) { const double2 v = __ldcg(zp + nb * 32); x = fma(v.x, La[2 * nb], x); x = fma(v.y, La[2 * nb + 1], x); }
+                        x += __shfl_xor_sync(0xffffffffu, x, 1);
+                        x += __shfl_xor_sync(0xffffffffu, x, 2);
+                        if (a.f_zero_rowsum && cstL) x = 0.0;
+                        if (valid[r] && q == 0 && x != 0.0 && (!a.edge_mask || a.edge_mask[in_edge]))
+                            a.edge_out[(size_t)in_edge * a.Sc + sw + 8 * r + g] += dm_scale256(x, kz + kL);
+                    }
                 }
                 /* fn_a . data_a */
                 if (op.code_row >= 0) {
-                    const int code = my_codes[op.code_row * 8 + g];
-                    const double2 *dp = reinterpret_cast<const double2 *>(a.defsf + (size_t)code * W + q * 2 * NB);
 #pragma unroll
-                    for (int nb = 0; nb < NB; nb++) { const double2 v = __ldg(dp + nb); fn[2 * nb] *= v.x; fn[2 * nb + 1] *= v.y; }
+                    for (int r = 0; r < SG; r++) {
+                        const int code = my_codes[op.code_row * (8 * SG) + 8 * r + g];
+                        const double2 *dp = reinterpret_cast<const double2 *>(a.defsf + (size_t)code * W + q * 2 * NB);
+#pragma unroll
+                        for (int nb = 0; nb < NB; nb++) { const double2 v = __ldg(dp + nb); fn[r][2 * nb] *= v.x; fn[r][2 * nb + 1] *= v.y; }
+                    }
                 }
                 /* children: tips in any order, internal ones from the last to the first so that the stack unwinds in
                  * the reverse of the inside pass */
 #pragma unroll 1
                 for (int j = op.nchild - 1; j >= 0; j--) {
-                    const F4Child ch = a.children[op.first_child + j];
-                    double fe[2 * NB];
-                    int kfe = kf;
+                    const DmChV ch = dm_ch(prog, op.first_child + j);
+                    double fe[SG][2 * NB];
+                    int kfe[SG];
 #pragma unroll
-                    for (int i = 0; i < 2 * NB; i++) fe[i] = fn[i];
+                    for (int r = 0; r < SG; r++) {
+                        kfe[r] = kf[r];
+#pragma unroll
+                        for (int i = 0; i < 2 * NB; i++) fe[r][i] = fn[r][i];
+                    }
                     int nmul = 0;
 #pragma unroll 1
                     for (int j2 = 0; j2 < op.nchild; j2++) {
                         if (j2 == j) continue;
-                        const F4Child ch2 = a.children[op.first_child + j2];
-                        const DmChildRef r = dm_child_ref<NB>(a, ch2, c, sw, lane, g, q, my_codes);
+                        const DmChV ch2 = dm_ch(prog, op.first_child + j2);
+                        ++nmul;
 #pragma unroll
-                        for (int nb = 0; nb < NB; nb++) { const double2 v = r.p[nb * r.stride]; fe[2 * nb] *= v.x; fe[2 * nb + 1] *= v.y; }
-                        kfe += r.k;
-                        if ((++nmul & 1) == 0) dm_rescale_both<NB>(fe, kfe);
+                        for (int r = 0; r < SG; r++) {
+                            const DmChildRef ref = dm_child_ref<NB, SG>(a, ch2, c, gw, r, lane, g, q, my_codes);
+#pragma unroll
+                            for (int nb = 0; nb < NB; nb++) { const double2 v = ref.p[nb * ref.stride]; fe[r][2 * nb] *= v.x; fe[r][2 * nb + 1] *= v.y; }
+                            kfe[r] += ref.k;
+                            if ((nmul & 1) == 0) dm_rescale_both<NB>(fe[r], kfe[r]);
+                        }
                     }
-                    dm_rescale_both<NB>(fe, kfe);
-                    if (ch.kind == F4_KIND_TIP) {
-                        const int code = my_codes[ch.code_row * 8 + g];
-                        const double2 *tf = reinterpret_cast<const double2 *>(TFc + ((size_t)ch.mat * a.K + code) * W);
-                        double x = 0.0;
 #pragma unroll
-                        for (int nb = 0; nb < NB; nb++) { const double2 v = __ldg(tf + nb); x = fma(v.x, fe[2 * nb], x); x = fma(v.y, fe[2 * nb + 1], x); }
-                        x += __shfl_xor_sync(0xffffffffu, x, 1);
-                        x += __shfl_xor_sync(0xffffffffu, x, 2);
-                        if (valid && q == 0 && x != 0.0 && (!a.edge_mask || a.edge_mask[ch.edge]))
-                            a.edge_out[(size_t)ch.edge * a.Sc + site] += x * dm_pow256(kfe);
+                    for (int r = 0; r < SG; r++) dm_rescale_both<NB>(fe[r], kfe[r]);
+                    if (ch.kind == F4_KIND_TIP) {
+#pragma unroll
+                        for (int r = 0; r < SG; r++) {
+                            const int code = my_codes[ch.code_row * (8 * SG) + 8 * r + g];
+                            const double2 *tf = reinterpret_cast<const double2 *>(TFc + ((size_t)ch.mat * a.K + code) * W);
+                            double x = 0.0;
+#pragma unroll
+                            for (int nb = 0; nb < NB; nb++) { const double2 v = __ldg(tf + nb); x = fma(v.x, fe[r][2 * nb], x); x = fma(v.y, fe[r][2 * nb + 1], x); }
+                            x += __shfl_xor_sync(0xffffffffu, x, 1);
+                            x += __shfl_xor_sync(0xffffffffu, x, 2);
+                            if (valid[r] && q == 0 && x != 0.0 && (!a.edge_mask || a.edge_mask[ch.edge]))
+                                a.edge_out[(size_t)ch.edge * a.Sc + sw + 8 * r + g] += dm_scale256(x, kfe[r]);
+                        }
                     } else {
-                        double2 *st = my_stack + (size_t)sp * (2 * NB * 32) + lane;
-                        int m = 0;
+                        double2 *st = my_stack + (size_t)sp * SG * (2 * NB * 32) + lane;
+                        int m[SG];
+#pragma unroll
+                        for (int r = 0; r < SG; r++) m[r] = 0;
                         /* fn_b = P_e^T fe (util.c:464-498), then z_b = F_e^T fe */
 #pragma unroll 1
                         for (int which = 0; which < 2; which++) {
                             const double2 *sl = ring.acquire(G, lane);
 #pragma unroll
                             for (int pc = 0; pc < NCH; pc++) {
-                                double em[4][2];
-                                dm_gemm_chunk<NB>(fe, sl, pc, em);
+                                double em[SG][4][2];
+                                dm_gemm_chunk<NB, SG>(fe, sl, pc, em);
 #pragma unroll
-                                for (int i = 0; i < 4; i++) {
-                                    const int nb = 4 * pc + i;
-                                    if (nb < NB) {
-                                        __stcg(st + (which * NB + nb) * 32, make_double2(em[i][0], em[i][1]));
-                                        if (which == 0) m = max(m, max(__double2hiint(em[i][0]), __double2hiint(em[i][1])));
+                                for (int r = 0; r < SG; r++) {
+#pragma unroll
+                                    for (int i = 0; i < 4; i++) {
+                                        const int nb = 4 * pc + i;
+                                        if (nb < NB) {
+                                            __stcg(st + r * (2 * NB * 32) + (which * NB + nb) * 32, make_double2(em[r][i][0], em[r][i][1]));
+                                            if (which == 0) m[r] = max(m[r], max(__double2hiint(em[r][i][0]), __double2hiint(em[r][i][1])));
+                                        }
                                     }
                                 }
                             }
-                            ring.release(G, lane);
+                            ring.release(G, lane, nact);
                             G++;
                         }
-                        m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
-                        m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
-                        my_stack_meta[sp * 32 + lane] = make_int4(kfe, m, ch.edge, 0);
+#pragma unroll
+                        for (int r = 0; r < SG; r++) {
+                            m[r] = max(m[r], __shfl_xor_sync(0xffffffffu, m[r], 1));
+                            m[r] = max(m[r], __shfl_xor_sync(0xffffffffu, m[r], 2));
+                            my_stack_meta[(sp * SG + r) * 32 + lane] = make_int4(kfe[r], m[r], ch.edge, 0);
+                        }
                         sp++;
                     }
                 }
             }
         }
+        if (nact < NW) __syncthreads();
     }
 }
 
@@ -669,9 +819,26 @@ int dm_blocks_for(int n)
 
 size_t dm_slot_doubles_host(int NB) { return (size_t)dm_slot_doubles(NB); }
 
-size_t dm_smem_bytes(int NB, int R, int nrows)
+size_t dm_smem_bytes(int NB, int R, int nrows, int nops, int nchildren)
 {
-    return (size_t)R * dm_slot_doubles(NB) * 8 + DM_MAX_R * 8 + DM_MAX_R * 4 + (size_t)DM_NW * nrows * 8 + 16;
+    return (size_t)R * dm_slot_doubles(NB) * 8 + DM_MAX_R * 8 + DM_MAX_R * 4 + 16 + (size_t)(nops + nchildren) * 16 +
+           (size_t)DM_GROUPS * nrows * 8 + 16;
+}
+
+void dm_tiling(int ngroups, int items_per_tile, int grid, int *tiles_full, int *tail_gs, int *ntiles)
+{
+    const long long cap = (long long)grid * DM_GROUPS;
+    const long long waves = ((long long)ngroups * items_per_tile) / cap;
+    int tf = (int)(waves * grid / items_per_tile);
+    if (tf > ngroups / DM_GROUPS) tf = ngroups / DM_GROUPS;
+    const int rest = ngroups - tf * DM_GROUPS;
+    *tiles_full = tf;
+    if (rest == 0) { *tail_gs = DM_GROUPS; *ntiles = tf; return; }
+    const int tiles_tail = grid / items_per_tile > 0 ? grid / items_per_tile : 1;
+    int gs = (rest + tiles_tail - 1) / tiles_tail;
+    if (gs > DM_GROUPS) gs = DM_GROUPS;
+    *tail_gs = gs;
+    *ntiles = tf + (rest + gs - 1) / gs;
 }
 
 cudaError_t dm_pack(const double *src, const double *src2, const int *src_index, const int *transpose, int nmat,
@@ -693,29 +860,32 @@ cudaError_t dm_tip_table(const double *M, const double *defs, const unsigned cha
     return cudaGetLastError();
 }
 
-template <int NB>
+template <int NB, int SG>
 static cudaError_t dm_launch_t(const DmArgs &a, int grid, bool outside, cudaStream_t st)
 {
-    const size_t smem = dm_smem_bytes(NB, a.R, a.nrows);
+    constexpr int NW = DM_GROUPS / SG;
+    const size_t smem = dm_smem_bytes(NB, a.R, a.nrows, a.nops, a.nchildren);
     cudaError_t r;
     if (outside) {
-        r = cudaFuncSetAttribute(dm_outside_kernel<NB, DM_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        r = cudaFuncSetAttribute(dm_outside_kernel<NB, NW, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (r != cudaSuccess) return r;
-        dm_outside_kernel<NB, DM_NW><<<grid, DM_NW * 32, smem, st>>>(a);
+        dm_outside_kernel<NB, NW, SG><<<grid, NW * 32, smem, st>>>(a);
     } else {
-        r = cudaFuncSetAttribute(dm_inside_kernel<NB, DM_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        r = cudaFuncSetAttribute(dm_inside_kernel<NB, NW, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (r != cudaSuccess) return r;
-        dm_inside_kernel<NB, DM_NW><<<grid, DM_NW * 32, smem, st>>>(a);
+        dm_inside_kernel<NB, NW, SG><<<grid, NW * 32, smem, st>>>(a);
     }
     return cudaGetLastError();
 }
 
 static cudaError_t dm_launch(const DmArgs &a, int NB, int grid, bool outside, cudaStream_t st)
 {
-    switch (NB) {
-    case 3: return dm_launch_t<3>(a, grid, outside, st);
-    case 4: return dm_launch_t<4>(a, grid, outside, st);
-    case 8: return dm_launch_t<8>(a, grid, outside, st);
+    /* a.sg: site groups per warp.  Only 1 (16 warps of 8 sites) is instantiated: with 2 (8 warps of 16 sites, every B
+     * fragment feeding two site groups) the shared-memory traffic halves but the kernel is no faster (measured). */
+    switch (NB * 10 + a.sg) {
+    case 31: return dm_launch_t<3, 1>(a, grid, outside, st);
+    case 41: return dm_launch_t<4, 1>(a, grid, outside, st);
+    case 81: return dm_launch_t<8, 1>(a, grid, outside, st);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -13,14 +13,15 @@
 #include "f4prog.h"
 
 #define DM_MAX_R 8        /* slots of the matrix ring */
-#define DM_NW 16          /* warps per CTA; a warp owns 8 site patterns */
-#define DM_TILE (8 * DM_NW)
+#define DM_GROUPS 16      /* 8-site groups per full tile (16 warps of one group or 8 warps of two) */
+#define DM_TILE (8 * DM_GROUPS)
 
 struct DmArgs {
     int n, C, K;
     int nops;
-    const F4Op *ops;
-    const F4Child *children;
+    int nchildren;
+    const int4 *ops4;                /* [nops] {first_child, nchild, code_row, spill_before} */
+    const int4 *ch4;                 /* [nchildren] {kind, mat, code_row, csr edge} */
     int Ei, Et;                      /* internal-child (GEMM) edges, tip edges */
     int nrows;                       /* rows of the code tile (nodes that may carry data) */
     const int *code_row_node;        /* [nrows] */
@@ -34,11 +35,14 @@ struct DmArgs {
     const double *rootf;             /* [8NB] root prior weights in thread order (zero padded) */
     int root_const_ok;               /* uniform / equilibrium prior: a constant column has expectation = its value */
     double *cat_lh; int *cat_k;      /* [C][Sc] */
-    int ntiles;                      /* tiles of DM_TILE sites in the chunk */
+    int ntiles;                      /* tiles of the chunk: tiles_full of DM_GROUPS 8-site groups, the rest of tail_gs groups */
+    int tiles_full, tail_gs;
     int R;                           /* ring slots in use (2..DM_MAX_R) */
+    int sg;                          /* site groups per warp (1) */
+    int stagger;                     /* clocks between the start of successive warps of a scheduler */
     int stack_depth;                 /* entries of the per-warp stacks */
-    double2 *stack;                  /* inside: [ctas][NW][depth][NB][32]; outside: [ctas][NW][depth][2][NB][32] */
-    int *stack_meta;                 /* inside: [ctas][NW][depth][32];     outside: [ctas][NW][depth][32][4] */
+    double2 *stack;                  /* inside: [ctas][groups][depth][NB][32]; outside: [ctas][groups][depth][2][NB][32] */
+    int *stack_meta;                 /* inside: [ctas][groups][depth][32];     outside: [ctas][groups][depth][32][4] */
     /* keep mode (an outside pass follows): the edge vectors em_e = P_e L_b of the internal-child edges */
     double2 *slab;                   /* [C][Ei][ngroups][NB][32] or NULL */
     int *slab_meta;                  /* [C][Ei][ngroups][32]: exponent of the child * 2 + constant flag */
@@ -58,7 +62,10 @@ struct DmArgs {
 int dm_blocks_for(int n);
 size_t dm_slot_doubles_host(int NB);
 /* dynamic shared memory of a launch with R ring slots */
-size_t dm_smem_bytes(int NB, int R, int nrows);
+size_t dm_smem_bytes(int NB, int R, int nrows, int nops, int nchildren);
+/* tiles of a chunk of ngroups 8-site groups for a persistent grid: full tiles while whole waves can be filled, then
+ * smaller tiles that spread the remainder evenly over the CTAs (items_per_tile = categories for the inside pass) */
+void dm_tiling(int ngroups, int items_per_tile, int grid, int *tiles_full, int *tail_gs, int *ntiles);
 
 /* pack nmat matrices per category into the B-fragment order (see dmma.cu) */
 cudaError_t dm_pack(const double *src, const double *src2, const int *src_index, const int *transpose, int nmat,

@@ -36,60 +36,13 @@
 
 #include "f4prog.h"
 
-struct F4Args {
-    int nops, nchildren;
-    const F4Op *ops;
-    const F4Child *children;
-    int E, K, Ei, Et;                /* edges, characters, internal-child edges, tip edges */
-    int64_t S;
-    int ncode_rows;
-    const int *code_row_node;        /* [ncode_rows] node whose codes fill the row */
-    const unsigned char *codes;      /* [N][S] */
-    const double *defs;              /* [K][4] */
-    const unsigned char *def_const;  /* [K] */
-    const double *Pint;              /* [C][Ei][16] */
-    const double *TP;                /* [C][Et][K][4] */
-    const double *Fint;              /* [C][Ei][16] or NULL; marginal mode: P of the tip edges, [C][Et][16] */
-    const double *TF;                /* [C][Et][K][4] or NULL */
-    int f_zero_rowsum;
-    const double *cat_prior;
-    int root_mode;
-    double root_vec[4];
-    const double *site_w;            /* [S] or NULL */
-    const unsigned char *edge_mask;  /* [E] or NULL */
-    int stack_depth;                 /* ll-only mode: shared-memory stack entries (0 when the stack is global) */
-    int gstack;                      /* ll-only mode: pending partials go to scratch / scratchS (L2-resident) */
-    int nslots;
-    double4 *scratch;                /* [nslots][C][T] */
-    unsigned int *scratchS;          /* [nslots][T]: byte c = rescale count | const flag << 6 */
-    double *site_ll;                 /* [S] or NULL */
-    double *edge_site_out;           /* [E][S] or NULL */
-    int64_t s_begin, s_end;          /* this launch covers sites [s_begin, s_end) (a chunk of the data) */
-    int N;                           /* nodes */
-    double *marg_site_out;           /* marginal mode: [N][4][S] or NULL */
-    double *block_marg;              /* marginal mode: [grid * warps][N][4], zeroed by the host, accumulated here */
-    double *block_ll;                /* [grid] */
-    double *block_edge;              /* [grid][E] */
-    int *error_flag;
-};
+#include "../../include/plf.h"
+#include "plf_consts.h"
+#include "fused4_args.h"
 
-/*
- * Constant-memory variant (CM): the compact matrices of the internal-child edges live in __constant__
- * memory and the tree program travels as a kernel parameter.  Everything the op loop decodes is then
- * warp-uniform by construction (loop counters -> constant bank), so the compiler keeps it in uniform
- * registers and the 4x4 matrices enter the DFMAs as uniform operands (LDCU) instead of costing one
- * shared-memory wavefront per 16 bytes -- the kernel is bound by the LSU pipe, not by fp64 issue.
- */
-#define F4_CM_MAXD 4064      /* doubles per matrix set: C * Ei * 16 <= 4064 (2 sets = 65024 of the 65536 bytes) */
-#define F4_CM_MAXOPS 128
-#define F4_CM_MAXCH 256
 __constant__ double f4_cP[F4_CM_MAXD];
 __constant__ double f4_cF[F4_CM_MAXD];
 
-struct F4Prog {
-    F4Op ops[F4_CM_MAXOPS];
-    F4Child ch[F4_CM_MAXCH];
-};
 
 __device__ __forceinline__ void f4_matvec(const double *__restrict__ M, const double v[4], double out[4])
 {
@@ -194,8 +147,6 @@ __device__ __forceinline__ double f4_warp_sum(double x)
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
     return x;
 }
-
-__host__ __device__ inline size_t f4_align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 /* character code of this thread's site for tile row r */
 template <int BD, bool PACK>
@@ -691,12 +642,20 @@ __global__ void __launch_bounds__(BD) fused4_kernel(const F4Args a, const __grid
     for (int c = 0; c < C; c++) prior[c] = a.cat_prior[c];
 
     double ll_acc = 0.0;
-    const int64_t ntiles = (a.s_end - a.s_begin + bd - 1) / bd;
+    /* Every CTA owns one contiguous block of sites, the same number (a multiple of the warp size) for all of them, and
+     * walks it in steps of bd; warps whose 32 sites lie beyond the block skip the step.  A launch whose sites are not
+     * a whole number of waves (a shard of a strong-scaling run) then costs its share of sites per SM, not a whole
+     * extra wave on some of the SMs. */
+    const int64_t per_cta = (((a.s_end - a.s_begin) + gridDim.x - 1) / gridDim.x + 31) / 32 * 32;
+    const int64_t blk0 = a.s_begin + (int64_t)blockIdx.x * per_cta;
+    const int64_t blk1 = (blk0 + per_cta < a.s_end) ? blk0 + per_cta : a.s_end;
 
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int64_t site_raw = a.s_begin + t * bd + tid;
-        const bool valid = site_raw < a.s_end;
-        const int64_t site = valid ? site_raw : a.s_end - 1;
+    for (int64_t s0 = blk0; s0 < blk1; s0 += bd) {
+        const int64_t site_raw = s0 + tid;
+        const bool valid = site_raw < blk1;
+        /* (a vote, so that the compiler still sees warp-uniform control flow: the constant-memory kernels depend on it) */
+        if (!__any_sync(0xffffffffu, valid)) continue;
+        const int64_t site = valid ? site_raw : blk1 - 1;
         const double w = valid ? (a.site_w ? a.site_w[site] : 1.0) : 0.0;
         /* stage this tile's character codes: each thread only ever reads its own column */
         if (PACK) {
@@ -958,28 +917,3 @@ __global__ void __launch_bounds__(BD) fused4_kernel(const F4Args a, const __grid
     }
 }
 
-/* second stage: out[j] = sum over rows of part[row][j], fixed order (Kahan) */
-__global__ void sum_rows_kernel(const double *part, int rows, int cols, double *out)
-{
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= cols) return;
-    double s = 0.0, comp = 0.0;
-    for (int r = 0; r < rows; r++) {
-        double yv = part[(size_t)r * cols + j] - comp;
-        double tsum = s + yv;
-        comp = (tsum - s) - yv;
-        s = tsum;
-    }
-    out[j] = s;
-}
-
-/* gather the matrices of internal-child edges: out[c][ie] = M[c][edge_of[ie]] (16 doubles each) */
-__global__ void compact_matrices_kernel(const double *M, const int *edge_of, int C, int E, int Ei, double *out)
-{
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    int total = C * Ei * 16;
-    if (idx >= total) return;
-    int k = idx & 15, r = idx >> 4;
-    int ie = r % Ei, c = r / Ei;
-    out[idx] = M[((size_t)c * E + edge_of[ie]) * 16 + k];
-}

@@ -21,7 +21,7 @@
 #pragma once
 #include <stdint.h>
 
-#define PLF_SCALE_BITS 256
+#include "plf_consts.h"
 #define PLF_TS 128   /* threads (sites) per CTA in the generic kernels */
 
 struct TreeDev {
@@ -78,8 +78,6 @@ __device__ __forceinline__ int plf_code_at(const void *codes, int code_bytes, in
     return ((const int *)codes)[(size_t)node * S + site];
 }
 
-#define PLF_TWO_P256 1.157920892373162e+77      /* 2^256  */
-#define PLF_TWO_M256 8.636168555094445e-78      /* 2^-256 */
 
 /* inside pass: thread = (site, category) ; blockIdx.y = category */
 __global__ void __launch_bounds__(PLF_TS) generic_inside_kernel(GenericArgs a)
@@ -336,4 +334,315 @@ __global__ void generic_leaf_kernel(GenericArgs a, int write_vectors)
         a.Kg[(cN + nd) * Sc + s] = 0;
         a.Cg[(cN + nd) * Sc + s] = (unsigned char)cst;
     }
+}
+
+/* ------------------------------------------------------------------ */
+/* second order: Hessian of the log likelihood w.r.t. the edge rates   */
+/* ------------------------------------------------------------------ */
+
+/*
+ * The reference (arbplfhess.c:502-829) obtains d^2 L / dt_i dt_j by substituting Q P for P on both edges and
+ * re-walking the two root paths for every pair of edges, O(E^2 depth) prune updates per (site, category).  The
+ * site likelihood is multilinear in the per-edge matrices, so the same numbers come out of ONE tangent sweep per
+ * edge j on top of the stored inside / outside vectors (O(E^2) updates per (site, category) in total):
+ *
+ *   - v = rate Q em_j is the tangent of edge j's vector; carried up j's root path, v <- P_p (base_a . v . prod
+ *     sibling vectors), it gives the pairs (ancestor edge p, j) as fe_p . (rate Q v);
+ *   - at every node a of that path the tangent also enters the OTHER children's subtrees through their outside
+ *     vectors, dfe_e' = fn_a . base_a . v . prod(other sibling vectors), and travels down like the outside pass
+ *     (dfn_b = P^T dfe); every edge i met on the way gives the pair (i, j) as dfe_i . (rate Q em_i);
+ *   - the diagonal is fe_j . (rate^2 Q Q em_j).
+ * Each unordered pair is accumulated once, into H[max(i,j)][min(i,j)] (csr indices): a disjoint pair is met from
+ * both sides, only the side where i ranks above j (BFS position of the child node) counts, and subtrees that hold no
+ * rank above j's are not entered.
+ *
+ * The kernel adds sum_s w_s [ sum_c prior_c rate_c^2 H_c ] / L_s into Hpart[cta][E][E]; the g g^T / L^2 part of
+ * _lhood_hess_to_ll_hess (arbplfhess.c:455-495) is a weighted Gram matrix of the per-site derivatives
+ * (gram_rows_kernel).  thread = site, categories looped inside; all control flow is uniform over the CTA.
+ */
+struct HessTree {
+    const int *parent_node;   /* [E]  node above csr edge idx (idx_to_a, util.c:369-389) */
+    const int *parent_edge;   /* [N]  csr edge above a node, -1 at the root (b_to_idx) */
+    const int *dfs_nodes;     /* [N]  nodes in depth-first pre-order */
+    const int *dfs_pos;       /* [N]  position of a node in dfs_nodes */
+    const int *sub_end;       /* [N]  end (exclusive) of the node's subtree in dfs_nodes */
+    const int *erank;         /* [E]  rank of an edge = position of its child node in the BFS order: ancestors rank lower */
+    const int *sub_max;       /* [E]  largest rank in the subtree hanging from edge idx (idx itself included) */
+};
+
+__device__ __forceinline__ double hess_warp_sum(double x)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+/* |max| rescale of a signed per-thread vector v[i * PLF_TS] into [2^-256, 2^256] */
+__device__ __forceinline__ void hess_rescale(double *v, int n, int &k)
+{
+    double mx = 0.0;
+    for (int i = 0; i < n; i++) mx = fmax(mx, fabs(v[i * PLF_TS]));
+    if (!(mx > 0.0) || !isfinite(mx)) return;
+    double sc = 1.0;
+    while (mx * sc > PLF_TWO_P256) { sc *= PLF_TWO_M256; k += 1; }
+    while (mx * sc < PLF_TWO_M256) { sc *= PLF_TWO_P256; k -= 1; }
+    if (sc != 1.0) for (int i = 0; i < n; i++) v[i * PLF_TS] *= sc;
+}
+
+__global__ void __launch_bounds__(PLF_TS) generic_hess_kernel(GenericArgs a, HessTree ht, const double *Q /*[n][n] scaled*/,
+                                                              const double *cat_rates, const double *site_w /*[S] or NULL*/,
+                                                              double *Yg /*[C][E][n][Sc] scratch*/, double *dFg /*[N][n][Sc] scratch*/,
+                                                              int *dFk /*[N][Sc]*/, double *Hpart /*[grid][E][E]*/, int *err)
+{
+    extern __shared__ double gsm[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int n = a.n, Sc = a.Sc, E = a.t.E;
+    double *v = gsm + tid;                              /* tangent of the edge vector on j's root path */
+    double *t1 = gsm + (size_t)n * PLF_TS + tid;        /* work: dfe / dL */
+    double *t2 = gsm + (size_t)2 * n * PLF_TS + tid;    /* work: matrix-vector results */
+    double *buf = gsm + (size_t)3 * n * PLF_TS;         /* [E] this CTA's sums for the current j */
+    double *myH = Hpart + (size_t)blockIdx.x * E * E;
+
+    for (int tile = blockIdx.x; tile * PLF_TS < Sc; tile += gridDim.x) {
+        const int s_raw = tile * PLF_TS + tid;
+        const bool valid = s_raw < Sc;
+        const int s = valid ? s_raw : Sc - 1;
+        const int64_t gs = a.s0 + s;
+        const double site_m = a.site_m[s];
+        const int site_k = a.site_k[s];
+        const double w = valid ? (site_w ? site_w[gs] : 1.0) : 0.0;
+
+        /* y_idx = rate Q em_idx for every edge and category (exponent: that of the child) */
+        for (int c = 0; c < a.C; c++) {
+            const double rate = cat_rates[c];
+            const size_t cE = (size_t)c * E;
+            for (int idx = 0; idx < E; idx++) {
+                const double *Em = a.Eg + ((cE + idx) * n) * Sc + s;
+                double *Y = Yg + ((cE + idx) * n) * Sc + s;
+                const int bc = a.Cg[((size_t)c * a.t.N + a.t.indices[idx]) * Sc + s];
+                for (int k = 0; k < n; k++) t1[k * PLF_TS] = Em[(size_t)k * Sc];
+                for (int i = 0; i < n; i++) {
+                    double acc = 0.0;
+                    if (!bc) for (int k = 0; k < n; k++) acc = fma(Q[i * n + k], t1[k * PLF_TS], acc);   /* util.c:338-344 */
+                    Y[(size_t)i * Sc] = acc * rate;
+                }
+            }
+        }
+
+        for (int j = 0; j < E; j++) {
+            const int rank_j = ht.erank[j];
+            for (int i = tid; i < E; i += PLF_TS) buf[i] = 0.0;
+            __syncthreads();
+            for (int c = 0; c < a.C; c++) {
+                const size_t cN = (size_t)c * a.t.N, cE = (size_t)c * E;
+                const double rate = cat_rates[c];
+                const double lhc = a.cat_prior[c] * a.cat_lh[(size_t)c * Sc + s];
+                if (valid && w != 0.0 && !(lhc > 0.0) && rate != 0.0) atomicOr(err, 2);      /* arbplfhess.c:640-660: infeasible */
+                const double coef = (lhc > 0.0 && site_m > 0.0) ? w * a.cat_prior[c] / site_m : 0.0;
+                if (rate == 0.0) continue;          /* uniform over the CTA: a zero-rate category has no derivatives */
+
+                /* fe of an edge, rebuilt from fn of its parent and the siblings' vectors: into t1, exponent returned */
+                auto build_fe = [&](int idx, double *dst) -> int {
+                    const int p = ht.parent_node[idx];
+                    const double *Fa = a.Fg + ((cN + p) * n) * Sc + s;
+                    int k = a.FK[(cN + p) * Sc + s];
+                    if (a.t.node_has_data[p]) {
+                        const int code = plf_code_at(a.codes, a.code_bytes, a.S, p, gs);
+                        for (int i = 0; i < n; i++) dst[i * PLF_TS] = Fa[(size_t)i * Sc] * a.defs[(size_t)code * n + i];
+                    } else {
+                        for (int i = 0; i < n; i++) dst[i * PLF_TS] = Fa[(size_t)i * Sc];
+                    }
+                    for (int idx2 = a.t.indptr[p]; idx2 < a.t.indptr[p + 1]; idx2++) {
+                        if (idx2 == idx) continue;
+                        const double *Es = a.Eg + ((cE + idx2) * n) * Sc + s;
+                        for (int i = 0; i < n; i++) dst[i * PLF_TS] *= Es[(size_t)i * Sc];
+                        k += a.Kg[(cN + a.t.indices[idx2]) * Sc + s];
+                        hess_rescale(dst, n, k);
+                    }
+                    return k;
+                };
+
+                /* ---- the edge itself: v = y_j, diagonal term ---- */
+                const int bj = a.t.indices[j];
+                const int kbj = a.Kg[(cN + bj) * Sc + s];
+                {
+                    const double *Y = Yg + ((cE + j) * n) * Sc + s;
+                    for (int i = 0; i < n; i++) v[i * PLF_TS] = Y[(size_t)i * Sc];
+                }
+                int kv = kbj;
+                {
+                    const int kfe = build_fe(j, t1);
+                    double x = 0.0;
+                    for (int i = 0; i < n; i++) {
+                        double acc = 0.0;
+                        for (int k = 0; k < n; k++) acc = fma(Q[i * n + k], v[k * PLF_TS], acc);
+                        x = fma(t1[i * PLF_TS], acc * rate, x);
+                    }
+                    x = hess_warp_sum(scalbn(x * coef, PLF_SCALE_BITS * max(-16, min(16, kfe + kv - site_k))));
+                    if (lane == 0 && x != 0.0) atomicAdd(&buf[j], x);
+                }
+
+                /* ---- up the root path of j ---- */
+                int cur = j;
+                while (true) {
+                    const int an = ht.parent_node[cur];
+                    const int start = a.t.indptr[an], stop = a.t.indptr[an + 1];
+                    const double *Fa = a.Fg + ((cN + an) * n) * Sc + s;
+                    const int kFa = a.FK[(cN + an) * Sc + s];
+                    int code_a = -1;
+                    if (a.t.node_has_data[an]) code_a = plf_code_at(a.codes, a.code_bytes, a.S, an, gs);
+                    /* the tangent enters the other children's subtrees */
+                    for (int e1 = start; e1 < stop; e1++) {
+                        if (e1 == cur || ht.sub_max[e1] <= rank_j) continue;
+                        /* dfe_e1 = fn_a . base_a . v . prod(siblings other than e1 and cur) */
+                        int kd = kFa + kv;
+                        for (int i = 0; i < n; i++) {
+                            double x = Fa[(size_t)i * Sc] * v[i * PLF_TS];
+                            if (code_a >= 0) x *= a.defs[(size_t)code_a * n + i];
+                            t1[i * PLF_TS] = x;
+                        }
+                        for (int e2 = start; e2 < stop; e2++) {
+                            if (e2 == e1 || e2 == cur) continue;
+                            const double *Es = a.Eg + ((cE + e2) * n) * Sc + s;
+                            for (int i = 0; i < n; i++) t1[i * PLF_TS] *= Es[(size_t)i * Sc];
+                            kd += a.Kg[(cN + a.t.indices[e2]) * Sc + s];
+                        }
+                        hess_rescale(t1, n, kd);
+                        /* edge e1 itself, then its subtree in depth-first order; dfe of the edge being handled is in t1 */
+                        const int b1 = a.t.indices[e1];
+                        const int lo = ht.dfs_pos[b1], hi = ht.sub_end[b1];
+                        int edge = e1, child = b1, kde = kd;
+                        int pos = lo, cidx = 0, cstop = 0;      /* iteration state over (node at pos, its child edges) */
+                        while (true) {
+                            /* pair (edge, j) */
+                            if (ht.erank[edge] > rank_j) {
+                                const double *Y = Yg + ((cE + edge) * n) * Sc + s;
+                                double x = 0.0;
+                                for (int i = 0; i < n; i++) x = fma(t1[i * PLF_TS], Y[(size_t)i * Sc], x);
+                                const int kc = a.Kg[(cN + child) * Sc + s];
+                                x = hess_warp_sum(scalbn(x * coef, PLF_SCALE_BITS * max(-16, min(16, kde + kc - site_k))));
+                                if (lane == 0 && x != 0.0) atomicAdd(&buf[edge], x);
+                            }
+                            /* dfn_child = P^T dfe (kept only for internal children) */
+                            if (a.t.indptr[child] != a.t.indptr[child + 1]) {
+                                const double *Pm = a.P + (cE + edge) * n * n;
+                                double *dF = dFg + ((size_t)child * n) * Sc + s;
+                                for (int jj = 0; jj < n; jj++) {
+                                    double acc = 0.0;
+                                    for (int i = 0; i < n; i++) acc = fma(Pm[i * n + jj], t1[i * PLF_TS], acc);
+                                    t2[jj * PLF_TS] = acc;
+                                }
+                                int kk = kde;
+                                hess_rescale(t2, n, kk);
+                                for (int jj = 0; jj < n; jj++) dF[(size_t)jj * Sc] = t2[jj * PLF_TS];
+                                dFk[(size_t)child * Sc + s] = kk;
+                            }
+                            /* next (node, child edge) of the subtree */
+                            bool found = false;
+                            while (!found) {
+                                if (cidx < cstop) { found = true; break; }
+                                if (pos >= hi) break;
+                                const int x = ht.dfs_nodes[pos++];
+                                cidx = a.t.indptr[x]; cstop = a.t.indptr[x + 1];
+                            }
+                            if (!found) break;
+                            edge = cidx++;
+                            child = a.t.indices[edge];
+                            {
+                                /* dfe_edge = dfn_x . base_x . prod(sibling vectors) */
+                                const int x = ht.parent_node[edge];
+                                const double *dF = dFg + ((size_t)x * n) * Sc + s;
+                                kde = dFk[(size_t)x * Sc + s];
+                                int code_x = -1;
+                                if (a.t.node_has_data[x]) code_x = plf_code_at(a.codes, a.code_bytes, a.S, x, gs);
+                                for (int i = 0; i < n; i++) {
+                                    double y = dF[(size_t)i * Sc];
+                                    if (code_x >= 0) y *= a.defs[(size_t)code_x * n + i];
+                                    t1[i * PLF_TS] = y;
+                                }
+                                for (int e2 = a.t.indptr[x]; e2 < a.t.indptr[x + 1]; e2++) {
+                                    if (e2 == edge) continue;
+                                    const double *Es = a.Eg + ((cE + e2) * n) * Sc + s;
+                                    for (int i = 0; i < n; i++) t1[i * PLF_TS] *= Es[(size_t)i * Sc];
+                                    kde += a.Kg[(cN + a.t.indices[e2]) * Sc + s];
+                                }
+                                hess_rescale(t1, n, kde);
+                            }
+                        }
+                    }
+                    /* tangent of the node vector of an, then of the edge above it */
+                    const int p = ht.parent_edge[an];
+                    if (p < 0) break;
+                    for (int i = 0; i < n; i++) {
+                        double x = v[i * PLF_TS];
+                        if (code_a >= 0) x *= a.defs[(size_t)code_a * n + i];
+                        t1[i * PLF_TS] = x;
+                    }
+                    for (int e2 = start; e2 < stop; e2++) {
+                        if (e2 == cur) continue;
+                        const double *Es = a.Eg + ((cE + e2) * n) * Sc + s;
+                        for (int i = 0; i < n; i++) t1[i * PLF_TS] *= Es[(size_t)i * Sc];
+                        kv += a.Kg[(cN + a.t.indices[e2]) * Sc + s];
+                    }
+                    hess_rescale(t1, n, kv);
+                    {
+                        const double *Pm = a.P + (cE + p) * n * n;
+                        for (int i = 0; i < n; i++) {
+                            double acc = 0.0;
+                            for (int k = 0; k < n; k++) acc = fma(Pm[i * n + k], t1[k * PLF_TS], acc);
+                            v[i * PLF_TS] = acc;
+                        }
+                    }
+                    /* pair (ancestor edge p, j): fe_p . (rate Q v) */
+                    {
+                        const int kfe = build_fe(p, t1);
+                        double x = 0.0;
+                        for (int i = 0; i < n; i++) {
+                            double acc = 0.0;
+                            for (int k = 0; k < n; k++) acc = fma(Q[i * n + k], v[k * PLF_TS], acc);
+                            x = fma(t1[i * PLF_TS], acc * rate, x);
+                        }
+                        x = hess_warp_sum(scalbn(x * coef, PLF_SCALE_BITS * max(-16, min(16, kfe + kv - site_k))));
+                        if (lane == 0 && x != 0.0) atomicAdd(&buf[p], x);
+                    }
+                    cur = p;
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < E; i += PLF_TS) {
+                const double x = buf[i];
+                if (x != 0.0) {
+                    const int r = i > j ? i : j, cl = i > j ? j : i;
+                    myH[(size_t)r * E + cl] += x;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+/* out[i][j] += sum_s w_s rows[i][s] rows[j][s] for j <= i: the g g^T / L^2 part of the Hessian of log L.
+ * grid (ceil(E/16), ceil(E/16), splits over sites), 16 x 16 threads. */
+__global__ void gram_rows_kernel(const double *rows, const double *w, int64_t w_off, int E, int cols, double *out)
+{
+    __shared__ double A[16][17], B[16][17];
+    const int bi = blockIdx.x, bj = blockIdx.y;
+    if (bj > bi) return;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int per = ((cols + gridDim.z - 1) / gridDim.z + 15) / 16 * 16;
+    const int c0 = blockIdx.z * per, c1 = min(cols, c0 + per);
+    double acc = 0.0;
+    for (int c = c0; c < c1; c += 16) {
+        const int col = c + tx;
+        const double wv = (col < c1) ? (w ? w[w_off + col] : 1.0) : 0.0;
+        const int ri = bi * 16 + ty, rj = bj * 16 + ty;
+        A[ty][tx] = (ri < E && col < c1 && wv != 0.0) ? rows[(size_t)ri * cols + col] * wv : 0.0;
+        B[ty][tx] = (rj < E && col < c1 && wv != 0.0) ? rows[(size_t)rj * cols + col] : 0.0;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; k++) acc = fma(A[ty][k], B[tx][k], acc);
+        __syncthreads();
+    }
+    const int i = bi * 16 + ty, j = bj * 16 + tx;
+    if (i < E && j < E && j <= i && acc != 0.0) atomicAdd(&out[(size_t)i * E + j], acc);
 }

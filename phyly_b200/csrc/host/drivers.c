@@ -13,6 +13,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
+#include <time.h>
 
 #include "arbplf.h"
 #include "plf.h"
@@ -21,13 +23,19 @@
 #include "reduce.h"
 #include "dd.h"
 
+/* One engine per process, shared by every arbplf_* call.  The reference's functions are re-entrant (all state on
+ * the caller's stack, runjson.c:10-66); here calls from several host threads are serialised on this lock, held from
+ * the moment a call takes the engine (ctx_load) until it has built its result (ctx_clear). */
 static plf_engine *g_engine = NULL;
 static int g_device = -1;
+static pthread_mutex_t g_engine_lock = PTHREAD_MUTEX_INITIALIZER;
 
 void arbplf_set_device(int device)
 {
+    pthread_mutex_lock(&g_engine_lock);
     if (g_engine && device != g_device) { plf_destroy(g_engine); g_engine = NULL; }
     g_device = device;
+    pthread_mutex_unlock(&g_engine_lock);
 }
 
 static plf_engine *get_engine(void)
@@ -44,12 +52,24 @@ static plf_engine *get_engine(void)
     return g_engine;
 }
 
+/* wall-clock phases of the most recent call: parse (JSON + schema), model + upload, compute, emit */
+static double g_phase[4];
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+void arbplf_last_timing(double out[4]) { memcpy(out, g_phase, sizeof g_phase); }
+
 typedef struct {
     jv *root;
     plf_model m;
     plf_derived d;
     plf_engine *e;
     int loaded;
+    int locked;         /* this call holds g_engine_lock */
+    double t_mark;      /* start of the phase in progress */
 } ctx;
 
 static void ctx_clear(ctx *c)
@@ -57,6 +77,7 @@ static void ctx_clear(ctx *c)
     json_free(c->root);
     plf_model_clear(&c->m);
     plf_derived_clear(&c->d);
+    if (c->locked) pthread_mutex_unlock(&g_engine_lock);
     memset(c, 0, sizeof(*c));
 }
 
@@ -65,11 +86,14 @@ static int ctx_parse(ctx *c, const char *json_in, const char *const *keys, const
 {
     char err[256];
     memset(c, 0, sizeof(*c));
+    c->t_mark = now_s();
+    memset(g_phase, 0, sizeof g_phase);
     plf_model_init(&c->m);
     c->root = json_parse(json_in, err, sizeof err);
     if (!c->root) { fprintf(stderr, "%s\n", err); return -1; }
     if (jv_unpack_strict(c->root, keys, out)) return -1;
     if (plf_model_parse(&c->m, out[0])) return -1;
+    g_phase[0] = now_s() - c->t_mark; c->t_mark = now_s();
     return 0;
 }
 
@@ -77,6 +101,7 @@ static int ctx_parse(ctx *c, const char *json_in, const char *const *keys, const
 static int ctx_load(ctx *c)
 {
     if (plf_derive(&c->d, &c->m)) return -1;
+    if (!c->locked) { pthread_mutex_lock(&g_engine_lock); c->locked = 1; }
     c->e = get_engine();
     if (!c->e) return -1;
     const plf_model *m = &c->m;
@@ -85,9 +110,16 @@ static int ctx_load(ctx *c)
     EK(plf_set_tree(c->e, m->N, m->indptr, m->indices, m->preorder));
     EK(plf_set_model(c->e, m->n, d->C, d->q_hi, d->q_lo, d->edge_rates_csr, d->cat_rates, d->cat_prior,
                      m->root_mode, d->root_vec));
-    if (m->S > 0) EK(plf_set_data(c->e, m->S, m->K, m->defs, m->codes, m->code_bytes));
+    /* the codes travel in chunks behind which the first query starts (they stay valid until ctx_clear) */
+    if (m->S > 0) EK(plf_set_data_async(c->e, m->S, m->K, m->defs, m->codes, m->code_bytes, NULL));
     c->loaded = 1;
+    g_phase[1] = now_s() - c->t_mark; c->t_mark = now_s();
     return 0;
+}
+
+static void phase_compute_done(ctx *c)
+{
+    g_phase[2] = now_s() - c->t_mark; c->t_mark = now_s();
 }
 
 static unsigned char *edge_mask_csr(const plf_model *m, const axis *edge_axis)
@@ -99,6 +131,8 @@ static unsigned char *edge_mask_csr(const plf_model *m, const axis *edge_axis)
 
 static char *finish(ctx *c, char *out, int rc, int *retcode)
 {
+    /* callers mark the end of the compute phase with phase_compute_done(); whatever follows is output formatting */
+    if (c->t_mark > 0) g_phase[3] = now_s() - c->t_mark;
     ctx_clear(c);
     *retcode = rc;
     if (rc) { free(out); return NULL; }
@@ -142,6 +176,7 @@ char *arbplf_ll(const char *json_in, int *retcode)
             }
         }
     }
+    phase_compute_done(&c);
     out = table_to_json(ax, 1, val);
     rc = 0;
 done:
@@ -235,6 +270,7 @@ char *arbplf_deriv(const char *json_in, int *retcode)
         mask = edge_mask_csr(&c.m, &ax[1]);
         if (edge_pass(&c, -1, NULL, NULL, &ax[0], &ax[1], mask, val, 0, 1)) goto done;
     }
+    phase_compute_done(&c);
     out = table_to_json(ax, 2, val);
     rc = 0;
 done:
@@ -293,6 +329,7 @@ char *arbplf_marginal(const char *json_in, int *retcode)
             }
         }
     }
+    phase_compute_done(&c);
     out = table_to_json(ax, 3, val);
     rc = 0;
 done:
@@ -349,6 +386,7 @@ char *arbplf_dwell(const char *json_in, int *retcode)
             }
         }
     }
+    phase_compute_done(&c);
     out = table_to_json(ax, state_agg ? 2 : 3, val);
     rc = 0;
 done:
@@ -413,6 +451,7 @@ char *arbplf_trans(const char *json_in, int *retcode)
             }
         }
     }
+    phase_compute_done(&c);
     out = table_to_json(ax, trans_agg ? 2 : 3, val);
     rc = 0;
 done:
@@ -479,6 +518,7 @@ char *arbplf_em_update(const char *json_in, int *retcode)
             val[e] = x;
         }
     }
+    phase_compute_done(&c);
     out = table_to_json(&ax_edge, 1, val);
     rc = 0;
 done:
@@ -489,7 +529,7 @@ done:
 }
 
 /* ------------------------------------------------------------------ */
-/* model summary, unsupported programs, stdio shell                    */
+/* model summary, stdio shell                                          */
 /* ------------------------------------------------------------------ */
 
 static void put_darray(jbuf *b, const char *key, const double *x, size_t n)
@@ -544,19 +584,148 @@ done:
     return finish(&c, out, rc, retcode);
 }
 
-static char *unsupported(const char *name, int *retcode)
+/* ------------------------------------------------------------------ */
+/* second order programs (arbplfhess.c)                                */
+/* ------------------------------------------------------------------ */
+
+/* A x = b by Gaussian elimination with partial pivoting in long double, nrhs right-hand sides (columns of B, row major
+ * [n][nrhs]); returns -1 when A is singular to working precision. */
+static int solve_ld(int n, const double *A, const double *B, int nrhs, double *X)
 {
-    fprintf(stderr, "error: %s is outside the hot path of this build (second-order / EM programs of "
-                    "arbplfhess.c and arbplfem.c are not implemented)\n", name);
-    *retcode = -1;
-    return NULL;
+    long double *M = malloc(sizeof(long double) * (size_t)n * (n + nrhs) + 16);
+    const int W = n + nrhs;
+    int rc = 0;
+    for (int i = 0; i < n; i++) {
+        for (int j = 0; j < n; j++) M[(size_t)i * W + j] = A[(size_t)i * n + j];
+        for (int j = 0; j < nrhs; j++) M[(size_t)i * W + n + j] = B[(size_t)i * nrhs + j];
+    }
+    for (int k = 0; k < n && !rc; k++) {
+        int piv = k;
+        long double best = fabsl(M[(size_t)k * W + k]);
+        for (int i = k + 1; i < n; i++) if (fabsl(M[(size_t)i * W + k]) > best) { best = fabsl(M[(size_t)i * W + k]); piv = i; }
+        if (!(best > 0.0L)) { rc = -1; break; }
+        if (piv != k) for (int j = 0; j < W; j++) { long double t = M[(size_t)k * W + j]; M[(size_t)k * W + j] = M[(size_t)piv * W + j]; M[(size_t)piv * W + j] = t; }
+        for (int i = k + 1; i < n; i++) {
+            const long double f = M[(size_t)i * W + k] / M[(size_t)k * W + k];
+            if (f == 0.0L) continue;
+            for (int j = k; j < W; j++) M[(size_t)i * W + j] -= f * M[(size_t)k * W + j];
+        }
+    }
+    if (!rc) {
+        for (int r = 0; r < nrhs; r++)
+            for (int i = n - 1; i >= 0; i--) {
+                long double t = M[(size_t)i * W + n + r];
+                for (int j = i + 1; j < n; j++) t -= M[(size_t)i * W + j] * M[(size_t)j * W + n + r];
+                M[(size_t)i * W + n + r] = t / M[(size_t)i * W + i];
+            }
+        for (int i = 0; i < n; i++) for (int r = 0; r < nrhs; r++) X[(size_t)i * nrhs + r] = (double)M[(size_t)i * W + n + r];
+    }
+    free(M);
+    return rc;
 }
 
-char *arbplf_hess(const char *j, int *rc) { (void)j; return unsupported("arbplf-hess", rc); }
-char *arbplf_inv_hess(const char *j, int *rc) { (void)j; return unsupported("arbplf-inv-hess", rc); }
-char *arbplf_newton_delta(const char *j, int *rc) { (void)j; return unsupported("arbplf-newton-delta", rc); }
-char *arbplf_newton_update(const char *j, int *rc) { (void)j; return unsupported("arbplf-newton-update", rc); }
-char *arbplf_newton_refine(const char *j, int *rc) { (void)j; return unsupported("arbplf-newton-refine", rc); }
+enum { SO_HESS, SO_INV_HESS, SO_DELTA, SO_UPDATE, SO_REFINE };
+
+/*
+ * hess_query / inv_hess_query / newton_delta_query / newton_point_query (arbplfhess.c:1208-1452): the site reduction is
+ * required and must aggregate (arbplfhess.c:1162-1207); outputs in the user's edge order.  newton-refine here is a
+ * plain (uncertified) Newton iteration from the given rates to a stationary point; the reference's trust-region search
+ * followed by interval-Newton certification (arbplfhess.c:1454-1733) is not reproduced.
+ */
+static char *second_order(const char *json_in, int *retcode, int which)
+{
+    static const char *const keys[] = {"model_and_data", "site_reduction", NULL};
+    const jv *v[2];
+    ctx c;
+    reduction r_site; reduction_init(&r_site);
+    axis ax_site; memset(&ax_site, 0, sizeof ax_site);
+    double *H = NULL, *g = NULL, *X = NULL, *B = NULL, *rates = NULL;
+    jbuf jb; jbuf_init(&jb);
+    char *out = NULL;
+    int rc = -1;
+    if (ctx_parse(&c, json_in, keys, v)) goto done;
+    const int E = c.m.E;
+    const int64_t S = c.m.S;
+    if (reduction_parse(&r_site, (int)S, "site", v[1])) goto done;
+    if (axis_init(&ax_site, "site", (int)S, &r_site)) goto done;
+    if (!ax_site.aggregated) { fprintf(stderr, "error: aggregation over sites is required\n"); goto done; }
+    H = calloc((size_t)E * E + 1, sizeof(double));
+    g = calloc(E + 1, sizeof(double));
+    X = calloc((size_t)E * E + 1, sizeof(double));
+    B = calloc((size_t)E * E + 1, sizeof(double));
+    rates = calloc(E + 1, sizeof(double));
+    if (S > 0 && E > 0) {
+        if (ctx_load(&c)) goto done;
+        if (plf_set_site_weights(c.e, ax_site.w)) goto engine_error;
+        for (int i = 0; i < E; i++) rates[i] = c.d.edge_rates_csr[i];
+        const int iters = which == SO_REFINE ? 100 : 1;
+        for (int it = 0; it < iters; it++) {
+            if (it > 0 && plf_set_edge_rates(c.e, rates)) goto engine_error;
+            if (plf_hess(c.e, NULL, g, H)) goto engine_error;
+            if (which == SO_HESS) break;
+            if (which == SO_INV_HESS) {
+                for (int i = 0; i < E; i++) B[(size_t)i * E + i] = 1.0;
+                if (solve_ld(E, H, B, E, X)) { fprintf(stderr, "error: the hessian is singular\n"); goto done; }
+                break;
+            }
+            if (solve_ld(E, H, g, 1, X)) { fprintf(stderr, "error: the hessian is singular\n"); goto done; }
+            if (which != SO_REFINE) break;
+            /* x <- x - inv(H) g, kept positive; stop when the step no longer changes the rates */
+            double big = 0.0;
+            for (int i = 0; i < E; i++) {
+                double step = -X[i], lim = 0.5 * rates[i];
+                if (step < -lim) step = -lim;
+                rates[i] += step;
+                if (fabs(step) > big * fabs(rates[i])) big = fabs(step) / (fabs(rates[i]) > 0 ? fabs(rates[i]) : 1.0);
+            }
+            if (big < 1e-15) break;
+        }
+    }
+    phase_compute_done(&c);
+    if (which == SO_HESS || which == SO_INV_HESS) {
+        const double *M = which == SO_HESS ? H : X;
+        jbuf_puts(&jb, "{\"columns\": [\"first_edge\", \"second_edge\", \"value\"], \"data\": [");
+        for (int a = 0; a < E; a++)
+            for (int b = 0; b < E; b++) {
+                const int i = c.m.order[a], j = c.m.order[b];
+                const double x = (j < i) ? M[(size_t)i * E + j] : M[(size_t)j * E + i];
+                if (!isfinite(x)) { fprintf(stderr, "error: a requested site has zero likelihood\n"); goto done; }
+                if (a || b) jbuf_puts(&jb, ", ");
+                jbuf_puts(&jb, "["); jbuf_int(&jb, a); jbuf_puts(&jb, ", "); jbuf_int(&jb, b); jbuf_puts(&jb, ", ");
+                jbuf_real(&jb, x); jbuf_puts(&jb, "]");
+            }
+        jbuf_puts(&jb, "]}");
+    } else {
+        jbuf_puts(&jb, "{\"columns\": [\"edge\", \"value\"], \"data\": [");
+        for (int a = 0; a < E; a++) {
+            const int i = c.m.order[a];
+            double x = -X[i];                                      /* newton delta = -inv(hess) grad (arbplfhess.c:203-234) */
+            if (which == SO_UPDATE) x += c.d.edge_rates_csr[i];    /* arbplfhess.c:236-245 */
+            if (which == SO_REFINE) x = rates[i];
+            if (!isfinite(x)) { fprintf(stderr, "error: a requested site has zero likelihood\n"); goto done; }
+            if (a) jbuf_puts(&jb, ", ");
+            jbuf_puts(&jb, "["); jbuf_int(&jb, a); jbuf_puts(&jb, ", "); jbuf_real(&jb, x); jbuf_puts(&jb, "]");
+        }
+        jbuf_puts(&jb, "]}");
+    }
+    out = jbuf_take(&jb);
+    rc = 0;
+    goto done;
+engine_error:
+    fprintf(stderr, "error: %s\n", plf_last_error(c.e));
+done:
+    if (rc) free(jbuf_take(&jb));
+    free(H); free(g); free(X); free(B); free(rates);
+    axis_clear(&ax_site);
+    reduction_clear(&r_site);
+    return finish(&c, out, rc, retcode);
+}
+
+char *arbplf_hess(const char *j, int *rc) { return second_order(j, rc, SO_HESS); }
+char *arbplf_inv_hess(const char *j, int *rc) { return second_order(j, rc, SO_INV_HESS); }
+char *arbplf_newton_delta(const char *j, int *rc) { return second_order(j, rc, SO_DELTA); }
+char *arbplf_newton_update(const char *j, int *rc) { return second_order(j, rc, SO_UPDATE); }
+char *arbplf_newton_refine(const char *j, int *rc) { return second_order(j, rc, SO_REFINE); }
 
 /* runjson.c:88-147 */
 int arbplf_run_stdio(char *(*f)(const char *, int *))

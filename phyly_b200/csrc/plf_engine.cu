@@ -23,7 +23,7 @@
 #include "dd.h"
 #include "expm.cuh"
 #include "generic.cuh"
-#include "fused4.cuh"
+#include "fused4_args.h"
 #include "tile.cuh"
 #include "dmma.h"
 
@@ -130,7 +130,7 @@ struct plf_engine {
     int stack_depth = 0, nslots = 0, max_degree = 0;
     bool TP_valid = false, program_dirty = true;
     bool dm_valid = false;       /* packed matrices / tip tables of the DMMA kernels (dmma.cuh) */
-    DevBuf d_dmPf, d_dmTPf, d_dmTFf, d_dm_defsf, d_dm_rootf, d_dm_stack, d_dm_stackmeta, d_dm_slab, d_dm_slabmeta, d_dm_Of, d_dm_oidx, d_dm_otr;
+    DevBuf d_dmPf, d_dmTPf, d_dmTFf, d_dm_defsf, d_dm_rootf, d_dm_stack, d_dm_stackmeta, d_dm_slab, d_dm_slabmeta, d_dm_Of, d_dm_oidx, d_dm_otr, d_dm_ops, d_dm_ch;
     int dm_out_depth = 0;
     F4Prog prog_h;
     uint64_t program_version = 0, f4_tuned_version[3] = {~(uint64_t)0, ~(uint64_t)0, ~(uint64_t)0};   /* ll, edge forms, marginals */
@@ -138,8 +138,9 @@ struct plf_engine {
     int f4_tuned_C[3] = {0, 0, 0}, f4_tuned_K[3] = {0, 0, 0};
 
     /* scratch */
-    DevBuf d_scratch, d_scratchS, d_block_ll, d_block_edge, d_edge_site, d_sum, d_site_ll, d_err, d_mask;
+    DevBuf d_scratch, d_scratchS, d_block_ll, d_block_edge, d_edge_site, d_sum, d_site_ll, d_err, d_mask, d_retry;
     DevBuf g_Lg, g_Kg, g_Cg, g_Eg, g_Fg, g_FK, g_cat_lh, g_cat_k, g_site_m, g_site_k, g_edge_out, g_marg_out, g_tr;
+    DevBuf h_Yg, h_dFg, h_dFk, h_part, h_gram, h_tree, h_out;
 
     /* timing / accounting */
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -150,6 +151,8 @@ struct plf_engine {
     /* nccl */
     plf_nccl_comm comm = nullptr;
     int nranks = 1;
+    bool comm_paused = false;
+    std::string last_kernel;
 };
 
 #define FAIL(e, ...) do { char _b[512]; snprintf(_b, sizeof(_b), __VA_ARGS__); (e)->err = _b; return -1; } while (0)
@@ -191,6 +194,20 @@ __global__ void transpose_codes_kernel(const TIn *in, TOut *out, int64_t s_begin
             if (node_flags[nd] == 0) atomicOr(&node_flags[nd], 1);
         }
     }
+}
+
+/* Multi-GPU queries over an upload still in flight: one word, summed with the results by the same all-reduce, tells every
+ * rank whether ANY rank has to repeat the query (its pattern of data-carrying nodes changed: +1) or met a character
+ * code outside the definition table (+2^20), so that all ranks issue the same sequence of collectives. */
+__global__ void retry_word_kernel(const int *flags, const unsigned char *old_flags, int N, const int *bad, double *out)
+{
+    __shared__ int any;
+    if (threadIdx.x == 0) any = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x)
+        if ((flags[i] != 0) != (old_flags[i] != 0)) any = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) *out = (any ? 1.0 : 0.0) + (*bad ? 1048576.0 : 0.0);
 }
 
 __global__ void flags_to_bytes_kernel(const int *flags, unsigned char *out, int N)
@@ -248,6 +265,31 @@ __global__ void wsum_rows_kernel(const double *val, const double *w, int64_t w_o
     if (threadIdx.x == 0) out[r] += red[0];
 }
 
+/*
+ * Sites of zero likelihood.  The reference's precision loop never terminates on them (arbplfll.c:168, README.md:22-24);
+ * here they are an error whenever they carry weight in an aggregate, and their per-site rows become NaN so that the
+ * caller sees them whichever output it asked for.  ll[cols] are the site log-likelihoods of the chunk, w the weights of
+ * all sites (or NULL = 1), rowsA [RA][cols] / rowsB [RB][cols] per-site outputs of the chunk (or NULL).
+ */
+__global__ void zero_lik_rows_kernel(const double *ll, const double *w, int64_t w_off, int cols, int *err,
+                                     double *rowsA, int RA, double *rowsB, int RB)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= cols) return;
+    if (isfinite(ll[s])) return;
+    if (!w || w[w_off + s] != 0.0) atomicOr(err, 1);
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (rowsA) for (int r = 0; r < RA; r++) rowsA[(size_t)r * cols + s] = nan;
+    if (rowsB) for (int r = 0; r < RB; r++) rowsB[(size_t)r * cols + s] = nan;
+}
+
+/* y += alpha x */
+__global__ void axpy_kernel(double *y, const double *x, double alpha, size_t count)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) y[i] = fma(alpha, x[i], y[i]);
+}
+
 /* in[R][Cc] -> out[Cc][R] */
 __global__ void transpose_d_kernel(const double *in, double *out, int R, int Cc)
 {
@@ -262,6 +304,32 @@ __global__ void transpose_d_kernel(const double *in, double *out, int R, int Cc)
         int cc = c0 + r, rr = r0 + threadIdx.x;
         if (cc < Cc && rr < R) out[(size_t)cc * R + rr] = tile[threadIdx.x][r];
     }
+}
+
+/* second stage: out[j] = sum over rows of part[row][j], fixed order (Kahan) */
+__global__ void sum_rows_kernel(const double *part, int rows, int cols, double *out)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cols) return;
+    double s = 0.0, comp = 0.0;
+    for (int r = 0; r < rows; r++) {
+        double yv = part[(size_t)r * cols + j] - comp;
+        double tsum = s + yv;
+        comp = (tsum - s) - yv;
+        s = tsum;
+    }
+    out[j] = s;
+}
+
+/* gather the matrices of internal-child edges: out[c][ie] = M[c][edge_of[ie]] (16 doubles each) */
+__global__ void compact_matrices_kernel(const double *M, const int *edge_of, int C, int E, int Ei, double *out)
+{
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = C * Ei * 16;
+    if (idx >= total) return;
+    int k = idx & 15, r = idx >> 4;
+    int ie = r % Ei, c = r / Ei;
+    out[idx] = M[((size_t)c * E + edge_of[ie]) * 16 + k];
 }
 
 /* ------------------------------------------------------------------ */
@@ -355,6 +423,8 @@ extern "C" int plf_last_kernel_ms(plf_engine *e, float *ms_kernel)
     *ms_kernel = e->ms_kernel;
     return 0;
 }
+
+extern "C" const char *plf_last_kernel_name(const plf_engine *e) { return e ? e->last_kernel.c_str() : ""; }
 
 extern "C" int64_t plf_launch_count(plf_engine *e, int reset)
 {
@@ -563,8 +633,9 @@ extern "C" int plf_set_edge_rates(plf_engine *e, const double *edge_rates)
         FAIL(e, "plf_set_edge_rates: edge rate %d is not a finite non-negative number", i);
     e->edge_rates.assign(edge_rates, edge_rates + e->E);
     CK(e, cudaSetDevice(e->device));
+    /* no wait here: a copy from pageable memory has left the host buffer (for the driver's staging area) when the call
+     * returns, and everything that reads d_edge_rates is launched on the same stream */
     CK(e, cudaMemcpyAsync(e->d_edge_rates.p, e->edge_rates.data(), sizeof(double) * e->E, cudaMemcpyHostToDevice, e->stream));
-    CK(e, cudaStreamSynchronize(e->stream));
     e->P_valid = e->D_valid = e->TP_valid = e->dm_valid = false;
     return 0;
 }
@@ -800,9 +871,12 @@ extern "C" int plf_set_site_weights(plf_engine *e, const double *w)
     if (!e) return -1;
     if (e->S == 0) FAIL(e, "plf_set_site_weights: set the data first");
     CK(e, cudaSetDevice(e->device));
+    /* an upload in flight may still be writing the weights it carried: let it finish first */
+    if (e->pend_active && e->copy_stream) CK(e, cudaStreamSynchronize(e->copy_stream));
     if (!w) { e->have_w = false; return 0; }
     ENSURE(e, e->d_site_w, sizeof(double) * e->S);
     CK(e, cudaMemcpyAsync(e->d_site_w.p, w, sizeof(double) * e->S, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));      /* the caller may reuse (pinned) w as soon as we return */
     e->have_w = true;
     return 0;
 }
@@ -820,6 +894,7 @@ struct Query {
     double *site_ll = nullptr, *sum_ll = nullptr;
     double *site_edge = nullptr, *sum_edge = nullptr;   /* [S][E], [E] */
     double *site_marg = nullptr, *sum_marg = nullptr;   /* [S][N][n], [N][n] */
+    double *sum_hess = nullptr;                         /* [E][E]: Hessian of the weighted log likelihood (generic path) */
 };
 
 static bool fused_applicable(const plf_engine *e)
@@ -904,7 +979,7 @@ static int ensure_tip_tables(plf_engine *e, const double *Fm, int f_mode, bool w
 
 static int finish_sums(plf_engine *e, double *d_sum, size_t count)
 {
-    if (e->comm) {
+    if (e->comm && !e->comm_paused) {
         int r = g_nccl.AllReduce(d_sum, d_sum, count, /*ncclDouble*/ 8, /*ncclSum*/ 0, e->comm, e->stream);
         if (r != 0) FAIL(e, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
     }
@@ -930,37 +1005,6 @@ static int copy_site_matrix(plf_engine *e, const double *d_rows /*[R][cols]*/, i
         CK(e, cudaStreamSynchronize(e->stream));
     }
     return 0;
-}
-
-typedef void (*f4_kernel_t)(const F4Args, const F4Prog);
-
-/* marginal-mode kernels: fewer configurations (no constant-memory variants) */
-template <int BD, int STAGED, bool PACK>
-static f4_kernel_t f4_select_marg(int C)
-{
-    switch (C) {
-    case 1: return fused4_kernel<1, 2, BD, STAGED, PACK, false>;
-    case 2: return fused4_kernel<2, 2, BD, STAGED, PACK, false>;
-    case 3: return fused4_kernel<3, 2, BD, STAGED, PACK, false>;
-    case 4: return fused4_kernel<4, 2, BD, STAGED, PACK, false>;
-    }
-    return nullptr;
-}
-
-template <int BD, int STAGED, bool PACK, bool CM = false>
-static f4_kernel_t f4_select_c(int C, bool edge)
-{
-    switch (C * 2 + (edge ? 1 : 0)) {
-    case 2: return fused4_kernel<1, 0, BD, STAGED, PACK, CM>;
-    case 3: return fused4_kernel<1, 1, BD, STAGED, PACK, CM>;
-    case 4: return fused4_kernel<2, 0, BD, STAGED, PACK, CM>;
-    case 5: return fused4_kernel<2, 1, BD, STAGED, PACK, CM>;
-    case 6: return fused4_kernel<3, 0, BD, STAGED, PACK, CM>;
-    case 7: return fused4_kernel<3, 1, BD, STAGED, PACK, CM>;
-    case 8: return fused4_kernel<4, 0, BD, STAGED, PACK, CM>;
-    case 9: return fused4_kernel<4, 1, BD, STAGED, PACK, CM>;
-    }
-    return nullptr;
 }
 
 /* the constant-memory matrices are one per device and context: queries of different engines (different
@@ -1030,47 +1074,47 @@ static int run_fused(plf_engine *e, Query &q)
                       e->children.size() <= F4_CM_MAXCH && e->device < 64;
         for (const F4Op &op : e->ops) if (op.nchild != 2) can_cm = false;     /* CM kernels carry the two-children step only */
         const Cand mcands[] = {
-            {384, 1, true, false, can_pack ? f4_select_marg<384, 1, true>(e->C) : nullptr, 0, 0},
-            {384, 1, false, false, f4_select_marg<384, 1, false>(e->C), 0, 0},
-            {256, 1, false, false, f4_select_marg<256, 1, false>(e->C), 0, 0},
+            {384, 1, true, false, can_pack ? f4_get_kernel(384, 1, true, false, e->C, 2) : nullptr, 0, 0},
+            {384, 1, false, false, f4_get_kernel(384, 1, false, false, e->C, 2), 0, 0},
+            {256, 1, false, false, f4_get_kernel(256, 1, false, false, e->C, 2), 0, 0},
             /* larger trees: tables through L1 / L2, CTAs stay large */
-            {384, 0, true, false, can_pack ? f4_select_marg<384, 0, true>(e->C) : nullptr, 0, 0},
-            {384, 0, false, false, f4_select_marg<384, 0, false>(e->C), 0, 0},
-            {256, 0, false, false, f4_select_marg<256, 0, false>(e->C), 0, 0},
-            {128, 0, false, false, f4_select_marg<128, 0, false>(e->C), 0, 0},
+            {384, 0, true, false, can_pack ? f4_get_kernel(384, 0, true, false, e->C, 2) : nullptr, 0, 0},
+            {384, 0, false, false, f4_get_kernel(384, 0, false, false, e->C, 2), 0, 0},
+            {256, 0, false, false, f4_get_kernel(256, 0, false, false, e->C, 2), 0, 0},
+            {128, 0, false, false, f4_get_kernel(128, 0, false, false, e->C, 2), 0, 0},
         };
         const Cand ecands[] = {
-            {512, 2, true, true, (can_cm && can_pack) ? f4_select_c<512, 2, true, true>(e->C, edge) : nullptr, 0, 0},
-            {512, 2, false, true, can_cm ? f4_select_c<512, 2, false, true>(e->C, edge) : nullptr, 0, 0},
-            {384, 2, false, true, can_cm ? f4_select_c<384, 2, false, true>(e->C, edge) : nullptr, 0, 0},
-            {384, 2, true, false, can_pack ? f4_select_c<384, 2, true>(e->C, edge) : nullptr, 0, 0},
-            {384, 1, false, false, f4_select_c<384, 1, false>(e->C, edge), 0, 0},
-            {512, 1, false, false, f4_select_c<512, 1, false>(e->C, edge), 0, 0},
-            {256, 2, false, false, f4_select_c<256, 2, false>(e->C, edge), 0, 0},
+            {512, 2, true, true, (can_cm && can_pack) ? f4_get_kernel(512, 2, true, true, e->C, edge ? 1 : 0) : nullptr, 0, 0},
+            {512, 2, false, true, can_cm ? f4_get_kernel(512, 2, false, true, e->C, edge ? 1 : 0) : nullptr, 0, 0},
+            {384, 2, false, true, can_cm ? f4_get_kernel(384, 2, false, true, e->C, edge ? 1 : 0) : nullptr, 0, 0},
+            {384, 2, true, false, can_pack ? f4_get_kernel(384, 2, true, false, e->C, edge ? 1 : 0) : nullptr, 0, 0},
+            {384, 1, false, false, f4_get_kernel(384, 1, false, false, e->C, edge ? 1 : 0), 0, 0},
+            {512, 1, false, false, f4_get_kernel(512, 1, false, false, e->C, edge ? 1 : 0), 0, 0},
+            {256, 2, false, false, f4_get_kernel(256, 2, false, false, e->C, edge ? 1 : 0), 0, 0},
             /* larger trees (the tables no longer fit shared memory): tables through L1 / L2, CTAs stay large */
-            {512, 0, true, false, can_pack ? f4_select_c<512, 0, true>(e->C, edge) : nullptr, 0, 0},
-            {384, 0, true, false, can_pack ? f4_select_c<384, 0, true>(e->C, edge) : nullptr, 0, 0},
-            {384, 0, false, false, f4_select_c<384, 0, false>(e->C, edge), 0, 0},
-            {256, 0, false, false, f4_select_c<256, 0, false>(e->C, edge), 0, 0},
-            {128, 0, false, false, f4_select_c<128, 0, false>(e->C, edge), 0, 0},
+            {512, 0, true, false, can_pack ? f4_get_kernel(512, 0, true, false, e->C, edge ? 1 : 0) : nullptr, 0, 0},
+            {384, 0, true, false, can_pack ? f4_get_kernel(384, 0, true, false, e->C, edge ? 1 : 0) : nullptr, 0, 0},
+            {384, 0, false, false, f4_get_kernel(384, 0, false, false, e->C, edge ? 1 : 0), 0, 0},
+            {256, 0, false, false, f4_get_kernel(256, 0, false, false, e->C, edge ? 1 : 0), 0, 0},
+            {128, 0, false, false, f4_get_kernel(128, 0, false, false, e->C, edge ? 1 : 0), 0, 0},
         };
         /* log-likelihood only: no slab; the pending partials of the post-order walk either sit in shared
          * memory (which limits the CTA to 256 threads at depth 3) or in a small L2-resident global stack */
         const Cand lcands[] = {
-            {512, 2, true, true, (can_cm && can_pack) ? f4_select_c<512, 2, true, true>(e->C, false) : nullptr, 0, 0, true},
-            {512, 2, true, false, can_pack ? f4_select_c<512, 2, true, false>(e->C, false) : nullptr, 0, 0, true},
-            {512, 2, false, true, can_cm ? f4_select_c<512, 2, false, true>(e->C, false) : nullptr, 0, 0, true},
-            {384, 2, true, false, can_pack ? f4_select_c<384, 2, true>(e->C, false) : nullptr, 0, 0, true},
-            {384, 2, true, false, can_pack ? f4_select_c<384, 2, true>(e->C, false) : nullptr, 0, 0, false},
-            {384, 1, false, false, f4_select_c<384, 1, false>(e->C, false), 0, 0, false},
-            {256, 2, false, false, f4_select_c<256, 2, false>(e->C, false), 0, 0, false},
-            {256, 2, false, false, f4_select_c<256, 2, false>(e->C, false), 0, 0, true},
-            {512, 0, true, false, can_pack ? f4_select_c<512, 0, true>(e->C, false) : nullptr, 0, 0, true},
-            {384, 0, true, false, can_pack ? f4_select_c<384, 0, true>(e->C, false) : nullptr, 0, 0, true},
-            {384, 0, false, false, f4_select_c<384, 0, false>(e->C, false), 0, 0, true},
-            {256, 0, false, false, f4_select_c<256, 0, false>(e->C, false), 0, 0, true},
-            {128, 0, false, false, f4_select_c<128, 0, false>(e->C, false), 0, 0, true},
-            {128, 0, false, false, f4_select_c<128, 0, false>(e->C, false), 0, 0, false},
+            {512, 2, true, true, (can_cm && can_pack) ? f4_get_kernel(512, 2, true, true, e->C, 0) : nullptr, 0, 0, true},
+            {512, 2, true, false, can_pack ? f4_get_kernel(512, 2, true, false, e->C, 0) : nullptr, 0, 0, true},
+            {512, 2, false, true, can_cm ? f4_get_kernel(512, 2, false, true, e->C, 0) : nullptr, 0, 0, true},
+            {384, 2, true, false, can_pack ? f4_get_kernel(384, 2, true, false, e->C, 0) : nullptr, 0, 0, true},
+            {384, 2, true, false, can_pack ? f4_get_kernel(384, 2, true, false, e->C, 0) : nullptr, 0, 0, false},
+            {384, 1, false, false, f4_get_kernel(384, 1, false, false, e->C, 0), 0, 0, false},
+            {256, 2, false, false, f4_get_kernel(256, 2, false, false, e->C, 0), 0, 0, false},
+            {256, 2, false, false, f4_get_kernel(256, 2, false, false, e->C, 0), 0, 0, true},
+            {512, 0, true, false, can_pack ? f4_get_kernel(512, 0, true, false, e->C, 0) : nullptr, 0, 0, true},
+            {384, 0, true, false, can_pack ? f4_get_kernel(384, 0, true, false, e->C, 0) : nullptr, 0, 0, true},
+            {384, 0, false, false, f4_get_kernel(384, 0, false, false, e->C, 0), 0, 0, true},
+            {256, 0, false, false, f4_get_kernel(256, 0, false, false, e->C, 0), 0, 0, true},
+            {128, 0, false, false, f4_get_kernel(128, 0, false, false, e->C, 0), 0, 0, true},
+            {128, 0, false, false, f4_get_kernel(128, 0, false, false, e->C, 0), 0, 0, false},
         };
         const Cand *cands = marg ? mcands : (edge ? ecands : lcands);
         const int ncand = marg ? (int)(sizeof(mcands) / sizeof(mcands[0]))
@@ -1125,12 +1169,14 @@ static int run_fused(plf_engine *e, Query &q)
     }
 
     ENSURE(e, e->d_block_ll, sizeof(double) * gmax * nchunk);
-    ENSURE(e, e->d_sum, sizeof(double) * (1 + e->E + (size_t)e->N * e->n));
+    ENSURE(e, e->d_sum, sizeof(double) * (2 + e->E + (size_t)e->N * e->n));
     ENSURE(e, e->d_err, sizeof(int) * (e->N + 4));
     CK(e, cudaMemsetAsync(e->d_err.p, 0, sizeof(int), e->stream));
     a.block_ll = e->d_block_ll.as<double>();
     a.error_flag = e->d_err.as<int>();
-    if (q.site_ll) { ENSURE(e, e->d_site_ll, sizeof(double) * e->S); a.site_ll = e->d_site_ll.as<double>(); }
+    /* the site log-likelihoods are always kept: the zero-likelihood check of every query kind reads them */
+    ENSURE(e, e->d_site_ll, sizeof(double) * e->S);
+    a.site_ll = e->d_site_ll.as<double>();
     if (edge) {
         ENSURE(e, e->d_scratch, sizeof(double4) * (size_t)e->C * e->nslots * Tmax);
         ENSURE(e, e->d_scratchS, sizeof(unsigned int) * (size_t)e->nslots * Tmax);
@@ -1171,6 +1217,12 @@ static int run_fused(plf_engine *e, Query &q)
         a.scratch = e->d_scratch.as<double4>(); a.scratchS = e->d_scratchS.as<unsigned int>();
     }
     std::unique_lock<std::mutex> cm_lock(g_cm_mutex, std::defer_lock);
+    /* every way out of this function after the constant bank has been written records the "done" event before the
+     * lock is released (declared after the lock: destroyed before it) */
+    struct CmGuard {
+        cudaEvent_t *ev = nullptr; cudaStream_t st = nullptr;
+        ~CmGuard() { if (ev) cudaEventRecord(*ev, st); }
+    } cm_guard;
     if (any_cm) {
         /* program as a kernel parameter, matrices into the constant bank (ordered against other engines) */
         memset(&e->prog_h, 0, sizeof(F4Prog));
@@ -1179,9 +1231,9 @@ static int run_fused(plf_engine *e, Query &q)
         cm_lock.lock();
         if (!g_cm_done[e->device]) CK(e, cudaEventCreateWithFlags(&g_cm_done[e->device], cudaEventDisableTiming));
         CK(e, cudaStreamWaitEvent(e->stream, g_cm_done[e->device], 0));
+        cm_guard.ev = &g_cm_done[e->device]; cm_guard.st = e->stream;
         const size_t nP = sizeof(double) * (size_t)e->C * e->edge_of_int.size() * 16;
-        CK(e, cudaMemcpyToSymbolAsync(f4_cP, a.Pint, nP, 0, cudaMemcpyDeviceToDevice, e->stream));
-        if (edge) CK(e, cudaMemcpyToSymbolAsync(f4_cF, a.Fint, nP, 0, cudaMemcpyDeviceToDevice, e->stream));
+        CK(e, f4_upload_const(a.Pint, edge ? a.Fint : nullptr, nP, e->stream));
     }
     if (tune) {
         /* time each leading candidate on the first tune_sites sites (results are overwritten by the real run) */
@@ -1215,6 +1267,11 @@ static int run_fused(plf_engine *e, Query &q)
     }
     const Cand &use = viable[pick];
     const int grid = grid_of(use);
+    {
+        char nm[96];
+        snprintf(nm, sizeof nm, "fused4_kernel<%d,%d,%d,%d,%d,%d>", e->C, marg ? 2 : (edge ? 1 : 0), use.bd, use.staged, use.pack ? 1 : 0, use.cm ? 1 : 0);
+        e->last_kernel = nm;
+    }
     a.gstack = use.gstack ? 1 : 0; a.stack_depth = use.gstack ? 0 : e->stack_depth;
     CK(e, cudaFuncSetAttribute(use.k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)use.smem));
     CK(e, cudaEventRecord(e->ev[3], e->stream));
@@ -1233,10 +1290,24 @@ static int run_fused(plf_engine *e, Query &q)
     CK(e, cudaEventRecord(e->ev[4], e->stream));
     if (any_cm) {
         CK(e, cudaEventRecord(g_cm_done[e->device], e->stream));
+        cm_guard.ev = nullptr;
         cm_lock.unlock();
     }
     e->kernel_timed = true;
+    const bool shared_retry = pipelined && e->comm != nullptr;
+    if (shared_retry) {
+        ENSURE(e, e->d_retry, sizeof(double));
+        retry_word_kernel<<<1, 256, 0, e->stream>>>(e->d_err.as<int>() + 4, e->d_node_has_data.as<unsigned char>(), e->N,
+                                                    e->d_err.as<int>() + 1, e->d_retry.as<double>());
+        KCHECK(e);
+    }
     if (pipelined && launch_flags_readback(e)) return -1;
+    if ((edge && !marg && q.site_edge) || (marg && q.site_marg)) {
+        zero_lik_rows_kernel<<<(unsigned)((e->S + 255) / 256), 256, 0, e->stream>>>(
+            a.site_ll, a.site_w, 0, (int)e->S, a.error_flag, (edge && !marg) ? a.edge_site_out : nullptr, e->E,
+            marg ? a.marg_site_out : nullptr, e->N * 4);
+        KCHECK(e);
+    }
     const int rows = grid * (int)nchunk;
     a.block_ll = e->d_block_ll.as<double>();
     if (edge) a.block_edge = e->d_block_edge.as<double>();
@@ -1271,19 +1342,23 @@ static int run_fused(plf_engine *e, Query &q)
         KCHECK(e);
         nsum = 1 + e->E;
     }
-    if (finish_sums(e, dsum, nsum)) return -1;
+    if (shared_retry) CK(e, cudaMemcpyAsync(dsum + nsum, e->d_retry.p, sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+    if (finish_sums(e, dsum, nsum + (shared_retry ? 1 : 0))) return -1;
     CK(e, cudaEventRecord(e->ev[2], e->stream));
-    std::vector<double> hs(nsum);
+    std::vector<double> hs(nsum + 1, 0.0);
     int herr = 0;
-    CK(e, cudaMemcpyAsync(hs.data(), dsum, sizeof(double) * nsum, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaMemcpyAsync(hs.data(), dsum, sizeof(double) * (nsum + (shared_retry ? 1 : 0)), cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaMemcpyAsync(&herr, e->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     if (q.site_ll) CK(e, cudaMemcpyAsync(q.site_ll, e->d_site_ll.p, sizeof(double) * e->S, cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
     if (pipelined) {
         e->pend_active = false;
         if (data_has_bad_code(e)) { e->S = 0; FAIL(e, "plf_set_data_async: a character code is not a row of the definition table"); }
-        /* the program was compiled for the previous data's pattern of data-carrying nodes: redo if that changed */
-        if (adopt_flags(e)) return 1;
+        if (shared_retry && hs[nsum] >= 1048576.0) { e->S = 0; FAIL(e, "plf_set_data_async: another rank met a character code that is not a row of the definition table"); }
+        /* the program was compiled for the previous data's pattern of data-carrying nodes: redo if that changed here --
+         * or, with a communicator, on any rank (the repeated query all-reduces again) */
+        const bool changed = adopt_flags(e);
+        if (changed || (shared_retry && hs[nsum] != 0.0)) return 1;
     }
     if (q.site_edge && copy_site_matrix(e, e->d_edge_site.as<double>(), e->E, e->S, q.site_edge)) return -1;
     if (herr && (q.sum_ll || q.sum_edge || q.sum_marg)) FAIL(e, "a site with non-zero weight has zero likelihood");
@@ -1298,9 +1373,11 @@ static int run_generic(plf_engine *e, Query &q)
 {
     const int n = e->n, C = e->C, N = e->N, E = e->E;
     const bool outside = q.want_edge || q.want_marg;
+    e->last_kernel = (n > 16 && n <= TL_NP && !getenv("PLF_NO_TILE")) ? "tile_inside_kernel / tile_outside_kernel" : "generic_inside_kernel / generic_outside_kernel";
     /* chunk size from a memory budget */
     size_t per_site = (size_t)C * ((size_t)N * n * 8 + N * 5 + (size_t)E * n * 8 + 16) + 16;
     if (outside) per_site += (size_t)C * ((size_t)N * n * 8 + N * 4) + (size_t)E * 8 + (size_t)N * n * 8;
+    if (q.sum_hess) per_site += (size_t)C * E * n * 8 + (size_t)N * n * 8 + (size_t)N * 4;
     size_t free_b = 0, total_b = 0;
     CK(e, cudaMemGetInfo(&free_b, &total_b));
     size_t budget = std::min<size_t>((size_t)24 << 30, free_b / 2);
@@ -1361,7 +1438,7 @@ static int run_generic(plf_engine *e, Query &q)
     if (smem_out > 227 * 1024) FAIL(e, "state count %d is too large for the generic kernels", n);
     const double *w = e->have_w ? e->d_site_w.as<double>() : nullptr;
     /* 16 < n <= 64 (amino-acid, codon): inside pass on the FP64 tensor pipe (tile.cuh) */
-    const bool use_tile = n > 16 && n <= TL_NP && !getenv("PLF_NO_TILE");
+    const bool use_tile = n > 16 && n <= TL_NP && !getenv("PLF_NO_TILE") && !q.sum_hess;
     if (use_tile && e->K <= 4096 && !getenv("PLF_NO_TIPTABLE")) {
         /* tip tables (P_e def_k) so that tip children need no GEMM */
         if (ensure_program(e)) return -1;
@@ -1423,6 +1500,66 @@ static int run_generic(plf_engine *e, Query &q)
         CK(e, cudaFuncSetAttribute(tile_outside_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile_out));
     }
 
+    /* second order (plf_hess): tree navigation arrays, per-CTA partial Hessians, the Gram matrix of the derivatives */
+    HessTree ht;
+    memset(&ht, 0, sizeof(ht));
+    int hgrid = 0;
+    const size_t smem_hess = sizeof(double) * ((size_t)3 * n * PLF_TS + E);
+    if (q.sum_hess) {
+        std::vector<int> nav((size_t)3 * E + (size_t)4 * N, 0);
+        int *parent_node = nav.data(), *parent_edge = parent_node + E, *dfs_nodes = parent_edge + N, *dfs_pos = dfs_nodes + N,
+            *sub_end = dfs_pos + N, *sub_max = sub_end + N, *erank = sub_max + E;
+        for (int v = 0; v < N; v++) parent_edge[v] = -1;
+        for (int v = 0; v < N; v++)
+            for (int idx = e->indptr[v]; idx < e->indptr[v + 1]; idx++) { parent_node[idx] = v; parent_edge[e->indices[idx]] = idx; }
+        {
+            /* depth-first pre-order (children in csr order), subtree ends */
+            std::vector<int> st;
+            int pos = 0;
+            st.push_back(e->root);
+            std::vector<int> order;
+            while (!st.empty()) {
+                const int v = st.back(); st.pop_back();
+                dfs_pos[v] = pos; dfs_nodes[pos++] = v;
+                for (int idx = e->indptr[v + 1] - 1; idx >= e->indptr[v]; idx--) st.push_back(e->indices[idx]);
+            }
+            for (int p2 = N - 1; p2 >= 0; p2--) {
+                const int v = dfs_nodes[p2];
+                int end = p2 + 1;
+                for (int idx = e->indptr[v]; idx < e->indptr[v + 1]; idx++) end = std::max(end, sub_end[e->indices[idx]]);
+                sub_end[v] = end;
+            }
+            /* rank of an edge = BFS position of its child (csr indices follow the node labels, not the depth);
+             * largest rank below (and including) every edge, children before parents */
+            for (int u = 0; u < N; u++) { const int pe = parent_edge[e->preorder[u]]; if (pe >= 0) erank[pe] = u; }
+            for (int u = N - 1; u >= 0; u--) {
+                const int v = e->preorder[u], pe = parent_edge[v];
+                if (pe < 0) continue;
+                int mx = erank[pe];
+                for (int i2 = e->indptr[v]; i2 < e->indptr[v + 1]; i2++) mx = std::max(mx, sub_max[i2]);
+                sub_max[pe] = mx;
+            }
+        }
+        ENSURE(e, e->h_tree, sizeof(int) * nav.size());
+        CK(e, cudaMemcpyAsync(e->h_tree.p, nav.data(), sizeof(int) * nav.size(), cudaMemcpyHostToDevice, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+        const int *d = e->h_tree.as<int>();
+        ht.parent_node = d; ht.parent_edge = d + E; ht.dfs_nodes = d + E + N; ht.dfs_pos = d + E + 2 * (size_t)N;
+        ht.sub_end = d + E + 3 * (size_t)N; ht.sub_max = d + E + 4 * (size_t)N; ht.erank = d + 2 * (size_t)E + 4 * (size_t)N;
+        hgrid = (int)std::min<int64_t>((Sc + PLF_TS - 1) / PLF_TS, (int64_t)e->sm_count * 4);
+        while (hgrid > 1 && (size_t)hgrid * E * E * sizeof(double) > ((size_t)2 << 30)) hgrid /= 2;
+        ENSURE(e, e->h_part, sizeof(double) * (size_t)hgrid * E * E + 8);
+        ENSURE(e, e->h_gram, sizeof(double) * (size_t)E * E + 8);
+        ENSURE(e, e->h_out, sizeof(double) * (size_t)E * E + 8);
+        ENSURE(e, e->h_Yg, sizeof(double) * (size_t)C * E * n * Sc + 8);
+        ENSURE(e, e->h_dFg, sizeof(double) * (size_t)N * n * Sc + 8);
+        ENSURE(e, e->h_dFk, sizeof(int) * (size_t)N * Sc + 8);
+        CK(e, cudaMemsetAsync(e->h_part.p, 0, sizeof(double) * (size_t)hgrid * E * E, e->stream));
+        CK(e, cudaMemsetAsync(e->h_gram.p, 0, sizeof(double) * (size_t)E * E, e->stream));
+        if (smem_hess > 227 * 1024) FAIL(e, "state count %d / edge count %d too large for the Hessian kernel", n, E);
+        if (smem_hess > 48 * 1024) CK(e, cudaFuncSetAttribute(generic_hess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_hess));
+    }
+
     for (int64_t s0 = 0; s0 < e->S; s0 += Sc) {
         a.s0 = s0; a.Sc = (int)std::min<int64_t>(Sc, e->S - s0);
         const unsigned gx = (unsigned)((a.Sc + PLF_TS - 1) / PLF_TS);
@@ -1444,6 +1581,11 @@ static int run_generic(plf_engine *e, Query &q)
             wsum_rows_kernel<<<1, 256, 0, e->stream>>>(a.site_ll + s0, w, s0, a.Sc, dsum, e->d_err.as<int>(), 1);
             KCHECK(e);
         }
+        if (!outside) {
+            zero_lik_rows_kernel<<<(a.Sc + 255) / 256, 256, 0, e->stream>>>(a.site_ll + s0, w, s0, a.Sc, e->d_err.as<int>(),
+                                                                            nullptr, 0, nullptr, 0);
+            KCHECK(e);
+        }
         if (outside) {
             if (q.want_edge) CK(e, cudaMemsetAsync(a.edge_out, 0, sizeof(double) * (size_t)E * a.Sc, e->stream));
             if (q.want_marg) CK(e, cudaMemsetAsync(a.marg_out, 0, sizeof(double) * (size_t)N * n * a.Sc, e->stream));
@@ -1455,8 +1597,21 @@ static int run_generic(plf_engine *e, Query &q)
                 generic_outside_kernel<<<gx, PLF_TS, smem_out, e->stream>>>(a);
                 KCHECK(e);
             }
+            zero_lik_rows_kernel<<<(a.Sc + 255) / 256, 256, 0, e->stream>>>(a.site_ll + s0, w, s0, a.Sc, e->d_err.as<int>(),
+                                                                            a.edge_out, q.want_edge ? E : 0, a.marg_out, q.want_marg ? N * n : 0);
+            KCHECK(e);
             if (q.want_edge && q.sum_edge) {
                 wsum_rows_kernel<<<E, 256, 0, e->stream>>>(a.edge_out, w, s0, a.Sc, dsum + 1, e->d_err.as<int>(), 0);
+                KCHECK(e);
+            }
+            if (q.sum_hess) {
+                generic_hess_kernel<<<std::min<int>(hgrid, (int)gx), PLF_TS, smem_hess, e->stream>>>(
+                    a, ht, e->d_qhi.as<double>(), e->d_cat_rates.as<double>(), w, e->h_Yg.as<double>(), e->h_dFg.as<double>(),
+                    e->h_dFk.as<int>(), e->h_part.as<double>(), e->d_err.as<int>());
+                KCHECK(e);
+                const int nb16 = (E + 15) / 16;
+                const int splits = std::max(1, std::min(256, (a.Sc + 4095) / 4096));
+                gram_rows_kernel<<<dim3(nb16, nb16, splits), dim3(16, 16), 0, e->stream>>>(a.edge_out, w, s0, E, a.Sc, e->h_gram.as<double>());
                 KCHECK(e);
             }
             if (q.want_marg && q.sum_marg) {
@@ -1475,14 +1630,27 @@ static int run_generic(plf_engine *e, Query &q)
     }
     const size_t nsum = 1 + E + (size_t)N * n;
     if (finish_sums(e, dsum, nsum)) return -1;
+    if (q.sum_hess) {
+        /* H = sum of the per-CTA parts - Gram matrix of the per-site derivatives (lower triangle, csr order) */
+        sum_rows_kernel<<<(unsigned)(((size_t)E * E + 127) / 128), 128, 0, e->stream>>>(e->h_part.as<double>(), hgrid, E * E, e->h_out.as<double>());
+        KCHECK(e);
+        axpy_kernel<<<(unsigned)(((size_t)E * E + 255) / 256), 256, 0, e->stream>>>(e->h_out.as<double>(), e->h_gram.as<double>(), -1.0, (size_t)E * E);
+        KCHECK(e);
+        if (finish_sums(e, e->h_out.as<double>(), (size_t)E * E)) return -1;
+    }
     CK(e, cudaEventRecord(e->ev[2], e->stream));
     std::vector<double> hs(nsum);
     int herr = 0;
     CK(e, cudaMemcpyAsync(hs.data(), dsum, sizeof(double) * nsum, cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaMemcpyAsync(&herr, e->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     if (q.site_ll) CK(e, cudaMemcpyAsync(q.site_ll, e->d_site_ll.p, sizeof(double) * e->S, cudaMemcpyDeviceToHost, e->stream));
+    if (q.sum_hess) CK(e, cudaMemcpyAsync(q.sum_hess, e->h_out.p, sizeof(double) * (size_t)E * E, cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
-    if (herr && q.sum_ll) FAIL(e, "a site with non-zero weight has zero likelihood");
+    if ((herr & 2) && q.sum_hess) FAIL(e, "infeasible: a rate category with a non-zero rate has zero likelihood at a weighted site");
+    if ((herr & 1) && (q.sum_ll || q.sum_edge || q.sum_marg)) FAIL(e, "a site with non-zero weight has zero likelihood");
+    if (q.sum_hess) {
+        for (int i = 0; i < E; i++) for (int j = 0; j < i; j++) q.sum_hess[(size_t)j * E + i] = q.sum_hess[(size_t)i * E + j];
+    }
     if (q.sum_ll) *q.sum_ll = hs[0];
     if (q.sum_edge) memcpy(q.sum_edge, hs.data() + 1, sizeof(double) * E);
     if (q.sum_marg) memcpy(q.sum_marg, hs.data() + 1 + E, sizeof(double) * (size_t)N * n);
@@ -1526,6 +1694,16 @@ static int ensure_dm_tables(plf_engine *e, int NB, const double *Fm, int f_zero_
             }
         }
         e->dm_out_depth = std::max(depth, 1);
+        /* the program in the compact form the kernels stage in shared memory */
+        std::vector<int4> ops4(e->ops.size()), ch4(e->children.size());
+        for (size_t o = 0; o < e->ops.size(); o++)
+            ops4[o] = make_int4(e->ops[o].first_child, e->ops[o].nchild, e->ops[o].code_row, e->ops[o].spill_before);
+        for (size_t j = 0; j < e->children.size(); j++)
+            ch4[j] = make_int4(e->children[j].kind, e->children[j].mat, e->children[j].code_row, e->children[j].edge);
+        ENSURE(e, e->d_dm_ops, sizeof(int4) * (ops4.size() + 1));
+        ENSURE(e, e->d_dm_ch, sizeof(int4) * (ch4.size() + 1));
+        CK(e, cudaMemcpyAsync(e->d_dm_ops.p, ops4.data(), sizeof(int4) * ops4.size(), cudaMemcpyHostToDevice, e->stream));
+        CK(e, cudaMemcpyAsync(e->d_dm_ch.p, ch4.data(), sizeof(int4) * ch4.size(), cudaMemcpyHostToDevice, e->stream));
         ENSURE(e, e->d_dm_oidx, sizeof(int) * (oidx.size() + 1));
         ENSURE(e, e->d_dm_otr, sizeof(int) * (otr.size() + 1));
         std::vector<double> rootf(W, 0.0);
@@ -1572,10 +1750,11 @@ static int run_dmma(plf_engine *e, Query &q)
     const int nrows = (int)e->code_row_node.size();
 
     /* ring slots that fit beside the warps' code tiles */
-    int R = DM_MAX_R;
-    while (R > 2 && dm_smem_bytes(NB, R, nrows) > 227 * 1024) R--;
-    if (dm_smem_bytes(NB, R, nrows) > 227 * 1024) FAIL(e, "tree too large for the tensor-pipe kernels (%d code rows)", nrows);
-    if (const char *s = getenv("PLF_DM_R")) R = std::max(2, std::min(R, atoi(s)));
+    const int nops = (int)e->ops.size(), nch = (int)e->children.size();
+    int R = 4;      /* measured: more slots buy nothing, and shared memory not used here is L1 for the tip tables */
+    if (const char *s = getenv("PLF_DM_R")) R = std::max(2, std::min(DM_MAX_R, atoi(s)));
+    while (R > 2 && dm_smem_bytes(NB, R, nrows, nops, nch) > 227 * 1024) R--;
+    if (dm_smem_bytes(NB, R, nrows, nops, nch) > 227 * 1024) FAIL(e, "tree too large for the tensor-pipe kernels (%d code rows)", nrows);
 
     /* chunk of sites: the slab of edge vectors (keep mode) is the only large buffer */
     const size_t per_group = q.want_edge ? (size_t)C * Ei * ((size_t)NB * 32 * 16 + 32 * 4) + (size_t)E * 64 : 0;
@@ -1593,8 +1772,8 @@ static int run_dmma(plf_engine *e, Query &q)
     const int64_t ngroups_max = (Sc + 7) / 8;
 
     const int grid_max = e->sm_count;
-    ENSURE(e, e->d_dm_stack, sizeof(double2) * (size_t)grid_max * DM_NW * std::max(1, std::max(e->stack_depth, q.want_edge ? 2 * e->dm_out_depth : 0)) * NB * 32);
-    ENSURE(e, e->d_dm_stackmeta, sizeof(int) * (size_t)grid_max * DM_NW * std::max(1, std::max(e->stack_depth, q.want_edge ? 4 * e->dm_out_depth : 0)) * 32);
+    ENSURE(e, e->d_dm_stack, sizeof(double2) * (size_t)grid_max * DM_GROUPS * std::max(1, std::max(e->stack_depth, q.want_edge ? 2 * e->dm_out_depth : 0)) * NB * 32);
+    ENSURE(e, e->d_dm_stackmeta, sizeof(int) * (size_t)grid_max * DM_GROUPS * std::max(1, std::max(e->stack_depth, q.want_edge ? 4 * e->dm_out_depth : 0)) * 32);
     ENSURE(e, e->g_cat_lh, sizeof(double) * (size_t)C * Sc);
     ENSURE(e, e->g_cat_k, sizeof(int) * (size_t)C * Sc);
     ENSURE(e, e->g_site_m, sizeof(double) * Sc);
@@ -1618,7 +1797,7 @@ static int run_dmma(plf_engine *e, Query &q)
     DmArgs a;
     memset(&a, 0, sizeof(a));
     a.n = n; a.C = C; a.K = e->K;
-    a.nops = (int)e->ops.size(); a.ops = e->d_ops.as<F4Op>(); a.children = e->d_children.as<F4Child>();
+    a.nops = nops; a.nchildren = nch; a.ops4 = e->d_dm_ops.as<int4>(); a.ch4 = e->d_dm_ch.as<int4>();
     a.Ei = Ei; a.Et = Et; a.nrows = nrows; a.code_row_node = e->d_code_row_node.as<int>();
     a.codes = e->d_codes.as<unsigned char>(); a.S = e->S;
     a.def_const = e->d_def_const.as<unsigned char>(); a.defsf = e->d_dm_defsf.as<double>();
@@ -1626,6 +1805,9 @@ static int run_dmma(plf_engine *e, Query &q)
     a.root_const_ok = (e->root_mode == PLF_ROOT_UNIFORM || e->root_mode == PLF_ROOT_EQUILIBRIUM) ? 1 : 0;
     a.cat_lh = e->g_cat_lh.as<double>(); a.cat_k = e->g_cat_k.as<int>();
     a.R = R;
+    a.sg = 1;
+    a.stagger = 3000;
+    if (const char *sg = getenv("PLF_DM_STAGGER")) a.stagger = atoi(sg);
     a.stack = e->d_dm_stack.as<double2>(); a.stack_meta = e->d_dm_stackmeta.as<int>();
     a.Of = e->d_dm_Of.as<double>(); a.TFf = e->d_dmTFf.as<double>();
     a.cat_prior = e->d_cat_prior.as<double>();
@@ -1641,11 +1823,16 @@ static int run_dmma(plf_engine *e, Query &q)
     ga.site_m = e->g_site_m.as<double>(); ga.site_k = e->g_site_k.as<int>(); ga.site_ll = e->d_site_ll.as<double>();
 
     const double *w = e->have_w ? e->d_site_w.as<double>() : nullptr;
+    {
+        char nm[96];
+        snprintf(nm, sizeof nm, q.want_edge ? "dm_inside_kernel<%d,16,1> + dm_outside_kernel<%d,16,1>" : "dm_inside_kernel<%d,16,1>", NB, NB);
+        e->last_kernel = nm;
+    }
     CK(e, cudaEventRecord(e->ev[3], e->stream));
     for (int64_t s0 = 0; s0 < e->S; s0 += Sc) {
         a.s0 = s0; a.Sc = (int)std::min<int64_t>(Sc, e->S - s0);
-        a.ntiles = (a.Sc + DM_TILE - 1) / DM_TILE;
         a.ngroups = (a.Sc + 7) / 8;
+        dm_tiling(a.ngroups, C, grid_max, &a.tiles_full, &a.tail_gs, &a.ntiles);
         a.slab = q.want_edge ? e->d_dm_slab.as<double2>() : nullptr;
         a.slab_meta = q.want_edge ? e->d_dm_slabmeta.as<int>() : nullptr;
         a.stack_depth = std::max(1, e->stack_depth);
@@ -1659,11 +1846,20 @@ static int run_dmma(plf_engine *e, Query &q)
             wsum_rows_kernel<<<1, 256, 0, e->stream>>>(ga.site_ll + s0, w, s0, a.Sc, dsum, e->d_err.as<int>(), 1);
             KCHECK(e);
         }
+        if (!q.want_edge) {
+            zero_lik_rows_kernel<<<(a.Sc + 255) / 256, 256, 0, e->stream>>>(ga.site_ll + s0, w, s0, a.Sc, e->d_err.as<int>(),
+                                                                            nullptr, 0, nullptr, 0);
+            KCHECK(e);
+        }
         if (q.want_edge) {
             CK(e, cudaMemsetAsync(a.edge_out, 0, sizeof(double) * (size_t)E * a.Sc, e->stream));
             a.stack_depth = e->dm_out_depth;
+            dm_tiling(a.ngroups, 1, grid_max, &a.tiles_full, &a.tail_gs, &a.ntiles);
             CK(e, dm_launch_outside(a, NB, std::min(grid_max, a.ntiles), e->stream));
             e->launches++;
+            zero_lik_rows_kernel<<<(a.Sc + 255) / 256, 256, 0, e->stream>>>(ga.site_ll + s0, w, s0, a.Sc, e->d_err.as<int>(),
+                                                                            a.edge_out, E, nullptr, 0);
+            KCHECK(e);
             if (q.sum_edge) {
                 wsum_rows_kernel<<<E, 256, 0, e->stream>>>(a.edge_out, w, s0, a.Sc, dsum + 1, e->d_err.as<int>(), 0);
                 KCHECK(e);
@@ -1685,7 +1881,7 @@ static int run_dmma(plf_engine *e, Query &q)
     CK(e, cudaMemcpyAsync(&herr, e->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     if (q.site_ll) CK(e, cudaMemcpyAsync(q.site_ll, e->d_site_ll.p, sizeof(double) * e->S, cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
-    if (herr && q.sum_ll) FAIL(e, "a site with non-zero weight has zero likelihood");
+    if (herr && (q.sum_ll || q.sum_edge)) FAIL(e, "a site with non-zero weight has zero likelihood");
     if (q.sum_ll) *q.sum_ll = hs[0];
     if (q.sum_edge) memcpy(q.sum_edge, hs.data() + 1, sizeof(double) * E);
     return 0;
@@ -1696,7 +1892,7 @@ static int run_query_once(plf_engine *e, Query &q, bool need_D, const double *l_
 {
     if (e->S == 0 || e->n == 0 || e->N == 0) FAIL(e, "engine is not fully configured (tree, model and data are required)");
     CK(e, cudaSetDevice(e->device));
-    bool use_fused = fused_applicable(e);
+    bool use_fused = fused_applicable(e) && !q.sum_hess;
     /* per-site marginals of a huge alignment: the generic path works in chunks of sites */
     if (q.want_marg && q.site_marg && (size_t)e->N * 4 * e->S * sizeof(double) > ((size_t)32 << 30)) use_fused = false;
     if (e->path == PLF_PATH_GENERIC) use_fused = false;
@@ -1726,7 +1922,8 @@ static int run_query_once(plf_engine *e, Query &q, bool need_D, const double *l_
     if (use_fused && ensure_tip_tables(e, q.want_edge ? q.Fm : nullptr, f_mode, q.want_marg)) return -1;
     CK(e, cudaEventRecord(e->ev[1], e->stream));
     e->kernel_timed = false;
-    int rc = use_fused ? run_fused(e, q) : (e->path != PLF_PATH_GENERIC && dmma_applicable(e, q)) ? run_dmma(e, q) : run_generic(e, q);
+    int rc = use_fused ? run_fused(e, q)
+                       : (e->path != PLF_PATH_GENERIC && !q.sum_hess && dmma_applicable(e, q)) ? run_dmma(e, q) : run_generic(e, q);
     if (rc) return rc;
     cudaEventElapsedTime(&e->ms_mat, e->ev[0], e->ev[1]);
     cudaEventElapsedTime(&e->ms_sites, e->ev[1], e->ev[2]);
@@ -1757,6 +1954,18 @@ extern "C" int plf_deriv(plf_engine *e, const unsigned char *edge_mask, double *
     Query q;
     q.want_edge = true; q.edge_mask_h = edge_mask;
     q.site_ll = site_ll; q.sum_ll = sum_ll; q.site_edge = site_deriv; q.sum_edge = sum_deriv;
+    return run_query(e, q, true, nullptr, nullptr, 0);
+}
+
+extern "C" int plf_hess(plf_engine *e, double *sum_ll, double *sum_deriv, double *sum_hess)
+{
+    if (!e) return -1;
+    if (!sum_hess) FAIL(e, "plf_hess: sum_hess is required");
+    Query q;
+    q.want_edge = true;
+    q.sum_ll = sum_ll; q.sum_edge = sum_deriv; q.sum_hess = sum_hess;
+    std::vector<double> tmp;
+    if (!q.sum_edge) { tmp.resize(e->E > 0 ? e->E : 1); q.sum_edge = tmp.data(); }
     return run_query(e, q, true, nullptr, nullptr, 0);
 }
 
@@ -1824,6 +2033,13 @@ extern "C" int plf_comm_unique_id(char id[128])
     plf_nccl_id u;
     if (g_nccl.GetUniqueId(&u) != 0) return -1;
     memcpy(id, u.internal, 128);
+    return 0;
+}
+
+extern "C" int plf_comm_pause(plf_engine *e, int paused)
+{
+    if (!e) return -1;
+    e->comm_paused = paused != 0;
     return 0;
 }
 

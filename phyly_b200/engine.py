@@ -167,6 +167,12 @@ class Engine:
         self._lib.plf_last_kernel_ms(self._h, ctypes.byref(a))
         return a.value
 
+    def last_kernel_name(self):
+        return (self._lib.plf_last_kernel_name(self._h) or b"").decode()
+
+    def comm_pause(self, paused=True):
+        self._ck(self._lib.plf_comm_pause(self._h, 1 if paused else 0))
+
     def launch_count(self, reset=False):
         return int(self._lib.plf_launch_count(self._h, 1 if reset else 0))
 

@@ -72,6 +72,9 @@ CASES = [
     ("fels_em_full", "em_update", "Felsenstein.2004.fig.16.4/em-update/with.full.data/in.json", "Felsenstein.2004.fig.16.4/em-update/with.full.data/out.json"),
     ("fels_em_leaf", "em_update", "Felsenstein.2004.fig.16.4/em-update/with.leaf.data/in.json", "Felsenstein.2004.fig.16.4/em-update/with.leaf.data/out.json"),
     ("fels_em_none", "em_update", "Felsenstein.2004.fig.16.4/em-update/with.no.data/in.json", "Felsenstein.2004.fig.16.4/em-update/with.no.data/out.json"),
+    ("fels_hess_full", "hess", "Felsenstein.2004.fig.16.4/hess/with.full.data/in.json", "Felsenstein.2004.fig.16.4/hess/with.full.data/out.json"),
+    ("fels_hess_leaf", "hess", "Felsenstein.2004.fig.16.4/hess/with.leaf.data/in.json", "Felsenstein.2004.fig.16.4/hess/with.leaf.data/out.json"),
+    ("fels_hess_none", "hess", "Felsenstein.2004.fig.16.4/hess/with.no.data/in.json", "Felsenstein.2004.fig.16.4/hess/with.no.data/out.json"),
 ]
 
 

@@ -51,6 +51,8 @@ def _paths(m, C, K):
     p = [E.PATH_GENERIC]
     if m.n == 4 and C <= 4 and maxdeg <= 3 and K <= 256:
         p.append(E.PATH_FUSED4)
+    if 16 < m.n <= 64 and K <= 256:
+        p.append(E.PATH_AUTO)           # ll and edge forms on the tensor-pipe kernels (generic = tile / scalar kernels)
     return p
 
 
@@ -70,6 +72,9 @@ RANDOM = [
     dict(seed=10, ntips=40, n=4, S=24, ncat=4, mixture="gamma", edge_scale=0.05),
     dict(seed=11, ntips=6, n=3, S=300, ncat=2, missing=0.5),
     dict(seed=12, ntips=24, n=4, S=70, ncat=2, root="equilibrium_distribution", missing=0.3),
+    # codon- and amino-acid-sized state spaces: the FP64 tensor-pipe kernels (dmma.cu) against the 320-bit oracle
+    dict(seed=13, ntips=4, n=61, S=9, ncat=1, missing=0.15),
+    dict(seed=14, ntips=6, n=20, S=19, ncat=2, missing=0.2, root="equilibrium_distribution"),
 ]
 
 

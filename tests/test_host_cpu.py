@@ -202,12 +202,17 @@ def test_malformed_json_is_rejected():
             A.arbplf_ll(s)
 
 
-def test_unsupported_programs_fail_cleanly():
+def test_second_order_programs_require_site_aggregation():
+    # arbplfhess.c:1162-1207: "site_reduction" is required and must aggregate; rejected before any device work
     import phyly_b200.arbplf as A
     for f in (A.arbplf_hess, A.arbplf_inv_hess, A.arbplf_newton_delta, A.arbplf_newton_update,
               A.arbplf_newton_refine):
         with pytest.raises(RuntimeError):
-            f(json.dumps(GOOD))
+            f(json.dumps({"model_and_data": GOOD["model_and_data"]}))
+        with pytest.raises(RuntimeError):
+            f(json.dumps(dict(GOOD, site_reduction={"selection": [0]})))
+        with pytest.raises(RuntimeError):
+            f(json.dumps(dict(GOOD, site_reduction={"aggregation": "sum"}, edge_reduction={"aggregation": "sum"})))
 
 
 def test_em_update_requires_site_aggregation():

@@ -24,7 +24,7 @@ pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CASES = H.manifest()
-SUPPORTED = {"ll", "deriv", "marginal", "dwell", "trans", "em_update"}
+SUPPORTED = {"ll", "deriv", "marginal", "dwell", "trans", "em_update", "hess"}
 
 # Absolute floors, only where the reference's exact arithmetic cancels to a
 # value far below the magnitude of the terms (see tests/test_engine_gpu.py):
@@ -202,3 +202,71 @@ def test_em_update_against_oracle_with_mixture_and_weights():
         want = O.run("em_update", doc, mode="mp")
         got = _run("em_update", doc)
         _check(got, want, "em_update %s" % json.dumps(red)[:40])
+
+
+# ---------------------------------------------------------------------------
+# second order programs (arbplfhess.c): hess / inv-hess / newton-delta / newton-update against the 320-bit oracle
+# ---------------------------------------------------------------------------
+
+SECOND_ORDER = [
+    dict(seed=21, ntips=5, n=4, S=6, ncat=1),
+    dict(seed=22, ntips=7, n=4, S=9, ncat=3, mixture="gamma", missing=0.2),
+    dict(seed=23, ntips=6, n=4, S=7, ncat=2, root="equilibrium_distribution", root_degree=3, internal_data=True),
+    dict(seed=24, ntips=5, n=3, S=8, ncat=2, root="uniform_distribution"),
+    dict(seed=25, ntips=9, n=4, S=12, ncat=2, mixture="median_inv", max_degree=3),
+    dict(seed=26, ntips=4, n=20, S=5, ncat=1),
+]
+
+
+def _second_order_expected(name, program, doc):
+    return H.expected_json("so_%s_%s" % (program, name), program, doc)
+
+
+@pytest.mark.parametrize("kw", SECOND_ORDER, ids=["random%d" % k["seed"] for k in SECOND_ORDER])
+def test_second_order_programs_against_oracle(kw):
+    prob = H.random_problem(**kw)
+    S = len(prob["model_and_data"].get("probability_array", prob["model_and_data"].get("character_data")))
+    w = [0.5 + (7 * i % 5) for i in range(S)]
+    doc = {"model_and_data": prob["model_and_data"],
+           "site_reduction": {"selection": list(range(S)), "aggregation": w}}
+    name = "random%d" % kw["seed"]
+    for program, rtol in (("hess", 1e-11), ("newton_delta", 1e-9), ("newton_update", 1e-9), ("inv_hess", 1e-9)):
+        got = _run(program, doc)
+        want = _second_order_expected(name, program, doc)
+        # inverse / solve amplify the 1e-13 of the Hessian entries by its condition number: looser, stated bound
+        _check(got, want, "%s %s" % (program, name), rtol=rtol)
+
+
+def test_hess_closed_form_truncated_path():
+    """test_scripts/test_path_exponential_absorbing.py:124-135: two-state path with an absorbing state, last node
+    observed in state 1: every entry of the Hessian is the second derivative of log(1 - exp(-T)), T = total rate."""
+    import math
+    rates = [1.0, 2.0, 3.0]
+    N = len(rates) + 1
+    pa = [[[1, 0]] + [[1, 1]] * (N - 2) + [[0, 1]]]
+    doc = {"model_and_data": {"edges": [[i, i + 1] for i in range(N - 1)], "edge_rate_coefficients": rates,
+                              "rate_matrix": [[0, 1], [0, 0]], "probability_array": pa},
+           "site_reduction": {"aggregation": "sum"}}
+    got = _run("hess", doc)
+    T = sum(rates)
+    want = -math.exp(T) / math.expm1(T) ** 2
+    assert len(got["data"]) == 9
+    for r in got["data"]:
+        assert abs(r[-1] - want) <= 1e-11 * abs(want), (r, want)
+
+
+def test_newton_refine_reaches_a_stationary_point():
+    prob = H.random_problem(seed=22, ntips=7, n=4, S=9, ncat=3, mixture="gamma", missing=0.2)
+    S = len(prob["model_and_data"].get("probability_array", prob["model_and_data"].get("character_data")))
+    doc = {"model_and_data": prob["model_and_data"], "site_reduction": {"aggregation": "sum"}}
+    out = _run("newton_refine", doc)
+    assert out["columns"] == ["edge", "value"]
+    md = json.loads(json.dumps(prob["model_and_data"]))
+    md["edge_rate_coefficients"] = [max(r[-1], 1e-300) for r in out["data"]]
+    g = _run("deriv", {"model_and_data": md, "site_reduction": {"aggregation": "sum"}})
+    ll0 = _run("ll", {"model_and_data": prob["model_and_data"], "site_reduction": {"aggregation": "sum"}})["data"][0][-1]
+    ll1 = _run("ll", {"model_and_data": md, "site_reduction": {"aggregation": "sum"}})["data"][0][-1]
+    assert ll1 >= ll0 - 1e-9
+    # interior coordinates are stationary; a rate pushed to the boundary keeps a non-positive derivative
+    for (e, x), (_, gv) in zip(out["data"], [(r[0], r[-1]) for r in g["data"]]):
+        assert abs(gv) <= 1e-6 * S or (x < 1e-6 and gv <= 1e-6 * S), (e, x, gv)

@@ -3,7 +3,8 @@ Parity at BASELINE.json's sizes, where the 320-bit oracle
   cfg2  1M sites x 64 taxa, GTR+Gamma4: fused kernel vs the C restatement (itself pinned on the
         320-bit oracle, tests/test_oracle_c.py) on ALL sites, plus linearity in the site weights;
   cfg3  HKY85+I marginals on 128 taxa: posterior marginals sum to 1 at every (site, node);
-  cfg4  61-state codon model: generic kernels vs the C restatement, matrices vs scipy expm;
+  cfg4  61-state codon model: tensor-pipe kernels vs the C restatement (16 taxa, and 256 taxa x 100k sites),
+        matrices vs scipy expm;
   cfg5  dwell / trans on the cfg2 model: dwell over all states is exactly the edge (1 per site),
         fused path vs generic path (independent kernels) for a weighted trans direction.
 """
@@ -137,33 +138,9 @@ def test_cfg3_marginals_sum_to_one():
     eng.close()
 
 
-def _codon_model(kappa=2.0, omega=0.5, seed=4):
-    """GY94-style 61-state rate matrix with F3x4 frequencies."""
-    rng = np.random.default_rng(seed)
-    nts = "TCAG"
-    code = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"
-    codons = [(a, b_, c) for a in range(4) for b_ in range(4) for c in range(4)]
-    aa = {cd: code[16 * cd[0] + 4 * cd[1] + cd[2]] for cd in codons}
-    sense = [cd for cd in codons if aa[cd] != "*"]
-    f = rng.dirichlet(np.ones(4) * 5, size=3)
-    pi = np.array([f[0][cd[0]] * f[1][cd[1]] * f[2][cd[2]] for cd in sense])
-    pi /= pi.sum()
-    n = len(sense)
-    Q = np.zeros((n, n))
-    transitions = {(0, 1), (1, 0), (2, 3), (3, 2)}       # T<->C, A<->G
-    for i, ci in enumerate(sense):
-        for j, cj in enumerate(sense):
-            diff = [k for k in range(3) if ci[k] != cj[k]]
-            if len(diff) != 1:
-                continue
-            k = diff[0]
-            r = pi[j]
-            if (ci[k], cj[k]) in transitions:
-                r *= kappa
-            if aa[ci] != aa[cj]:
-                r *= omega
-            Q[i, j] = r
-    return Q, pi
+def _codon_model(**kw):
+    """GY94-style 61-state rate matrix with F3x4 frequencies; bench.py owns the definition."""
+    return _bench().codon_model(**kw)
 
 
 def test_cfg4_codon_generic_path_against_c_port():
@@ -211,12 +188,76 @@ def test_cfg4_codon_generic_path_against_c_port():
                                             s["root_mode"], np.array(s["root_vec"]), codes, defs, w=w)
     np.testing.assert_allclose(site_ll, ref_ll, rtol=1e-11)
     assert abs(r["sum_ll"] - sum_ll) <= 1e-11 * abs(sum_ll)
-    np.testing.assert_allclose(r["sum_deriv"], sum_d, rtol=1e-10, atol=1e-10 * np.abs(sum_d).max())
+    np.testing.assert_allclose(r["sum_deriv"], sum_d, rtol=1e-11, atol=1e-12 * np.abs(sum_d).max())
+    # the same through the tile / scalar kernels (forced generic path)
+    from phyly_b200 import engine as E
+    eng.set_path(E.PATH_GENERIC)
+    rg = eng.deriv(per_site=False)
+    np.testing.assert_allclose(rg["sum_deriv"], sum_d, rtol=1e-11, atol=1e-12 * np.abs(sum_d).max())
+    eng.close()
+
+
+def test_cfg4_full_size_against_c_port():
+    """BASELINE cfg4 at its full size: 61-state codon model, 256 taxa x 100 000 sites (deep-tree rescaling inside the
+    tensor-pipe kernels, ragged tiles, the evenly spread last wave).  Per-site ll of a fixed 1000-site subsample and
+    the derivative sums over that subsample against the C restatement at 1e-11; all sites through linearity."""
+    import phyly_b200.arbplf as A
+    from oracle import c_port
+    from phyly_b200.engine import Engine
+    b = _bench()
+    Q, pi = _codon_model()
+    n = Q.shape[0]
+    taxa, S = 256, 100000
+    edges, N = b.yule_tree(taxa, seed=21)
+    rng = np.random.default_rng(23)
+    defs = np.vstack([np.eye(n), np.ones((1, n))])
+    md = {"edges": edges, "edge_rate_coefficients": [float(x) for x in rng.exponential(0.05, len(edges))],
+          "rate_matrix": Q.tolist(), "root_prior": "equilibrium_distribution", "rate_divisor": "equilibrium_exit_rate",
+          "character_definitions": defs.tolist(), "character_data": [[n] * N]}
+    s = json.loads(A.arbplf_model_summary(json.dumps({"model_and_data": md})))
+    eng = Engine(0)
+    eng.set_tree(s["indptr"], s["indices"], s["preorder"])
+    eng.set_model(np.array(s["q_hi"]).reshape(n, n), np.array(s["q_lo"]).reshape(n, n), s["edge_rates_csr"], s["cat_rates"],
+                  s["cat_prior"], s["root_mode"], s["root_vec"])
+    P = eng.transition_matrices()
+    D = eng.derivative_matrices()
+    # columns evolved down the tree (realistic, deep underflow): 25 000 simulated, repeated with fresh missing data
+    base = np.full((S // 4, N), n, dtype=np.uint8)
+    b.simulate_codes(s, P, S // 4, seed=24, out=base, pi=np.array(s["equilibrium"]), missing=0.0)
+    codes = np.tile(base, (4, 1))
+    leaves = np.array([a for a in range(N) if s["indptr"][a] == s["indptr"][a + 1]])
+    sub = codes[:, leaves]
+    sub[rng.random(sub.shape) < 0.02] = n
+    codes[:, leaves] = sub
+    eng.set_data(defs, codes)
+    idx = np.sort(rng.choice(S, 1000, replace=False))
+    w = np.zeros(S)
+    w[idx] = 1.0 + rng.poisson(3.0, idx.size)
+    eng.set_site_weights(w)
+    r = eng.deriv(per_site=False)
+    site_ll, tot = eng.ll()
+    assert site_ll.min() < -700.0                           # below the double range as a plain product
+    ref_ll, sum_ll, sum_d = c_port.ll_deriv(s["indptr"], s["indices"], s["preorder"], P, D, np.array(s["cat_prior"]),
+                                            s["root_mode"], np.array(s["root_vec"]), codes[idx], defs, w=w[idx])
+    np.testing.assert_allclose(site_ll[idx], ref_ll, rtol=1e-11)
+    assert abs(r["sum_ll"] - sum_ll) <= 1e-11 * abs(sum_ll)
+    assert abs(tot - sum_ll) <= 1e-11 * abs(sum_ll)
+    np.testing.assert_allclose(r["sum_deriv"], sum_d, rtol=1e-11, atol=1e-12 * np.abs(sum_d).max())
+    # every site: the two halves of a random split add up to the whole (ll and derivative sums)
+    wa = 1.0 + rng.poisson(2.0, S).astype(np.float64)
+    w1 = wa * (rng.random(S) < 0.5)
+    eng.set_site_weights(wa); ra = eng.deriv(per_site=False)
+    eng.set_site_weights(w1); r1 = eng.deriv(per_site=False)
+    eng.set_site_weights(wa - w1); r2 = eng.deriv(per_site=False)
+    assert abs(r1["sum_ll"] + r2["sum_ll"] - ra["sum_ll"]) <= 1e-12 * abs(ra["sum_ll"])
+    scale = np.abs(ra["sum_deriv"]).max()
+    assert np.all(np.abs(r1["sum_deriv"] + r2["sum_deriv"] - ra["sum_deriv"]) <= 1e-11 * np.abs(ra["sum_deriv"]) + 1e-12 * scale)
+    assert abs(np.dot(wa, site_ll) - ra["sum_ll"]) <= 1e-12 * abs(ra["sum_ll"])
     eng.close()
 
 
 def test_amino_acid_sized_model_against_c_port():
-    """A 20-state reversible model (the 32-row instantiation of the DMMA tile kernels): ll, ll+deriv and
+    """A 20-state reversible model (3 state blocks in the tensor-pipe kernels of dmma.cu): ll, ll+deriv and
     marginals on a 40-taxon tree against the C restatement / the independent scalar kernels."""
     import phyly_b200.arbplf as A
     from oracle import c_port
@@ -258,7 +299,7 @@ def test_amino_acid_sized_model_against_c_port():
                                             s["root_mode"], np.array(s["root_vec"]), codes, defs, w=w)
     np.testing.assert_allclose(site_ll, ref_ll, rtol=1e-11)
     assert abs(r["sum_ll"] - sum_ll) <= 1e-11 * abs(sum_ll)
-    np.testing.assert_allclose(r["sum_deriv"], sum_d, rtol=1e-10, atol=1e-10 * np.abs(sum_d).max())
+    np.testing.assert_allclose(r["sum_deriv"], sum_d, rtol=1e-11, atol=1e-12 * np.abs(sum_d).max())
     # marginals: tile kernels against the scalar generic kernels (PLF_NO_TILE is read per query)
     sm, tot = eng.marginal()
     np.testing.assert_allclose(sm.sum(axis=2), 1.0, rtol=0, atol=1e-12)
@@ -268,8 +309,8 @@ def test_amino_acid_sized_model_against_c_port():
         r_g = eng.deriv(per_site=False)
     finally:
         del os.environ["PLF_NO_TILE"]
-    np.testing.assert_allclose(sm, sm_g, rtol=1e-10, atol=1e-13)
-    np.testing.assert_allclose(r["sum_deriv"], r_g["sum_deriv"], rtol=1e-10, atol=1e-10 * np.abs(sum_d).max())
+    np.testing.assert_allclose(sm, sm_g, rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(r["sum_deriv"], r_g["sum_deriv"], rtol=1e-11, atol=1e-12 * np.abs(sum_d).max())
     eng.close()
 
 
