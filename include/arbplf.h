@@ -39,6 +39,9 @@ char *arbplf_dwell(const char *json_in, int *retcode);
 char *arbplf_trans(const char *json_in, int *retcode);
 char *arbplf_em_update(const char *json_in, int *retcode);
 
+/* arbplf-ll answered with an enclosure {"lower": table, "upper": table} (certified mode, directed rounding) */
+char *arbplf_ll_certified(const char *json_in, int *retcode);
+
 char *arbplf_hess(const char *json_in, int *retcode);
 char *arbplf_inv_hess(const char *json_in, int *retcode);
 char *arbplf_newton_delta(const char *json_in, int *retcode);

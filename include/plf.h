@@ -105,6 +105,16 @@ int plf_set_data_async(plf_engine *e, int64_t site_count, int def_count,
                        const double *defs /*[K][n]*/, const void *codes /*[S][N]*/, int code_bytes,
                        const double *site_weights /*[S] or NULL*/);
 
+/*
+ * Site-pattern compression (the reference leaves it to its input generators, examples/BEAST.GTRG/mknuc.py:57-66):
+ * identical rows of codes[S][N] are merged.  Patterns come out in order of first occurrence: codes_out[P][N] (room for
+ * S rows), counts_out[P] their multiplicities (the site weights of the compressed alignment), site_to_pattern[S] the
+ * pattern of every site (scatter-back map when the site axis is kept).  Outputs other than n_patterns may be NULL.
+ * Hash + full row comparison on the device; integer results, identical to the oracle's.
+ */
+int plf_compress_patterns(plf_engine *e, int64_t site_count, int node_count, const void *codes, int code_bytes,
+                          int64_t *n_patterns, void *codes_out, int64_t *counts_out, int64_t *site_to_pattern);
+
 /* Per-site weights used by the *_sum outputs (NULL = all ones).  reduction.c:24-118. */
 int plf_set_site_weights(plf_engine *e, const double *w /*[S] or NULL*/);
 
@@ -118,6 +128,17 @@ int plf_ll(plf_engine *e, double *site_ll, double *sum);
  */
 int plf_deriv(plf_engine *e, const unsigned char *edge_mask,
               double *site_ll, double *sum_ll, double *site_deriv, double *sum_deriv);
+
+/*
+ * Certified mode: enclosures site_lo[s] <= log L_s <= site_hi[s] computed with directed rounding (interval arithmetic
+ * on the pruning recursion and on the matrix exponentials; csrc/certified.cuh), in place of the reference's Arb balls
+ * (util.c:12-50, arbplfll.c:206-224).  Rigorous for inputs within the stated relative uncertainties: delta_rate on
+ * rate_c * t_e and on an equilibrium root prior (the host's gamma quantiles / linear solve are accurate to 1e-14, not
+ * certified; 4e-15 is the documented default), delta_q on the scaled rate matrix and the derived category priors
+ * (2^-60).  sum_lo / sum_hi enclose sum_s w_s log L_s.  Any output may be NULL.
+ */
+int plf_ll_certified(plf_engine *e, double delta_rate, double delta_q, double *site_lo, double *site_hi,
+                     double *sum_lo, double *sum_hi);
 
 /*
  * Second order (arbplfhess.c:502-829): sum_ll = sum_s w_s log L_s, sum_deriv[E] its gradient and sum_hess[E][E] its

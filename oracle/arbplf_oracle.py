@@ -1616,6 +1616,30 @@ def run_newton_update(root, mode="mp"):
     return _edge_table(m, be, [x[i] + d[i] for i in range(len(d))])
 
 
+def compress_patterns(codes):
+    """
+    Site-pattern compression as the reference's input generators do it
+    (examples/BEAST.GTRG/mknuc.py:57-66: an insertion-ordered dictionary
+    column -> count): patterns in order of first occurrence, their counts, and
+    the pattern index of every site.  Returns (patterns[P,N], counts[P], site_to_pattern[S]).
+    """
+    codes = np.asarray(codes)
+    seen = {}
+    counts = []
+    smap = np.empty(codes.shape[0], dtype=np.int64)
+    for s_, row in enumerate(map(bytes, np.ascontiguousarray(codes))):
+        k = seen.get(row)
+        if k is None:
+            k = seen[row] = len(counts)
+            counts.append(0)
+        counts[k] += 1
+        smap[s_] = k
+    first = np.full(len(counts), -1, dtype=np.int64)
+    for s_ in range(codes.shape[0] - 1, -1, -1):
+        first[smap[s_]] = s_
+    return codes[first], np.array(counts, dtype=np.int64), smap
+
+
 PROGRAMS = {
     "ll": run_ll,
     "deriv": run_deriv,

@@ -56,6 +56,12 @@ def load():
     lib.plf_last_kernel_name.restype = c.c_char_p
     lib.plf_comm_pause.argtypes = [P, c.c_int]
     lib.plf_comm_pause.restype = c.c_int
+    lib.plf_compress_patterns.argtypes = [P, c.c_int64, c.c_int, P, c.c_int, c.POINTER(c.c_int64), P, P, P]
+    lib.plf_compress_patterns.restype = c.c_int
+    lib.plf_ll_certified.argtypes = [P, c.c_double, c.c_double, P, P, P, P]
+    lib.plf_ll_certified.restype = c.c_int
+    lib.plf_hess.argtypes = [P, P, P, P]
+    lib.plf_hess.restype = c.c_int
     lib.plf_comm_unique_id.argtypes = [c.c_char_p]
     lib.plf_comm_init.argtypes = [P, c.c_int, c.c_int, c.c_char_p]
     lib.plf_stream.argtypes = [P]

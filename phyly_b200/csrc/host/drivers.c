@@ -585,6 +585,66 @@ done:
 }
 
 /* ------------------------------------------------------------------ */
+/* arbplf-ll, certified mode                                           */
+/* ------------------------------------------------------------------ */
+
+/*
+ * The same request as arbplf-ll, answered with an enclosure: {"lower": <table>, "upper": <table>}, both tables in the
+ * format of arbplf-ll, lower <= log-likelihood <= upper entry by entry (directed rounding on the device,
+ * csrc/certified.cuh).  The reference certifies every output through Arb balls (arbplfll.c:206-224); this is the fp64
+ * counterpart for the log-likelihood.  Weighted aggregation with negative weights swaps the bounds of those sites.
+ */
+char *arbplf_ll_certified(const char *json_in, int *retcode)
+{
+    static const char *const keys[] = {"model_and_data", "?site_reduction", NULL};
+    const jv *v[2];
+    ctx c;
+    reduction r_site; reduction_init(&r_site);
+    axis ax[1]; memset(ax, 0, sizeof ax);
+    double *lo = NULL, *hi = NULL, *slo = NULL, *shi = NULL;
+    char *out = NULL, *t_lo = NULL, *t_hi = NULL;
+    int rc = -1;
+    if (ctx_parse(&c, json_in, keys, v)) goto done;
+    const int64_t S = c.m.S;
+    if (reduction_parse(&r_site, (int)S, "site", v[1])) goto done;
+    if (axis_init(&ax[0], "site", (int)S, &r_site)) goto done;
+    lo = calloc(ax[0].aggregated ? 1 : (S > 0 ? S : 1), sizeof(double));
+    hi = calloc(ax[0].aggregated ? 1 : (S > 0 ? S : 1), sizeof(double));
+    if (S > 0) {
+        if (ctx_load(&c)) goto done;
+        const double d_rate = 4e-15, d_q = 8.673617379884035e-19;       /* 2^-60 */
+        if (ax[0].aggregated) {
+            if (plf_set_site_weights(c.e, ax[0].w) || plf_ll_certified(c.e, d_rate, d_q, NULL, NULL, &lo[0], &hi[0])) {
+                fprintf(stderr, "error: %s\n", plf_last_error(c.e)); goto done;
+            }
+        } else {
+            slo = malloc(sizeof(double) * S); shi = malloc(sizeof(double) * S);
+            if (plf_set_site_weights(c.e, NULL) || plf_ll_certified(c.e, d_rate, d_q, slo, shi, NULL, NULL)) {
+                fprintf(stderr, "error: %s\n", plf_last_error(c.e)); goto done;
+            }
+            for (int64_t s = 0; s < S; s++) {
+                if (!ax[0].requested[s]) continue;
+                if (!isfinite(slo[s]) || !isfinite(shi[s])) { fprintf(stderr, "error: site %lld has zero likelihood\n", (long long)s); goto done; }
+                lo[s] = slo[s]; hi[s] = shi[s];
+            }
+        }
+    }
+    phase_compute_done(&c);
+    t_lo = table_to_json(ax, 1, lo);
+    t_hi = table_to_json(ax, 1, hi);
+    {
+        jbuf b; jbuf_init(&b);
+        jbuf_puts(&b, "{\"lower\": "); jbuf_puts(&b, t_lo); jbuf_puts(&b, ", \"upper\": "); jbuf_puts(&b, t_hi); jbuf_puts(&b, "}");
+        out = jbuf_take(&b);
+    }
+    rc = 0;
+done:
+    free(lo); free(hi); free(slo); free(shi); free(t_lo); free(t_hi);
+    axis_clear(&ax[0]); reduction_clear(&r_site);
+    return finish(&c, out, rc, retcode);
+}
+
+/* ------------------------------------------------------------------ */
 /* second order programs (arbplfhess.c)                                */
 /* ------------------------------------------------------------------ */
 

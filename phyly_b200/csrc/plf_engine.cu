@@ -26,6 +26,9 @@
 #include "fused4_args.h"
 #include "tile.cuh"
 #include "dmma.h"
+#include "compress.cuh"
+#include "certified.cuh"
+#include <cfenv>
 
 /* ------------------------------------------------------------------ */
 /* small utilities                                                     */
@@ -85,6 +88,8 @@ struct NcclApi {
 };
 static NcclApi g_nccl;
 
+struct Cand { int bd, staged; bool pack, cm; f4_kernel_t k; size_t smem; int per_sm; bool gstack; };
+
 struct plf_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -136,11 +141,14 @@ struct plf_engine {
     uint64_t program_version = 0, f4_tuned_version[3] = {~(uint64_t)0, ~(uint64_t)0, ~(uint64_t)0};   /* ll, edge forms, marginals */
     size_t f4_tuned_pick[3] = {0, 0, 0};
     int f4_tuned_C[3] = {0, 0, 0}, f4_tuned_K[3] = {0, 0, 0};
+    std::string f4_cand_key[3];
+    std::vector<Cand> f4_cands[3];
 
     /* scratch */
     DevBuf d_scratch, d_scratchS, d_block_ll, d_block_edge, d_edge_site, d_sum, d_site_ll, d_err, d_mask, d_retry;
     DevBuf g_Lg, g_Kg, g_Cg, g_Eg, g_Fg, g_FK, g_cat_lh, g_cat_k, g_site_m, g_site_k, g_edge_out, g_marg_out, g_tr;
     DevBuf h_Yg, h_dFg, h_dFk, h_part, h_gram, h_tree, h_out;
+    DevBuf c_Plo, c_Phi, c_ws, c_cat_hi, c_site_lo, c_site_hi, c_small;
 
     /* timing / accounting */
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -1065,9 +1073,16 @@ static int run_fused(plf_engine *e, Query &q)
 
     /* candidate configurations (block size, which tables are staged in shared memory, packed codes, matrices
      * in constant memory), preferred first.  PLF_F4_CONFIG=<index> forces one (tuning aid, edge queries). */
-    struct Cand { int bd, staged; bool pack, cm; f4_kernel_t k; size_t smem; int per_sm; bool gstack; };
+    /* the candidates that fit (shared memory, occupancy) depend only on the program, the model's shape and the query
+     * kind: scanned once and remembered -- the occupancy queries of a dozen instantiations cost more host time per
+     * query than the matrix kernels take on the device */
+    const int tm0 = marg ? 2 : (edge ? 1 : 0);
+    const char *force0 = getenv(marg ? "PLF_F4_CONFIG_MARG" : (edge ? "PLF_F4_CONFIG" : "PLF_F4_CONFIG_LL"));
+    const std::string cand_key = std::to_string(e->program_version) + "/" + std::to_string(e->C) + "/" + std::to_string(e->K) + "/" +
+                                 std::to_string(e->E) + "/" + (force0 ? force0 : "");
     std::vector<Cand> viable;
-    {
+    if (e->f4_cand_key[tm0] == cand_key) viable = e->f4_cands[tm0];
+    if (viable.empty()) {
         const size_t smem_cap = 227 * 1024;
         const bool can_pack = e->K <= 16;
         bool can_cm = (size_t)e->C * e->edge_of_int.size() * 16 <= F4_CM_MAXD && e->ops.size() <= F4_CM_MAXOPS &&
@@ -1132,6 +1147,8 @@ static int run_fused(plf_engine *e, Query &q)
             if (c.per_sm >= 1) viable.push_back(c);
         }
         if (viable.empty()) FAIL(e, "fused kernel: no configuration fits (C = %d, %zu bytes of shared memory)", e->C, smem);
+        e->f4_cand_key[tm0] = cand_key;
+        e->f4_cands[tm0] = viable;
     }
     /* one launch per chunk of sites: a single chunk normally, the upload's chunks while it is still in flight */
     const bool pipelined = e->pend_active;
@@ -2019,6 +2036,202 @@ extern "C" int plf_get_frechet_matrices(plf_engine *e, const double *l_hi, const
     ENSURE(e, e->d_F, sizeof(double) * (size_t)e->C * e->E * e->n * e->n);
     if (run_expm(e, nullptr, nullptr, e->d_F.as<double>(), 0, nullptr, e->d_lhi.as<double>(), e->d_llo.as<double>())) return -1;
     CK(e, cudaMemcpyAsync(f_out, e->d_F.p, sizeof(double) * (size_t)e->C * e->E * e->n * e->n, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* certified mode                                                      */
+/* ------------------------------------------------------------------ */
+
+/* v (1 - d) rounded down / v (1 + d) rounded up, for v >= 0 */
+static double cert_lo_h(double v, double d) { return v <= 0.0 ? 0.0 : std::nextafter(v * (1.0 - d), -INFINITY); }
+static double cert_hi_h(double v, double d) { return v <= 0.0 ? 0.0 : std::nextafter(v * (1.0 + d), INFINITY); }
+
+extern "C" int plf_ll_certified(plf_engine *e, double delta_rate, double delta_q, double *site_lo, double *site_hi,
+                                double *sum_lo, double *sum_hi)
+{
+    if (!e) return -1;
+    if (e->S == 0 || e->n == 0 || e->N == 0) FAIL(e, "engine is not fully configured (tree, model and data are required)");
+    if (!(delta_rate >= 0.0) || !(delta_q >= 0.0) || delta_rate > 1e-3 || delta_q > 1e-3) FAIL(e, "plf_ll_certified: bad input uncertainties");
+    CK(e, cudaSetDevice(e->device));
+    if (resolve_pending(e)) return -1;
+    const int n = e->n, C = e->C, N = e->N, E = e->E;
+    const size_t nn = (size_t)n * n;
+    ENSURE(e, e->c_Plo, sizeof(double) * C * E * nn + 8);
+    ENSURE(e, e->c_Phi, sizeof(double) * C * E * nn + 8);
+    ENSURE(e, e->c_ws, sizeof(double) * C * E * 8 * nn + 8);
+    if (E > 0) {
+        cert_expm_kernel<<<dim3(E, C), 128, 0, e->stream>>>(n, E, C, e->d_qhi.as<double>(), e->d_qlo.as<double>(), e->d_edge_rates.as<double>(),
+                                                            e->d_cat_rates.as<double>(), delta_rate, delta_q, e->c_ws.as<double>(),
+                                                            e->c_Plo.as<double>(), e->c_Phi.as<double>());
+        KCHECK(e);
+    }
+    /* enclosures of the root weights and of the category priors (exact when they are the user's own numbers) */
+    std::vector<double> small(2 * (size_t)n + 2 * (size_t)C);
+    double *rlo = small.data(), *rhi = rlo + n, *plo = rhi + n, *phi = plo + C;
+    for (int i = 0; i < n; i++) {
+        if (e->root_mode == PLF_ROOT_NONE) { rlo[i] = rhi[i] = 1.0; }
+        else if (e->root_mode == PLF_ROOT_UNIFORM) { rlo[i] = std::nextafter(1.0 / n, 0.0); rhi[i] = std::nextafter(1.0 / n, 1.0); }
+        else if (e->root_mode == PLF_ROOT_CUSTOM) { rlo[i] = rhi[i] = e->root_vec[i]; }
+        else { rlo[i] = cert_lo_h(e->root_vec[i], delta_rate); rhi[i] = cert_hi_h(e->root_vec[i], delta_rate); }
+    }
+    for (int c = 0; c < C; c++) { plo[c] = cert_lo_h(e->cat_prior[c], delta_q); phi[c] = cert_hi_h(e->cat_prior[c], delta_q); }
+    ENSURE(e, e->c_small, sizeof(double) * small.size());
+    CK(e, cudaMemcpyAsync(e->c_small.p, small.data(), sizeof(double) * small.size(), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+
+    const size_t per_site = (size_t)C * ((size_t)2 * N * n * 8 + (size_t)N * 5 + 24) + 16;
+    size_t free_b = 0, total_b = 0;
+    CK(e, cudaMemGetInfo(&free_b, &total_b));
+    const size_t budget = std::min<size_t>((size_t)24 << 30, free_b / 2 + e->g_Lg.cap + e->g_Fg.cap);
+    int64_t Sc = std::max<int64_t>(CERT_TS, std::min<int64_t>(e->S, (int64_t)(budget / per_site)));
+    Sc = std::min<int64_t>(Sc, 1 << 20);
+    if (Sc < e->S) Sc = (Sc / CERT_TS) * CERT_TS;
+    ENSURE(e, e->g_Lg, sizeof(double) * (size_t)C * N * n * Sc);
+    ENSURE(e, e->g_Fg, sizeof(double) * (size_t)C * N * n * Sc);
+    ENSURE(e, e->g_Kg, sizeof(int) * (size_t)C * N * Sc);
+    ENSURE(e, e->g_Cg, (size_t)C * N * Sc);
+    ENSURE(e, e->g_cat_lh, sizeof(double) * (size_t)C * Sc);
+    ENSURE(e, e->c_cat_hi, sizeof(double) * (size_t)C * Sc);
+    ENSURE(e, e->g_cat_k, sizeof(int) * (size_t)C * Sc);
+    ENSURE(e, e->c_site_lo, sizeof(double) * e->S);
+    ENSURE(e, e->c_site_hi, sizeof(double) * e->S);
+
+    CertArgs a;
+    memset(&a, 0, sizeof(a));
+    a.t.N = N; a.t.E = E; a.t.root = e->root;
+    a.t.indptr = e->d_indptr.as<int>(); a.t.indices = e->d_indices.as<int>(); a.t.preorder = e->d_preorder.as<int>();
+    a.t.node_has_data = e->d_node_has_data.as<unsigned char>();
+    a.n = n; a.C = C; a.K = e->K; a.S = e->S;
+    a.codes = e->d_codes.p; a.code_bytes = e->code_bytes;
+    a.defs = e->d_defs.as<double>(); a.def_const = e->d_def_const.as<unsigned char>();
+    a.Plo = e->c_Plo.as<double>(); a.Phi = e->c_Phi.as<double>();
+    a.root_mode = e->root_mode;
+    a.root_lo = e->c_small.as<double>(); a.root_hi = a.root_lo + n; a.prior_lo = a.root_hi + n; a.prior_hi = a.prior_lo + C;
+    a.Llo = e->g_Lg.as<double>(); a.Lhi = e->g_Fg.as<double>(); a.Kg = e->g_Kg.as<int>(); a.Cg = e->g_Cg.as<unsigned char>();
+    a.cat_lo = e->g_cat_lh.as<double>(); a.cat_hi = e->c_cat_hi.as<double>(); a.cat_k = e->g_cat_k.as<int>();
+    a.site_lo = e->c_site_lo.as<double>(); a.site_hi = e->c_site_hi.as<double>();
+    const size_t smem = sizeof(double) * 4 * n * CERT_TS;
+    if (smem > 227 * 1024) FAIL(e, "state count %d is too large for the certified kernels", n);
+    if (smem > 48 * 1024) CK(e, cudaFuncSetAttribute(cert_inside_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    e->last_kernel = "cert_expm_kernel + cert_inside_kernel";
+    for (int64_t s0 = 0; s0 < e->S; s0 += Sc) {
+        a.s0 = s0; a.Sc = (int)std::min<int64_t>(Sc, e->S - s0);
+        cert_inside_kernel<<<dim3((a.Sc + CERT_TS - 1) / CERT_TS, C), CERT_TS, smem, e->stream>>>(a);
+        KCHECK(e);
+        cert_site_kernel<<<(a.Sc + 255) / 256, 256, 0, e->stream>>>(a);
+        KCHECK(e);
+    }
+    std::vector<double> lo_h, hi_h;
+    double *lo_p = site_lo, *hi_p = site_hi;
+    if (!lo_p) { lo_h.resize(e->S); lo_p = lo_h.data(); }
+    if (!hi_p) { hi_h.resize(e->S); hi_p = hi_h.data(); }
+    CK(e, cudaMemcpyAsync(lo_p, e->c_site_lo.p, sizeof(double) * e->S, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaMemcpyAsync(hi_p, e->c_site_hi.p, sizeof(double) * e->S, cudaMemcpyDeviceToHost, e->stream));
+    std::vector<double> w_h;
+    if (e->have_w && (sum_lo || sum_hi)) {
+        w_h.resize(e->S);
+        CK(e, cudaMemcpyAsync(w_h.data(), e->d_site_w.p, sizeof(double) * e->S, cudaMemcpyDeviceToHost, e->stream));
+    }
+    CK(e, cudaStreamSynchronize(e->stream));
+    if (sum_lo || sum_hi) {
+        /* weighted sums of the enclosures with the host's rounding mode set for each bound */
+        const int old = fegetround();
+        volatile double acc_lo = 0.0, acc_hi = 0.0;
+        bool bad = false;
+        fesetround(FE_DOWNWARD);
+        for (int64_t i = 0; i < e->S; i++) {
+            const double w = w_h.empty() ? 1.0 : w_h[i];
+            if (w == 0.0) continue;
+            volatile double term = w * (w > 0.0 ? lo_p[i] : hi_p[i]);
+            if (!std::isfinite(term)) bad = true;
+            acc_lo = acc_lo + term;
+        }
+        fesetround(FE_UPWARD);
+        for (int64_t i = 0; i < e->S; i++) {
+            const double w = w_h.empty() ? 1.0 : w_h[i];
+            if (w == 0.0) continue;
+            volatile double term = w * (w > 0.0 ? hi_p[i] : lo_p[i]);
+            if (!std::isfinite(term)) bad = true;
+            acc_hi = acc_hi + term;
+        }
+        fesetround(old);
+        if (bad) FAIL(e, "a site with non-zero weight has zero likelihood");
+        if (sum_lo) *sum_lo = acc_lo;
+        if (sum_hi) *sum_hi = acc_hi;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* site-pattern compression                                            */
+/* ------------------------------------------------------------------ */
+
+extern "C" int plf_compress_patterns(plf_engine *e, int64_t S, int N, const void *codes, int code_bytes,
+                                     int64_t *n_patterns, void *codes_out, int64_t *counts_out, int64_t *site_to_pattern)
+{
+    if (!e) return -1;
+    if (S < 0 || N <= 0 || !codes || !n_patterns) FAIL(e, "plf_compress_patterns: bad arguments");
+    if (code_bytes != 1 && code_bytes != 4) FAIL(e, "plf_compress_patterns: code_bytes must be 1 or 4");
+    if (S >= ((int64_t)1 << 31) - 1) FAIL(e, "plf_compress_patterns: more than 2^31 - 2 sites");
+    *n_patterns = 0;
+    if (S == 0) return 0;
+    CK(e, cudaSetDevice(e->device));
+    const int row_bytes = N * code_bytes;
+    size_t M = 1;
+    while (M < (size_t)S * 2) M <<= 1;
+    DevBuf d_in, d_table, d_first, d_slot, d_flags, d_scan, d_bsum, d_map, d_counts, d_out, d_total;
+    const int nblocks = (int)((S + 1023) / 1024);
+    ENSURE(e, d_in, (size_t)S * row_bytes);
+    ENSURE(e, d_table, sizeof(int) * M);
+    ENSURE(e, d_first, sizeof(int) * M);
+    ENSURE(e, d_slot, sizeof(int) * S);
+    ENSURE(e, d_flags, sizeof(int) * S);
+    ENSURE(e, d_scan, sizeof(int) * S);
+    ENSURE(e, d_bsum, sizeof(int) * (nblocks + 1));
+    ENSURE(e, d_map, sizeof(int) * S);
+    ENSURE(e, d_counts, sizeof(int) * S);
+    ENSURE(e, d_out, (size_t)S * row_bytes);
+    ENSURE(e, d_total, sizeof(int));
+    CK(e, cudaMemcpyAsync(d_in.p, codes, (size_t)S * row_bytes, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaMemsetAsync(d_table.p, 0xFF, sizeof(int) * M, e->stream));          /* PC_EMPTY */
+    CK(e, cudaMemsetAsync(d_first.p, 0x7F, sizeof(int) * M, e->stream));          /* large */
+    CK(e, cudaMemsetAsync(d_counts.p, 0, sizeof(int) * S, e->stream));
+    const unsigned gs = (unsigned)((S + 255) / 256);
+    pc_insert_kernel<<<gs, 256, 0, e->stream>>>(d_in.as<unsigned char>(), S, row_bytes, d_table.as<int>(), (unsigned long long)(M - 1), d_slot.as<int>());
+    KCHECK(e);
+    pc_first_kernel<<<gs, 256, 0, e->stream>>>(S, d_slot.as<int>(), d_first.as<int>());
+    KCHECK(e);
+    pc_flag_kernel<<<gs, 256, 0, e->stream>>>(S, d_slot.as<int>(), d_first.as<int>(), d_flags.as<int>());
+    KCHECK(e);
+    pc_block_sum_kernel<<<nblocks, 1024, 0, e->stream>>>(d_flags.as<int>(), S, d_bsum.as<int>());
+    KCHECK(e);
+    pc_scan_sums_kernel<<<1, 1024, 0, e->stream>>>(d_bsum.as<int>(), nblocks, d_total.as<int>());
+    KCHECK(e);
+    pc_scan_final_kernel<<<nblocks, 1024, 0, e->stream>>>(d_flags.as<int>(), S, d_bsum.as<int>(), d_scan.as<int>());
+    KCHECK(e);
+    pc_emit_kernel<<<gs, 256, 0, e->stream>>>(d_in.as<unsigned char>(), S, row_bytes, d_slot.as<int>(), d_first.as<int>(), d_scan.as<int>(),
+                                              d_flags.as<int>(), d_map.as<int>(), d_counts.as<int>(), d_out.as<unsigned char>());
+    KCHECK(e);
+    int total = 0;
+    CK(e, cudaMemcpyAsync(&total, d_total.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    *n_patterns = total;
+    if (codes_out) CK(e, cudaMemcpyAsync(codes_out, d_out.p, (size_t)total * row_bytes, cudaMemcpyDeviceToHost, e->stream));
+    std::vector<int> tmp;
+    if (counts_out) {
+        tmp.resize(total);
+        CK(e, cudaMemcpyAsync(tmp.data(), d_counts.p, sizeof(int) * total, cudaMemcpyDeviceToHost, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+        for (int i = 0; i < total; i++) counts_out[i] = tmp[i];
+    }
+    if (site_to_pattern) {
+        tmp.resize(S);
+        CK(e, cudaMemcpyAsync(tmp.data(), d_map.p, sizeof(int) * S, cudaMemcpyDeviceToHost, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+        for (int64_t i = 0; i < S; i++) site_to_pattern[i] = tmp[i];
+    }
     CK(e, cudaStreamSynchronize(e->stream));
     return 0;
 }

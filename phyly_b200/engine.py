@@ -156,6 +156,39 @@ class Engine:
         self._ck(self._lib.plf_get_frechet_matrices(self._h, _ptr(_f64(l_hi)), _ptr(_f64(l_lo)), _ptr(out)))
         return out
 
+    def ll_certified(self, delta_rate=4e-15, delta_q=2.0 ** -60):
+        """Enclosures of the site log-likelihoods and of their weighted sum: (site_lo, site_hi, sum_lo, sum_hi)."""
+        lo = np.zeros(self.S)
+        hi = np.zeros(self.S)
+        slo = np.zeros(1)
+        shi = np.zeros(1)
+        self._ck(self._lib.plf_ll_certified(self._h, delta_rate, delta_q, _ptr(lo), _ptr(hi), _ptr(slo), _ptr(shi)))
+        return lo, hi, float(slo[0]), float(shi[0])
+
+    def hess(self):
+        """sum_ll, gradient [E] and Hessian [E, E] of the weighted log likelihood w.r.t. the edge rates (csr order)."""
+        ll = np.zeros(1)
+        grad = np.zeros(self.E)
+        H = np.zeros((self.E, self.E))
+        self._ck(self._lib.plf_hess(self._h, _ptr(ll), _ptr(grad), _ptr(H)))
+        return float(ll[0]), grad, H
+
+    def compress_patterns(self, codes):
+        """Merge identical columns: (codes of the patterns in order of first occurrence, counts, site -> pattern map)."""
+        codes = np.ascontiguousarray(codes)
+        if codes.dtype not in (np.uint8, np.int32):
+            codes = codes.astype(np.int32)
+        S, N = codes.shape
+        npat = ctypes.c_int64(0)
+        out = np.empty_like(codes)
+        counts = np.zeros(S, dtype=np.int64)
+        smap = np.zeros(S, dtype=np.int64)
+        self._ck(self._lib.plf_compress_patterns(self._h, S, N, codes.ctypes.data_as(ctypes.c_void_p), codes.dtype.itemsize,
+                                                 ctypes.byref(npat), out.ctypes.data_as(ctypes.c_void_p),
+                                                 counts.ctypes.data_as(ctypes.c_void_p), smap.ctypes.data_as(ctypes.c_void_p)))
+        P = int(npat.value)
+        return out[:P].copy(), counts[:P].copy(), smap
+
     def last_timing(self):
         a = ctypes.c_float()
         b = ctypes.c_float()

@@ -305,3 +305,46 @@ def test_out_of_range_character_code_is_an_error():
         eng.set_data(defs, np.ascontiguousarray(codes.astype(np.uint8)))
         eng.ll()
         eng.close()
+
+
+def test_site_pattern_compression_is_bit_exact():
+    """plf_compress_patterns against the oracle's restatement of the reference-side generator
+    (examples/BEAST.GTRG/mknuc.py:57-66): patterns in order of first occurrence, integer counts, site -> pattern map."""
+    rng = np.random.default_rng(3)
+    eng = _engine()
+    for S, N, K, dtype in ((1, 5, 3, np.uint8), (1000, 7, 2, np.uint8), (20000, 11, 5, np.uint8), (5000, 9, 300, np.int32),
+                           (4097, 127, 5, np.uint8)):
+        codes = rng.integers(0, K, (S, N)).astype(dtype)
+        if S > 2000:
+            codes[rng.integers(0, S, S // 2)] = codes[rng.integers(0, S, S // 2)]      # plenty of duplicates
+        pat, cnt, smap = eng.compress_patterns(codes)
+        opat, ocnt, osmap = O.compress_patterns(codes)
+        assert pat.shape == opat.shape and np.array_equal(pat, opat), (S, N)
+        assert np.array_equal(cnt, ocnt) and np.array_equal(smap, osmap), (S, N)
+        assert cnt.sum() == S and np.array_equal(pat[smap], codes)
+    eng.close()
+
+
+def test_compressed_alignment_gives_the_same_sums():
+    """test_scripts/test_site_weights.py:60-97: an alignment with repeated columns and its compressed form with the
+    multiplicities as site weights give the same aggregated outputs; the map scatters per-pattern values back."""
+    prob = H.random_problem(seed=2, ntips=12, n=4, S=33, ncat=4, mixture="gamma", missing=0.2)
+    m = O.parse_model(prob["model_and_data"])
+    defs, codes = H.dedupe_rows(m.dense_pmat())
+    rng = np.random.default_rng(5)
+    rep = rng.integers(0, codes.shape[0], 500)
+    big = np.ascontiguousarray(codes[rep]).astype(np.uint8)
+    eng = _engine()
+    H.fill_engine(eng, m)
+    eng.set_data(defs, big)
+    full = eng.deriv(per_site=True, per_site_ll=True)
+    pat, cnt, smap = eng.compress_patterns(big)
+    assert pat.shape[0] <= codes.shape[0]
+    eng.set_data(defs, pat)
+    eng.set_site_weights(cnt.astype(np.float64))
+    comp = eng.deriv(per_site=True, per_site_ll=True)
+    assert abs(comp["sum_ll"] - full["sum_ll"]) <= 1e-12 * abs(full["sum_ll"])
+    np.testing.assert_allclose(comp["sum_deriv"], full["sum_deriv"], rtol=1e-11, atol=1e-12 * np.abs(full["sum_deriv"]).max())
+    assert np.array_equal(comp["site_ll"][smap], full["site_ll"])
+    assert np.array_equal(comp["site_deriv"][smap], full["site_deriv"])
+    eng.close()

@@ -270,3 +270,49 @@ def test_newton_refine_reaches_a_stationary_point():
     # interior coordinates are stationary; a rate pushed to the boundary keeps a non-positive derivative
     for (e, x), (_, gv) in zip(out["data"], [(r[0], r[-1]) for r in g["data"]]):
         assert abs(gv) <= 1e-6 * S or (x < 1e-6 and gv <= 1e-6 * S), (e, x, gv)
+
+
+# ---------------------------------------------------------------------------
+# certified mode: the enclosure of arbplf-ll contains the reference's certified value
+# ---------------------------------------------------------------------------
+
+LL_GOLDENS = [c for c in CASES if c["program"] == "ll"]
+
+
+@pytest.mark.parametrize("case", LL_GOLDENS, ids=[c["name"] for c in LL_GOLDENS])
+def test_certified_enclosure_contains_the_golden_value(case):
+    """north_star: 'In certified mode, the GPU enclosure must contain the Arb midpoint.'  Every arbplf-ll golden of
+    the reference (correctly rounded doubles of its certified balls) lies inside [lower, upper], and the enclosure is
+    tight: its width stays below 1e-10 of the value."""
+    got = _run("ll_certified", H.golden_in(case["name"]))
+    want = H.golden_out(case["name"])
+    lo, hi = got["lower"], got["upper"]
+    assert lo["columns"] == want["columns"] and hi["columns"] == want["columns"]
+    assert len(lo["data"]) == len(want["data"]) == len(hi["data"])
+    for a, b, w in zip(lo["data"], hi["data"], want["data"]):
+        assert a[:-1] == w[:-1] == b[:-1]
+        assert a[-1] <= w[-1] <= b[-1], (case["name"], a, w, b)
+        assert b[-1] - a[-1] <= 1e-10 * max(abs(w[-1]), 1e-3), (case["name"], a, w, b)
+
+
+def test_certified_enclosure_contains_the_oracle_on_random_problems():
+    from oracle import arbplf_oracle as O
+    for kw in (dict(seed=2, ntips=12, n=4, S=33, ncat=4, mixture="gamma", missing=0.2),
+               dict(seed=4, ntips=10, n=4, S=8, ncat=2, root="uniform_distribution", internal_data=True),
+               dict(seed=7, ntips=6, n=5, S=7, ncat=1, soft=True, internal_data=True),
+               dict(seed=10, ntips=40, n=4, S=24, ncat=4, mixture="gamma", edge_scale=0.05),
+               dict(seed=14, ntips=6, n=20, S=19, ncat=2, missing=0.2, root="equilibrium_distribution")):
+        prob = H.random_problem(**kw)
+        doc = {"model_and_data": prob["model_and_data"]}
+        got = _run("ll_certified", doc)
+        want = H.expected_json("ll_random%d" % kw["seed"], "ll", doc)
+        for a, b, w in zip(got["lower"]["data"], got["upper"]["data"], want["data"]):
+            assert a[-1] <= w[-1] <= b[-1], (kw["seed"], a, w, b)
+            assert b[-1] - a[-1] <= 1e-10 * max(abs(w[-1]), 1e-3), (kw["seed"], a, w, b)
+        # aggregated with weights of both signs
+        S = len(want["data"])
+        wts = [((-1) ** i) * (0.5 + i % 3) for i in range(S)]
+        docw = dict(doc, site_reduction={"selection": list(range(S)), "aggregation": wts})
+        g2 = _run("ll_certified", docw)
+        tot = sum(wt * r[-1] for wt, r in zip(wts, want["data"]))
+        assert g2["lower"]["data"][0][-1] <= tot <= g2["upper"]["data"][0][-1]
