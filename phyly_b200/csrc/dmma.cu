@@ -244,6 +244,7 @@ struct DmRing {
 /* the tree program in shared memory: ops {first_child, nchild, code_row, spill_before}, children {kind, mat, code_row, edge} */
 struct DmProg {
     const int4 *ops, *ch;
+    const unsigned char *def_const;
     unsigned char *after;
 };
 __device__ __forceinline__ DmProg dm_stage_program(const DmArgs &a, unsigned char *smem, int tid, int nthreads)
@@ -254,7 +255,12 @@ __device__ __forceinline__ DmProg dm_stage_program(const DmArgs &a, unsigned cha
     for (int i = tid; i < a.nops; i += nthreads) o[i] = a.ops4[i];
     for (int i = tid; i < a.nchildren; i += nthreads) c[i] = a.ch4[i];
     __syncthreads();
-    p.ops = o; p.ch = c; p.after = reinterpret_cast<unsigned char *>(c + a.nchildren);
+    /* constant-row flags of the character definitions: read once per tip child, so keep them on chip too */
+    unsigned char *dc = reinterpret_cast<unsigned char *>(c + a.nchildren);
+    for (int i = tid; i < a.K; i += nthreads) dc[i] = a.def_const[i];
+    __syncthreads();
+    p.ops = o; p.ch = c; p.def_const = dc;
+    p.after = dc + ((a.K + 15) & ~15);
     return p;
 }
 struct DmOpV { int first_child, nchild, code_row, spill_before; };
@@ -377,18 +383,6 @@ __global__ void __launch_bounds__(NW * 32, 1) dm_inside_kernel(const DmArgs a)
 #pragma unroll 1
         for (int o = 0; o < a.nops; o++) {
             const DmOpV op = dm_op(prog, o);
-            /* the rows this op and the next one will take from the tip table */
-#pragma unroll 1
-            for (int oo = (o == 0 ? 0 : o + 1); oo <= o + 1 && oo < a.nops; oo++) {
-                const DmOpV opn = dm_op(prog, oo);
-                for (int j = 0; j < opn.nchild; j++) {
-                    const DmChV ch = dm_ch(prog, opn.first_child + j);
-                    if (ch.kind == F4_KIND_TIP) {
-#pragma unroll
-                        for (int r = 0; r < SG; r++) dm_prefetch(TPc + ((size_t)ch.mat * a.K + my_codes[ch.code_row * (8 * SG) + 8 * r + g]) * W);
-                    }
-                }
-            }
             if (op.spill_before) {
                 double2 *st = my_stack + (size_t)sp * (SG * NB * 32) + lane;
 #pragma unroll
@@ -410,7 +404,7 @@ __global__ void __launch_bounds__(NW * 32, 1) dm_inside_kernel(const DmArgs a)
                     const double2 *dp = reinterpret_cast<const double2 *>(a.defsf + (size_t)code * W + q * 2 * NB);
 #pragma unroll
                     for (int nb = 0; nb < NB; nb++) { const double2 v = __ldg(dp + nb); acc[r][2 * nb] = v.x; acc[r][2 * nb + 1] = v.y; }
-                    cst[r] = a.def_const[code];
+                    cst[r] = prog.def_const[code];
                 } else {
 #pragma unroll
                     for (int i = 0; i < 2 * NB; i++) acc[r][i] = 1.0;
@@ -424,7 +418,7 @@ __global__ void __launch_bounds__(NW * 32, 1) dm_inside_kernel(const DmArgs a)
 #pragma unroll
                     for (int r = 0; r < SG; r++) {
                         const int code = my_codes[ch.code_row * (8 * SG) + 8 * r + g];
-                        bc[r] = a.def_const[code];
+                        bc[r] = prog.def_const[code];
                         const double2 *tp = reinterpret_cast<const double2 *>(TPc + ((size_t)ch.mat * a.K + code) * W);
 #pragma unroll
                         for (int nb = 0; nb < NB; nb++) { const double2 v = __ldg(tp + nb); acc[r][2 * nb] *= v.x; acc[r][2 * nb + 1] *= v.y; }
@@ -533,7 +527,7 @@ struct DmChildRef {
 };
 
 template <int NB, int SG>
-__device__ __forceinline__ DmChildRef dm_child_ref(const DmArgs &a, const DmChV &ch, int c, int gw, int r, int lane, int g, int q,
+__device__ __forceinline__ DmChildRef dm_child_ref(const DmArgs &a, const DmProg &prog, const DmChV &ch, int c, int gw, int r, int lane, int g, int q,
                                                    const unsigned char *my_codes)
 {
     DmChildRef ref;
@@ -542,7 +536,7 @@ __device__ __forceinline__ DmChildRef dm_child_ref(const DmArgs &a, const DmChV 
         const int code = my_codes[ch.code_row * (8 * SG) + 8 * r + g];
         ref.p = reinterpret_cast<const double2 *>(a.TPf + (((size_t)c * a.Et + ch.mat) * a.K + code) * W + q * 2 * NB);
         ref.stride = 1;
-        ref.k = 0; ref.bc = a.def_const[code];
+        ref.k = 0; ref.bc = prog.def_const[code];
     } else {
         /* groups beyond the chunk read the chunk's last group (their results are not written) */
         const size_t cell = ((size_t)c * a.Ei + ch.mat) * a.ngroups + (size_t)min(gw + r, a.ngroups - 1);
@@ -652,72 +646,189 @@ __global__ void __launch_bounds__(NW * 32, 1) dm_outside_kernel(const DmArgs a)
 #pragma unroll
                 for (int nb = 0; nb < NB; nb++) { const double2 rv = __ldg(rp + nb); fn[r][2 * nb] = rv.x * coef; fn[r][2 * nb + 1] = rv.y * coef; }
             }
+            bool fn_in_regs = true;               /* the root's fn was formed above */
 #pragma unroll 1
             for (int o = a.nops - 1; o >= 0; o--) {
                 const DmOpV op = dm_op(prog, o);
-                if (o != a.nops - 1) {
+                static_assert(SG == 1, "the outside pass is written for one site group per warp");
+                constexpr int r = 0;
+                const bool popped = (o != a.nops - 1);
+                const double2 *zp = nullptr;
+                int in_edge = -1, kz = 0;
+                if (popped) {
+                    /* (fn, z) of this node: z always comes from the stack entry; fn only when the node is not the last
+                     * internal child of the op handled just before (then it is still in registers, unscaled) */
                     sp--;
+                    const double2 *st = my_stack + (size_t)sp * (2 * NB * 32) + lane;
+                    const int4 meta = my_stack_meta[sp * 32 + lane];
+                    in_edge = meta.z; kz = meta.x;          /* z keeps the exponent it was computed with */
+                    kf[r] = meta.x;
+                    int m = meta.y;
+                    double sc = 1.0;
+                    if (m > 0) {
+                        while (m < DM_HI_M256) { m += 0x10000000; sc *= DM_TWO_P256; kf[r] -= 1; }
+                        while (m >= DM_HI_P256) { m -= 0x10000000; sc *= DM_TWO_M256; kf[r] += 1; }
+                    }
+                    if (fn_in_regs) {
+                        if (sc != 1.0) {
 #pragma unroll
-                    for (int r = 0; r < SG; r++) {
-                        const double2 *st = my_stack + ((size_t)sp * SG + r) * (2 * NB * 32) + lane;
-                        const int4 meta = my_stack_meta[(sp * SG + r) * 32 + lane];
-                        const int in_edge = meta.z, kz = meta.x;         /* z keeps the exponent it was computed with */
-                        kf[r] = meta.x;
-                        int m = meta.y;
-                        double sc = 1.0;
-                        if (m > 0) {
-                            while (m < DM_HI_M256) { m += 0x10000000; sc *= DM_TWO_P256; kf[r] -= 1; }
-                            while (m >= DM_HI_P256) { m -= 0x10000000; sc *= DM_TWO_M256; kf[r] += 1; }
+                            for (int i = 0; i < 2 * NB; i++) fn[r][i] *= sc;
                         }
+                    } else {
 #pragma unroll
                         for (int nb = 0; nb < NB; nb++) { const double2 v = __ldcg(st + nb * 32); fn[r][2 * nb] = v.x * sc; fn[r][2 * nb + 1] = v.y * sc; }
-                        const double2 *zp = st + NB * 32;
-                        /* L_a from the children's edge vectors, then x_e = z . L_a (evaluate_site_frechet.c:18-39) */
-                        double La[2 * NB];
-                        int kL = 0, cstL = 1;
-                        if (op.code_row >= 0) {
-                            const int code = my_codes[op.code_row * (8 * SG) + 8 * r + g];
-                            const double2 *dp = reinterpret_cast<const double2 *>(a.defsf + (size_t)code * W + q * 2 * NB);
-#pragma unroll
-                            for (int nb = 0; nb < NB; nb++) { const double2 v = __ldg(dp + nb); La[2 * nb] = v.x; La[2 * nb + 1] = v.y; }
-                            cstL = a.def_const[code];
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 2 * NB; i++) La[i] = 1.0;
-                        }
+                    }
+                    zp = st + NB * 32;
+                }
+                fn_in_regs = false;
+
+                /* contraction of fe with (P_e, F_e) of an internal child: fn_b into `dst_fn` (registers, when the child is
+                 * the next op's node) or into the stack entry, z_b always into the stack entry */
+                auto contract_and_push = [&](const double (&fe)[SG][2 * NB], int kfe, int edge, bool keep_fn) {
+                    double2 *st = my_stack + (size_t)sp * (2 * NB * 32) + lane;
+                    int m = 0;
 #pragma unroll 1
-                        for (int j = 0; j < op.nchild; j++) {
-                            const DmChildRef ref = dm_child_ref<NB, SG>(a, dm_ch(prog, op.first_child + j), c, gw, r, lane, g, q, my_codes);
+                    for (int which = 0; which < 2; which++) {
+                        const double2 *sl = ring.acquire(G, lane);
 #pragma unroll
-                            for (int nb = 0; nb < NB; nb++) { const double2 v = ref.p[nb * ref.stride]; La[2 * nb] *= v.x; La[2 * nb + 1] *= v.y; }
-                            kL += ref.k; cstL &= ref.bc;
-                            if ((j & 1) || j == op.nchild - 1) {
-                                const double sc2 = dm_scale_up(dm_site_max_hi<NB>(La), kL);
-                                if (sc2 != 1.0) {
+                        for (int pc = 0; pc < NCH; pc++) {
+                            double em[SG][4][2];
+                            dm_gemm_chunk<NB, SG>(fe, sl, pc, em);
 #pragma unroll
-                                    for (int i = 0; i < 2 * NB; i++) La[i] *= sc2;
+                            for (int i = 0; i < 4; i++) {
+                                const int nb = 4 * pc + i;
+                                if (nb < NB) {
+                                    if (which == 0) {
+                                        m = max(m, max(__double2hiint(em[r][i][0]), __double2hiint(em[r][i][1])));
+                                        if (keep_fn) { fn[r][2 * nb] = em[r][i][0]; fn[r][2 * nb + 1] = em[r][i][1]; }
+                                        else __stcg(st + nb * 32, make_double2(em[r][i][0], em[r][i][1]));
+                                    } else {
+                                        __stcg(st + (NB + nb) * 32, make_double2(em[r][i][0], em[r][i][1]));
+                                    }
                                 }
                             }
                         }
-                        double x = 0.0;
+                        ring.release(G, lane, nact);
+                        G++;
+                    }
+                    m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                    m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
+                    my_stack_meta[sp * 32 + lane] = make_int4(kfe, m, edge, 0);
+                    sp++;
+                };
+                auto emit = [&](double x, int edge, int k) {
+                    x += __shfl_xor_sync(0xffffffffu, x, 1);
+                    x += __shfl_xor_sync(0xffffffffu, x, 2);
+                    if (valid[r] && q == 0 && (!a.edge_mask || a.edge_mask[edge])) {
+                        double *dst = a.edge_out + (size_t)edge * a.Sc + sw + 8 * r + g;
+                        /* the first category writes, the others add: no read-modify-write (a dependent global load) for C = 1 */
+                        if (c == 0) *dst = dm_scale256(x, k);
+                        else if (x != 0.0) *dst += dm_scale256(x, k);
+                    }
+                };
+                /* the slab rows the next op (o - 1) will read come from HBM: ask for them one op ahead */
+                if (o > 0) {
+                    const DmOpV opn = dm_op(prog, o - 1);
+                    for (int j = 0; j < opn.nchild; j++) {
+                        const DmChV chn = dm_ch(prog, opn.first_child + j);
+                        if (chn.kind == F4_KIND_TIP) continue;
+                        const size_t cell = ((size_t)c * a.Ei + chn.mat) * a.ngroups + (size_t)min(gw, a.ngroups - 1);
+                        const double2 *pp = a.slab + cell * (NB * 32) + lane;
 #pragma unroll
-                        for (int nb = 0; nb < NB; nb++) { const double2 v = __ldcg(zp + nb * 32); x = fma(v.x, La[2 * nb], x); x = fma(v.y, La[2 * nb + 1], x); }
-                        x += __shfl_xor_sync(0xffffffffu, x, 1);
-                        x += __shfl_xor_sync(0xffffffffu, x, 2);
-                        if (a.f_zero_rowsum && cstL) x = 0.0;
-                        if (valid[r] && q == 0 && x != 0.0 && (!a.edge_mask || a.edge_mask[in_edge]))
-                            a.edge_out[(size_t)in_edge * a.Sc + sw + 8 * r + g] += dm_scale256(x, kz + kL);
+                        for (int nb = 0; nb < NB; nb += 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + nb * 32));
                     }
                 }
-                /* fn_a . data_a */
-                if (op.code_row >= 0) {
+
+                if (op.nchild == 2 && op.code_row < 0) {
+                    /* ---- two children, no data at the node: every vector is loaded once ---- */
+                    const DmChV c0 = dm_ch(prog, op.first_child), c1 = dm_ch(prog, op.first_child + 1);
+                    const DmChildRef r0 = dm_child_ref<NB, SG>(a, prog, c0, c, gw, r, lane, g, q, my_codes);
+                    const DmChildRef r1 = dm_child_ref<NB, SG>(a, prog, c1, c, gw, r, lane, g, q, my_codes);
+                    const bool int0 = c0.kind != F4_KIND_TIP, int1 = c1.kind != F4_KIND_TIP;
+                    const double2 *tf0 = nullptr, *tf1 = nullptr;
+                    if (!int0) tf0 = reinterpret_cast<const double2 *>(TFc + ((size_t)c0.mat * a.K + my_codes[c0.code_row * (8 * SG) + 8 * r + g]) * W);
+                    if (!int1) tf1 = reinterpret_cast<const double2 *>(TFc + ((size_t)c1.mat * a.K + my_codes[c1.code_row * (8 * SG) + 8 * r + g]) * W);
+                    double fe[SG][2 * NB];
+                    double xa = 0.0, x0 = 0.0, x1 = 0.0;
+                    /* fe <- fn . em0 (the outside vector of child 1) when child 1 is internal, else fn . em1 (child 0's) */
 #pragma unroll
-                    for (int r = 0; r < SG; r++) {
+                    for (int nb = 0; nb < NB; nb++) {
+                        const double2 v0 = r0.p[nb * r0.stride], v1 = r1.p[nb * r1.stride];
+                        if (popped) {
+                            const double2 zz = __ldcg(zp + nb * 32);
+                            xa = fma(zz.x, v0.x * v1.x, xa); xa = fma(zz.y, v0.y * v1.y, xa);
+                        }
+                        const double f0x = fn[r][2 * nb] * v1.x, f0y = fn[r][2 * nb + 1] * v1.y;     /* child 0: fn . em1 */
+                        const double f1x = fn[r][2 * nb] * v0.x, f1y = fn[r][2 * nb + 1] * v0.y;     /* child 1: fn . em0 */
+                        if (!int0) { const double2 t = __ldg(tf0 + nb); x0 = fma(t.x, f0x, x0); x0 = fma(t.y, f0y, x0); }
+                        if (!int1) { const double2 t = __ldg(tf1 + nb); x1 = fma(t.x, f1x, x1); x1 = fma(t.y, f1y, x1); }
+                        if (int1) { fe[r][2 * nb] = f1x; fe[r][2 * nb + 1] = f1y; }
+                        else { fe[r][2 * nb] = f0x; fe[r][2 * nb + 1] = f0y; }
+                    }
+                    if (popped) {
+                        if (a.f_zero_rowsum && (r0.bc & r1.bc)) xa = 0.0;
+                        emit(xa, in_edge, kz + r0.k + r1.k);
+                    }
+                    if (!int0) emit(x0, c0.edge, kf[r] + r1.k);
+                    if (!int1) emit(x1, c1.edge, kf[r] + r0.k);
+                    if (int1) {
+                        /* both internal: child 1 first (it goes to the stack), then child 0 with em1 loaded again */
+                        int kfe = kf[r] + r0.k;
+                        dm_rescale_both<NB>(fe[r], kfe);
+                        contract_and_push(fe, kfe, c1.edge, false);
+#pragma unroll
+                        for (int nb = 0; nb < NB; nb++) { const double2 v1 = r1.p[nb * r1.stride]; fe[r][2 * nb] = fn[r][2 * nb] * v1.x; fe[r][2 * nb + 1] = fn[r][2 * nb + 1] * v1.y; }
+                    }
+                    if (int0) {
+                        int kfe = kf[r] + r1.k;
+                        dm_rescale_both<NB>(fe[r], kfe);
+                        contract_and_push(fe, kfe, c0.edge, true);
+                        fn_in_regs = true;
+                    }
+                    continue;
+                }
+
+                /* ---- general shape ---- */
+                if (popped) {
+                    /* L_a from the children's edge vectors, then x_e = z . L_a (evaluate_site_frechet.c:18-39) */
+                    double La[2 * NB];
+                    int kL = 0, cstL = 1;
+                    if (op.code_row >= 0) {
                         const int code = my_codes[op.code_row * (8 * SG) + 8 * r + g];
                         const double2 *dp = reinterpret_cast<const double2 *>(a.defsf + (size_t)code * W + q * 2 * NB);
 #pragma unroll
-                        for (int nb = 0; nb < NB; nb++) { const double2 v = __ldg(dp + nb); fn[r][2 * nb] *= v.x; fn[r][2 * nb + 1] *= v.y; }
+                        for (int nb = 0; nb < NB; nb++) { const double2 v = __ldg(dp + nb); La[2 * nb] = v.x; La[2 * nb + 1] = v.y; }
+                        cstL = prog.def_const[code];
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 2 * NB; i++) La[i] = 1.0;
                     }
+#pragma unroll 1
+                    for (int j = 0; j < op.nchild; j++) {
+                        const DmChildRef ref = dm_child_ref<NB, SG>(a, prog, dm_ch(prog, op.first_child + j), c, gw, r, lane, g, q, my_codes);
+#pragma unroll
+                        for (int nb = 0; nb < NB; nb++) { const double2 v = ref.p[nb * ref.stride]; La[2 * nb] *= v.x; La[2 * nb + 1] *= v.y; }
+                        kL += ref.k; cstL &= ref.bc;
+                        if ((j & 1) || j == op.nchild - 1) {
+                            const double sc2 = dm_scale_up(dm_site_max_hi<NB>(La), kL);
+                            if (sc2 != 1.0) {
+#pragma unroll
+                                for (int i = 0; i < 2 * NB; i++) La[i] *= sc2;
+                            }
+                        }
+                    }
+                    double x = 0.0;
+#pragma unroll
+                    for (int nb = 0; nb < NB; nb++) { const double2 v = __ldcg(zp + nb * 32); x = fma(v.x, La[2 * nb], x); x = fma(v.y, La[2 * nb + 1], x); }
+                    if (a.f_zero_rowsum && cstL) x = 0.0;
+                    emit(x, in_edge, kz + kL);
+                }
+                /* fn_a . data_a */
+                if (op.code_row >= 0) {
+                    const int code = my_codes[op.code_row * (8 * SG) + 8 * r + g];
+                    const double2 *dp = reinterpret_cast<const double2 *>(a.defsf + (size_t)code * W + q * 2 * NB);
+#pragma unroll
+                    for (int nb = 0; nb < NB; nb++) { const double2 v = __ldg(dp + nb); fn[r][2 * nb] *= v.x; fn[r][2 * nb + 1] *= v.y; }
                 }
                 /* children: tips in any order, internal ones from the last to the first so that the stack unwinds in
                  * the reverse of the inside pass */
@@ -725,78 +836,29 @@ __global__ void __launch_bounds__(NW * 32, 1) dm_outside_kernel(const DmArgs a)
                 for (int j = op.nchild - 1; j >= 0; j--) {
                     const DmChV ch = dm_ch(prog, op.first_child + j);
                     double fe[SG][2 * NB];
-                    int kfe[SG];
+                    int kfe = kf[r];
 #pragma unroll
-                    for (int r = 0; r < SG; r++) {
-                        kfe[r] = kf[r];
-#pragma unroll
-                        for (int i = 0; i < 2 * NB; i++) fe[r][i] = fn[r][i];
-                    }
+                    for (int i = 0; i < 2 * NB; i++) fe[r][i] = fn[r][i];
                     int nmul = 0;
 #pragma unroll 1
                     for (int j2 = 0; j2 < op.nchild; j2++) {
                         if (j2 == j) continue;
-                        const DmChV ch2 = dm_ch(prog, op.first_child + j2);
-                        ++nmul;
+                        const DmChildRef ref = dm_child_ref<NB, SG>(a, prog, dm_ch(prog, op.first_child + j2), c, gw, r, lane, g, q, my_codes);
 #pragma unroll
-                        for (int r = 0; r < SG; r++) {
-                            const DmChildRef ref = dm_child_ref<NB, SG>(a, ch2, c, gw, r, lane, g, q, my_codes);
-#pragma unroll
-                            for (int nb = 0; nb < NB; nb++) { const double2 v = ref.p[nb * ref.stride]; fe[r][2 * nb] *= v.x; fe[r][2 * nb + 1] *= v.y; }
-                            kfe[r] += ref.k;
-                            if ((nmul & 1) == 0) dm_rescale_both<NB>(fe[r], kfe[r]);
-                        }
+                        for (int nb = 0; nb < NB; nb++) { const double2 v = ref.p[nb * ref.stride]; fe[r][2 * nb] *= v.x; fe[r][2 * nb + 1] *= v.y; }
+                        kfe += ref.k;
+                        if ((++nmul & 1) == 0) dm_rescale_both<NB>(fe[r], kfe);
                     }
-#pragma unroll
-                    for (int r = 0; r < SG; r++) dm_rescale_both<NB>(fe[r], kfe[r]);
+                    dm_rescale_both<NB>(fe[r], kfe);
                     if (ch.kind == F4_KIND_TIP) {
+                        const int code = my_codes[ch.code_row * (8 * SG) + 8 * r + g];
+                        const double2 *tf = reinterpret_cast<const double2 *>(TFc + ((size_t)ch.mat * a.K + code) * W);
+                        double x = 0.0;
 #pragma unroll
-                        for (int r = 0; r < SG; r++) {
-                            const int code = my_codes[ch.code_row * (8 * SG) + 8 * r + g];
-                            const double2 *tf = reinterpret_cast<const double2 *>(TFc + ((size_t)ch.mat * a.K + code) * W);
-                            double x = 0.0;
-#pragma unroll
-                            for (int nb = 0; nb < NB; nb++) { const double2 v = __ldg(tf + nb); x = fma(v.x, fe[r][2 * nb], x); x = fma(v.y, fe[r][2 * nb + 1], x); }
-                            x += __shfl_xor_sync(0xffffffffu, x, 1);
-                            x += __shfl_xor_sync(0xffffffffu, x, 2);
-                            if (valid[r] && q == 0 && x != 0.0 && (!a.edge_mask || a.edge_mask[ch.edge]))
-                                a.edge_out[(size_t)ch.edge * a.Sc + sw + 8 * r + g] += dm_scale256(x, kfe[r]);
-                        }
+                        for (int nb = 0; nb < NB; nb++) { const double2 v = __ldg(tf + nb); x = fma(v.x, fe[r][2 * nb], x); x = fma(v.y, fe[r][2 * nb + 1], x); }
+                        emit(x, ch.edge, kfe);
                     } else {
-                        double2 *st = my_stack + (size_t)sp * SG * (2 * NB * 32) + lane;
-                        int m[SG];
-#pragma unroll
-                        for (int r = 0; r < SG; r++) m[r] = 0;
-                        /* fn_b = P_e^T fe (util.c:464-498), then z_b = F_e^T fe */
-#pragma unroll 1
-                        for (int which = 0; which < 2; which++) {
-                            const double2 *sl = ring.acquire(G, lane);
-#pragma unroll
-                            for (int pc = 0; pc < NCH; pc++) {
-                                double em[SG][4][2];
-                                dm_gemm_chunk<NB, SG>(fe, sl, pc, em);
-#pragma unroll
-                                for (int r = 0; r < SG; r++) {
-#pragma unroll
-                                    for (int i = 0; i < 4; i++) {
-                                        const int nb = 4 * pc + i;
-                                        if (nb < NB) {
-                                            __stcg(st + r * (2 * NB * 32) + (which * NB + nb) * 32, make_double2(em[r][i][0], em[r][i][1]));
-                                            if (which == 0) m[r] = max(m[r], max(__double2hiint(em[r][i][0]), __double2hiint(em[r][i][1])));
-                                        }
-                                    }
-                                }
-                            }
-                            ring.release(G, lane, nact);
-                            G++;
-                        }
-#pragma unroll
-                        for (int r = 0; r < SG; r++) {
-                            m[r] = max(m[r], __shfl_xor_sync(0xffffffffu, m[r], 1));
-                            m[r] = max(m[r], __shfl_xor_sync(0xffffffffu, m[r], 2));
-                            my_stack_meta[(sp * SG + r) * 32 + lane] = make_int4(kfe[r], m[r], ch.edge, 0);
-                        }
-                        sp++;
+                        contract_and_push(fe, kfe, ch.edge, false);
                     }
                 }
             }
@@ -822,7 +884,7 @@ size_t dm_slot_doubles_host(int NB) { return (size_t)dm_slot_doubles(NB); }
 size_t dm_smem_bytes(int NB, int R, int nrows, int nops, int nchildren)
 {
     return (size_t)R * dm_slot_doubles(NB) * 8 + DM_MAX_R * 8 + DM_MAX_R * 4 + 16 + (size_t)(nops + nchildren) * 16 +
-           (size_t)DM_GROUPS * nrows * 8 + 16;
+           (size_t)DM_GROUPS * nrows * 8 + 16 + 272;          /* + the constant-row flags (K <= 256) */
 }
 
 void dm_tiling(int ngroups, int items_per_tile, int grid, int *tiles_full, int *tail_gs, int *ntiles)

@@ -1768,7 +1768,7 @@ static int run_dmma(plf_engine *e, Query &q)
 
     /* ring slots that fit beside the warps' code tiles */
     const int nops = (int)e->ops.size(), nch = (int)e->children.size();
-    int R = 4;      /* measured: more slots buy nothing, and shared memory not used here is L1 for the tip tables */
+    int R = 3;      /* measured (2..6): 3 is best by 1-3 %; shared memory not used by the ring is L1 for the tip tables and the slab */
     if (const char *s = getenv("PLF_DM_R")) R = std::max(2, std::min(DM_MAX_R, atoi(s)));
     while (R > 2 && dm_smem_bytes(NB, R, nrows, nops, nch) > 227 * 1024) R--;
     if (dm_smem_bytes(NB, R, nrows, nops, nch) > 227 * 1024) FAIL(e, "tree too large for the tensor-pipe kernels (%d code rows)", nrows);
@@ -1823,7 +1823,7 @@ static int run_dmma(plf_engine *e, Query &q)
     a.cat_lh = e->g_cat_lh.as<double>(); a.cat_k = e->g_cat_k.as<int>();
     a.R = R;
     a.sg = 1;
-    a.stagger = 3000;
+    a.stagger = 0;          /* measured 0..8000 clocks: no effect on either kernel */
     if (const char *sg = getenv("PLF_DM_STAGGER")) a.stagger = atoi(sg);
     a.stack = e->d_dm_stack.as<double2>(); a.stack_meta = e->d_dm_stackmeta.as<int>();
     a.Of = e->d_dm_Of.as<double>(); a.TFf = e->d_dmTFf.as<double>();

@@ -51,6 +51,73 @@ __global__ void k16816(double *out, int iters)
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+
+// the loop shape of dm_gemm_chunk: 2 NB = 16 k-steps, per k-step two 16-byte LDS of B fragments feeding 4 DMMAs that share
+// the A register; 4 accumulator pairs.  Measures what the tensor pipe sustains when every DMMA reads a fresh B operand
+// from shared memory (no operand reuse), as a function of the warps per SM.
+__global__ void k884_lds(double *out, int iters)
+{
+    extern __shared__ double2 slot[];          // [16 k-steps][2 pairs][32 lanes] double2 = 16 KB
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 16 * 2 * 32; i += blockDim.x) slot[i] = make_double2(1.0 + i * 1e-9, 1.0 - i * 1e-9);
+    __syncthreads();
+    double A[16];
+    for (int i = 0; i < 16; i++) A[i] = threadIdx.x * 1e-3 + i;
+    double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    const double2 *sl = slot + lane;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int kk = 0; kk < 16; kk++) {
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                const double2 b = sl[(kk * 2 + p) * 32];
+                MMA884(c[2 * p][0], c[2 * p][1], A[kk], b.x);
+                MMA884(c[2 * p + 1][0], c[2 * p + 1][1], A[kk], b.y);
+            }
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = c[0][0] + c[0][1] + c[1][0] + c[1][1] + c[2][0] + c[2][1] + c[3][0] + c[3][1];
+}
+
+// the same DMMA stream with the B operands in registers (distinct registers, no shared memory)
+__global__ void k884_regs(double *out, int iters)
+{
+    double A[16], B[8];
+    for (int i = 0; i < 16; i++) A[i] = threadIdx.x * 1e-3 + i;
+    for (int i = 0; i < 8; i++) B[i] = 1.0 + threadIdx.x * 1e-6 + i;
+    double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int kk = 0; kk < 16; kk++) {
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                MMA884(c[2 * p][0], c[2 * p][1], A[kk], B[(2 * kk + p) & 7]);
+                MMA884(c[2 * p + 1][0], c[2 * p + 1][1], A[kk], B[(2 * kk + p + 3) & 7]);
+            }
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = c[0][0] + c[0][1] + c[1][0] + c[1][1] + c[2][0] + c[2][1] + c[3][0] + c[3][1];
+}
+
+template <typename K>
+static double tflops_smem(K k, double *out, int sms, int warps_per_sm, int iters, double flop_per_warp_iter, size_t smem)
+{
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k<<<sms, warps_per_sm * 32, smem>>>(out, iters / 10);
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int r = 0; r < 3; r++) {
+        cudaEventRecord(e0);
+        k<<<sms, warps_per_sm * 32, smem>>>(out, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    return flop_per_warp_iter * iters * (double)sms * warps_per_sm / (best * 1e-3) / 1e12;
+}
+
 template <typename K>
 static double tflops(K k, double *out, int sms, int warps_per_sm, int iters, double flop_per_warp_iter)
 {
@@ -122,6 +189,13 @@ int main()
         printf("%s\"warps%d\": {\"chains1\": %.2f, \"chains2\": %.2f, \"chains4\": %.2f, \"chains8\": %.2f}", wi ? ", " : "", w,
                tflops(k884<1>, out, sms, w, it, f * 1), tflops(k884<2>, out, sms, w, it, f * 2),
                tflops(k884<4>, out, sms, w, it, f * 4), tflops(k884<8>, out, sms, w, it, f * 8));
+    }
+    printf("},\n \"m8n8k4_gemm_loop_tflops\": {");
+    for (int wi = 0; wi < 4; wi++) {
+        const int w = ws[wi];
+        const double f = 2.0 * 8 * 8 * 4 * 64;        /* 64 DMMAs per iteration */
+        printf("%s\"warps%d\": {\"B_from_shared_memory\": %.2f, \"B_in_registers\": %.2f}", wi ? ", " : "", w,
+               tflops_smem(k884_lds, out, sms, w, it / 16, f, 16384), tflops_smem(k884_regs, out, sms, w, it / 16, f, 0));
     }
     printf("},\n \"m16n8k16_tflops\": {");
     for (int wi = 0; wi < 3; wi++) {
