@@ -29,7 +29,8 @@ ranks in contiguous blocks of sites (strong scaling, BASELINE.json configs[1]:
 weak-scaling measurement (a whole alignment per GPU) is reported beside it.
 
 At N = 1 the line also carries "cfg4" (61-state codon model on the FP64 tensor
-pipe) and "json_e2e" (the cfg2 document through the arbplf-deriv drop-in).
+pipe), "cfg3" (HKY85+I marginals and the Hessian query) and "json_e2e" (the cfg2
+document through the arbplf-deriv drop-in).
 """
 import argparse
 import ctypes
@@ -343,6 +344,69 @@ def bench_cfg4(local, peaks_fp64, taxa=256, sites=100000, steps=10):
     return out
 
 
+def bench_cfg3(local, taxa=128, sites=500000, hess_sites=500000, steps=5):
+    """BASELINE.json configs[2] (cfg3): HKY85+I (kappa 2, invariant category), 128 taxa x 500 000 sites: posterior
+    marginals summed over sites, and the second-order query (gradient + Hessian of the log likelihood, E x E) that
+    arbplf-hess / newton-update need (the Hessian kernel is O(E^2) per site; one timed evaluation after one warm-up)."""
+    import torch
+    import phyly_b200.arbplf as A
+    from phyly_b200.engine import Engine
+    edges, N = yule_tree(taxa, seed=11)
+    rng = np.random.default_rng(12)
+    pi = (0.3, 0.2, 0.25, 0.25)
+    Q = [[0.0] * 4 for _ in range(4)]
+    for i in range(4):
+        for j in range(4):
+            if i != j:
+                Q[i][j] = pi[j] * (2.0 if (i, j) in ((0, 2), (2, 0), (1, 3), (3, 1)) else 1.0)
+    md = {"edges": edges, "edge_rate_coefficients": [float(x) for x in rng.exponential(0.05, len(edges))],
+          "rate_matrix": Q, "root_prior": list(pi), "rate_divisor": "equilibrium_exit_rate",
+          "rate_mixture": {"rates": [0.0, 2.0], "prior": [0.5, 0.5]},
+          "character_definitions": DEFS, "character_data": [[4] * N]}
+    s = json.loads(A.arbplf_model_summary(json.dumps({"model_and_data": md})))
+    eng = Engine(local)
+    eng.set_tree(s["indptr"], s["indices"], s["preorder"])
+    eng.set_model(np.array(s["q_hi"]).reshape(4, 4), np.array(s["q_lo"]).reshape(4, 4), s["edge_rates_csr"], s["cat_rates"],
+                  s["cat_prior"], s["root_mode"], s["root_vec"])
+    P = eng.transition_matrices()
+    codes = np.empty((sites, N), dtype=np.uint8)
+    simulate_codes(s, P, sites, seed=13, out=codes)
+    defs = np.array(DEFS, dtype=np.float64)
+    E = N - 1
+    stream = torch.cuda.ExternalStream(eng.stream(), device=local)
+
+    def timed(fn, n, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(n):
+            r = fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n, r
+
+    out = {"workload": "cfg3: HKY85 (kappa 2) + invariant category x %d-taxon Yule tree x %d sites, C = 2, data resident" % (taxa, sites),
+           "taxa": taxa, "sites": sites, "edges": E}
+    eng.set_data(defs, codes)
+    ms, r = timed(lambda: eng.marginal(per_site=False), steps)
+    out["marginal_site_sum"] = {"ms_per_step": ms, "updates_per_s": float(sites) * E * 2 / (ms * 1e-3), "kernel": eng.last_kernel_name()}
+    ms, r = timed(lambda: eng.deriv(per_site=False), steps)
+    out["ll_deriv"] = {"ms_per_step": ms, "updates_per_s": float(sites) * E * 2 / (ms * 1e-3), "kernel": eng.last_kernel_name()}
+    eng.set_data(defs, codes[:hess_sites])
+    ms, r = timed(lambda: eng.hess(), 1, warm=1)
+    H = r[2]
+    out["hess"] = {"sites": hess_sites, "ms_per_step": ms, "ms_per_1000_sites": ms / hess_sites * 1000.0,
+                   "extrapolated_ms_at_full_size": ms / hess_sites * sites,
+                   "pair_updates_per_s": float(hess_sites) * 2 * E * (E + 1) / 2 / (ms * 1e-3),
+                   "kernel": "generic_inside / generic_outside / generic_hess_kernel / gram_rows_kernel (scalar fp64, thread = site)",
+                   "hessian_is_symmetric": bool(np.array_equal(H, H.T)), "sum_ll": r[0],
+                   "note": "one tangent sweep per edge, O(E^2) per (site, category); the reference re-walks two root paths per pair, O(E^2 depth)"}
+    eng.close()
+    return out
+
+
 def json_document_bytes(doc, codes):
     """The arbplf JSON document of the workload with its character_data, built without a Python-level loop."""
     S, N = codes.shape
@@ -627,6 +691,10 @@ def run_ours(args):
             line["cfg4"] = bench_cfg4(local, fp64)
         except Exception as ex:       # a supplementary measurement must not lose the headline
             line["cfg4"] = {"error": repr(ex)}
+        try:
+            line["cfg3"] = bench_cfg3(local)
+        except Exception as ex:
+            line["cfg3"] = {"error": repr(ex)}
         try:
             line["json_e2e"] = bench_json_e2e(pb, args.json_sites)
         except Exception as ex:

@@ -1776,9 +1776,12 @@ static int run_dmma(plf_engine *e, Query &q)
     /* chunk of sites: the slab of edge vectors (keep mode) is the only large buffer */
     const size_t per_group = q.want_edge ? (size_t)C * Ei * ((size_t)NB * 32 * 16 + 32 * 4) + (size_t)E * 64 : 0;
     size_t free_b = 0, total_b = 0;
-    CK(e, cudaMemGetInfo(&free_b, &total_b));
     int64_t Sc = e->S;
-    if (per_group) {
+    /* (the device is only asked for its free memory when the buffers of an earlier query do not already hold the whole alignment) */
+    const bool slab_fits = per_group && e->d_dm_slab.cap >= sizeof(double2) * (size_t)C * Ei * ((e->S + 7) / 8) * NB * 32 + 16 &&
+                           e->g_edge_out.cap >= sizeof(double) * (size_t)E * e->S && e->S <= ((int64_t)1 << 24);
+    if (per_group && !slab_fits) {
+        CK(e, cudaMemGetInfo(&free_b, &total_b));
         const size_t have = e->d_dm_slab.cap + e->d_dm_slabmeta.cap + e->g_edge_out.cap;
         const size_t budget = std::min<size_t>((size_t)32 << 30, (free_b + have) / 2);
         const int64_t groups = std::max<int64_t>(DM_TILE / 8, (int64_t)(budget / per_group));
