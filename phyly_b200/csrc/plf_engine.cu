@@ -138,11 +138,14 @@ struct plf_engine {
     DevBuf d_dmPf, d_dmTPf, d_dmTFf, d_dm_defsf, d_dm_rootf, d_dm_stack, d_dm_stackmeta, d_dm_slab, d_dm_slabmeta, d_dm_Of, d_dm_oidx, d_dm_otr, d_dm_ops, d_dm_ch;
     int dm_out_depth = 0;
     F4Prog prog_h;
-    uint64_t program_version = 0, f4_tuned_version[3] = {~(uint64_t)0, ~(uint64_t)0, ~(uint64_t)0};   /* ll, edge forms, marginals */
-    size_t f4_tuned_pick[3] = {0, 0, 0};
-    int f4_tuned_C[3] = {0, 0, 0}, f4_tuned_K[3] = {0, 0, 0};
-    std::string f4_cand_key[3];
-    std::vector<Cand> f4_cands[3];
+    /* tuning / candidate caches of the fused kernel: slot = 5 * kind (ll, edge forms, marginals) + categories of the launch */
+    uint64_t program_version = 0, f4_tuned_version[15];
+    size_t f4_tuned_pick[15] = {0};
+    int f4_tuned_C[15] = {0}, f4_tuned_K[15] = {0};
+    std::string f4_cand_key[15];
+    std::vector<Cand> f4_cands[15];
+    DevBuf f4w_ll, f4w_edge, f4w_marg;      /* per-window per-site outputs when C > 4 (run_fused_windows) */
+    plf_engine() { for (int i = 0; i < 15; i++) f4_tuned_version[i] = ~(uint64_t)0; }
 
     /* scratch */
     DevBuf d_scratch, d_scratchS, d_block_ll, d_block_edge, d_edge_site, d_sum, d_site_ll, d_err, d_mask, d_retry;
@@ -152,7 +155,7 @@ struct plf_engine {
 
     /* timing / accounting */
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    float ms_mat = 0.f, ms_sites = 0.f, ms_kernel = 0.f;
+    float ms_mat = 0.f, ms_sites = 0.f, ms_kernel = 0.f, ms_kernel_override = -1.f;
     bool kernel_timed = false;
     int64_t launches = 0;
 
@@ -907,7 +910,8 @@ struct Query {
 
 static bool fused_applicable(const plf_engine *e)
 {
-    return e->n == 4 && e->C <= 4 && e->code_bytes == 1 && e->K <= 256 && e->max_degree <= F4_MAXD;
+    /* more than 4 rate categories (Gamma4+I, Gamma8 ...) run as windows of <= 4 (run_fused_windows) */
+    return e->n == 4 && e->C <= 16 && e->code_bytes == 1 && e->K <= 256 && e->max_degree <= F4_MAXD;
 }
 
 static bool fused_fits(const plf_engine *e, bool edge);
@@ -1025,7 +1029,7 @@ static size_t f4_smem_bytes(const plf_engine *e, bool edge, int bd, int staged, 
                             bool marg = false, bool gstack = false)
 {
     const int sdepth = gstack ? 0 : e->stack_depth;
-    const int C = e->C, Ei = cm ? 0 : (int)e->edge_of_int.size(), Et = (int)e->edge_of_tip.size();
+    const int C = std::min(e->C, 4), Ei = cm ? 0 : (int)e->edge_of_int.size(), Et = (int)e->edge_of_tip.size();
     size_t off = 0;
     off = f4_align16(off + (cm ? 0 : sizeof(F4Op) * e->ops.size()));
     off = f4_align16(off + (cm ? 0 : sizeof(F4Child) * e->children.size()));
@@ -1047,7 +1051,14 @@ static bool fused_fits(const plf_engine *e, bool edge)
     return f4_smem_bytes(e, edge, 128, 0) <= 227 * 1024;
 }
 
-static int run_fused(plf_engine *e, Query &q)
+/* A launch over a window of <= 4 rate categories [c0, c0 + e->C) of a model with more (run_fused_windows): per-site
+ * outputs go to device buffers and nothing is reduced or copied here. */
+struct F4Window {
+    int c0 = 0;
+    double *site_ll = nullptr, *site_edge = nullptr, *site_marg = nullptr;
+};
+
+static int run_fused(plf_engine *e, Query &q, const F4Window *win = nullptr)
 {
     const bool marg = q.want_marg;              /* outside pass producing node marginals */
     const bool edge = q.want_edge || marg;      /* an outside pass runs (slab, no stack) */
@@ -1070,13 +1081,21 @@ static int run_fused(plf_engine *e, Query &q)
     for (int i = 0; i < 4; i++) a.root_vec[i] = e->root_vec[i];
     a.site_w = e->have_w ? e->d_site_w.as<double>() : nullptr;
     a.stack_depth = e->stack_depth; a.nslots = e->nslots;
+    if (win) {
+        /* the tables are laid out [category][...]: a window is a pointer offset */
+        const size_t c0 = (size_t)win->c0;
+        a.Pint += c0 * a.Ei * 16; a.TP += c0 * a.Et * a.K * 4;
+        if (a.Fint) a.Fint += marg ? c0 * a.Et * 16 : c0 * a.Ei * 16;
+        if (a.TF) a.TF += c0 * a.Et * a.K * 4;
+        a.cat_prior += c0;
+    }
 
     /* candidate configurations (block size, which tables are staged in shared memory, packed codes, matrices
      * in constant memory), preferred first.  PLF_F4_CONFIG=<index> forces one (tuning aid, edge queries). */
     /* the candidates that fit (shared memory, occupancy) depend only on the program, the model's shape and the query
      * kind: scanned once and remembered -- the occupancy queries of a dozen instantiations cost more host time per
      * query than the matrix kernels take on the device */
-    const int tm0 = marg ? 2 : (edge ? 1 : 0);
+    const int tm0 = 5 * (marg ? 2 : (edge ? 1 : 0)) + e->C;
     const char *force0 = getenv(marg ? "PLF_F4_CONFIG_MARG" : (edge ? "PLF_F4_CONFIG" : "PLF_F4_CONFIG_LL"));
     const std::string cand_key = std::to_string(e->program_version) + "/" + std::to_string(e->C) + "/" + std::to_string(e->K) + "/" +
                                  std::to_string(e->E) + "/" + (force0 ? force0 : "");
@@ -1166,7 +1185,7 @@ static int run_fused(plf_engine *e, Query &q)
      * on a sample of the sites and keeps the fastest. */
     const int64_t tune_sites = (int64_t)e->sm_count * 512 * 2;
     const bool can_tune = viable.size() > 1 && e->S >= tune_sites / 2 && !getenv("PLF_F4_NOTUNE");
-    const int tm = marg ? 2 : (edge ? 1 : 0);      /* tuning slot: ll, edge forms, marginals */
+    const int tm = 5 * (marg ? 2 : (edge ? 1 : 0)) + e->C;      /* tuning slot: (ll, edge forms, marginals) x categories */
     size_t pick = 0;
     bool tune = false;
     if (can_tune) {
@@ -1193,14 +1212,17 @@ static int run_fused(plf_engine *e, Query &q)
     a.error_flag = e->d_err.as<int>();
     /* the site log-likelihoods are always kept: the zero-likelihood check of every query kind reads them */
     ENSURE(e, e->d_site_ll, sizeof(double) * e->S);
-    a.site_ll = e->d_site_ll.as<double>();
+    a.site_ll = win ? win->site_ll : e->d_site_ll.as<double>();
     if (edge) {
         ENSURE(e, e->d_scratch, sizeof(double4) * (size_t)e->C * e->nslots * Tmax);
         ENSURE(e, e->d_scratchS, sizeof(unsigned int) * (size_t)e->nslots * Tmax);
         if (!marg) ENSURE(e, e->d_block_edge, sizeof(double) * (size_t)gmax * e->E * nchunk);
         a.scratch = e->d_scratch.as<double4>(); a.scratchS = e->d_scratchS.as<unsigned int>();
         a.block_edge = e->d_block_edge.as<double>();
-        if (marg && q.site_marg) {
+        if (marg && win) {
+            CK(e, cudaMemsetAsync(win->site_marg, 0, sizeof(double) * (size_t)e->N * 4 * e->S, e->stream));
+            a.marg_site_out = win->site_marg;
+        } else if (marg && q.site_marg) {
             ENSURE(e, e->d_marg_site, sizeof(double) * (size_t)e->N * 4 * e->S);
             CK(e, cudaMemsetAsync(e->d_marg_site.p, 0, sizeof(double) * (size_t)e->N * 4 * e->S, e->stream));
             a.marg_site_out = e->d_marg_site.as<double>();
@@ -1216,7 +1238,10 @@ static int run_fused(plf_engine *e, Query &q)
             CK(e, cudaMemcpyAsync(e->d_mask.p, q.edge_mask_h, e->E, cudaMemcpyHostToDevice, e->stream));
             a.edge_mask = e->d_mask.as<unsigned char>();
         }
-        if (q.site_edge) {
+        if (win && !marg) {
+            CK(e, cudaMemsetAsync(win->site_edge, 0, sizeof(double) * (size_t)e->E * e->S, e->stream));
+            a.edge_site_out = win->site_edge;
+        } else if (q.site_edge) {
             ENSURE(e, e->d_edge_site, sizeof(double) * (size_t)e->E * e->S);
             CK(e, cudaMemsetAsync(e->d_edge_site.p, 0, sizeof(double) * (size_t)e->E * e->S, e->stream));
             a.edge_site_out = e->d_edge_site.as<double>();
@@ -1311,6 +1336,7 @@ static int run_fused(plf_engine *e, Query &q)
         cm_lock.unlock();
     }
     e->kernel_timed = true;
+    if (win) return 0;          /* run_fused_windows combines the windows, reduces and copies */
     const bool shared_retry = pipelined && e->comm != nullptr;
     if (shared_retry) {
         ENSURE(e, e->d_retry, sizeof(double));
@@ -1383,6 +1409,105 @@ static int run_fused(plf_engine *e, Query &q)
     if (q.sum_edge && !marg && nsum > 1) memcpy(q.sum_edge, hs.data() + 1, sizeof(double) * e->E);
     if (marg && q.site_marg && copy_site_matrix(e, e->d_marg_site.as<double>(), e->N * 4, e->S, q.site_marg)) return -1;
     if (marg && q.sum_marg) memcpy(q.sum_marg, hs.data() + 1 + e->E, sizeof(double) * e->N * 4);
+    return 0;
+}
+
+/* combine the windows of a site: ll = log sum_w exp(ll_w); rows of window 0 <- sum_w exp(ll_w - ll) rows_w
+ * (each window's per-site values are normalised by its own likelihood share) */
+__global__ void f4_combine_windows_kernel(int nwin, int64_t S, double *w_ll /*[nwin][S]*/, double *site_ll /*[S]*/,
+                                          double *rowsA /*[nwin][RA][S] or NULL*/, int RA, double *rowsB, int RB)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    double mx = -INFINITY;
+    for (int w = 0; w < nwin; w++) mx = fmax(mx, w_ll[(size_t)w * S + s]);
+    double wt[4], tot = 0.0;
+    for (int w = 0; w < nwin; w++) {
+        const double l = w_ll[(size_t)w * S + s];
+        wt[w] = (isfinite(mx) && isfinite(l)) ? exp(l - mx) : 0.0;
+        tot += wt[w];
+    }
+    site_ll[s] = isfinite(mx) ? mx + log(tot) : -INFINITY;
+    for (int w = 0; w < nwin; w++) wt[w] = tot > 0.0 ? wt[w] / tot : 0.0;
+    if (rowsA) for (int r = 0; r < RA; r++) {
+        double acc = 0.0;
+        for (int w = 0; w < nwin; w++) if (wt[w] != 0.0) acc = fma(wt[w], rowsA[((size_t)w * RA + r) * S + s], acc);
+        rowsA[(size_t)r * S + s] = acc;
+    }
+    if (rowsB) for (int r = 0; r < RB; r++) {
+        double acc = 0.0;
+        for (int w = 0; w < nwin; w++) if (wt[w] != 0.0) acc = fma(wt[w], rowsB[((size_t)w * RB + r) * S + s], acc);
+        rowsB[(size_t)r * S + s] = acc;
+    }
+}
+
+/*
+ * n = 4 with more than 4 rate categories (GTR+Gamma4+I has 5, Gamma8 has 8): the fused kernel is instantiated for up to 4
+ * categories in lock-step, so the categories are processed in windows of <= 4 -- each a launch of the tuned kernel with
+ * per-site outputs -- and combined per site.  The site likelihood is a sum over categories, L = sum_w L_w, and every
+ * per-site output a likelihood-weighted mean, x = sum_w x_w L_w / L, so the combination is exact up to rounding.
+ */
+static int run_fused_windows(plf_engine *e, Query &q)
+{
+    const int Ctot = e->C, nwin = (Ctot + 3) / 4, E = e->E, N = e->N;
+    const int64_t S = e->S;
+    const bool marg = q.want_marg, edge = q.want_edge && !marg;
+    if (nwin > 4) FAIL(e, "more than 16 rate categories");
+    if (resolve_pending(e)) return -1;
+    ENSURE(e, e->f4w_ll, sizeof(double) * (size_t)nwin * S);
+    if (edge) ENSURE(e, e->f4w_edge, sizeof(double) * (size_t)nwin * E * S);
+    if (marg) ENSURE(e, e->f4w_marg, sizeof(double) * (size_t)nwin * N * 4 * S);
+    ENSURE(e, e->d_site_ll, sizeof(double) * S);
+    ENSURE(e, e->d_sum, sizeof(double) * (2 + E + (size_t)N * 4));
+    float ms_total = 0.f;
+    for (int w = 0; w < nwin; w++) {
+        F4Window win;
+        win.c0 = 4 * w;
+        win.site_ll = e->f4w_ll.as<double>() + (size_t)w * S;
+        win.site_edge = edge ? e->f4w_edge.as<double>() + (size_t)w * E * S : nullptr;
+        win.site_marg = marg ? e->f4w_marg.as<double>() + (size_t)w * N * 4 * S : nullptr;
+        e->C = std::min(4, Ctot - 4 * w);
+        const int rc = run_fused(e, q, &win);
+        e->C = Ctot;
+        if (rc) return rc;
+        float t = 0.f;
+        CK(e, cudaEventSynchronize(e->ev[4]));
+        cudaEventElapsedTime(&t, e->ev[3], e->ev[4]);
+        ms_total += t;
+    }
+    e->last_kernel += " (x" + std::to_string(nwin) + " category windows)";
+    double *site_ll = e->d_site_ll.as<double>();
+    f4_combine_windows_kernel<<<(unsigned)((S + 255) / 256), 256, 0, e->stream>>>(
+        nwin, S, e->f4w_ll.as<double>(), site_ll, edge ? e->f4w_edge.as<double>() : nullptr, E,
+        marg ? e->f4w_marg.as<double>() : nullptr, N * 4);
+    KCHECK(e);
+    const double *w = e->have_w ? e->d_site_w.as<double>() : nullptr;
+    double *dsum = e->d_sum.as<double>();
+    const size_t nsum = 1 + E + (size_t)N * 4;
+    CK(e, cudaMemsetAsync(dsum, 0, sizeof(double) * nsum, e->stream));
+    CK(e, cudaMemsetAsync(e->d_err.p, 0, sizeof(int), e->stream));
+    zero_lik_rows_kernel<<<(unsigned)((S + 255) / 256), 256, 0, e->stream>>>(site_ll, w, 0, (int)S, e->d_err.as<int>(),
+                                                                            edge ? e->f4w_edge.as<double>() : nullptr, E,
+                                                                            marg ? e->f4w_marg.as<double>() : nullptr, N * 4);
+    KCHECK(e);
+    if (q.sum_ll) { wsum_rows_kernel<<<1, 256, 0, e->stream>>>(site_ll, w, 0, (int)S, dsum, e->d_err.as<int>(), 1); KCHECK(e); }
+    if (edge && q.sum_edge) { wsum_rows_kernel<<<E, 256, 0, e->stream>>>(e->f4w_edge.as<double>(), w, 0, (int)S, dsum + 1, e->d_err.as<int>(), 0); KCHECK(e); }
+    if (marg && q.sum_marg) { wsum_rows_kernel<<<N * 4, 256, 0, e->stream>>>(e->f4w_marg.as<double>(), w, 0, (int)S, dsum + 1 + E, e->d_err.as<int>(), 0); KCHECK(e); }
+    if (finish_sums(e, dsum, nsum)) return -1;
+    CK(e, cudaEventRecord(e->ev[2], e->stream));
+    std::vector<double> hs(nsum);
+    int herr = 0;
+    CK(e, cudaMemcpyAsync(hs.data(), dsum, sizeof(double) * nsum, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaMemcpyAsync(&herr, e->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    if (q.site_ll) CK(e, cudaMemcpyAsync(q.site_ll, site_ll, sizeof(double) * S, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    if (herr && (q.sum_ll || q.sum_edge || q.sum_marg)) FAIL(e, "a site with non-zero weight has zero likelihood");
+    if (q.sum_ll) *q.sum_ll = hs[0];
+    if (edge && q.sum_edge) memcpy(q.sum_edge, hs.data() + 1, sizeof(double) * E);
+    if (marg && q.sum_marg) memcpy(q.sum_marg, hs.data() + 1 + E, sizeof(double) * (size_t)N * 4);
+    if (edge && q.site_edge && copy_site_matrix(e, e->f4w_edge.as<double>(), E, S, q.site_edge)) return -1;
+    if (marg && q.site_marg && copy_site_matrix(e, e->f4w_marg.as<double>(), N * 4, S, q.site_marg)) return -1;
+    e->ms_kernel_override = ms_total;
     return 0;
 }
 
@@ -1942,13 +2067,15 @@ static int run_query_once(plf_engine *e, Query &q, bool need_D, const double *l_
     if (use_fused && ensure_tip_tables(e, q.want_edge ? q.Fm : nullptr, f_mode, q.want_marg)) return -1;
     CK(e, cudaEventRecord(e->ev[1], e->stream));
     e->kernel_timed = false;
-    int rc = use_fused ? run_fused(e, q)
+    e->ms_kernel_override = -1.f;
+    int rc = use_fused ? (e->C > 4 ? run_fused_windows(e, q) : run_fused(e, q))
                        : (e->path != PLF_PATH_GENERIC && !q.sum_hess && dmma_applicable(e, q)) ? run_dmma(e, q) : run_generic(e, q);
     if (rc) return rc;
     cudaEventElapsedTime(&e->ms_mat, e->ev[0], e->ev[1]);
     cudaEventElapsedTime(&e->ms_sites, e->ev[1], e->ev[2]);
     e->ms_kernel = 0.f;
     if (e->kernel_timed) cudaEventElapsedTime(&e->ms_kernel, e->ev[3], e->ev[4]);
+    if (e->ms_kernel_override >= 0.f) e->ms_kernel = e->ms_kernel_override;
     return 0;
 }
 

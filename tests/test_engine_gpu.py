@@ -49,8 +49,8 @@ def _paths(m, C, K):
     t = m.tree
     maxdeg = max(t.indptr[i + 1] - t.indptr[i] for i in range(t.node_count))
     p = [E.PATH_GENERIC]
-    if m.n == 4 and C <= 4 and maxdeg <= 3 and K <= 256:
-        p.append(E.PATH_FUSED4)
+    if m.n == 4 and C <= 16 and maxdeg <= 3 and K <= 256:
+        p.append(E.PATH_FUSED4)          # more than 4 categories: windows of <= 4 (run_fused_windows)
     if 16 < m.n <= 64 and K <= 256:
         p.append(E.PATH_AUTO)           # ll and edge forms on the tensor-pipe kernels (generic = tile / scalar kernels)
     return p
@@ -75,6 +75,9 @@ RANDOM = [
     # codon- and amino-acid-sized state spaces: the FP64 tensor-pipe kernels (dmma.cu) against the 320-bit oracle
     dict(seed=13, ntips=4, n=61, S=9, ncat=1, missing=0.15),
     dict(seed=14, ntips=6, n=20, S=19, ncat=2, missing=0.2, root="equilibrium_distribution"),
+    # more than 4 rate categories on the fused path: Gamma8, and Gamma6 + invariant (7 categories, one of rate 0)
+    dict(seed=15, ntips=11, n=4, S=40, ncat=8, mixture="gamma", missing=0.1),
+    dict(seed=16, ntips=9, n=4, S=25, ncat=7, mixture="median_inv", root="equilibrium_distribution"),
 ]
 
 
