@@ -13,6 +13,7 @@ typedef struct {
     char *err;
     size_t errlen;
     int depth;
+    size_t hint;        /* length of the array parsed last: rows of a matrix have one length, so the next one is sized right at once */
 } parser;
 
 static void fail(parser *ps, const char *msg)
@@ -33,7 +34,7 @@ static void free_contents(jv *v)
 {
     if (v->type == JV_STRING) free(v->u.s);
     else if (v->type == JV_ARRAY) {
-        for (uint32_t i = 0; i < v->len; i++) free_contents(&v->u.items[i]);
+        for (uint32_t i = 0; i < v->len; i++) if (v->u.items[i].type >= JV_STRING) free_contents(&v->u.items[i]);
         free(v->u.items);
     } else if (v->type == JV_OBJECT) {
         for (uint32_t i = 0; i < 2 * v->len; i++) free_contents(&v->u.items[i]);
@@ -145,7 +146,7 @@ static int parse_number(parser *ps, jv *out)
 
 static int parse_array(parser *ps, jv *out)
 {
-    size_t cap = 8, len = 0;
+    size_t cap = (ps->hint >= 8 && ps->hint <= (1u << 20)) ? ps->hint : 8, len = 0;
     jv *items = malloc(cap * sizeof(jv));
     if (!items) { fail(ps, "out of memory"); return -1; }
     ps->p++;
@@ -159,6 +160,30 @@ static int parse_array(parser *ps, jv *out)
             items = t;
         }
         skip_ws(ps);
+        {
+            /* fast path for what a large document consists of: short non-negative integers (character codes) directly
+             * followed by ',' or ']'.  Anything else -- signs, fractions, exponents, leading zeros -- takes the general
+             * route and its checks. */
+            const char *q = ps->p;
+            if (*q >= '1' && *q <= '9') {
+                int64_t v = *q++ - '0';
+                int nd = 1;
+                while (*q >= '0' && *q <= '9' && nd < 9) { v = v * 10 + (*q++ - '0'); nd++; }
+                if (*q == ',' || *q == ']') {
+                    items[len].type = JV_INT; items[len].len = 0; items[len].u.i = v;
+                    len++;
+                    ps->p = q + 1;
+                    if (*q == ',') continue;
+                    break;
+                }
+            } else if (*q == '0' && (q[1] == ',' || q[1] == ']')) {
+                items[len].type = JV_INT; items[len].len = 0; items[len].u.i = 0;
+                len++;
+                ps->p = q + 2;
+                if (q[1] == ',') continue;
+                break;
+            }
+        }
         if (parse_value(ps, &items[len])) goto bad;
         len++;
         skip_ws(ps);
@@ -169,6 +194,7 @@ static int parse_array(parser *ps, jv *out)
     }
 done:
     if (len < cap && len > 0) { jv *t = realloc(items, len * sizeof(jv)); if (t) items = t; }
+    ps->hint = len;
     out->type = JV_ARRAY; out->len = (uint32_t)len; out->u.items = items;
     return 0;
 bad:
@@ -251,7 +277,7 @@ static int parse_value(parser *ps, jv *out)
 
 jv *json_parse(const char *text, char *err, size_t errlen)
 {
-    parser ps = {text, text, err, errlen, 0};
+    parser ps = {text, text, err, errlen, 0, 0};
     if (err && errlen) err[0] = 0;
     jv *root = malloc(sizeof(jv));
     if (!root) { fail(&ps, "out of memory"); return NULL; }

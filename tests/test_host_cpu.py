@@ -236,3 +236,25 @@ def test_no_cpu_fallback_without_gpu():
         A.arbplf_ll(json.dumps(GOOD))
     with pytest.raises(EngineError):
         Engine(0)
+
+
+def test_integer_fast_path_of_the_json_reader():
+    """Arrays of short non-negative integers (character codes) take a tight loop in host/json.c; everything it does not
+    recognise -- leading zeros, signs, fractions, long integers, blanks -- must still get the general route's treatment."""
+    import phyly_b200.arbplf as A
+    md = {"edges": [[0, 1], [0, 2]], "edge_rate_coefficients": [1, 2], "rate_matrix": [[0, 1], [1, 0]],
+          "character_definitions": [[1, 0], [0, 1], [1, 1]], "character_data": [[2, 0, 1], [2, 1, 1]]}
+    good = json.dumps({"model_and_data": md})
+    s = json.loads(A.arbplf_model_summary(good))
+    assert s["edge_rates_csr"] == [1.0, 2.0]
+    spaced = good.replace("[2, 0, 1]", "[ 2 ,0\n, 1 ]")
+    assert json.loads(A.arbplf_model_summary(spaced)) == s
+    for bad in (good.replace("[2, 0, 1]", "[2, 00, 1]"), good.replace("[2, 0, 1]", "[2, 01, 1]"),
+                good.replace("[2, 0, 1]", "[2, -0, 1]").replace("-0", "-1"), good.replace("[2, 0, 1]", "[2, 0.5, 1]"),
+                good.replace("[2, 0, 1]", "[2, 3, 1]"), good.replace("[2, 0, 1]", "[2, 12345678901234567890, 1]"),
+                good.replace("[2, 0, 1]", "[2, 0, 1,]"), good.replace("[2, 0, 1]", "[2 0 1]")):
+        with pytest.raises(RuntimeError):
+            A.arbplf_model_summary(bad)
+    # integers where reals are expected stay valid, long integers keep their value
+    ok = good.replace('"edge_rate_coefficients": [1, 2]', '"edge_rate_coefficients": [1234567890123, 2]')
+    assert json.loads(A.arbplf_model_summary(ok))["edge_rates_csr"][0] == 1234567890123.0
