@@ -90,7 +90,7 @@ def test_reductions_against_oracle(name, program, doc):
 def test_cli_executables():
     exe = os.path.join(ROOT, "phyly_b200", "bin")
     for name, prog in (("fels_ll", "ll"), ("bpp_deriv", "deriv"), ("beast_anc_marginal", "marginal"),
-                       ("mj_rewards", "dwell"), ("mj_jumps", "trans")):
+                       ("mj_rewards", "dwell"), ("mj_jumps", "trans"), ("fels_hess_leaf", "hess"), ("fels_em_leaf", "em-update")):
         text = json.dumps(H.golden_in(name))
         p = subprocess.run([os.path.join(exe, "arbplf-" + prog)], input=text, capture_output=True, text=True)
         assert p.returncode == 0, p.stderr
@@ -99,8 +99,17 @@ def test_cli_executables():
     # errors: non-zero exit status, message on stderr, nothing on stdout (arbplf-ll.c:13-14)
     p = subprocess.run([os.path.join(exe, "arbplf-ll")], input='{"model_and_data": {}}', capture_output=True, text=True)
     assert p.returncode != 0 and p.stdout == "" and "error" in p.stderr
+    # arbplf-hess without an aggregating site reduction (arbplfhess.c:1196-1200)
     p = subprocess.run([os.path.join(exe, "arbplf-hess")], input=json.dumps(H.golden_in("fels_ll")), capture_output=True, text=True)
-    assert p.returncode != 0
+    assert p.returncode != 0 and p.stdout == ""
+    # the other second-order programs and the certified ll run through their executables too
+    doc = json.dumps(H.golden_in("fels_hess_leaf"))
+    for prog in ("inv-hess", "newton-delta", "newton-update", "newton-refine"):
+        p = subprocess.run([os.path.join(exe, "arbplf-" + prog)], input=doc, capture_output=True, text=True)
+        assert p.returncode == 0 and json.loads(p.stdout)["columns"][-1] == "value", (prog, p.stderr)
+    p = subprocess.run([os.path.join(exe, "arbplf-ll-certified")], input=json.dumps(H.golden_in("fels_ll")), capture_output=True, text=True)
+    out = json.loads(p.stdout)
+    assert out["lower"]["data"][0][-1] <= -11.297288182875496 <= out["upper"]["data"][0][-1]
 
 
 def test_output_formatting_matches_jansson():
