@@ -751,12 +751,36 @@ def cpu_baseline(pb, target_seconds=15.0, sample=None):
             "seconds": dt, "sample_sites": sample}
 
 
+def build_problem_reference(args):
+    """The same workload set up WITHOUT the product: model quantities and matrices from the oracle (fp64 back end), so that
+    the reference arm never maps libarbplf_b200.so."""
+    from oracle import arbplf_oracle as O
+    doc, N = model_document(args.taxa)
+    be = O.get_backend("fp64")
+    m = O.parse_model(doc["model_and_data"])
+    cs = O.cross_site(m, be)
+    t = m.tree
+    summary = {"indptr": list(t.indptr), "indices": list(t.indices), "preorder": list(t.preorder),
+               "cat_prior": [float(x) for x in cs.prior], "root_mode": int(m.root_mode),
+               "root_vec": [float(x) for x in O.root_prior_vector(m, cs, be)]}
+    P = np.asarray(cs.P, dtype=np.float64)
+    D = np.empty_like(P)
+    Q = np.asarray(cs.Q, dtype=np.float64)
+    for c in range(cs.C):
+        for e in range(cs.E):
+            D[c, e] = float(cs.rates[c]) * (Q @ P[c, e])
+    S = args.sites
+    codes = np.empty((S, N), dtype=np.uint8)
+    simulate_codes(summary, P, S, seed=3, out=codes)
+    return dict(eng=None, summary=summary, N=N, E=N - 1, n=m.n, C=cs.C, S=S, codes=codes, P=P, D=D, doc=doc)
+
+
 def run_reference(args):
     """Reference arm: the reference's CPU algorithm (C restatement; Arb cannot be built here) on host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    pb = build_problem(args, 0, 0, use_engine=False)
+    pb = build_problem_reference(args)
     from oracle import c_port
     threads = host_threads()
     # size each step so that the whole run ends within a few minutes
@@ -773,15 +797,19 @@ def run_reference(args):
     value = sample * pb["E"] * pb["C"] * args.steps / dt
     cb = {"value": value, "unit": "updates/s", "cores": threads, "kind": "port",
           "sample": "%d of %d site patterns per step, ll+deriv, oracle/c/plf_oracle.c (OpenMP, fp64)" % (sample, pb["S"])}
+    Eg, C = pb["E"], pb["C"]
     line = {
         "impl": "reference", "metric": "site-edge-category updates/s (ll+deriv)", "value": value, "unit": "updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg2: GTR+Gamma4 (examples/BEAST.GTRG model) x %d-taxon Yule tree x %d site patterns "
-                               "(bounded sample of %d per step), arbplf-ll + arbplf-deriv, site axis summed"
-                               % (args.taxa, pb["S"], sample),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        # the same keys and workload string as the product arm (the GPUs only shard it; this arm has none)
+        "config": {"workload": "cfg2: GTR+Gamma4 (examples/BEAST.GTRG model) x %d-taxon Yule tree x %d site patterns in total, "
+                               "sharded over the GPUs, arbplf-ll + arbplf-deriv, site axis summed" % (args.taxa, pb["S"]),
+                   "sites_total": pb["S"], "taxa": args.taxa, "edges": Eg, "categories": C, "states": pb["n"],
+                   "sample": "each step evaluates %d of the %d site patterns (bounded sample), all host threads" % (sample, pb["S"]),
                    "note": "the Arb reference cannot be compiled in this image (no arb/flint/gmp/jansson headers); "
-                           "this is its algorithm restated in C (oracle/c), fp64, one OpenMP thread per host core"},
+                           "this is its algorithm restated in C (oracle/c), fp64, one OpenMP thread per host core; "
+                           "set up from the oracle alone, the product library is not loaded"},
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
