@@ -70,6 +70,7 @@ struct NcclApi {
     int (*GetUniqueId)(plf_nccl_id *) = nullptr;
     int (*CommInitRank)(plf_nccl_comm *, int, plf_nccl_id, int) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, plf_nccl_comm, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, plf_nccl_comm, cudaStream_t) = nullptr;
     int (*CommDestroy)(plf_nccl_comm) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     bool load()
@@ -81,12 +82,16 @@ struct NcclApi {
         GetUniqueId = (int (*)(plf_nccl_id *))dlsym(lib, "ncclGetUniqueId");
         CommInitRank = (int (*)(plf_nccl_comm *, int, plf_nccl_id, int))dlsym(lib, "ncclCommInitRank");
         AllReduce = (int (*)(const void *, void *, size_t, int, int, plf_nccl_comm, cudaStream_t))dlsym(lib, "ncclAllReduce");
+        AllGather = (int (*)(const void *, void *, size_t, int, plf_nccl_comm, cudaStream_t))dlsym(lib, "ncclAllGather");
         CommDestroy = (int (*)(plf_nccl_comm))dlsym(lib, "ncclCommDestroy");
         GetErrorString = (const char *(*)(int))dlsym(lib, "ncclGetErrorString");
         return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
     }
 };
 static NcclApi g_nccl;
+
+#define PLF_PEER_MAX 16
+#define PLF_PEER_CAP 8192          /* doubles per (sender, parity) slot of an inbox */
 
 struct Cand { int bd, staged; bool pack, cm; f4_kernel_t k; size_t smem; int per_sm; bool gstack; };
 
@@ -164,6 +169,13 @@ struct plf_engine {
     int nranks = 1;
     bool comm_paused = false;
     std::string last_kernel;
+    /* all-reduce of the (short) sum vectors over peer memory instead of NCCL (peer_allreduce_kernel) */
+    int rank = 0;
+    bool peer_ready = false;
+    void *peer_local = nullptr;                 /* this rank's inbox + flags (cudaMalloc, exported through CUDA IPC) */
+    void *peer_ptr[PLF_PEER_MAX] = {nullptr};   /* every rank's inbox as mapped here (own entry = peer_local) */
+    DevBuf d_peer_ptrs;
+    unsigned long long peer_seq = 0;
 };
 
 #define FAIL(e, ...) do { char _b[512]; snprintf(_b, sizeof(_b), __VA_ARGS__); (e)->err = _b; return -1; } while (0)
@@ -294,6 +306,69 @@ __global__ void zero_lik_rows_kernel(const double *ll, const double *w, int64_t 
     if (rowsB) for (int r = 0; r < RB; r++) rowsB[(size_t)r * cols + s] = nan;
 }
 
+/*
+ * All-reduce (sum) of a short vector over NVLink peer memory, fused with nothing but itself: one CTA per GPU.
+ * Every rank stores its vector into the inbox of every rank (slot [sender][parity of the sequence number]), publishes
+ * the sequence number in that inbox's flag for the sender with a system-scope release, waits until the flags of all
+ * senders in its own inbox carry the sequence number, and adds the nranks vectors in rank order -- so every rank gets
+ * the same bits.  Two parities suffice: a rank can only be one collective ahead of the slowest one, because the next
+ * collective needs that rank's flag.  A bounded spin turns a lost peer into an error flag instead of a hung GPU.
+ * Inbox layout: double data[PLF_PEER_MAX][2][PLF_PEER_CAP]; unsigned long long flag[PLF_PEER_MAX][2].
+ */
+__global__ void peer_allreduce_kernel(double *vec, int count, unsigned long long seq, int rank, int nranks,
+                                      void *const *inbox_of, int *err,
+                                      const double *part_ll, const double *part_edge, int rows, int E)
+{
+    /* fused with the second stage of the reduction: vec[0] = sum of the per-CTA log-likelihood sums, vec[1 + e] = sum of
+     * the per-CTA sums of edge e (fixed order, compensated), when the partial sums are handed in instead of a finished vec */
+    if (part_ll) {
+        for (int j = threadIdx.x; j < count; j += blockDim.x) {
+            const double *col = (j == 0) ? part_ll : part_edge + (j - 1);
+            const int stride = (j == 0) ? 1 : E;
+            double sum = 0.0, comp = 0.0;
+            for (int r = 0; r < rows; r++) {
+                const double y = col[(size_t)r * stride] - comp, t = sum + y;
+                comp = (t - sum) - y;
+                sum = t;
+            }
+            vec[j] = sum;
+        }
+        __syncthreads();
+    }
+    const int par = (int)(seq & 1);
+    const size_t flag_off = sizeof(double) * (size_t)PLF_PEER_MAX * 2 * PLF_PEER_CAP;
+    for (int p = 0; p < nranks; p++) {
+        double *dst = reinterpret_cast<double *>(inbox_of[p]) + ((size_t)rank * 2 + par) * PLF_PEER_CAP;
+        for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = vec[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < nranks) {
+        unsigned long long *flag = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(inbox_of[threadIdx.x]) + flag_off) + rank * 2 + par;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
+    }
+    __shared__ int ok;
+    if (threadIdx.x == 0) ok = 1;
+    __syncthreads();
+    if (threadIdx.x < nranks) {
+        const unsigned long long *flag = reinterpret_cast<const unsigned long long *>(reinterpret_cast<const char *>(inbox_of[rank]) + flag_off) + threadIdx.x * 2 + par;
+        unsigned long long v = 0;
+        long long spins = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+        } while (v != seq && ++spins < 4000000LL);          /* a few seconds */
+        if (v != seq) ok = 0;
+    }
+    __syncthreads();
+    if (!ok) { if (threadIdx.x == 0) atomicOr(err, 4); return; }
+    const double *mine = reinterpret_cast<const double *>(inbox_of[rank]);
+    for (int i = threadIdx.x; i < count; i += blockDim.x) {
+        double acc = 0.0;
+        for (int r = 0; r < nranks; r++) acc += mine[((size_t)r * 2 + par) * PLF_PEER_CAP + i];
+        vec[i] = acc;
+    }
+}
+
 /* y += alpha x */
 __global__ void axpy_kernel(double *y, const double *x, double alpha, size_t count)
 {
@@ -382,6 +457,9 @@ extern "C" void plf_destroy(plf_engine *e)
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
+    for (int p = 0; p < e->nranks && p < PLF_PEER_MAX; p++)
+        if (e->peer_ptr[p] && e->peer_ptr[p] != e->peer_local) cudaIpcCloseMemHandle(e->peer_ptr[p]);
+    if (e->peer_local) cudaFree(e->peer_local);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     DevBuf *bufs[] = {&e->d_indptr, &e->d_indices, &e->d_preorder, &e->d_node_has_data, &e->d_qhi, &e->d_qlo,
                       &e->d_edge_rates, &e->d_cat_rates, &e->d_cat_prior, &e->d_root_vec, &e->d_P, &e->d_D, &e->d_F,
@@ -989,8 +1067,21 @@ static int ensure_tip_tables(plf_engine *e, const double *Fm, int f_mode, bool w
     return 0;
 }
 
+static bool peer_path(const plf_engine *e, size_t count)
+{
+    return e->comm && !e->comm_paused && e->peer_ready && count <= PLF_PEER_CAP && !getenv("PLF_NO_PEER_ALLREDUCE");
+}
+
 static int finish_sums(plf_engine *e, double *d_sum, size_t count)
 {
+    if (e->comm && !e->comm_paused && e->peer_ready && count <= PLF_PEER_CAP && !getenv("PLF_NO_PEER_ALLREDUCE")) {
+        ENSURE(e, e->d_err, sizeof(int) * (e->N + 4));
+        e->peer_seq++;
+        peer_allreduce_kernel<<<1, 256, 0, e->stream>>>(d_sum, (int)count, e->peer_seq, e->rank, e->nranks,
+                                                        e->d_peer_ptrs.as<void *>(), e->d_err.as<int>(), nullptr, nullptr, 0, 0);
+        KCHECK(e);
+        return 0;
+    }
     if (e->comm && !e->comm_paused) {
         int r = g_nccl.AllReduce(d_sum, d_sum, count, /*ncclDouble*/ 8, /*ncclSum*/ 0, e->comm, e->stream);
         if (r != 0) FAIL(e, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
@@ -1355,8 +1446,12 @@ static int run_fused(plf_engine *e, Query &q, const F4Window *win = nullptr)
     a.block_ll = e->d_block_ll.as<double>();
     if (edge) a.block_edge = e->d_block_edge.as<double>();
     double *dsum = e->d_sum.as<double>();
-    sum_rows_kernel<<<1, 32, 0, e->stream>>>(a.block_ll, rows, 1, dsum);
-    KCHECK(e);
+    /* ll / ll + edge sums with a communicator: second-stage reduction and all-reduce are one kernel over peer memory */
+    const bool fuse_reduce = !marg && !q.site_edge && !pipelined && peer_path(e, 1 + (size_t)(edge ? e->E : 0));
+    if (!fuse_reduce) {
+        sum_rows_kernel<<<1, 32, 0, e->stream>>>(a.block_ll, rows, 1, dsum);
+        KCHECK(e);
+    }
     size_t nsum = 1;
     if (marg) {
         const int cols = e->N * 4;
@@ -1374,8 +1469,10 @@ static int run_fused(plf_engine *e, Query &q, const F4Window *win = nullptr)
         nsum = 1 + e->E + cols;
     }
     if (edge && !marg && !q.site_edge) {
-        sum_rows_kernel<<<(e->E + 127) / 128, 128, 0, e->stream>>>(a.block_edge, rows, e->E, dsum + 1);
-        KCHECK(e);
+        if (!fuse_reduce) {
+            sum_rows_kernel<<<(e->E + 127) / 128, 128, 0, e->stream>>>(a.block_edge, rows, e->E, dsum + 1);
+            KCHECK(e);
+        }
         nsum = 1 + e->E;
     }
     if (edge && !marg && q.site_edge && q.sum_edge) {
@@ -1386,7 +1483,12 @@ static int run_fused(plf_engine *e, Query &q, const F4Window *win = nullptr)
         nsum = 1 + e->E;
     }
     if (shared_retry) CK(e, cudaMemcpyAsync(dsum + nsum, e->d_retry.p, sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
-    if (finish_sums(e, dsum, nsum + (shared_retry ? 1 : 0))) return -1;
+    if (fuse_reduce) {
+        e->peer_seq++;
+        peer_allreduce_kernel<<<1, 256, 0, e->stream>>>(dsum, (int)nsum, e->peer_seq, e->rank, e->nranks, e->d_peer_ptrs.as<void *>(),
+                                                        e->d_err.as<int>(), a.block_ll, edge ? a.block_edge : nullptr, rows, e->E);
+        KCHECK(e);
+    } else if (finish_sums(e, dsum, nsum + (shared_retry ? 1 : 0))) return -1;
     CK(e, cudaEventRecord(e->ev[2], e->stream));
     std::vector<double> hs(nsum + 1, 0.0);
     int herr = 0;
@@ -1404,7 +1506,8 @@ static int run_fused(plf_engine *e, Query &q, const F4Window *win = nullptr)
         if (changed || (shared_retry && hs[nsum] != 0.0)) return 1;
     }
     if (q.site_edge && copy_site_matrix(e, e->d_edge_site.as<double>(), e->E, e->S, q.site_edge)) return -1;
-    if (herr && (q.sum_ll || q.sum_edge || q.sum_marg)) FAIL(e, "a site with non-zero weight has zero likelihood");
+    if (herr & 4) FAIL(e, "all-reduce over peer memory timed out (a rank is missing)");
+    if ((herr & 1) && (q.sum_ll || q.sum_edge || q.sum_marg)) FAIL(e, "a site with non-zero weight has zero likelihood");
     if (q.sum_ll) *q.sum_ll = hs[0];
     if (q.sum_edge && !marg && nsum > 1) memcpy(q.sum_edge, hs.data() + 1, sizeof(double) * e->E);
     if (marg && q.site_marg && copy_site_matrix(e, e->d_marg_site.as<double>(), e->N * 4, e->S, q.site_marg)) return -1;
@@ -1501,7 +1604,8 @@ static int run_fused_windows(plf_engine *e, Query &q)
     CK(e, cudaMemcpyAsync(&herr, e->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     if (q.site_ll) CK(e, cudaMemcpyAsync(q.site_ll, site_ll, sizeof(double) * S, cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
-    if (herr && (q.sum_ll || q.sum_edge || q.sum_marg)) FAIL(e, "a site with non-zero weight has zero likelihood");
+    if (herr & 4) FAIL(e, "all-reduce over peer memory timed out (a rank is missing)");
+    if ((herr & 1) && (q.sum_ll || q.sum_edge || q.sum_marg)) FAIL(e, "a site with non-zero weight has zero likelihood");
     if (q.sum_ll) *q.sum_ll = hs[0];
     if (edge && q.sum_edge) memcpy(q.sum_edge, hs.data() + 1, sizeof(double) * E);
     if (marg && q.sum_marg) memcpy(q.sum_marg, hs.data() + 1 + E, sizeof(double) * (size_t)N * 4);
@@ -1788,6 +1892,7 @@ static int run_generic(plf_engine *e, Query &q)
     if (q.site_ll) CK(e, cudaMemcpyAsync(q.site_ll, e->d_site_ll.p, sizeof(double) * e->S, cudaMemcpyDeviceToHost, e->stream));
     if (q.sum_hess) CK(e, cudaMemcpyAsync(q.sum_hess, e->h_out.p, sizeof(double) * (size_t)E * E, cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
+    if (herr & 4) FAIL(e, "all-reduce over peer memory timed out (a rank is missing)");
     if ((herr & 2) && q.sum_hess) FAIL(e, "infeasible: a rate category with a non-zero rate has zero likelihood at a weighted site");
     if ((herr & 1) && (q.sum_ll || q.sum_edge || q.sum_marg)) FAIL(e, "a site with non-zero weight has zero likelihood");
     if (q.sum_hess) {
@@ -2026,7 +2131,8 @@ static int run_dmma(plf_engine *e, Query &q)
     CK(e, cudaMemcpyAsync(&herr, e->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     if (q.site_ll) CK(e, cudaMemcpyAsync(q.site_ll, e->d_site_ll.p, sizeof(double) * e->S, cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
-    if (herr && (q.sum_ll || q.sum_edge)) FAIL(e, "a site with non-zero weight has zero likelihood");
+    if (herr & 4) FAIL(e, "all-reduce over peer memory timed out (a rank is missing)");
+    if ((herr & 1) && (q.sum_ll || q.sum_edge)) FAIL(e, "a site with non-zero weight has zero likelihood");
     if (q.sum_ll) *q.sum_ll = hs[0];
     if (q.sum_edge) memcpy(q.sum_edge, hs.data() + 1, sizeof(double) * E);
     return 0;
@@ -2396,5 +2502,53 @@ extern "C" int plf_comm_init(plf_engine *e, int nranks, int rank, const char id[
     int r = g_nccl.CommInitRank(&e->comm, nranks, u, rank);
     if (r != 0) { e->comm = nullptr; FAIL(e, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); }
     e->nranks = nranks;
+    e->rank = rank;
+    /* Peer-memory path for the short sum vectors: every rank exports an inbox through CUDA IPC, the handles travel once
+     * through ncclAllGather, and from then on the all-reduce is one small kernel of P2P stores and loads
+     * (peer_allreduce_kernel).  Any failure here simply leaves the NCCL path in place. */
+    e->peer_ready = false;
+    if (nranks <= PLF_PEER_MAX && g_nccl.AllGather && !getenv("PLF_NO_PEER_ALLREDUCE")) {
+        const size_t bytes = sizeof(double) * (size_t)PLF_PEER_MAX * 2 * PLF_PEER_CAP + sizeof(unsigned long long) * PLF_PEER_MAX * 2;
+        bool ok = cudaMalloc(&e->peer_local, bytes) == cudaSuccess && cudaMemset(e->peer_local, 0, bytes) == cudaSuccess;
+        cudaIpcMemHandle_t mine;
+        char *d_h = nullptr;
+        std::vector<cudaIpcMemHandle_t> all(nranks);
+        ok = ok && cudaIpcGetMemHandle(&mine, e->peer_local) == cudaSuccess;
+        ok = ok && cudaMalloc((void **)&d_h, sizeof(mine) * (nranks + 1)) == cudaSuccess;
+        /* the collective below must be entered by every rank, whatever happened locally: a failed rank sends zeros */
+        if (!ok) memset(&mine, 0, sizeof(mine));
+        if (d_h) {
+            cudaMemcpyAsync(d_h + sizeof(mine) * nranks, &mine, sizeof(mine), cudaMemcpyHostToDevice, e->stream);
+            const int rr = g_nccl.AllGather(d_h + sizeof(mine) * nranks, d_h, sizeof(mine), /*ncclChar*/ 0, e->comm, e->stream);
+            ok = ok && rr == 0;
+            cudaMemcpyAsync(all.data(), d_h, sizeof(mine) * nranks, cudaMemcpyDeviceToHost, e->stream);
+            ok = (cudaStreamSynchronize(e->stream) == cudaSuccess) && ok;
+            cudaFree(d_h);
+        }
+        const cudaIpcMemHandle_t zero = {};
+        for (int p = 0; ok && p < nranks; p++) if (!memcmp(&all[p], &zero, sizeof(zero))) ok = false;       /* some rank could not export */
+        for (int p = 0; ok && p < nranks; p++) {
+            if (p == rank) { e->peer_ptr[p] = e->peer_local; continue; }
+            if (cudaIpcOpenMemHandle(&e->peer_ptr[p], all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); }
+        }
+        if (ok && !e->d_peer_ptrs.ensure(sizeof(void *) * PLF_PEER_MAX))
+            ok = cudaMemcpy(e->d_peer_ptrs.p, e->peer_ptr, sizeof(void *) * PLF_PEER_MAX, cudaMemcpyHostToDevice) == cudaSuccess;
+        else ok = false;
+        /* every rank takes the peer path or none does */
+        double *d_ok = nullptr;
+        double h_ok = ok ? 1.0 : 0.0;
+        if (cudaMalloc((void **)&d_ok, sizeof(double)) == cudaSuccess) {
+            cudaMemcpyAsync(d_ok, &h_ok, sizeof(double), cudaMemcpyHostToDevice, e->stream);
+            const int rr = g_nccl.AllReduce(d_ok, d_ok, 1, /*ncclDouble*/ 8, /*ncclSum*/ 0, e->comm, e->stream);
+            cudaMemcpyAsync(&h_ok, d_ok, sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+            if (cudaStreamSynchronize(e->stream) != cudaSuccess || rr != 0) h_ok = 0.0;
+            cudaFree(d_ok);
+        } else {
+            FAIL(e, "plf_comm_init: out of device memory");
+        }
+        e->peer_ready = (h_ok == (double)nranks);
+        e->peer_seq = 0;
+        cudaGetLastError();
+    }
     return 0;
 }

@@ -24,7 +24,8 @@
 #define TL_NP 64          /* padded state count */
 #define TL_TS 64          /* sites per tile */
 #define TL_PS 68          /* row stride of the staged P (doubles) */
-#define TL_LS 72          /* row stride of the staged child partials (doubles) */
+#define TL_LS 68          /* row stride of the staged child partials (doubles): = 4 mod 16, so that the 16 lanes (4 rows x 4 columns)
+                             of a half-warp B-fragment load fall on 16 different 8-byte banks (72 put rows q and q + 2 on the same ones) */
 
 __device__ __forceinline__ void tl_dmma(double &d0, double &d1, double a, double b)
 {
