@@ -1,7 +1,8 @@
 """
-Two ranks, two GPUs, NCCL: each rank owns half of the site patterns; the in-stream ncclAllReduce of
-plf_engine.cu (plf_comm_init) must give every rank the sums of a single-GPU run over all sites -- for the
-log-likelihood + derivative query, a dwell query and the site-summed marginals.  Skipped on a one-GPU box
+Two ranks, two GPUs: each rank owns half of the site patterns; the in-stream all-reduce of plf_engine.cu
+(plf_comm_init: the peer-memory kernel, and ncclAllReduce as its fallback) must give every rank the sums of a
+single-GPU run over all sites -- for the log-likelihood + derivative query, a dwell query, the site-summed
+marginals and the Hessian query -- and the same bits on every rank.  Skipped on a one-GPU box
 (the driver's `pytest -m gpu` run); run with `gpurun --gpus 2 -- python -m pytest tests/test_multigpu_gpu.py`.
 """
 import os
@@ -33,7 +34,8 @@ def queries(e):
     r = e.deriv(per_site=False)
     _, dw = e.edge_expect(E.KIND_DWELL, np.eye(4), per_site=False)
     _, mg = e.marginal(per_site=False)
-    return np.concatenate([[r["sum_ll"]], r["sum_deriv"], dw, mg.ravel()])
+    hl, hg, H = e.hess()                                  # 47 x 47 doubles: the peer-memory all-reduce; ll+deriv: its fused form
+    return np.concatenate([[r["sum_ll"]], r["sum_deriv"], dw, mg.ravel(), [hl], hg, H.ravel()])
 # single-GPU reference over all sites (no communicator yet)
 eng.set_data(defs, codes); eng.set_site_weights(w)
 want = queries(eng)
@@ -44,8 +46,17 @@ dist.broadcast_object_list(uid, src=0)
 eng.comm_init(world, rank, uid[0])
 eng.set_data(defs, np.ascontiguousarray(codes[lo:hi])); eng.set_site_weights(w[lo:hi])
 got = queries(eng)
+# every rank holds the same bits (the peer-memory all-reduce adds the vectors in rank order on every rank)
+peers = [None] * world
+dist.all_gather_object(peers, got.tobytes())
+same = all(p == peers[0] for p in peers)
+# the NCCL fallback gives the same sums
+os.environ["PLF_NO_PEER_ALLREDUCE"] = "1"
+got_nccl = queries(eng)
+del os.environ["PLF_NO_PEER_ALLREDUCE"]
 scale = np.abs(want).max()
-ok = bool(np.all(np.abs(got - want) <= 1e-11 * np.abs(want) + 1e-13 * scale))
+same = same and bool(np.all(np.abs(got_nccl - got) <= 1e-12 * np.abs(got) + 1e-13 * scale))
+ok = same and bool(np.all(np.abs(got - want) <= 1e-11 * np.abs(want) + 1e-13 * scale))
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
