@@ -1524,7 +1524,7 @@ __global__ void f4_combine_windows_kernel(int nwin, int64_t S, double *w_ll /*[n
     if (s >= S) return;
     double mx = -INFINITY;
     for (int w = 0; w < nwin; w++) mx = fmax(mx, w_ll[(size_t)w * S + s]);
-    double wt[4], tot = 0.0;
+    double wt[16], tot = 0.0;
     for (int w = 0; w < nwin; w++) {
         const double l = w_ll[(size_t)w * S + s];
         wt[w] = (isfinite(mx) && isfinite(l)) ? exp(l - mx) : 0.0;
@@ -1550,12 +1550,12 @@ __global__ void f4_combine_windows_kernel(int nwin, int64_t S, double *w_ll /*[n
  * per-site outputs -- and combined per site.  The site likelihood is a sum over categories, L = sum_w L_w, and every
  * per-site output a likelihood-weighted mean, x = sum_w x_w L_w / L, so the combination is exact up to rounding.
  */
-static int run_fused_windows(plf_engine *e, Query &q)
+static int run_fused_windows(plf_engine *e, Query &q, int wsize = 4)
 {
-    const int Ctot = e->C, nwin = (Ctot + 3) / 4, E = e->E, N = e->N;
+    const int Ctot = e->C, nwin = (Ctot + wsize - 1) / wsize, E = e->E, N = e->N;
     const int64_t S = e->S;
     const bool marg = q.want_marg, edge = q.want_edge && !marg;
-    if (nwin > 4) FAIL(e, "more than 16 rate categories");
+    if (nwin > 16) FAIL(e, "more than 16 category windows");
     if (resolve_pending(e)) return -1;
     ENSURE(e, e->f4w_ll, sizeof(double) * (size_t)nwin * S);
     if (edge) ENSURE(e, e->f4w_edge, sizeof(double) * (size_t)nwin * E * S);
@@ -1565,11 +1565,11 @@ static int run_fused_windows(plf_engine *e, Query &q)
     float ms_total = 0.f;
     for (int w = 0; w < nwin; w++) {
         F4Window win;
-        win.c0 = 4 * w;
+        win.c0 = wsize * w;
         win.site_ll = e->f4w_ll.as<double>() + (size_t)w * S;
         win.site_edge = edge ? e->f4w_edge.as<double>() + (size_t)w * E * S : nullptr;
         win.site_marg = marg ? e->f4w_marg.as<double>() + (size_t)w * N * 4 * S : nullptr;
-        e->C = std::min(4, Ctot - 4 * w);
+        e->C = std::min(wsize, Ctot - wsize * w);
         const int rc = run_fused(e, q, &win);
         e->C = Ctot;
         if (rc) return rc;
@@ -2174,7 +2174,11 @@ static int run_query_once(plf_engine *e, Query &q, bool need_D, const double *l_
     CK(e, cudaEventRecord(e->ev[1], e->stream));
     e->kernel_timed = false;
     e->ms_kernel_override = -1.f;
-    int rc = use_fused ? (e->C > 4 ? run_fused_windows(e, q) : run_fused(e, q))
+    /* PLF_F4_WINDOW=<w> forces windows of w categories (experiments: smaller windows let larger trees use the
+     * constant-memory kernels at the price of per-site outputs and a combination pass) */
+    int wforce = 0;
+    if (const char *wf = getenv("PLF_F4_WINDOW")) wforce = std::max(1, std::min(4, atoi(wf)));
+    int rc = use_fused ? ((e->C > 4 || (wforce && wforce < e->C)) ? run_fused_windows(e, q, wforce ? wforce : 4) : run_fused(e, q))
                        : (e->path != PLF_PATH_GENERIC && !q.sum_hess && dmma_applicable(e, q)) ? run_dmma(e, q) : run_generic(e, q);
     if (rc) return rc;
     cudaEventElapsedTime(&e->ms_mat, e->ev[0], e->ev[1]);
