@@ -109,6 +109,21 @@ __global__ void __launch_bounds__(256) expm_dd_kernel(ExpmArgs a)
         }
         int s = 0;
         if (mu > 1.0) { int ex; frexp(mu, &ex); s = ex; /* mu < 2^ex */ }
+        /* Every extra halving of B costs one squaring and saves Taylor terms; both are one matrix product on the
+         * critical path (the kernel is latency bound: a handful of warps per SM), a squaring being the cheaper one.
+         * Take the number of halvings (<= 8) that minimises terms + squarings: 31 + 0 becomes about 14 + 6 at mu = 1.
+         * Squaring non-negative matrices keeps the relative accuracy; 8 squarings cost 2^8 dd roundings, 1e-29. */
+        if (mu > 0.0) {
+            int best = 1 << 30, best_j = 0;
+            for (int j = 0; j <= 8; j++) {
+                const double m = scalbn(mu, -(s + j));
+                double bound = 1.0;
+                int k = 1;
+                while (k < 40) { bound *= m / k; if (bound < 1.9e-34 && k >= 2) break; k++; }
+                if (k + j < best) { best = k + j; best_j = j; }
+            }
+            s += best_j;
+        }
         sh_mu = mu; sh_s = s;
     }
     __syncthreads();

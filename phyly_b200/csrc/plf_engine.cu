@@ -418,6 +418,39 @@ __global__ void compact_matrices_kernel(const double *M, const int *edge_of, int
     out[idx] = M[((size_t)c * E + edge_of[ie]) * 16 + k];
 }
 
+/* the tables of the fused 4-state kernel in one launch: tip tables and compact internal-edge matrices of P and,
+ * when Fm is given, of the edge-form matrices (four launches of the two kernels above otherwise) */
+__global__ void f4_tables_kernel(const double *P, const double *Fm, const double *defs, const unsigned char *def_const,
+                                 const int *edge_of_tip, const int *edge_of_int, int C, int E, int Et, int Ei, int K, int f_mode,
+                                 double *TP, double *Pint, double *TF, double *Fint)
+{
+    const size_t cntT = (size_t)C * Et * K * 4, cntP = (size_t)C * Ei * 16;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t per = cntT + cntP;
+    if (idx >= per * (Fm ? 2 : 1)) return;
+    const bool second = idx >= per;
+    if (second) idx -= per;
+    const double *M = second ? Fm : P;
+    const int mode = second ? f_mode : 0;
+    if (idx < cntT) {
+        const int i = (int)(idx % 4); size_t r = idx / 4;
+        const int k = (int)(r % K); r /= K;
+        const int te = (int)(r % Et), c = (int)(r / Et);
+        const double *row = M + (((size_t)c * E + edge_of_tip[te]) * 4 + i) * 4;
+        const double *d = defs + (size_t)k * 4;
+        double v;
+        if (def_const[k] && mode == 0) v = d[0];
+        else if (def_const[k] && mode == 1) v = 0.0;
+        else { v = 0.0; for (int j = 0; j < 4; j++) v = fma(row[j], d[j], v); }
+        (second ? TF : TP)[idx] = v;
+    } else {
+        idx -= cntT;
+        const int k = (int)(idx & 15); const size_t r = idx >> 4;
+        const int ie = (int)(r % Ei), c = (int)(r / Ei);
+        (second ? Fint : Pint)[idx] = M[((size_t)c * E + edge_of_int[ie]) * 16 + k];
+    }
+}
+
 /* ------------------------------------------------------------------ */
 /* lifecycle                                                           */
 /* ------------------------------------------------------------------ */
@@ -1032,6 +1065,21 @@ static int ensure_tip_tables(plf_engine *e, const double *Fm, int f_mode, bool w
                 e->d_P.as<double>(), e->d_edge_of_tip.as<int>(), e->C, e->E, Et, e->d_Ptip.as<double>());
             KCHECK(e);
         }
+    }
+    if (!e->TP_valid && Fm && cntT && cntP && e->n == 4) {
+        /* the usual case of an optimisation step (matrices changed, edge forms wanted): one launch for all four tables */
+        ENSURE(e, e->d_TP, sizeof(double) * (cntT + 1));
+        ENSURE(e, e->d_Pint, sizeof(double) * (cntP + 1));
+        ENSURE(e, e->d_TF, sizeof(double) * (cntT + 1));
+        ENSURE(e, e->d_Fint, sizeof(double) * (cntP + 1));
+        const size_t total = 2 * (cntT + cntP);
+        f4_tables_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, e->stream>>>(
+            e->d_P.as<double>(), Fm, e->d_defs.as<double>(), e->d_def_const.as<unsigned char>(), e->d_edge_of_tip.as<int>(),
+            e->d_edge_of_int.as<int>(), e->C, e->E, Et, Ei, e->K, f_mode, e->d_TP.as<double>(), e->d_Pint.as<double>(),
+            e->d_TF.as<double>(), e->d_Fint.as<double>());
+        KCHECK(e);
+        e->TP_valid = true;
+        return 0;
     }
     if (!e->TP_valid) {
         ENSURE(e, e->d_TP, sizeof(double) * (cntT + 1));
