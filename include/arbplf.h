@@ -57,7 +57,8 @@ int arbplf_run_stdio(char *(*f)(const char *, int *));
  * before the matrix exponentials (cross_site_ws.c:199-232) as JSON:
  * {"state_count", "category_count", "cat_rates", "cat_prior", "rate_divisor_expect",
  *  "equilibrium", "q_hi", "q_lo", "edge_rates_csr", "root_mode", "root_vec",
- *  "indptr", "indices", "preorder", "order"}.
+ *  "indptr", "indices", "preorder", "order", "definition_count", "codes_sum", "codes_weighted_sum"}
+ * (the last two: sums over the site data as read, codes in row-major order, modulo 2^64, as strings).
  * Used by tools that drive the device seam (plf.h) with binary site data.
  */
 char *arbplf_model_summary(const char *json_in, int *retcode);

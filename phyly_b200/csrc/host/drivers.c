@@ -576,6 +576,20 @@ char *arbplf_model_summary(const char *json_in, int *retcode)
         jbuf_puts(&b, ", "); put_iarray(&b, "indices", c.m.indices, c.m.E);
         jbuf_puts(&b, ", "); put_iarray(&b, "preorder", c.m.preorder, c.m.N);
         jbuf_puts(&b, ", "); put_iarray(&b, "order", c.m.order, c.m.E);
+        {
+            /* what the site data was read as: definition rows, and two sums over the codes in row-major order
+             * (plain, and weighted by position + 1; both modulo 2^64, printed as strings) */
+            unsigned long long plain = 0, weighted = 0;
+            const size_t total = (size_t)c.m.S * c.m.N;
+            for (size_t i = 0; i < total; i++) {
+                unsigned long long code = c.m.code_bytes == 1 ? ((const unsigned char *)c.m.codes)[i] : (unsigned long long)((const int *)c.m.codes)[i];
+                plain += code; weighted += (unsigned long long)(i + 1) * code;
+            }
+            char t[96];
+            jbuf_puts(&b, ", \"definition_count\": "); jbuf_int(&b, c.m.K);
+            snprintf(t, sizeof t, ", \"codes_sum\": \"%llu\", \"codes_weighted_sum\": \"%llu\"", plain, weighted);
+            jbuf_puts(&b, t);
+        }
         jbuf_puts(&b, "}");
         out = jbuf_take(&b);
     }

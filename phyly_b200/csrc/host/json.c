@@ -1,4 +1,5 @@
 #include "json.h"
+#include "par.h"
 
 #include <ctype.h>
 #include <errno.h>
@@ -6,10 +7,12 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
 
 typedef struct {
     const char *p;
     const char *start;
+    const char *end;    /* the terminating NUL */
     char *err;
     size_t errlen;
     int depth;
@@ -34,8 +37,13 @@ static void free_contents(jv *v)
 {
     if (v->type == JV_STRING) free(v->u.s);
     else if (v->type == JV_ARRAY) {
-        for (uint32_t i = 0; i < v->len; i++) if (v->u.items[i].type >= JV_STRING) free_contents(&v->u.items[i]);
-        free(v->u.items);
+        if (v->flags & JV_F_BLOCKS) {           /* rows of integers in shared blocks (parse_int_matrix) */
+            const jv *tail = v->u.items + v->len;
+            for (uint32_t t = 0; t < tail->len; t++) free(tail[1 + t].u.items);
+        } else if (!(v->flags & JV_F_BORROWED)) {
+            for (uint32_t i = 0; i < v->len; i++) if (v->u.items[i].type >= JV_STRING) free_contents(&v->u.items[i]);
+        }
+        if (!(v->flags & JV_F_BORROWED)) free(v->u.items);
     } else if (v->type == JV_OBJECT) {
         for (uint32_t i = 0; i < 2 * v->len; i++) free_contents(&v->u.items[i]);
         free(v->u.items);
@@ -93,7 +101,7 @@ static int parse_string(parser *ps, jv *out)
         q++;
     }
     s[len] = 0;
-    out->type = JV_STRING; out->len = (uint32_t)len; out->u.s = s;
+    out->type = JV_STRING; out->flags = 0; out->len = (uint32_t)len; out->u.s = s;
     ps->p = q;
     return 0;
 }
@@ -144,8 +152,155 @@ static int parse_number(parser *ps, jv *out)
     return 0;
 }
 
+/*
+ * A large array whose items are flat arrays of short non-negative integers -- the 'character_data' of an alignment,
+ * 2 bytes per code and 10^8 codes at the target size -- is read by several threads.  One pass finds the rows (the next
+ * ']' after each '['); each thread then reads a contiguous range of rows into one block of its own.  A row holding
+ * anything but such integers (a sign, a fraction, a nested array, a string, a stray comma ...) makes the whole attempt
+ * step aside: the array is then read again by the general route, which owns every check and every error message.
+ * Returns 0 when the array has been read, 1 when it is left to the general route.
+ */
+#define MATRIX_MIN_BYTES (1u << 20)
+#define MATRIX_MIN_ROWS 256
+
+typedef struct { const char *open, *close; } row_span;
+
+typedef struct {
+    const row_span *rows;
+    size_t nrows;
+    jv *row_out;
+    jv **blocks;
+    int failed;         /* written by any thread: only ever set */
+} matrix_job;
+
+static inline const char *skip_ws_to(const char *q)
+{
+    while (*q == ' ' || *q == '\t' || *q == '\n' || *q == '\r') q++;
+    return q;
+}
+
+/* a block of many megabytes that is written once, front to back: huge pages (where the kernel grants them on request)
+ * cut the page faults of first touch, which otherwise cost as much as reading the digits */
+static void *big_block(size_t bytes)
+{
+    const size_t huge = (size_t)2 << 20;
+    if (bytes >= 2 * huge) {
+        void *p = NULL;
+        if (posix_memalign(&p, huge, (bytes + huge - 1) / huge * huge) == 0 && p) {
+#ifdef MADV_HUGEPAGE
+            madvise(p, (bytes + huge - 1) / huge * huge, MADV_HUGEPAGE);
+#endif
+            return p;
+        }
+    }
+    return malloc(bytes);
+}
+
+static void matrix_worker(int tid, int nthreads, void *ctx)
+{
+    matrix_job *job = ctx;
+    const size_t r0 = job->nrows * (size_t)tid / (size_t)nthreads, r1 = job->nrows * (size_t)(tid + 1) / (size_t)nthreads;
+    /* an item takes at least two bytes of text (digit + separator) */
+    size_t bound = 1;
+    for (size_t r = r0; r < r1; r++) bound += (size_t)(job->rows[r].close - job->rows[r].open) / 2 + 1;
+    jv *block = big_block(bound * sizeof(jv));
+    job->blocks[tid] = block;
+    if (!block) { job->failed = 1; return; }
+    jv *cur = block;
+    for (size_t r = r0; r < r1; r++) {
+        const char *q = skip_ws_to(job->rows[r].open + 1);
+        const char *close = job->rows[r].close;
+        jv *first = cur;
+        if (q != close) {
+            for (;;) {
+                int64_t v;
+                if (*q >= '1' && *q <= '9') {
+                    int nd = 1;
+                    v = *q++ - '0';
+                    while (*q >= '0' && *q <= '9' && nd < 9) { v = v * 10 + (*q++ - '0'); nd++; }
+                } else if (*q == '0') {
+                    v = 0; q++;
+                } else { job->failed = 1; return; }
+                cur->type = JV_INT; cur->flags = 0; cur->len = 0; cur->u.i = v;
+                cur++;
+                q = skip_ws_to(q);
+                if (q == close) break;
+                if (*q != ',') { job->failed = 1; return; }
+                q = skip_ws_to(q + 1);
+            }
+        }
+        jv *row = &job->row_out[r];
+        row->type = JV_ARRAY; row->flags = JV_F_BORROWED; row->len = (uint32_t)(cur - first); row->u.items = first;
+    }
+}
+
+static int parse_int_matrix(parser *ps, jv *out)
+{
+    /* ps->p is at the '[' of the first row */
+    size_t cap = 1024, n = 0;
+    row_span *rows = malloc(cap * sizeof(row_span));
+    if (!rows) return 1;
+    const char *p = ps->p;
+    for (;;) {
+        if (*p != '[') goto step_aside;
+        const char *close = memchr(p + 1, ']', (size_t)(ps->end - (p + 1)));
+        if (!close) goto step_aside;
+        if (n == cap) {
+            cap *= 2;
+            row_span *t = realloc(rows, cap * sizeof(row_span));
+            if (!t) goto step_aside;
+            rows = t;
+        }
+        rows[n].open = p; rows[n].close = close; n++;
+        p = skip_ws_to(close + 1);
+        if (*p == ',') { p = skip_ws_to(p + 1); continue; }
+        if (*p == ']') { p++; break; }
+        goto step_aside;
+    }
+    if (n < MATRIX_MIN_ROWS || n >= 0xffffffffu) goto step_aside;
+    {
+        int nthreads = par_threads();
+        if ((size_t)nthreads > n / 64) nthreads = (int)(n / 64);
+        if (nthreads < 1) nthreads = 1;
+        jv *items = malloc((n + 1 + (size_t)nthreads) * sizeof(jv));
+        jv **blocks = calloc((size_t)nthreads, sizeof(jv *));
+        if (!items || !blocks) { free(items); free(blocks); goto step_aside; }
+        matrix_job job = {rows, n, items, blocks, 0};
+        par_run(nthreads, matrix_worker, &job);
+        if (job.failed) {
+            for (int t = 0; t < nthreads; t++) free(blocks[t]);
+            free(items); free(blocks);
+            goto step_aside;
+        }
+        jv *tail = items + n;
+        tail->type = JV_NULL; tail->flags = 0; tail->len = (uint32_t)nthreads; tail->u.i = 0;
+        for (int t = 0; t < nthreads; t++) {
+            tail[1 + t].type = JV_NULL; tail[1 + t].flags = 0; tail[1 + t].len = 0; tail[1 + t].u.items = blocks[t];
+        }
+        free(blocks);
+        if (getenv("ARBPLF_JSON_TRACE")) fprintf(stderr, "json: matrix of %zu rows read by %d threads\n", n, nthreads);
+        ps->hint = items[n - 1].len;
+        out->type = JV_ARRAY; out->flags = JV_F_BLOCKS; out->len = (uint32_t)n; out->u.items = items;
+    }
+    free(rows);
+    ps->p = p;
+    return 0;
+step_aside:
+    free(rows);
+    return 1;
+}
+
 static int parse_array(parser *ps, jv *out)
 {
+    if (ps->depth < 2000 && (size_t)(ps->end - ps->p) >= MATRIX_MIN_BYTES) {
+        const char *q = skip_ws_to(ps->p + 1);
+        if (*q == '[') {
+            const char *keep = ps->p;
+            ps->p = q;
+            if (parse_int_matrix(ps, out) == 0) return 0;
+            ps->p = keep;
+        }
+    }
     size_t cap = (ps->hint >= 8 && ps->hint <= (1u << 20)) ? ps->hint : 8, len = 0;
     jv *items = malloc(cap * sizeof(jv));
     if (!items) { fail(ps, "out of memory"); return -1; }
@@ -170,14 +325,14 @@ static int parse_array(parser *ps, jv *out)
                 int nd = 1;
                 while (*q >= '0' && *q <= '9' && nd < 9) { v = v * 10 + (*q++ - '0'); nd++; }
                 if (*q == ',' || *q == ']') {
-                    items[len].type = JV_INT; items[len].len = 0; items[len].u.i = v;
+                    items[len].type = JV_INT; items[len].flags = 0; items[len].len = 0; items[len].u.i = v;
                     len++;
                     ps->p = q + 1;
                     if (*q == ',') continue;
                     break;
                 }
             } else if (*q == '0' && (q[1] == ',' || q[1] == ']')) {
-                items[len].type = JV_INT; items[len].len = 0; items[len].u.i = 0;
+                items[len].type = JV_INT; items[len].flags = 0; items[len].len = 0; items[len].u.i = 0;
                 len++;
                 ps->p = q + 2;
                 if (q[1] == ',') continue;
@@ -257,7 +412,7 @@ bad:
 
 static int parse_value(parser *ps, jv *out)
 {
-    out->type = JV_NULL; out->len = 0; out->u.i = 0;
+    out->type = JV_NULL; out->flags = 0; out->len = 0; out->u.i = 0;
     if (++ps->depth > 2048) { fail(ps, "maximum parsing depth reached"); return -1; }
     int rc;
     skip_ws(ps);
@@ -277,7 +432,7 @@ static int parse_value(parser *ps, jv *out)
 
 jv *json_parse(const char *text, char *err, size_t errlen)
 {
-    parser ps = {text, text, err, errlen, 0, 0};
+    parser ps = {text, text, text + strlen(text), err, errlen, 0, 0};
     if (err && errlen) err[0] = 0;
     jv *root = malloc(sizeof(jv));
     if (!root) { fail(&ps, "out of memory"); return NULL; }

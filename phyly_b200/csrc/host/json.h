@@ -18,8 +18,14 @@
 
 enum { JV_NULL = 0, JV_FALSE, JV_TRUE, JV_INT, JV_REAL, JV_STRING, JV_ARRAY, JV_OBJECT };
 
+/* storage flags of an array (json.c only): a large matrix of short integers -- 'character_data' -- is read by several
+ * threads into a few big blocks instead of one allocation per row */
+enum { JV_F_BORROWED = 1,         /* items live in a block owned by the enclosing array */
+       JV_F_BLOCKS = 2 };         /* items[len].len blocks follow the rows: items[len + 1 + t].u.items */
+
 typedef struct jv {
     uint8_t type;
+    uint8_t flags;
     uint32_t len;                 /* array: items; object: pairs; string: bytes */
     union {
         int64_t i;

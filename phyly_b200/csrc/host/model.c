@@ -1,4 +1,5 @@
 #include "model.h"
+#include "par.h"
 
 #include <math.h>
 #include <stdio.h>
@@ -257,6 +258,32 @@ finish:
     return rc;
 }
 
+/* one thread's share of parsemodel.c:590-615: rows [S tid / T, S (tid+1) / T) */
+typedef struct { int kind, actual; } cd_fault;
+typedef struct { const jv *rows; int64_t S; int N, K, wide; void *codes; cd_fault *faults; } cd_job;
+
+static void cd_worker(int tid, int nthreads, void *ctx)
+{
+    cd_job *job = ctx;
+    const int N = job->N;
+    const int64_t r0 = job->S * tid / nthreads, r1 = job->S * (tid + 1) / nthreads;
+    cd_fault *f = &job->faults[tid];
+    for (int64_t i = r0; i < r1; i++) {
+        const jv *x = &job->rows[i];
+        if (!jv_is_array(x)) { f->kind = 1; return; }
+        if ((int)x->len != N) { f->kind = 2; f->actual = (int)x->len; return; }
+        const jv *y = x->u.items;
+        unsigned char *c8 = (unsigned char *)job->codes + (size_t)i * N;
+        int *c32 = (int *)job->codes + (size_t)i * N;
+        for (int j = 0; j < N; j++) {
+            if (!jv_is_int(&y[j])) { f->kind = 3; return; }
+            if (y[j].u.i < 0) { f->kind = 4; return; }
+            if (y[j].u.i >= job->K) { f->kind = 5; return; }
+            if (job->wide) c32[j] = (int)y[j].u.i; else c8[j] = (unsigned char)y[j].u.i;
+        }
+    }
+}
+
 /* parsemodel.c:514-628 */
 static int parse_character_data(plf_model *m, const jv *data, const jv *defs)
 {
@@ -275,32 +302,39 @@ static int parse_character_data(plf_model *m, const jv *data, const jv *defs)
             return -1;
         }
     }
-    int *codes = malloc(sizeof(int) * ((size_t)m->S * N + 1));
-    for (int64_t i = 0; i < m->S; i++) {
-        const jv *x = &data->u.items[i];
-        if (!jv_is_array(x)) { fprintf(stderr, "%s: expected an array\n", name); free(codes); return -1; }
-        if ((int)x->len != N) {
-            fprintf(stderr, "%s: failed to match the number of nodes: (actual: %d desired: %d)\n", name, (int)x->len, N);
-            free(codes); return -1;
+    /* rows -> codes, several threads for an alignment-sized matrix; the first offence in row-major order is the one
+     * reported, as in the reference's single loop */
+    const int wide = m->K > 256;
+    const size_t total = (size_t)m->S * N;
+    void *codes = malloc((wide ? sizeof(int) : 1) * (total + 1));
+    if (!codes) { fprintf(stderr, "%s: out of memory\n", name); return -1; }
+    int nthreads = total >= ((size_t)1 << 20) ? par_threads() : 1;
+    if ((int64_t)nthreads > m->S) nthreads = m->S > 0 ? (int)m->S : 1;
+    cd_fault *faults = calloc((size_t)nthreads, sizeof(cd_fault));
+    if (!faults) { fprintf(stderr, "%s: out of memory\n", name); free(codes); return -1; }
+    cd_job job = {data->u.items, m->S, N, m->K, wide, codes, faults};
+    par_run(nthreads, cd_worker, &job);
+    const cd_fault *f = NULL;
+    for (int t = 0; t < nthreads && !f; t++) if (faults[t].kind) f = &faults[t];     /* ranges ascend with t */
+    if (f) {
+        switch (f->kind) {
+        case 1: fprintf(stderr, "%s: expected an array\n", name); break;
+        case 2: fprintf(stderr, "%s: failed to match the number of nodes: (actual: %d desired: %d)\n", name, f->actual, N); break;
+        case 3: fprintf(stderr, "%s: character indices must be integers\n", name); break;
+        case 4: fprintf(stderr, "%s: character indices must be non-negative\n", name); break;
+        default: fprintf(stderr, "%s: character indices must each be less than the character count (%d)\n", name, m->K);
         }
-        for (int j = 0; j < N; j++) {
-            const jv *y = &x->u.items[j];
-            if (!jv_is_int(y)) { fprintf(stderr, "%s: character indices must be integers\n", name); free(codes); return -1; }
-            if (y->u.i < 0) { fprintf(stderr, "%s: character indices must be non-negative\n", name); free(codes); return -1; }
-            if (y->u.i >= m->K) {
-                fprintf(stderr, "%s: character indices must each be less than the character count (%d)\n", name, m->K);
-                free(codes); return -1;
-            }
-            codes[(size_t)i * N + j] = (int)y->u.i;
-        }
+        free(faults); free(codes);
+        return -1;
     }
+    free(faults);
     if (m->K == 0) {   /* only reachable with zero sites */
         free(m->defs);
         m->defs = malloc(sizeof(double) * (n > 0 ? n : 1));
         for (int k = 0; k < n; k++) m->defs[k] = 1.0;
         m->K = 1;
     }
-    compress_codes(m, codes);
+    m->codes = codes; m->code_bytes = wide ? 4 : 1;
     return 0;
 }
 

@@ -258,3 +258,128 @@ def test_integer_fast_path_of_the_json_reader():
     # integers where reals are expected stay valid, long integers keep their value
     ok = good.replace('"edge_rate_coefficients": [1, 2]', '"edge_rate_coefficients": [1234567890123, 2]')
     assert json.loads(A.arbplf_model_summary(ok))["edge_rates_csr"][0] == 1234567890123.0
+
+
+def _big_document(S, taxa=64, seed=0):
+    """A cfg2-shaped document whose character_data is large enough for the threaded reader of host/json.c
+    (>= 1 MB of text, >= 256 rows); returns (text, codes)."""
+    import bench
+    doc, N = bench.model_document(taxa)
+    codes = np.random.default_rng(seed).integers(0, 5, (S, N)).astype(np.uint8)
+    return _summary_document(bench, doc, codes), codes
+
+
+def _summary_document(bench, doc, codes):
+    text = bench.json_document_bytes(doc, codes).decode()
+    extra = ', "site_reduction": {"aggregation": "sum"}'
+    assert text.endswith(extra + "}")
+    return text[:-len(extra) - 1] + "}"
+
+
+def _code_sums(codes):
+    flat = codes.astype(np.uint64).ravel()
+    pos = np.arange(1, flat.size + 1, dtype=np.uint64)
+    return str(int(flat.sum())), str(int((flat * pos).sum(dtype=np.uint64)))
+
+
+def test_threaded_matrix_reader_matches_the_general_route(monkeypatch, capfd):
+    """host/json.c reads a large matrix of short integers with several threads into shared blocks, host/model.c turns it
+    into code bytes with several threads: the codes are those of the document, for any thread count, with blanks
+    anywhere JSON allows them."""
+    import phyly_b200.arbplf as A
+    text, codes = _big_document(6000)
+    assert len(text) > (1 << 20)
+    want = _code_sums(codes)
+    monkeypatch.setenv("ARBPLF_JSON_TRACE", "1")
+    monkeypatch.setenv("ARBPLF_HOST_THREADS", "4")
+    capfd.readouterr()
+    A.arbplf_model_summary(text)
+    assert "json: matrix of 6000 rows read by 4 threads" in capfd.readouterr().err       # the route under test is taken
+    monkeypatch.delenv("ARBPLF_JSON_TRACE")
+    for threads in ("1", "3", "16", None):
+        if threads is None:
+            monkeypatch.delenv("ARBPLF_HOST_THREADS", raising=False)
+        else:
+            monkeypatch.setenv("ARBPLF_HOST_THREADS", threads)
+        s = json.loads(A.arbplf_model_summary(text))
+        assert s["site_count"] == 6000 and s["definition_count"] == 5
+        assert (s["codes_sum"], s["codes_weighted_sum"]) == want, threads
+    monkeypatch.delenv("ARBPLF_HOST_THREADS", raising=False)
+    spaced = text.replace("],[", " ]\n,\t[ ").replace(",", " , ", 3000)
+    s = json.loads(A.arbplf_model_summary(spaced))
+    assert (s["codes_sum"], s["codes_weighted_sum"]) == want
+    # a short document (general route) with the same rows gives the same bytes
+    small, codes_small = _big_document(40)
+    s = json.loads(A.arbplf_model_summary(small))
+    assert (s["codes_sum"], s["codes_weighted_sum"]) == _code_sums(codes_small)
+    # more than 256 definitions: 4-byte codes
+    import bench
+    doc, N = bench.model_document(64)
+    K = 300
+    md = dict(doc["model_and_data"])
+    md["character_definitions"] = [[1, 1, 1, 1] if k % 7 == 0 else [float(k % 4 == j) for j in range(4)] for k in range(K)]
+    wide = np.random.default_rng(2).integers(0, K, (3000, N))
+    md["character_data"] = wide.tolist()
+    t = json.dumps({"model_and_data": md})
+    assert len(t) > (1 << 20)
+    s = json.loads(A.arbplf_model_summary(t))
+    assert s["definition_count"] == K and (s["codes_sum"], s["codes_weighted_sum"]) == _code_sums(wide)
+
+
+def test_threaded_matrix_reader_steps_aside_for_anything_else():
+    """A row that is not a flat array of short non-negative integers sends the whole matrix to the general route, which
+    rejects it (or accepts it) exactly as it would a small document; the tree's 'edges' -- also a matrix of
+    integers -- may be read by either route."""
+    import phyly_b200.arbplf as A
+    text, codes = _big_document(6000, seed=1)
+    N = codes.shape[1]
+    row = "[" + ",".join(str(int(x)) for x in codes[3000]) + "]"
+    assert text.count(row) >= 1
+    cells = row[1:-1].split(",")
+
+    def with_row(new):
+        head, tail = text.split(row, 1)
+        return head + new + tail
+
+    bad_rows = [
+        "[" + ",".join(["01"] + cells[1:]) + "]",                 # leading zero
+        "[" + ",".join(["-1"] + cells[1:]) + "]",                 # negative
+        "[" + ",".join(["0.0"] + cells[1:]) + "]",                # a real
+        "[" + ",".join(["7"] + cells[1:]) + "]",                  # not a row of the definitions
+        "[" + ",".join(["12345678901234567890"] + cells[1:]) + "]",
+        row[:-1] + ",]",                                          # stray comma
+        "[" + ",".join(cells[:-1]) + "]",                         # one node short
+        "[" + ",".join(["[0]"] + cells[1:]) + "]",                # nested array
+        "[" + ",".join(['"0"'] + cells[1:]) + "]",                # a string
+        "[" + " ".join(cells) + "]",                              # no commas
+        "0",                                                      # not an array
+    ]
+    for new in bad_rows:
+        with pytest.raises(RuntimeError):
+            A.arbplf_model_summary(with_row(new))
+    # the same faults at the very end and the very start of the matrix
+    last = "[" + ",".join(str(int(x)) for x in codes[-1]) + "]"
+    assert text.count(last + "]") >= 1
+    with pytest.raises(RuntimeError):
+        A.arbplf_model_summary(text.replace(last + "]", last[:-1] + ",9]]", 1))
+    with pytest.raises(RuntimeError):
+        A.arbplf_model_summary(text.replace('"character_data": [[', '"character_data": [[-0,', 1))
+    # an unterminated matrix is a syntax error, not a crash
+    cut = text[:text.index(row) + 40]
+    with pytest.raises(RuntimeError):
+        A.arbplf_model_summary(cut)
+    # a long integer that is valid JSON but no short code: general route, then the range check
+    ok_edges = json.loads(A.arbplf_model_summary(text))
+    # large tree: 'edges' has more than 256 rows and sits in front of > 1 MB of text
+    import bench
+    doc, N2 = bench.model_document(300)
+    c2 = np.random.default_rng(5).integers(0, 5, (1200, N2)).astype(np.uint8)
+    big = _summary_document(bench, doc, c2)
+    assert len(big) > (1 << 20) and len(doc["model_and_data"]["edges"]) > 256
+    sb = json.loads(A.arbplf_model_summary(big))
+    small = _summary_document(bench, doc, c2[:1])
+    ss = json.loads(A.arbplf_model_summary(small))
+    for k in ("indptr", "indices", "preorder", "order", "edge_rates_csr"):
+        assert sb[k] == ss[k], k
+    assert (sb["codes_sum"], sb["codes_weighted_sum"]) == _code_sums(c2)
+    assert ok_edges["site_count"] == 6000

@@ -87,6 +87,23 @@ def test_cfg5_dwell_is_one_and_paths_agree():
     eng.set_path(E.PATH_GENERIC)
     _, t_g = eng.edge_expect(E.KIND_TRANS, L, per_site=False)
     np.testing.assert_allclose(t_f, t_g, rtol=1e-11)
+    # per-site dwell / trans of a subsample of the 64-taxon alignment against the numpy oracle (fp64 back end)
+    from oracle import arbplf_oracle as O
+    rng = np.random.default_rng(17)
+    idx = np.sort(rng.choice(pb["S"], 48, replace=False))
+    md = dict(pb["doc"]["model_and_data"])
+    md["character_data"] = pb["codes"][idx].tolist()
+    m = O.parse_model(md)
+    be = O.get_backend("fp64")
+    Ld = np.diag([1.0, 0.0, 0.5, 0.0])
+    want_d, _ = O.per_site_edge_expect(m, be, list(range(idx.size)), Ld, trans=False)
+    want_t, _ = O.per_site_edge_expect(m, be, list(range(idx.size)), L, trans=True)
+    for path in (E.PATH_FUSED4, E.PATH_GENERIC):
+        eng.set_path(path)
+        so_d, _ = eng.edge_expect(E.KIND_DWELL, Ld)
+        so_t, _ = eng.edge_expect(E.KIND_TRANS, L)
+        np.testing.assert_allclose(so_d[idx], np.asarray(want_d, dtype=np.float64), rtol=1e-10, atol=1e-14)
+        np.testing.assert_allclose(so_t[idx], np.asarray(want_t, dtype=np.float64), rtol=1e-10, atol=1e-14)
     eng.close()
 
 
@@ -135,6 +152,15 @@ def test_cfg3_marginals_sum_to_one():
     sm_g, tot_g = eng.marginal()
     np.testing.assert_allclose(sm, sm_g, rtol=1e-11, atol=1e-14)
     np.testing.assert_allclose(tot, tot_g, rtol=1e-11, atol=1e-9)
+    # a subsample of the 128-taxon columns against the numpy oracle (fp64 back end; same node numbering)
+    from oracle import arbplf_oracle as O
+    idx = np.sort(np.random.default_rng(18).choice(S, 64, replace=False))
+    md = dict(doc["model_and_data"])
+    md["character_data"] = codes[idx].tolist()
+    m = O.parse_model(md)
+    want = np.asarray(O.per_site_marginal(m, O.get_backend("fp64"), list(range(idx.size))), dtype=np.float64)
+    np.testing.assert_allclose(sm[idx], want, rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(sm_g[idx], want, rtol=1e-10, atol=1e-14)
     eng.close()
 
 
