@@ -454,6 +454,23 @@ def bench_json_e2e(pb, max_sites):
         out["in_process_call_%d" % (rep + 1)] = {"wall_s": wall, "parse_s": ph[0], "model_and_upload_s": ph[1], "compute_s": ph[2],
                                                  "emit_s": ph[3], "updates_per_s": float(S) * pb["E"] * pb["C"] / wall}
     out["output_head"] = first[:120]
+    # the site axis kept: arbplf_ll without a site reduction writes one row per site pattern
+    tail = b', "site_reduction": {"aggregation": "sum"}}'
+    if text.endswith(tail):
+        lib.arbplf_ll.restype = c.c_void_p
+        lib.arbplf_ll.argtypes = [c.c_char_p, c.POINTER(c.c_int)]
+        per_site = text[:-len(tail)] + b"}"
+        rc = c.c_int(0)
+        t0 = time.perf_counter()
+        res = lib.arbplf_ll(per_site, c.byref(rc))
+        wall = time.perf_counter() - t0
+        if res and rc.value == 0:
+            nbytes = len(c.string_at(res))
+            libc.free(res)
+            ph = (c.c_double * 4)()
+            lib.arbplf_last_timing(ph)
+            out["per_site_ll_call"] = {"wall_s": wall, "parse_s": ph[0], "model_and_upload_s": ph[1], "compute_s": ph[2],
+                                       "emit_s": ph[3], "output_bytes": nbytes}
     exe = os.path.join(ROOT, "phyly_b200", "bin", "arbplf-deriv")
     if os.path.exists(exe):
         t0 = time.perf_counter()

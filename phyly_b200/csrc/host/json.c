@@ -517,6 +517,14 @@ void jbuf_puts(jbuf *b, const char *s)
     b->p[b->len] = 0;
 }
 
+void jbuf_append(jbuf *b, const char *s, size_t n)
+{
+    jbuf_reserve(b, n);
+    memcpy(b->p + b->len, s, n);
+    b->len += n;
+    b->p[b->len] = 0;
+}
+
 void jbuf_int(jbuf *b, long long v)
 {
     char tmp[32];

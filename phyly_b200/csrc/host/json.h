@@ -60,6 +60,7 @@ int jv_unpack_strict(const jv *obj, const char *const *keys, const jv **out);
 typedef struct { char *p; size_t len, cap; } jbuf;
 void jbuf_init(jbuf *b);
 void jbuf_puts(jbuf *b, const char *s);
+void jbuf_append(jbuf *b, const char *s, size_t n);
 void jbuf_int(jbuf *b, long long v);
 void jbuf_real(jbuf *b, double d);   /* jansson formatting, -0.0 scrubbed (util.c:44-48) */
 char *jbuf_take(jbuf *b);            /* malloc'd, NUL terminated; caller frees */

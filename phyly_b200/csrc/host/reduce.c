@@ -1,4 +1,5 @@
 #include "reduce.h"
+#include "par.h"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -183,8 +184,12 @@ int axis_init(axis *a, const char *name, int n, const reduction *r)
 
 void axis_clear(axis *a) { free(a->w); free(a->requested); memset(a, 0, sizeof(*a)); }
 
+/* rows of the output table in the reference's order (axes outermost first); at axis `split` only the entries
+ * [lo, hi) of its selection are visited, so that several threads can each write a contiguous run of rows */
+typedef struct { int split, lo, hi; } row_range;
+
 static void emit_rows(jbuf *b, const axis *axes, int ndim, const double *values, int d, size_t offset,
-                      const size_t *strides, long long *prefix, int *nprefix, int *first)
+                      const size_t *strides, long long *prefix, int *nprefix, int *first, const row_range *rr)
 {
     if (d == ndim) {
         jbuf_puts(b, *first ? "[" : ", [");
@@ -195,15 +200,29 @@ static void emit_rows(jbuf *b, const axis *axes, int ndim, const double *values,
         return;
     }
     const axis *a = &axes[d];
-    if (a->aggregated) { emit_rows(b, axes, ndim, values, d + 1, offset, strides, prefix, nprefix, first); return; }
-    for (int i = 0; i < a->r->selection_len; i++) {
+    if (a->aggregated) { emit_rows(b, axes, ndim, values, d + 1, offset, strides, prefix, nprefix, first, rr); return; }
+    const int i0 = d == rr->split ? rr->lo : 0, i1 = d == rr->split ? rr->hi : a->r->selection_len;
+    for (int i = i0; i < i1; i++) {
         int idx = a->r->selection[i];
         int saved = *nprefix;
         if (a->ncomp) for (int c = 0; c < a->ncomp; c++) prefix[(*nprefix)++] = a->comp_idx[c][i];
         else prefix[(*nprefix)++] = idx;
-        emit_rows(b, axes, ndim, values, d + 1, offset + (size_t)idx * strides[d], strides, prefix, nprefix, first);
+        emit_rows(b, axes, ndim, values, d + 1, offset + (size_t)idx * strides[d], strides, prefix, nprefix, first, rr);
         *nprefix = saved;
     }
+}
+
+typedef struct { const axis *axes; int ndim; const double *values; const size_t *strides; int split; jbuf *parts; } emit_job;
+
+static void emit_worker(int tid, int nthreads, void *ctx)
+{
+    emit_job *job = ctx;
+    const int len = job->axes[job->split].r->selection_len;
+    row_range rr = {job->split, (int)((long long)len * tid / nthreads), (int)((long long)len * (tid + 1) / nthreads)};
+    long long prefix[16];
+    int nprefix = 0, first = 1;
+    jbuf_init(&job->parts[tid]);
+    emit_rows(&job->parts[tid], job->axes, job->ndim, job->values, 0, 0, job->strides, prefix, &nprefix, &first, &rr);
 }
 
 char *table_to_json(const axis *axes, int ndim, const double *values)
@@ -219,9 +238,36 @@ char *table_to_json(const axis *axes, int ndim, const double *values)
         else { jbuf_puts(&b, "\""); jbuf_puts(&b, axes[d].name); jbuf_puts(&b, "\", "); }
     }
     jbuf_puts(&b, "\"value\"], \"data\": [");
-    long long prefix[16];
-    int nprefix = 0, first = 1;
-    emit_rows(&b, axes, ndim, values, 0, 0, strides, prefix, &nprefix, &first);
+    /* a table with the site axis kept has one row per site pattern (times edges, nodes, states): printing the reals
+     * is then the longest phase of the call, so the outermost kept axis is cut into one run of rows per host thread */
+    int split = -1;
+    size_t rows = 1;
+    for (int d = 0; d < ndim; d++) {
+        if (axes[d].aggregated) continue;
+        if (split < 0) split = d;
+        rows *= (size_t)axes[d].r->selection_len;
+    }
+    int nthreads = (split >= 0 && rows >= 65536) ? par_threads() : 1;
+    if (split >= 0 && nthreads > axes[split].r->selection_len) nthreads = axes[split].r->selection_len;
+    if (nthreads <= 1) {
+        long long prefix[16];
+        int nprefix = 0, first = 1;
+        row_range all = {-1, 0, 0};
+        emit_rows(&b, axes, ndim, values, 0, 0, strides, prefix, &nprefix, &first, &all);
+    } else {
+        emit_job job = {axes, ndim, values, strides, split, calloc((size_t)nthreads, sizeof(jbuf))};
+        if (!job.parts) { fprintf(stderr, "out of memory building JSON output\n"); abort(); }
+        par_run(nthreads, emit_worker, &job);
+        int first = 1;
+        for (int t = 0; t < nthreads; t++) {
+            if (!job.parts[t].len) { free(job.parts[t].p); continue; }
+            if (!first) jbuf_puts(&b, ", ");
+            first = 0;
+            jbuf_append(&b, job.parts[t].p, job.parts[t].len);
+            free(job.parts[t].p);
+        }
+        free(job.parts);
+    }
     jbuf_puts(&b, "]}");
     return jbuf_take(&b);
 }

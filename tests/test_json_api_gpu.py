@@ -325,3 +325,52 @@ def test_certified_enclosure_contains_the_oracle_on_random_problems():
         g2 = _run("ll_certified", docw)
         tot = sum(wt * r[-1] for wt, r in zip(wts, want["data"]))
         assert g2["lower"]["data"][0][-1] <= tot <= g2["upper"]["data"][0][-1]
+
+
+def test_large_tables_are_written_by_several_threads_in_the_same_bytes(monkeypatch):
+    """A table with the site axis kept and >= 65536 rows is written by one run of rows per host thread
+    (host/reduce.c:table_to_json): the text is the one a single thread writes, for every shape of table and for a
+    selection on the site axis; a large document is also read by the threaded reader (host/json.c)."""
+    import phyly_b200.arbplf as A
+    import bench
+    doc, N = bench.model_document(12)
+    S = 70001
+    codes = np.random.default_rng(8).integers(0, 5, (S, N)).astype(np.uint8)
+    leaves_only = np.ones(N, dtype=bool)
+    for a, b in doc["model_and_data"]["edges"]:
+        leaves_only[a] = False
+    codes[:, ~leaves_only] = 4
+    text = bench.json_document_bytes(doc, codes).decode()
+    assert len(text) > (1 << 20)
+    tail = ', "site_reduction": {"aggregation": "sum"}}'
+    assert text.endswith(tail)
+    body = text[:-len(tail)]
+    sel = list(range(S - 1, -1, -1))          # every site, backwards: the order of the selection is the order of the rows
+    cases = [("ll", body + "}"),
+             ("ll", body + ', "site_reduction": {"selection": %s}}' % json.dumps(sel)),
+             ("deriv", body + "}"),
+             ("deriv", body + ', "edge_reduction": {"aggregation": "sum"}}'),
+             ("marginal", body + ', "site_reduction": {"selection": %s}}' % json.dumps(list(range(0, S, 3)))),
+             ("dwell", body + ', "edge_reduction": {"aggregation": "avg"}}'),
+             ("trans", body + ', "trans_reduction": {"aggregation": "sum"}}')]
+    for prog, t in cases:
+        fn = getattr(A, "arbplf_" + prog)
+        monkeypatch.setenv("ARBPLF_HOST_THREADS", "1")
+        one = fn(t)
+        monkeypatch.setenv("ARBPLF_HOST_THREADS", "7")
+        many = fn(t)
+        monkeypatch.delenv("ARBPLF_HOST_THREADS")
+        auto = fn(t)
+        assert one == many == auto, prog
+    got = json.loads(A.arbplf_ll(cases[1][1]))
+    assert [r[0] for r in got["data"]] == sel
+    fwd = json.loads(A.arbplf_ll(cases[0][1]))
+    assert [r[1] for r in got["data"]] == [r[1] for r in fwd["data"]][::-1]
+    # against the oracle on a few of the sites
+    from oracle import arbplf_oracle as O
+    idx = [0, 1, 35000, S - 1]
+    md = dict(doc["model_and_data"])
+    md["character_data"] = codes[idx].tolist()
+    want = O.run_ll({"model_and_data": md}, mode="fp64")
+    for k, i in enumerate(idx):
+        assert abs(fwd["data"][i][1] - want["data"][k][1]) <= 1e-11 * abs(want["data"][k][1])
