@@ -249,8 +249,14 @@ def build_problem(args, local, rank, use_engine=True):
         codes_t, w_t = None, None
         codes = np.empty((S, N), dtype=np.uint8)
     simulate_codes(summary, P, S, seed=3, out=codes)
+    codes4_t = None
+    if use_engine:
+        # the same alignment as PLF_CODES_PACKED4 rows (include/plf.h): what the end-to-end step uploads
+        from phyly_b200.engine import pack4
+        codes4_t = torch.empty((S, (N + 1) // 2), dtype=torch.uint8, pin_memory=True)
+        pack4(codes, out=codes4_t.numpy())
     return dict(eng=eng, summary=summary, N=N, E=N - 1, n=n, C=C, S=S, codes_t=codes_t, codes=codes, w_t=w_t,
-                edge_rates=edge_rates, P=P, D=D, doc=doc)
+                codes4_t=codes4_t, edge_rates=edge_rates, P=P, D=D, doc=doc)
 
 
 def codon_model(kappa=2.0, omega=0.5, seed=4):
@@ -496,6 +502,8 @@ def run_ours(args):
         eng.comm_init(world, rank, uid[0])
     stream = torch.cuda.ExternalStream(eng.stream(), device=local)
     sync_upload = bool(os.environ.get("PLF_BENCH_SYNC_UPLOAD"))
+    packed = not os.environ.get("PLF_BENCH_UNPACKED")        # end-to-end step uploads 4-bit codes (two per byte)
+    row_bytes = (N + 1) // 2 if packed else N
 
     def barrier():
         torch.cuda.synchronize()
@@ -507,6 +515,8 @@ def run_ours(args):
         """Times the step on the site patterns [lo, hi) of the alignment: resident, end to end, ll only."""
         S = hi - lo
         codes_ptr = pb["codes_t"].data_ptr() + lo * N
+        e2e_ptr = pb["codes4_t"].data_ptr() + lo * row_bytes if packed else codes_ptr
+        e2e_cb = E.CODES_PACKED4 if packed else 1
         w_ptr = pb["w_t"].data_ptr() + 8 * lo
         w_np = pb["w_t"].numpy()[lo:hi]
 
@@ -516,10 +526,10 @@ def run_ours(args):
 
         def step_e2e():
             if sync_upload:
-                eng.set_data_ptr(defs, codes_ptr, S, 1)
+                eng.set_data_ptr(defs, e2e_ptr, S, e2e_cb)
                 eng.set_site_weights(w_np)
             else:       # chunked upload overlapped with the kernel
-                eng.set_data_async_ptr(defs, codes_ptr, S, w_ptr, 1)
+                eng.set_data_async_ptr(defs, e2e_ptr, S, w_ptr, e2e_cb)
             eng.set_edge_rates(pb["edge_rates"])
             return eng.deriv(per_site=False)
 
@@ -689,9 +699,10 @@ def run_ours(args):
                               "reduction_allreduce_readback": max(0.0, m["site_ms"] - k_ms),
                               "host_gaps": max(0.0, step_ms - m["mat_ms"] - m["site_ms"]),
                               "note": "CUDA events of rank 0 inside the step; host_gaps = step time not covered by them"},
-        "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(S * N + 8 * S + 8 * Eg),
+        "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(S * row_bytes + 8 * S + 8 * Eg),
                 "d2h_bytes_per_step": int(8 * (1 + Eg)), "steps": m["e2e_steps"], "ms_per_step": ms_e2e / m["e2e_steps"],
-                "api": ("plf_set_data + plf_set_site_weights" if sync_upload else "plf_set_data_async") + " + plf_set_edge_rates + plf_deriv (include/plf.h), pinned host buffers; bytes are per GPU"},
+                "api": ("plf_set_data + plf_set_site_weights" if sync_upload else "plf_set_data_async") + " + plf_set_edge_rates + plf_deriv (include/plf.h), pinned host buffers, codes as "
+                       + ("PLF_CODES_PACKED4 (two per byte)" if packed else "uint8") + "; bytes are per GPU"},
         "gpu_launches": int(m["launches"]),
         "clocks": clocks,
         "roofline": roofline,

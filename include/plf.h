@@ -86,10 +86,14 @@ int plf_set_edge_rates(plf_engine *e, const double *edge_rates /*[E]*/);
 
 /*
  * Data as character codes: codes[site][node] indexes rows of defs[K][n]
- * (parsemodel.c:514-628).  code_bytes is 1 (uint8) or 4 (int32).  A dense
+ * (parsemodel.c:514-628).  code_bytes is 1 (uint8), 4 (int32) or
+ * PLF_CODES_PACKED4: two codes per byte (def_count <= 16, the nucleotide case),
+ * rows of (N + 1) / 2 bytes, node 2j in the low and node 2j + 1 in the high
+ * nibble of byte j -- half the host-to-device traffic of uint8 codes.  A dense
  * probability_array is passed by first de-duplicating its rows into defs.
  * The copy to the device happens inside this call (pinned staging).
  */
+#define PLF_CODES_PACKED4 0
 int plf_set_data(plf_engine *e, int64_t site_count, int def_count,
                  const double *defs /*[K][n]*/, const void *codes /*[S][N]*/, int code_bytes);
 

@@ -188,7 +188,15 @@ struct plf_engine {
 /* small kernels                                                       */
 /* ------------------------------------------------------------------ */
 
-/* codes_in[S][N] (1 or 4 bytes) -> codes[N][S] (1 or 4 bytes); also flags nodes that carry data */
+/* input of PLF_CODES_PACKED4: two codes per byte, node 2j in the low nibble of byte j, rows of (N + 1) / 2 bytes */
+struct Packed4 { unsigned char b; };
+template <typename TIn> __device__ __forceinline__ int load_code(const TIn *in, int64_t s, int nd, int N) { return (int)in[(size_t)s * N + nd]; }
+template <> __device__ __forceinline__ int load_code<Packed4>(const Packed4 *in, int64_t s, int nd, int N)
+{
+    return (in[(size_t)s * ((N + 1) >> 1) + (nd >> 1)].b >> ((nd & 1) * 4)) & 15;
+}
+
+/* codes_in[S][N] (1 or 4 bytes, or packed nibbles) -> codes[N][S] (1 or 4 bytes); also flags nodes that carry data */
 template <typename TIn, typename TOut>
 __global__ void transpose_codes_kernel(const TIn *in, TOut *out, int64_t s_begin, int64_t s_end, int64_t S, int N,
                                        const unsigned char *def_ones, int *node_flags, int K, int *bad_code)
@@ -199,7 +207,7 @@ __global__ void transpose_codes_kernel(const TIn *in, TOut *out, int64_t s_begin
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         int64_t s = s0 + r;
         int nd = n0 + threadIdx.x;
-        tile[r][threadIdx.x] = (s < s_end && nd < N) ? (int)in[(size_t)s * N + nd] : -1;
+        tile[r][threadIdx.x] = (s < s_end && nd < N) ? load_code<TIn>(in, s, nd, N) : -1;
     }
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -825,7 +833,10 @@ static int launch_transpose(plf_engine *e, int64_t s0, int64_t s1, int in_bytes)
     int *flags = e->d_err.as<int>() + 4;
     int *bad = e->d_err.as<int>() + 1;          /* set when a code is not a row of the definition table */
     dim3 blk(32, 8), grid((unsigned)((s1 - s0 + 31) / 32), (unsigned)((N + 31) / 32));
-    if (in_bytes == 1)
+    if (in_bytes == PLF_CODES_PACKED4)
+        transpose_codes_kernel<Packed4, unsigned char><<<grid, blk, 0, e->stream>>>(
+            e->d_codes_in.as<Packed4>(), e->d_codes.as<unsigned char>(), s0, s1, S, N, e->d_def_ones.as<unsigned char>(), flags, e->K, bad);
+    else if (in_bytes == 1)
         transpose_codes_kernel<unsigned char, unsigned char><<<grid, blk, 0, e->stream>>>(
             e->d_codes_in.as<unsigned char>(), e->d_codes.as<unsigned char>(), s0, s1, S, N, e->d_def_ones.as<unsigned char>(), flags, e->K, bad);
     else if (e->code_bytes == 1)
@@ -888,8 +899,10 @@ static int set_data_common(plf_engine *e, int64_t S, int K, const double *defs, 
 {
     if (!e) return -1;
     if (e->N == 0 || e->n == 0) FAIL(e, "plf_set_data: set the tree and the model first");
-    if (S < 1 || K < 1 || !defs || !codes || (code_bytes != 1 && code_bytes != 4)) FAIL(e, "plf_set_data: invalid arguments");
+    if (S < 1 || K < 1 || !defs || !codes || (code_bytes != 1 && code_bytes != 4 && code_bytes != PLF_CODES_PACKED4))
+        FAIL(e, "plf_set_data: invalid arguments");
     if (code_bytes == 1 && K > 256) FAIL(e, "plf_set_data: %d definitions do not fit 1-byte codes", K);
+    if (code_bytes == PLF_CODES_PACKED4 && K > 16) FAIL(e, "plf_set_data: %d definitions do not fit 4-bit codes", K);
     const int n = e->n, N = e->N;
     CK(e, cudaSetDevice(e->device));
     std::vector<unsigned char> dconst(K), dones(K);
@@ -910,7 +923,8 @@ static int set_data_common(plf_engine *e, int64_t S, int K, const double *defs, 
     ENSURE(e, e->d_defs, sizeof(double) * K * n);
     ENSURE(e, e->d_def_const, K);
     ENSURE(e, e->d_def_ones, K);
-    ENSURE(e, e->d_codes_in, (size_t)S * N * code_bytes);
+    const size_t row = code_bytes == PLF_CODES_PACKED4 ? (size_t)(N + 1) / 2 : (size_t)N * code_bytes;    /* bytes per site of the input */
+    ENSURE(e, e->d_codes_in, (size_t)S * row);
     ENSURE(e, e->d_codes, (size_t)S * N * dev_bytes);
     ENSURE(e, e->d_node_has_data, N);
     ENSURE(e, e->d_err, sizeof(int) * (N + 4));
@@ -924,7 +938,6 @@ static int set_data_common(plf_engine *e, int64_t S, int K, const double *defs, 
     CK(e, cudaMemcpyAsync(e->d_def_ones.p, dones.data(), K, cudaMemcpyHostToDevice, e->stream));
     CK(e, cudaMemsetAsync(e->d_err.p, 0, sizeof(int) * (N + 4), e->stream));
     if (w) ENSURE(e, e->d_site_w, sizeof(double) * S);
-    const size_t row = (size_t)N * code_bytes;
     if (!async) {
         CK(e, cudaMemcpyAsync(e->d_codes_in.p, codes, (size_t)S * row, cudaMemcpyHostToDevice, e->stream));
         if (w) { CK(e, cudaMemcpyAsync(e->d_site_w.p, w, sizeof(double) * S, cudaMemcpyHostToDevice, e->stream)); e->have_w = true; }

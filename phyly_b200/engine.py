@@ -13,6 +13,25 @@ KIND_DWELL, KIND_TRANS = 0, 1
 PATH_AUTO, PATH_GENERIC, PATH_FUSED4 = 0, 1, 2
 
 
+CODES_PACKED4 = 0       # include/plf.h: PLF_CODES_PACKED4
+
+
+def pack4(codes, out=None):
+    """[S][N] codes below 16 -> [S][(N + 1) // 2] bytes, node 2j in the low and node 2j + 1 in the high nibble."""
+    codes = np.asarray(codes)
+    S, N = codes.shape
+    if codes.size and int(codes.max()) > 15:
+        raise ValueError("pack4: codes must be below 16")
+    M = (N + 1) // 2
+    if out is None:
+        out = np.empty((S, M), dtype=np.uint8)
+    np.copyto(out[:, :N // 2], codes[:, 1:2 * (N // 2):2].astype(np.uint8) << 4)
+    out[:, :N // 2] |= codes[:, 0:2 * (N // 2):2].astype(np.uint8)
+    if N % 2:
+        out[:, M - 1] = codes[:, N - 1]
+    return out
+
+
 class EngineError(RuntimeError):
     pass
 
@@ -83,6 +102,21 @@ class Engine:
         codes = np.ascontiguousarray(codes)
         self.S = codes.shape[0]
         self._ck(self._lib.plf_set_data(self._h, self.S, defs.shape[0], _ptr(defs), _ptr(codes), cb))
+
+    def set_data_packed(self, defs, packed, weights=None, asynchronous=False):
+        """Codes as PLF_CODES_PACKED4 rows (pack4): half the upload of uint8 codes."""
+        defs = _f64(defs)
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        self.S = packed.shape[0]
+        if asynchronous:
+            weights = None if weights is None else _f64(weights)
+            self._pending_host = (packed, weights)
+            self._ck(self._lib.plf_set_data_async(self._h, self.S, defs.shape[0], _ptr(defs), _ptr(packed), CODES_PACKED4,
+                                                  _ptr(weights)))
+        else:
+            self._ck(self._lib.plf_set_data(self._h, self.S, defs.shape[0], _ptr(defs), _ptr(packed), CODES_PACKED4))
+            if weights is not None:
+                self.set_site_weights(weights)
 
     def set_data_ptr(self, defs, codes_ptr, S, code_bytes=1):
         defs = _f64(defs)

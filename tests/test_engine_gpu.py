@@ -351,3 +351,47 @@ def test_compressed_alignment_gives_the_same_sums():
     assert np.array_equal(comp["site_ll"][smap], full["site_ll"])
     assert np.array_equal(comp["site_deriv"][smap], full["site_deriv"])
     eng.close()
+
+
+def test_packed_nibble_codes_are_the_same_upload():
+    """PLF_CODES_PACKED4 (two codes per byte, include/plf.h) against uint8 codes: identical per-site results, for an odd
+    and an even node count, through plf_set_data and plf_set_data_async; more than 16 definitions are refused."""
+    from phyly_b200 import engine as E
+    import bench
+
+    class A:
+        pass
+    args = A(); args.taxa = 24; args.sites = 5003
+    pb = bench.build_problem(args, 0, 0)
+    eng = pb["eng"]
+    defs = np.array(bench.DEFS, dtype=np.float64)
+    codes = pb["codes"]
+    assert codes.shape[1] % 2 == 1
+    w = 1.0 + np.random.default_rng(1).poisson(2.0, pb["S"]).astype(np.float64)
+    eng.set_data(defs, codes); eng.set_site_weights(w)
+    want = eng.deriv(per_site=True, per_site_ll=True)
+    packed = E.pack4(codes)
+    assert packed.shape == (pb["S"], (codes.shape[1] + 1) // 2)
+    for asynchronous in (False, True):
+        eng.set_data_packed(defs, packed, weights=w, asynchronous=asynchronous)
+        got = eng.deriv(per_site=True, per_site_ll=True)
+        assert np.array_equal(got["site_ll"], want["site_ll"])
+        assert np.array_equal(got["site_deriv"], want["site_deriv"])
+        assert got["sum_ll"] == want["sum_ll"] and np.array_equal(got["sum_deriv"], want["sum_deriv"])
+    eng.close()
+    # even node count: a star with three leaves
+    eng = _engine()
+    eng.set_tree([0, 3, 3, 3, 3], [1, 2, 3], [0, 1, 2, 3])
+    Q = np.array([[0, 1, 2, 1], [1, 0, 1, 2], [2, 1, 0, 1], [1, 2, 1, 0]], dtype=np.float64)
+    Q = Q - np.diag(Q.sum(axis=1))
+    eng.set_model(Q, np.zeros((4, 4)), [0.1, 0.2, 0.3], [1.0], [1.0], 3, [0.25] * 4)
+    c4 = np.random.default_rng(2).integers(0, 5, (301, 4)).astype(np.uint8)
+    c4[:, 0] = 4
+    eng.set_data(defs, c4)
+    want_ll, _ = eng.ll()
+    eng.set_data_packed(defs, E.pack4(c4))
+    got_ll, _ = eng.ll()
+    assert np.array_equal(got_ll, want_ll)
+    with pytest.raises(E.EngineError):
+        eng.set_data_packed(np.vstack([np.eye(4)] * 5), E.pack4(c4))
+    eng.close()
