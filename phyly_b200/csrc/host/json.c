@@ -154,24 +154,16 @@ static int parse_number(parser *ps, jv *out)
 
 /*
  * A large array whose items are flat arrays of short non-negative integers -- the 'character_data' of an alignment,
- * 2 bytes per code and 10^8 codes at the target size -- is read by several threads.  One pass finds the rows (the next
- * ']' after each '['); each thread then reads a contiguous range of rows into one block of its own.  A row holding
- * anything but such integers (a sign, a fraction, a nested array, a string, a stray comma ...) makes the whole attempt
+ * 2 bytes per code and 10^8 codes at the target size -- is read by the host threads in two passes over disjoint ranges:
+ * first every ']' of the remaining text is located (memchr), then each thread reads a contiguous range of rows (the text
+ * between one ']' and the next) into one block of its own.  The row after which the array's own ']' follows ends the
+ * matrix; threads that were handed text beyond it have read garbage, which is dropped.  A row holding anything but such
+ * integers (a sign, a fraction, a nested array, a string, a stray comma ...) before that point makes the whole attempt
  * step aside: the array is then read again by the general route, which owns every check and every error message.
  * Returns 0 when the array has been read, 1 when it is left to the general route.
  */
 #define MATRIX_MIN_BYTES (1u << 20)
 #define MATRIX_MIN_ROWS 256
-
-typedef struct { const char *open, *close; } row_span;
-
-typedef struct {
-    const row_span *rows;
-    size_t nrows;
-    jv *row_out;
-    jv **blocks;
-    int failed;         /* written by any thread: only ever set */
-} matrix_job;
 
 static inline const char *skip_ws_to(const char *q)
 {
@@ -196,20 +188,73 @@ static void *big_block(size_t bytes)
     return malloc(bytes);
 }
 
+/* pass 1: the positions of every ']' in [lo, hi), one list per thread */
+typedef struct { const char *lo, *hi; const char **pos; size_t n; int oom; } scan_part;
+typedef struct { const char *lo, *hi; scan_part *parts; } scan_job;
+
+static void scan_worker(int tid, int nthreads, void *ctx)
+{
+    scan_job *job = ctx;
+    const size_t span = (size_t)(job->hi - job->lo);
+    scan_part *sp = &job->parts[tid];
+    sp->lo = job->lo + span * (size_t)tid / (size_t)nthreads;
+    sp->hi = job->lo + span * (size_t)(tid + 1) / (size_t)nthreads;
+    size_t cap = (size_t)(sp->hi - sp->lo) / 128 + 64;
+    sp->pos = malloc(cap * sizeof(const char *));
+    sp->n = 0;
+    if (!sp->pos) { sp->oom = 1; return; }
+    for (const char *p = sp->lo; p < sp->hi; p++) {
+        p = memchr(p, ']', (size_t)(sp->hi - p));
+        if (!p) break;
+        if (sp->n == cap) {
+            cap *= 2;
+            const char **t = realloc(sp->pos, cap * sizeof(const char *));
+            if (!t) { sp->oom = 1; return; }
+            sp->pos = t;
+        }
+        sp->pos[sp->n++] = p;
+    }
+}
+
+/* pass 2: rows [r0, r1) of the matrix, row r being the text that ends at closes[r] */
+enum { EV_NONE = 0, EV_END, EV_INVALID };
+typedef struct { int kind; size_t row; } row_event;
+
+typedef struct {
+    const char *first_open;
+    const char *const *closes;
+    size_t nclose;
+    jv *row_out;
+    jv **blocks;
+    row_event *events;
+} matrix_job;
+
 static void matrix_worker(int tid, int nthreads, void *ctx)
 {
     matrix_job *job = ctx;
-    const size_t r0 = job->nrows * (size_t)tid / (size_t)nthreads, r1 = job->nrows * (size_t)(tid + 1) / (size_t)nthreads;
+    const size_t r0 = job->nclose * (size_t)tid / (size_t)nthreads, r1 = job->nclose * (size_t)(tid + 1) / (size_t)nthreads;
+    row_event *ev = &job->events[tid];
+    ev->kind = EV_NONE;
+    if (r0 == r1) return;
     /* an item takes at least two bytes of text (digit + separator) */
-    size_t bound = 1;
-    for (size_t r = r0; r < r1; r++) bound += (size_t)(job->rows[r].close - job->rows[r].open) / 2 + 1;
+    const char *from = r0 ? job->closes[r0 - 1] : job->first_open;
+    const size_t bound = (size_t)(job->closes[r1 - 1] - from) / 2 + (r1 - r0) + 1;
     jv *block = big_block(bound * sizeof(jv));
     job->blocks[tid] = block;
-    if (!block) { job->failed = 1; return; }
+    if (!block) { ev->kind = EV_INVALID; ev->row = r0; return; }
     jv *cur = block;
     for (size_t r = r0; r < r1; r++) {
-        const char *q = skip_ws_to(job->rows[r].open + 1);
-        const char *close = job->rows[r].close;
+        const char *q;
+        if (r == 0) q = job->first_open;
+        else {
+            q = skip_ws_to(job->closes[r - 1] + 1);
+            if (*q == ']') { ev->kind = EV_END; ev->row = r; return; }       /* the array's own bracket: rows 0 .. r-1 */
+            if (*q != ',') { ev->kind = EV_INVALID; ev->row = r; return; }
+            q = skip_ws_to(q + 1);
+        }
+        if (*q != '[') { ev->kind = EV_INVALID; ev->row = r; return; }
+        const char *close = job->closes[r];
+        q = skip_ws_to(q + 1);
         jv *first = cur;
         if (q != close) {
             for (;;) {
@@ -220,12 +265,12 @@ static void matrix_worker(int tid, int nthreads, void *ctx)
                     while (*q >= '0' && *q <= '9' && nd < 9) { v = v * 10 + (*q++ - '0'); nd++; }
                 } else if (*q == '0') {
                     v = 0; q++;
-                } else { job->failed = 1; return; }
+                } else { ev->kind = EV_INVALID; ev->row = r; return; }
                 cur->type = JV_INT; cur->flags = 0; cur->len = 0; cur->u.i = v;
                 cur++;
                 q = skip_ws_to(q);
                 if (q == close) break;
-                if (*q != ',') { job->failed = 1; return; }
+                if (*q != ',') { ev->kind = EV_INVALID; ev->row = r; return; }
                 q = skip_ws_to(q + 1);
             }
         }
@@ -236,58 +281,74 @@ static void matrix_worker(int tid, int nthreads, void *ctx)
 
 static int parse_int_matrix(parser *ps, jv *out)
 {
-    /* ps->p is at the '[' of the first row */
-    size_t cap = 1024, n = 0;
-    row_span *rows = malloc(cap * sizeof(row_span));
-    if (!rows) return 1;
-    const char *p = ps->p;
-    for (;;) {
-        if (*p != '[') goto step_aside;
-        const char *close = memchr(p + 1, ']', (size_t)(ps->end - (p + 1)));
-        if (!close) goto step_aside;
-        if (n == cap) {
-            cap *= 2;
-            row_span *t = realloc(rows, cap * sizeof(row_span));
-            if (!t) goto step_aside;
-            rows = t;
-        }
-        rows[n].open = p; rows[n].close = close; n++;
-        p = skip_ws_to(close + 1);
-        if (*p == ',') { p = skip_ws_to(p + 1); continue; }
-        if (*p == ']') { p++; break; }
-        goto step_aside;
-    }
-    if (n < MATRIX_MIN_ROWS || n >= 0xffffffffu) goto step_aside;
+    /* ps->p is at the '[' of the first row.  A matrix that ends within MATRIX_MIN_ROWS rows (a rate matrix, a small
+     * tree's edges) is not worth a pass over the rest of the document */
     {
-        int nthreads = par_threads();
-        if ((size_t)nthreads > n / 64) nthreads = (int)(n / 64);
-        if (nthreads < 1) nthreads = 1;
-        jv *items = malloc((n + 1 + (size_t)nthreads) * sizeof(jv));
-        jv **blocks = calloc((size_t)nthreads, sizeof(jv *));
-        if (!items || !blocks) { free(items); free(blocks); goto step_aside; }
-        matrix_job job = {rows, n, items, blocks, 0};
-        par_run(nthreads, matrix_worker, &job);
-        if (job.failed) {
-            for (int t = 0; t < nthreads; t++) free(blocks[t]);
-            free(items); free(blocks);
-            goto step_aside;
+        const char *p = ps->p;
+        for (int r = 0; r < MATRIX_MIN_ROWS; r++) {
+            if (*p != '[') return 1;
+            const char *close = memchr(p + 1, ']', (size_t)(ps->end - (p + 1)));
+            if (!close) return 1;
+            p = skip_ws_to(close + 1);
+            if (*p != ',') return 1;
+            p = skip_ws_to(p + 1);
         }
+    }
+    int nthreads = par_threads();
+    const int scan_threads = nthreads;
+    scan_part *parts = calloc((size_t)nthreads, sizeof(scan_part));
+    if (!parts) return 1;
+    scan_job sj = {ps->p, ps->end, parts};
+    par_run(nthreads, scan_worker, &sj);
+    size_t nclose = 0;
+    int bad = 0;
+    for (int t = 0; t < nthreads; t++) { nclose += parts[t].n; bad |= parts[t].oom; }
+    const char **closes = bad ? NULL : malloc((nclose + 1) * sizeof(const char *));
+    jv *items = NULL;
+    jv **blocks = NULL;
+    row_event *events = NULL;
+    int rc = 1;
+    if (!closes || nclose <= MATRIX_MIN_ROWS || nclose >= 0xffffffffu) goto done;
+    {
+        size_t k = 0;
+        for (int t = 0; t < nthreads; t++) { memcpy(closes + k, parts[t].pos, parts[t].n * sizeof(const char *)); k += parts[t].n; }
+    }
+    if ((size_t)nthreads > nclose / 64) nthreads = (int)(nclose / 64);
+    if (nthreads < 1) nthreads = 1;
+    items = malloc((nclose + 1 + (size_t)nthreads) * sizeof(jv));
+    blocks = calloc((size_t)nthreads, sizeof(jv *));
+    events = calloc((size_t)nthreads, sizeof(row_event));
+    if (!items || !blocks || !events) goto done;
+    {
+        matrix_job job = {ps->p, closes, nclose, items, blocks, events};
+        par_run(nthreads, matrix_worker, &job);
+    }
+    {
+        /* ranges ascend with the thread index: the first event is the earliest row that is not a row */
+        size_t n = 0;
+        int kind = EV_NONE;
+        for (int t = 0; t < nthreads && kind == EV_NONE; t++) if (events[t].kind != EV_NONE) { kind = events[t].kind; n = events[t].row; }
+        if (kind != EV_END || n < MATRIX_MIN_ROWS) goto done;
         jv *tail = items + n;
         tail->type = JV_NULL; tail->flags = 0; tail->len = (uint32_t)nthreads; tail->u.i = 0;
         for (int t = 0; t < nthreads; t++) {
+            if (nclose * (size_t)t / (size_t)nthreads >= n) { free(blocks[t]); blocks[t] = NULL; }     /* text beyond the matrix */
             tail[1 + t].type = JV_NULL; tail[1 + t].flags = 0; tail[1 + t].len = 0; tail[1 + t].u.items = blocks[t];
+            blocks[t] = NULL;
         }
-        free(blocks);
         if (getenv("ARBPLF_JSON_TRACE")) fprintf(stderr, "json: matrix of %zu rows read by %d threads\n", n, nthreads);
         ps->hint = items[n - 1].len;
         out->type = JV_ARRAY; out->flags = JV_F_BLOCKS; out->len = (uint32_t)n; out->u.items = items;
+        items = NULL;
+        ps->p = closes[n] + 1;          /* the ']' after the last row is the array's own */
+        rc = 0;
     }
-    free(rows);
-    ps->p = p;
-    return 0;
-step_aside:
-    free(rows);
-    return 1;
+done:
+    if (blocks) for (int t = 0; t < nthreads; t++) free(blocks[t]);
+    free(blocks); free(events); free(items); free(closes);
+    for (int t = 0; t < scan_threads; t++) free(parts[t].pos);
+    free(parts);
+    return rc;
 }
 
 static int parse_array(parser *ps, jv *out)

@@ -308,6 +308,18 @@ def test_threaded_matrix_reader_matches_the_general_route(monkeypatch, capfd):
     spaced = text.replace("],[", " ]\n,\t[ ").replace(",", " , ", 3000)
     s = json.loads(A.arbplf_model_summary(spaced))
     assert (s["codes_sum"], s["codes_weighted_sum"]) == want
+    # the matrix need not come last: text behind it (with brackets of its own) is handed to some threads, which drop it
+    key = '"character_data": '
+    i = text.index(key)
+    j = text.index("]]", i) + 2
+    moved = '{"model_and_data": {' + text[i:j] + ", " + text[len('{"model_and_data": {'):i].rstrip(", ") + text[j:]
+    assert json.loads(moved)["model_and_data"].keys() == json.loads(text)["model_and_data"].keys()
+    monkeypatch.setenv("ARBPLF_JSON_TRACE", "1")
+    capfd.readouterr()
+    s = json.loads(A.arbplf_model_summary(moved))
+    assert "json: matrix of 6000 rows" in capfd.readouterr().err
+    monkeypatch.delenv("ARBPLF_JSON_TRACE")
+    assert (s["codes_sum"], s["codes_weighted_sum"]) == want
     # a short document (general route) with the same rows gives the same bytes
     small, codes_small = _big_document(40)
     s = json.loads(A.arbplf_model_summary(small))
