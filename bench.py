@@ -206,6 +206,30 @@ def dist_setup(n_gpus):
     return rank, world, local
 
 
+def bind_near_gpu(local):
+    """Multi-rank runs: keep this process (and the pinned buffers it is about to allocate, which land on the NUMA node of
+    the allocating thread) on the CPUs next to its GPU, as sysfs lists them.  Returns the cpulist string or None."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        text = open(path).read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return text
+    except Exception:
+        return None
+
+
 def host_matrices(summary):
     """P and rate*Q*P on the host (scipy), used only to simulate data and by the CPU reference arm."""
     import scipy.linalg
@@ -492,6 +516,7 @@ def run_ours(args):
     from phyly_b200 import engine as E
     rank, world, local = dist_setup(args.gpus)
     torch.cuda.set_device(local)
+    numa = bind_near_gpu(local) if world > 1 and not os.environ.get("PLF_BENCH_NO_BIND") else None
     pb = build_problem(args, local, rank)
     eng = pb["eng"]
     S_total, Eg, C, N = pb["S"], pb["E"], pb["C"], pb["N"]
@@ -716,6 +741,9 @@ def run_ours(args):
     }
     if allreduce_check:
         line["allreduce_check"] = allreduce_check
+    if world > 1:
+        line["host_binding"] = {"rank0_cpulist": numa, "note": "each rank pinned to the CPUs sysfs lists next to its GPU before its "
+                                "pinned buffers are allocated (null: sysfs entry not available, no binding)"}
     if weak:
         line["weak"] = weak
     if world == 1 and not args.no_extras:
