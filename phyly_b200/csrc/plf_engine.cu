@@ -782,6 +782,13 @@ static int run_expm(plf_engine *e, double *P, double *D, double *F, int f_scale_
     a.edge_mask = d_mask;
     a.P = P; a.D = D; a.F = F; a.f_scale_mode = f_scale_mode;
     const size_t nn = (size_t)e->n * e->n;
+    if (e->n == 4 && !F && !getenv("PLF_NO_EXPM4")) {
+        /* P (and D) of a 4-state model: half a warp per matrix, eight matrices per CTA */
+        a.ws = nullptr;
+        expm4_dd_kernel<<<(e->C * e->E + 7) / 8, 128, 0, e->stream>>>(a);
+        KCHECK(e);
+        return 0;
+    }
     size_t smem = 0;
     if (e->n <= 16) { a.ws = nullptr; smem = 8 * nn * sizeof(dd_t); }
     else {

@@ -395,3 +395,48 @@ def test_packed_nibble_codes_are_the_same_upload():
     with pytest.raises(E.EngineError):
         eng.set_data_packed(np.vstack([np.eye(4)] * 5), E.pack4(c4))
     eng.close()
+
+
+def test_four_state_expm_kernel_gives_the_bits_of_the_generic_one(monkeypatch):
+    """expm4_dd_kernel (half a warp per 4 x 4 matrix, shuffles) follows the arithmetic of expm_dd_kernel step by step:
+    P and D are identical to the last bit, for short, long and zero-length branches, an invariant category and a rate
+    matrix with structural zeros."""
+    import bench
+
+    class A:
+        pass
+    args = A(); args.taxa = 40; args.sites = 64
+    pb = bench.build_problem(args, 0, 0)
+    eng = pb["eng"]
+    rng = np.random.default_rng(9)
+    E = pb["E"]
+    cases = [pb["edge_rates"], rng.exponential(1.0, E) * 10.0 ** rng.integers(-12, 3, E), np.zeros(E),
+             np.full(E, 750.0), rng.exponential(0.01, E)]
+    for rates in cases:
+        monkeypatch.delenv("PLF_NO_EXPM4", raising=False)
+        eng.set_edge_rates(rates)
+        P4, D4 = eng.transition_matrices(), eng.derivative_matrices()
+        monkeypatch.setenv("PLF_NO_EXPM4", "1")
+        eng.set_edge_rates(rates)
+        Pg, Dg = eng.transition_matrices(), eng.derivative_matrices()
+        assert np.array_equal(P4, Pg) and np.array_equal(D4, Dg)
+        assert np.all(np.isfinite(P4)) and np.allclose(P4.sum(axis=3), 1.0, rtol=0, atol=1e-14)
+    eng.close()
+    # a sparse rate matrix (structural zeros are skipped in both kernels) with an invariant category
+    monkeypatch.delenv("PLF_NO_EXPM4", raising=False)
+    prob = H.random_problem(77, ntips=9, n=4, S=5, ncat=3)
+    md = prob["model_and_data"]
+    md["rate_matrix"] = [[0, 1, 0, 0], [0, 0, 2, 0], [0.5, 0, 0, 3], [0, 0, 0, 0]]
+    md["rate_divisor"] = 2.0
+    md["root_prior"] = [0.1, 0.2, 0.3, 0.4]
+    md["rate_mixture"] = {"rates": [0.0, 0.5, 3.0], "prior": [0.2, 0.3, 0.5]}
+    m = O.parse_model(md)
+    out = []
+    for env in (None, "1"):
+        if env:
+            monkeypatch.setenv("PLF_NO_EXPM4", env)
+        e2 = _engine()
+        H.fill_engine(e2, m)
+        out.append((e2.transition_matrices(), e2.derivative_matrices()))
+        e2.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
