@@ -15,6 +15,7 @@
 #include <cmath>
 #include <string>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 #include <algorithm>
 #include <dlfcn.h>
@@ -224,6 +225,60 @@ __global__ void transpose_codes_kernel(const TIn *in, TOut *out, int64_t s_begin
         if (any && threadIdx.x == 0 && nd < N) {
             if (node_flags[nd] == 0) atomicOr(&node_flags[nd], 1);
         }
+    }
+}
+
+/* The same for 1-byte output codes (K <= 256) from 1-byte or packed input, the shapes an alignment has: a CTA brings the
+ * rows of 128 sites (a contiguous run of the input) into shared memory and writes them out node by node, 32 consecutive
+ * sites per store.  The 32 x 32 tiles of the kernel above spend their time starting CTAs of 1 KB each: 350 us for the
+ * 127 MB of cfg2 against 60 us here, which the end-to-end step pays in full (the transposes sit between the chunk kernels). */
+#define TR_SITES 128
+#define TR_NODES 252
+template <typename TIn>
+__global__ void __launch_bounds__(256) transpose_codes_rows_kernel(const TIn *in, unsigned char *out, int64_t s_begin, int64_t s_end,
+                                                                   int64_t S, int N, const unsigned char *def_ones, int *node_flags,
+                                                                   int K, int *bad_code, int pad_words)
+{
+    extern __shared__ __align__(16) unsigned char tr_tile[];
+    const int64_t s0 = s_begin + (int64_t)blockIdx.x * TR_SITES;
+    const int n0 = blockIdx.y * TR_NODES, nt = min(TR_NODES, N - n0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int pad = pad_words * 4;
+    const int rows = (s_end - s0 < TR_SITES) ? (int)(s_end - s0) : TR_SITES;
+    if (sizeof(TIn) == 1 && !std::is_same<TIn, Packed4>::value) {
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(in);
+        for (int r = warp; r < rows; r += nw) {
+            const unsigned char *row = src + (size_t)(s0 + r) * N + n0;
+            for (int b = lane; b < nt; b += 32) tr_tile[r * pad + b] = row[b];
+        }
+    } else {
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(in);
+        const int rb = (N + 1) >> 1, b0 = n0 >> 1, nb = (nt + 1) >> 1;          /* TR_NODES is even: tiles start on a byte */
+        for (int r = warp; r < rows; r += nw) {
+            const unsigned char *row = src + (size_t)(s0 + r) * rb + b0;
+            for (int b = lane; b < nb; b += 32) {
+                const unsigned char v = row[b];
+                tr_tile[r * pad + 2 * b] = v & 15;
+                if (2 * b + 1 < nt) tr_tile[r * pad + 2 * b + 1] = v >> 4;
+            }
+        }
+    }
+    __syncthreads();
+    for (int nd = warp; nd < nt; nd += nw) {
+        unsigned any = 0;
+#pragma unroll
+        for (int k = 0; k < TR_SITES / 32; k++) {
+            const int r = lane + 32 * k;
+            bool has = false;
+            if (r < rows) {
+                int code = tr_tile[r * pad + nd];
+                if (code >= K) { *bad_code = 1; code = 0; }          /* reported by the host */
+                out[(size_t)(n0 + nd) * S + s0 + r] = (unsigned char)code;
+                has = !def_ones[code];
+            }
+            any |= __ballot_sync(0xffffffffu, has);
+        }
+        if (any && lane == 0 && node_flags[n0 + nd] == 0) atomicOr(&node_flags[n0 + nd], 1);
     }
 }
 
@@ -840,7 +895,19 @@ static int launch_transpose(plf_engine *e, int64_t s0, int64_t s1, int in_bytes)
     int *flags = e->d_err.as<int>() + 4;
     int *bad = e->d_err.as<int>() + 1;          /* set when a code is not a row of the definition table */
     dim3 blk(32, 8), grid((unsigned)((s1 - s0 + 31) / 32), (unsigned)((N + 31) / 32));
-    if (in_bytes == PLF_CODES_PACKED4)
+    if ((in_bytes == PLF_CODES_PACKED4 || in_bytes == 1) && !getenv("PLF_OLD_TRANSPOSE")) {
+        /* rows of 128 sites through shared memory; the row pitch is an odd number of words (conflict-free columns) */
+        const int nt = std::min(N, TR_NODES);
+        const int pad_words = ((nt + 3) / 4) | 1;
+        dim3 g((unsigned)((s1 - s0 + TR_SITES - 1) / TR_SITES), (unsigned)((N + TR_NODES - 1) / TR_NODES));
+        const size_t smem = (size_t)TR_SITES * pad_words * 4;
+        if (in_bytes == 1)
+            transpose_codes_rows_kernel<unsigned char><<<g, 256, smem, e->stream>>>(
+                e->d_codes_in.as<unsigned char>(), e->d_codes.as<unsigned char>(), s0, s1, S, N, e->d_def_ones.as<unsigned char>(), flags, e->K, bad, pad_words);
+        else
+            transpose_codes_rows_kernel<Packed4><<<g, 256, smem, e->stream>>>(
+                e->d_codes_in.as<Packed4>(), e->d_codes.as<unsigned char>(), s0, s1, S, N, e->d_def_ones.as<unsigned char>(), flags, e->K, bad, pad_words);
+    } else if (in_bytes == PLF_CODES_PACKED4)
         transpose_codes_kernel<Packed4, unsigned char><<<grid, blk, 0, e->stream>>>(
             e->d_codes_in.as<Packed4>(), e->d_codes.as<unsigned char>(), s0, s1, S, N, e->d_def_ones.as<unsigned char>(), flags, e->K, bad);
     else if (in_bytes == 1)
