@@ -378,6 +378,22 @@ __global__ void zero_lik_rows_kernel(const double *ll, const double *w, int64_t 
  * collective needs that rank's flag.  A bounded spin turns a lost peer into an error flag instead of a hung GPU.
  * Inbox layout: double data[PLF_PEER_MAX][2][PLF_PEER_CAP]; unsigned long long flag[PLF_PEER_MAX][2].
  */
+/* Second stage of every reduction over per-CTA partial sums: the rows are dealt to PLF_ROW_GROUPS interleaved groups, each
+ * summed in order with compensation by one thread, and the group sums are added in group order -- the same decomposition
+ * in sum_rows_kernel and in the fused stage of peer_allreduce_kernel, so that both give the same bits (bench.py's
+ * allreduce_check relies on it), and 8 times shorter than one thread walking all the rows. */
+#define PLF_ROW_GROUPS 8
+__device__ __forceinline__ double rows_group_sum(const double *col, size_t stride, int rows, int g)
+{
+    double s = 0.0, comp = 0.0;
+    for (int r = g; r < rows; r += PLF_ROW_GROUPS) {
+        const double yv = col[(size_t)r * stride] - comp, tsum = s + yv;
+        comp = (tsum - s) - yv;
+        s = tsum;
+    }
+    return s;
+}
+
 __global__ void peer_allreduce_kernel(double *vec, int count, unsigned long long seq, int rank, int nranks,
                                       void *const *inbox_of, int *err,
                                       const double *part_ll, const double *part_edge, int rows, int E)
@@ -385,18 +401,22 @@ __global__ void peer_allreduce_kernel(double *vec, int count, unsigned long long
     /* fused with the second stage of the reduction: vec[0] = sum of the per-CTA log-likelihood sums, vec[1 + e] = sum of
      * the per-CTA sums of edge e (fixed order, compensated), when the partial sums are handed in instead of a finished vec */
     if (part_ll) {
-        for (int j = threadIdx.x; j < count; j += blockDim.x) {
-            const double *col = (j == 0) ? part_ll : part_edge + (j - 1);
-            const int stride = (j == 0) ? 1 : E;
-            double sum = 0.0, comp = 0.0;
-            for (int r = 0; r < rows; r++) {
-                const double y = col[(size_t)r * stride] - comp, t = sum + y;
-                comp = (t - sum) - y;
-                sum = t;
+        /* launched with 128 * PLF_ROW_GROUPS threads for this form: thread = (column within a run of 128, row group) */
+        __shared__ double sm[PLF_ROW_GROUPS][128];
+        const int x = threadIdx.x & 127, g = threadIdx.x >> 7;
+        for (int jb = 0; jb < count; jb += 128) {
+            const int j = jb + x;
+            if (g < PLF_ROW_GROUPS)
+                sm[g][x] = (j < count) ? rows_group_sum((j == 0) ? part_ll : part_edge + (j - 1), (j == 0) ? (size_t)1 : (size_t)E, rows, g) : 0.0;
+            __syncthreads();
+            if (g == 0 && j < count) {
+                double s = sm[0][x];
+#pragma unroll
+                for (int w = 1; w < PLF_ROW_GROUPS; w++) s += sm[w][x];
+                vec[j] = s;
             }
-            vec[j] = sum;
+            __syncthreads();
         }
-        __syncthreads();
     }
     const int par = (int)(seq & 1);
     const size_t flag_off = sizeof(double) * (size_t)PLF_PEER_MAX * 2 * PLF_PEER_CAP;
@@ -456,18 +476,19 @@ __global__ void transpose_d_kernel(const double *in, double *out, int R, int Cc)
 }
 
 /* second stage: out[j] = sum over rows of part[row][j], fixed order (Kahan) */
-__global__ void sum_rows_kernel(const double *part, int rows, int cols, double *out)
+__global__ void __launch_bounds__(256) sum_rows_kernel(const double *part, int rows, int cols, double *out)
 {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= cols) return;
-    double s = 0.0, comp = 0.0;
-    for (int r = 0; r < rows; r++) {
-        double yv = part[(size_t)r * cols + j] - comp;
-        double tsum = s + yv;
-        comp = (tsum - s) - yv;
-        s = tsum;
+    /* block = (32 columns, PLF_ROW_GROUPS interleaved groups of rows); see rows_group_sum */
+    __shared__ double sm[PLF_ROW_GROUPS][33];
+    const int j = blockIdx.x * 32 + threadIdx.x, g = threadIdx.y;
+    sm[g][threadIdx.x] = (j < cols) ? rows_group_sum(part + j, (size_t)cols, rows, g) : 0.0;
+    __syncthreads();
+    if (g == 0 && j < cols) {
+        double s = sm[0][threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < PLF_ROW_GROUPS; w++) s += sm[w][threadIdx.x];
+        out[j] = s;
     }
-    out[j] = s;
 }
 
 /* gather the matrices of internal-child edges: out[c][ie] = M[c][edge_of[ie]] (16 doubles each) */
@@ -1584,7 +1605,7 @@ static int run_fused(plf_engine *e, Query &q, const F4Window *win = nullptr)
     /* ll / ll + edge sums with a communicator: second-stage reduction and all-reduce are one kernel over peer memory */
     const bool fuse_reduce = !marg && !q.site_edge && !pipelined && peer_path(e, 1 + (size_t)(edge ? e->E : 0));
     if (!fuse_reduce) {
-        sum_rows_kernel<<<1, 32, 0, e->stream>>>(a.block_ll, rows, 1, dsum);
+        sum_rows_kernel<<<1, dim3(32, PLF_ROW_GROUPS), 0, e->stream>>>(a.block_ll, rows, 1, dsum);
         KCHECK(e);
     }
     size_t nsum = 1;
@@ -1598,14 +1619,14 @@ static int run_fused(plf_engine *e, Query &q, const F4Window *win = nullptr)
                 KCHECK(e);
             }
         } else {
-            sum_rows_kernel<<<(cols + 127) / 128, 128, 0, e->stream>>>(a.block_marg, grid * (use.bd / 32), cols, dsum + 1 + e->E);
+            sum_rows_kernel<<<(cols + 31) / 32, dim3(32, PLF_ROW_GROUPS), 0, e->stream>>>(a.block_marg, grid * (use.bd / 32), cols, dsum + 1 + e->E);
             KCHECK(e);
         }
         nsum = 1 + e->E + cols;
     }
     if (edge && !marg && !q.site_edge) {
         if (!fuse_reduce) {
-            sum_rows_kernel<<<(e->E + 127) / 128, 128, 0, e->stream>>>(a.block_edge, rows, e->E, dsum + 1);
+            sum_rows_kernel<<<(e->E + 31) / 32, dim3(32, PLF_ROW_GROUPS), 0, e->stream>>>(a.block_edge, rows, e->E, dsum + 1);
             KCHECK(e);
         }
         nsum = 1 + e->E;
@@ -1620,8 +1641,8 @@ static int run_fused(plf_engine *e, Query &q, const F4Window *win = nullptr)
     if (shared_retry) CK(e, cudaMemcpyAsync(dsum + nsum, e->d_retry.p, sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
     if (fuse_reduce) {
         e->peer_seq++;
-        peer_allreduce_kernel<<<1, 256, 0, e->stream>>>(dsum, (int)nsum, e->peer_seq, e->rank, e->nranks, e->d_peer_ptrs.as<void *>(),
-                                                        e->d_err.as<int>(), a.block_ll, edge ? a.block_edge : nullptr, rows, e->E);
+        peer_allreduce_kernel<<<1, 128 * PLF_ROW_GROUPS, 0, e->stream>>>(dsum, (int)nsum, e->peer_seq, e->rank, e->nranks, e->d_peer_ptrs.as<void *>(),
+                                                                         e->d_err.as<int>(), a.block_ll, edge ? a.block_edge : nullptr, rows, e->E);
         KCHECK(e);
     } else if (finish_sums(e, dsum, nsum + (shared_retry ? 1 : 0))) return -1;
     CK(e, cudaEventRecord(e->ev[2], e->stream));
@@ -2013,7 +2034,7 @@ static int run_generic(plf_engine *e, Query &q)
     if (finish_sums(e, dsum, nsum)) return -1;
     if (q.sum_hess) {
         /* H = sum of the per-CTA parts - Gram matrix of the per-site derivatives (lower triangle, csr order) */
-        sum_rows_kernel<<<(unsigned)(((size_t)E * E + 127) / 128), 128, 0, e->stream>>>(e->h_part.as<double>(), hgrid, E * E, e->h_out.as<double>());
+        sum_rows_kernel<<<(unsigned)(((size_t)E * E + 31) / 32), dim3(32, PLF_ROW_GROUPS), 0, e->stream>>>(e->h_part.as<double>(), hgrid, E * E, e->h_out.as<double>());
         KCHECK(e);
         axpy_kernel<<<(unsigned)(((size_t)E * E + 255) / 256), 256, 0, e->stream>>>(e->h_out.as<double>(), e->h_gram.as<double>(), -1.0, (size_t)E * E);
         KCHECK(e);
