@@ -81,6 +81,11 @@ int plf_set_model(plf_engine *e, int state_count, int category_count,
                   const double *cat_rates /*[C]*/, const double *cat_prior /*[C]*/,
                   int root_mode, const double *root_vec /*[n] or NULL*/);
 
+/* Creates the CUDA context of a device ahead of the first plf_create (no engine, no message; 0 or -1): a process that
+ * answers one document (the arbplf-* executables, runjson.c:117-157) calls it from a second thread while it reads and
+ * parses its input. */
+int plf_warmup(int device);
+
 /* Change only the edge rate coefficients (csr order); recomputes matrices lazily. */
 int plf_set_edge_rates(plf_engine *e, const double *edge_rates /*[E]*/);
 

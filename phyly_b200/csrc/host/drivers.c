@@ -802,11 +802,23 @@ char *arbplf_newton_update(const char *j, int *rc) { return second_order(j, rc, 
 char *arbplf_newton_refine(const char *j, int *rc) { return second_order(j, rc, SO_REFINE); }
 
 /* runjson.c:88-147 */
+/* An arbplf-* process answers one document: creating the CUDA context (a few tenths of a second) overlaps reading and
+ * parsing the document instead of following it.  Failure here is silent -- the call itself tries again and reports. */
+static void *warm_engine(void *unused)
+{
+    (void)unused;
+    const char *s = getenv("ARBPLF_DEVICE");
+    plf_warmup(g_device >= 0 ? g_device : (s ? atoi(s) : 0));
+    return NULL;
+}
+
 int arbplf_run_stdio(char *(*f)(const char *, int *))
 {
+    pthread_t warm;
+    const int warming = pthread_create(&warm, NULL, warm_engine, NULL) == 0;
     size_t cap = 1 << 16, len = 0;
     char *s = malloc(cap);
-    if (!s) return -1;
+    if (!s) { if (warming) pthread_join(warm, NULL); return -1; }
     for (;;) {
         size_t got = fread(s + len, 1, cap - len - 1, stdin);
         len += got;
@@ -814,7 +826,7 @@ int arbplf_run_stdio(char *(*f)(const char *, int *))
         if (len + 1 >= cap) {
             cap *= 2;
             char *t = realloc(s, cap);
-            if (!t) { fprintf(stderr, "failed to read string from stdin\n"); free(s); return -1; }
+            if (!t) { fprintf(stderr, "failed to read string from stdin\n"); free(s); if (warming) pthread_join(warm, NULL); return -1; }
             s = t;
         }
     }
@@ -823,5 +835,6 @@ int arbplf_run_stdio(char *(*f)(const char *, int *))
     char *out = f(s, &rc);
     free(s);
     if (out) { puts(out); free(out); }
+    if (warming) pthread_join(warm, NULL);
     return rc;
 }

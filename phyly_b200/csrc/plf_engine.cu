@@ -539,6 +539,14 @@ __global__ void f4_tables_kernel(const double *P, const double *Fm, const double
 /* lifecycle                                                           */
 /* ------------------------------------------------------------------ */
 
+extern "C" int plf_warmup(int device)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return -1;
+    if (cudaSetDevice(device) != cudaSuccess || cudaFree(nullptr) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return 0;
+}
+
 extern "C" int plf_create(plf_engine **out, int device)
 {
     if (!out) return -1;
