@@ -30,10 +30,40 @@ static plf_engine *g_engine = NULL;
 static int g_device = -1;
 static pthread_mutex_t g_engine_lock = PTHREAD_MUTEX_INITIALIZER;
 
+/* what the shared engine holds from the previous call (guarded by g_engine_lock, like the engine) */
+static struct {
+    plf_engine *e;
+    int N, n, K;
+    int *indptr, *indices, *preorder;
+    double *defs;
+    jv_codes *data;
+} g_resident;
+
+static void resident_forget_data(void)
+{
+    if (g_resident.data) json_codes_release(g_resident.data);
+    free(g_resident.defs);
+    g_resident.data = NULL; g_resident.defs = NULL; g_resident.K = 0;
+}
+
+static void resident_forget(void)
+{
+    resident_forget_data();
+    free(g_resident.indptr); free(g_resident.indices); free(g_resident.preorder);
+    memset(&g_resident, 0, sizeof g_resident);
+}
+
+static int *copy_ints(const int *src, size_t n)
+{
+    int *p = malloc(sizeof(int) * (n ? n : 1));
+    if (p) memcpy(p, src, sizeof(int) * n);
+    return p;
+}
+
 void arbplf_set_device(int device)
 {
     pthread_mutex_lock(&g_engine_lock);
-    if (g_engine && device != g_device) { plf_destroy(g_engine); g_engine = NULL; }
+    if (g_engine && device != g_device) { plf_destroy(g_engine); g_engine = NULL; resident_forget(); }
     g_device = device;
     pthread_mutex_unlock(&g_engine_lock);
 }
@@ -107,11 +137,45 @@ static int ctx_load(ctx *c)
     const plf_model *m = &c->m;
     const plf_derived *d = &c->d;
 #define EK(call) do { if (call) { fprintf(stderr, "error: %s\n", plf_last_error(c->e)); return -1; } } while (0)
-    EK(plf_set_tree(c->e, m->N, m->indptr, m->indices, m->preorder));
+    /* What the engine already holds from the previous call stays there: the tree if it is the same, and the alignment
+     * if the reader recognised its text (json.h: the codes are then the very buffer that was uploaded last time) and the
+     * definitions are the same -- an optimiser that varies the edge rates re-sends both with every call. */
+    const int same_tree = g_resident.e == c->e && g_resident.N == m->N && g_resident.indptr &&
+                          !memcmp(g_resident.indptr, m->indptr, sizeof(int) * (size_t)(m->N + 1)) &&
+                          !memcmp(g_resident.indices, m->indices, sizeof(int) * (size_t)m->E) &&
+                          !memcmp(g_resident.preorder, m->preorder, sizeof(int) * (size_t)m->N);
+    if (!same_tree) {
+        resident_forget();
+        EK(plf_set_tree(c->e, m->N, m->indptr, m->indices, m->preorder));
+        g_resident.e = c->e; g_resident.N = m->N;
+        g_resident.indptr = copy_ints(m->indptr, (size_t)m->N + 1);
+        g_resident.indices = copy_ints(m->indices, (size_t)m->E);
+        g_resident.preorder = copy_ints(m->preorder, (size_t)m->N);
+        if (!g_resident.indptr || !g_resident.indices || !g_resident.preorder) resident_forget();
+    }
+    if (g_resident.n != m->n) resident_forget_data();       /* plf_set_model drops the data when the state count changes */
     EK(plf_set_model(c->e, m->n, d->C, d->q_hi, d->q_lo, d->edge_rates_csr, d->cat_rates, d->cat_prior,
                      m->root_mode, d->root_vec));
-    /* the codes travel in chunks behind which the first query starts (they stay valid until ctx_clear) */
-    if (m->S > 0) EK(plf_set_data_async(c->e, m->S, m->K, m->defs, m->codes, m->code_bytes, NULL));
+    g_resident.n = m->n;
+    const int same_data = same_tree && m->S > 0 && m->codes_shared && m->codes_shared == g_resident.data &&
+                          g_resident.K == m->K && g_resident.defs &&
+                          !memcmp(g_resident.defs, m->defs, sizeof(double) * (size_t)m->K * (size_t)m->n);
+    if (same_data) {
+        if (getenv("ARBPLF_JSON_TRACE")) fprintf(stderr, "drivers: alignment already on the device, no upload\n");
+    } else {
+        resident_forget_data();
+        /* the codes travel in chunks behind which the first query starts (they stay valid until ctx_clear) */
+        if (m->S > 0) EK(plf_set_data_async(c->e, m->S, m->K, m->defs, m->codes, m->code_bytes, NULL));
+        if (m->S > 0 && m->codes_shared && g_resident.e == c->e) {
+            g_resident.defs = malloc(sizeof(double) * ((size_t)m->K * (size_t)m->n + 1));
+            if (g_resident.defs) {
+                memcpy(g_resident.defs, m->defs, sizeof(double) * (size_t)m->K * (size_t)m->n);
+                g_resident.K = m->K;
+                json_codes_retain(m->codes_shared);
+                g_resident.data = m->codes_shared;
+            }
+        }
+    }
     c->loaded = 1;
     g_phase[1] = now_s() - c->t_mark; c->t_mark = now_s();
     return 0;
@@ -133,6 +197,7 @@ static char *finish(ctx *c, char *out, int rc, int *retcode)
 {
     /* callers mark the end of the compute phase with phase_compute_done(); whatever follows is output formatting */
     if (c->t_mark > 0) g_phase[3] = now_s() - c->t_mark;
+    if (rc && c->locked) resident_forget();     /* after a failed call nothing is assumed about what the engine holds */
     ctx_clear(c);
     *retcode = rc;
     if (rc) { free(out); return NULL; }

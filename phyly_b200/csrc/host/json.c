@@ -16,6 +16,7 @@ typedef struct {
     char *err;
     size_t errlen;
     int depth;
+    const char *key;    /* key of the object member whose value is about to be read, else NULL */
     size_t hint;        /* length of the array parsed last: rows of a matrix have one length, so the next one is sized right at once */
 } parser;
 
@@ -36,7 +37,9 @@ static void skip_ws(parser *ps)
 static void free_contents(jv *v)
 {
     if (v->type == JV_STRING) free(v->u.s);
-    else if (v->type == JV_ARRAY) {
+    else if (v->type == JV_ARRAY && (v->flags & JV_F_COMPACT)) {
+        json_codes_release((jv_codes *)v->u.items);
+    } else if (v->type == JV_ARRAY) {
         if (v->flags & JV_F_BLOCKS) {           /* rows of integers in shared blocks (parse_int_matrix) */
             const jv *tail = v->u.items + v->len;
             for (uint32_t t = 0; t < tail->len; t++) free(tail[1 + t].u.items);
@@ -150,6 +153,117 @@ static int parse_number(parser *ps, jv *out)
     }
     ps->p = q;
     return 0;
+}
+
+/* ---- the 'character_data' cache (json.h) ---- */
+
+#include <pthread.h>
+
+static pthread_mutex_t g_codes_lock = PTHREAD_MUTEX_INITIALIZER;
+static jv_codes *g_codes_entry = NULL;
+
+void json_codes_retain(jv_codes *d)
+{
+    if (!d) return;
+    pthread_mutex_lock(&g_codes_lock);
+    d->refs++;
+    pthread_mutex_unlock(&g_codes_lock);
+}
+
+void json_codes_release(jv_codes *d)
+{
+    if (!d) return;
+    pthread_mutex_lock(&g_codes_lock);
+    const int left = --d->refs;
+    pthread_mutex_unlock(&g_codes_lock);
+    if (left == 0) { free(d->codes); free(d); }
+}
+
+jv_codes *json_codes_publish(uint64_t h1, uint64_t h2, size_t text_len, void *codes, int code_bytes, int64_t rows, int row_len, int max_code)
+{
+    jv_codes *d = malloc(sizeof(jv_codes));
+    if (!d) return NULL;
+    d->codes = codes; d->code_bytes = code_bytes; d->rows = rows; d->row_len = row_len; d->max_code = max_code;
+    d->h1 = h1; d->h2 = h2; d->text_len = text_len;
+    d->refs = 2;                /* the cache's and the caller's */
+    pthread_mutex_lock(&g_codes_lock);
+    jv_codes *old = g_codes_entry;
+    g_codes_entry = d;
+    pthread_mutex_unlock(&g_codes_lock);
+    json_codes_release(old);
+    return d;
+}
+
+int jv_matrix_text_hash(const jv *v, uint64_t *h1, uint64_t *h2, size_t *text_len)
+{
+    if (!v || v->type != JV_ARRAY || !(v->flags & JV_F_HASHED) || !(v->flags & JV_F_BLOCKS)) return 0;
+    const jv *tail = v->u.items + v->len;
+    const jv *slot = tail + 1 + tail->len;
+    *h1 = (uint64_t)slot[0].u.i; *h2 = (uint64_t)slot[1].u.i; *text_len = (size_t)slot[2].u.i;
+    return 1;
+}
+
+/* 128 bits over a text: two multiply-xor chains per 1 MB chunk (the chunks go to the host threads; their size does not
+ * depend on the number of threads), the chunk values folded in order.  Not cryptographic: it guards against reading a
+ * different alignment as the cached one by accident, not against an adversary. */
+#define HASH_CHUNK ((size_t)1 << 20)
+typedef struct { const char *p; size_t len, nchunk; uint64_t *h; } hash_job;
+
+static inline uint64_t mix64(uint64_t x) { x ^= x >> 32; x *= 0xd6e8feb86659fd93ull; x ^= x >> 32; x *= 0xd6e8feb86659fd93ull; x ^= x >> 32; return x; }
+
+static void hash_worker(int tid, int nthreads, void *ctx)
+{
+    hash_job *job = ctx;
+    for (size_t c = (size_t)tid; c < job->nchunk; c += (size_t)nthreads) {
+        const char *p = job->p + c * HASH_CHUNK;
+        const size_t n = (c + 1 == job->nchunk) ? job->len - c * HASH_CHUNK : HASH_CHUNK;
+        uint64_t a = 0x9e3779b97f4a7c15ull ^ n, b = 0xc2b2ae3d27d4eb4full ^ (n << 1);
+        size_t i = 0;
+        for (; i + 8 <= n; i += 8) {
+            uint64_t w;
+            memcpy(&w, p + i, 8);
+            a = (a ^ w) * 0x100000001b3ull; a ^= a >> 29;
+            b = (b + w) * 0xff51afd7ed558ccdull; b ^= b >> 31;
+        }
+        uint64_t w = 0;
+        memcpy(&w, p + i, n - i);
+        a = (a ^ w) * 0x100000001b3ull; b = (b + w) * 0xff51afd7ed558ccdull;
+        job->h[2 * c] = mix64(a); job->h[2 * c + 1] = mix64(b);
+    }
+}
+
+static void text_hash(const char *p, size_t len, uint64_t *h1, uint64_t *h2)
+{
+    const size_t nchunk = (len + HASH_CHUNK - 1) / HASH_CHUNK;
+    uint64_t *h = malloc(sizeof(uint64_t) * 2 * (nchunk ? nchunk : 1));
+    *h1 = 0x243f6a8885a308d3ull ^ len; *h2 = 0x13198a2e03707344ull ^ len;
+    if (!h) { *h1 = *h2 = 0; return; }
+    hash_job job = {p, len, nchunk, h};
+    int nthreads = par_threads();
+    if ((size_t)nthreads > nchunk) nthreads = nchunk ? (int)nchunk : 1;
+    par_run(nthreads, hash_worker, &job);
+    for (size_t c = 0; c < nchunk; c++) {
+        *h1 = mix64(*h1 ^ h[2 * c]) + c;
+        *h2 = mix64(*h2 + h[2 * c + 1]) ^ (c << 7);
+    }
+    free(h);
+}
+
+/* the cached codes if the text at p (the matrix's opening bracket) is the text they were read from */
+static jv_codes *cache_probe(const char *p, const char *end)
+{
+    pthread_mutex_lock(&g_codes_lock);
+    jv_codes *d = g_codes_entry;
+    if (d) d->refs++;
+    pthread_mutex_unlock(&g_codes_lock);
+    if (!d) return NULL;
+    if ((size_t)(end - p) >= d->text_len && d->text_len >= 2 && p[d->text_len - 1] == ']') {
+        uint64_t h1, h2;
+        text_hash(p, d->text_len, &h1, &h2);
+        if (h1 == d->h1 && h2 == d->h2 && (h1 | h2) != 0) return d;
+    }
+    json_codes_release(d);
+    return NULL;
 }
 
 /*
@@ -315,7 +429,7 @@ static int parse_int_matrix(parser *ps, jv *out)
     }
     if ((size_t)nthreads > nclose / 64) nthreads = (int)(nclose / 64);
     if (nthreads < 1) nthreads = 1;
-    items = malloc((nclose + 1 + (size_t)nthreads) * sizeof(jv));
+    items = malloc((nclose + 4 + (size_t)nthreads) * sizeof(jv));
     blocks = calloc((size_t)nthreads, sizeof(jv *));
     events = calloc((size_t)nthreads, sizeof(row_event));
     if (!items || !blocks || !events) goto done;
@@ -353,12 +467,39 @@ done:
 
 static int parse_array(parser *ps, jv *out)
 {
+    const char *key = ps->key;
+    ps->key = NULL;             /* the items of this array are nobody's member */
     if (ps->depth < 2000 && (size_t)(ps->end - ps->p) >= MATRIX_MIN_BYTES) {
         const char *q = skip_ws_to(ps->p + 1);
         if (*q == '[') {
             const char *keep = ps->p;
+            const int is_data = key && !strcmp(key, "character_data") && !getenv("ARBPLF_NO_DATA_CACHE");
+            if (is_data) {
+                jv_codes *d = cache_probe(keep, ps->end);
+                if (d) {        /* the bytes of the matrix read last time: nothing to read */
+                    if (getenv("ARBPLF_JSON_TRACE")) fprintf(stderr, "json: character_data of %lld rows taken from the cache\n", (long long)d->rows);
+                    out->type = JV_ARRAY; out->flags = JV_F_COMPACT;
+                    out->len = d->rows > 0xffffffffLL ? 0xffffffffu : (uint32_t)d->rows;
+                    out->u.items = (jv *)d;
+                    ps->p = keep + d->text_len;
+                    return 0;
+                }
+            }
             ps->p = q;
-            if (parse_int_matrix(ps, out) == 0) return 0;
+            if (parse_int_matrix(ps, out) == 0) {
+                if (is_data) {
+                    /* remember what text this was: three hidden items behind the block list */
+                    jv *tail = out->u.items + out->len;
+                    jv *slot = tail + 1 + tail->len;
+                    uint64_t h1, h2;
+                    text_hash(keep, (size_t)(ps->p - keep), &h1, &h2);
+                    slot[0].type = slot[1].type = slot[2].type = JV_NULL;
+                    slot[0].flags = slot[1].flags = slot[2].flags = 0;
+                    slot[0].u.i = (int64_t)h1; slot[1].u.i = (int64_t)h2; slot[2].u.i = (int64_t)(ps->p - keep);
+                    out->flags |= JV_F_HASHED;
+                }
+                return 0;
+            }
             ps->p = keep;
         }
     }
@@ -441,7 +582,9 @@ static int parse_object(parser *ps, jv *out)
         if (*ps->p != ':') { free_contents(&items[2 * len]); fail(ps, "':' expected"); goto bad; }
         ps->p++;
         skip_ws(ps);
-        if (parse_value(ps, &items[2 * len + 1])) { free_contents(&items[2 * len]); goto bad; }
+        ps->key = items[2 * len].u.s;
+        if (parse_value(ps, &items[2 * len + 1])) { ps->key = NULL; free_contents(&items[2 * len]); goto bad; }
+        ps->key = NULL;
         /* jansson: a repeated key replaces the earlier value */
         {
             int dup = 0;
@@ -493,7 +636,7 @@ static int parse_value(parser *ps, jv *out)
 
 jv *json_parse(const char *text, char *err, size_t errlen)
 {
-    parser ps = {text, text, text + strlen(text), err, errlen, 0, 0};
+    parser ps = {text, text, text + strlen(text), err, errlen, 0, NULL, 0};
     if (err && errlen) err[0] = 0;
     jv *root = malloc(sizeof(jv));
     if (!root) { fail(&ps, "out of memory"); return NULL; }

@@ -21,7 +21,26 @@ enum { JV_NULL = 0, JV_FALSE, JV_TRUE, JV_INT, JV_REAL, JV_STRING, JV_ARRAY, JV_
 /* storage flags of an array (json.c only): a large matrix of short integers -- 'character_data' -- is read by several
  * threads into a few big blocks instead of one allocation per row */
 enum { JV_F_BORROWED = 1,         /* items live in a block owned by the enclosing array */
-       JV_F_BLOCKS = 2 };         /* items[len].len blocks follow the rows: items[len + 1 + t].u.items */
+       JV_F_BLOCKS = 2,           /* items[len].len blocks follow the rows: items[len + 1 + t].u.items */
+       JV_F_HASHED = 4,           /* with JV_F_BLOCKS: three more hidden items hold (h1, h2, length) of the matrix's text */
+       JV_F_COMPACT = 8 };        /* no items at all: u.items is a jv_codes (see below) */
+
+/*
+ * A process that calls arbplf_* again and again on one alignment (an optimiser varying the edge rates) sends the same
+ * 'character_data' text every time.  The reader keeps the codes of the last large 'character_data' matrix, keyed by a
+ * 128-bit hash of its text: when the same bytes come again the matrix is not read at all, its node says JV_F_COMPACT
+ * and carries the shared codes.  Only the consumer of 'character_data' (model.c) ever sees such a node; it also
+ * publishes the codes after a normal read (json_codes_publish).  ARBPLF_NO_DATA_CACHE=1 turns all of it off.
+ */
+typedef struct jv_codes {
+    void *codes;                  /* [rows][row_len], uint8 or int32 */
+    int code_bytes;
+    int64_t rows;
+    int row_len, max_code;
+    uint64_t h1, h2;              /* of the text the codes were read from */
+    size_t text_len;
+    int refs;                     /* holders: the cache, parsed documents, models, the driver's record of the upload */
+} jv_codes;
 
 typedef struct jv {
     uint8_t type;
@@ -47,6 +66,15 @@ static inline int jv_is_object(const jv *v) { return v && v->type == JV_OBJECT; 
 static inline int jv_is_null(const jv *v) { return v && v->type == JV_NULL; }
 static inline double jv_number(const jv *v) { return v->type == JV_INT ? (double)v->u.i : v->u.d; }
 const jv *jv_get(const jv *obj, const char *key);
+
+/* the shared codes of a JV_F_COMPACT node, or NULL */
+static inline jv_codes *jv_compact_codes(const jv *v) { return (v && v->type == JV_ARRAY && (v->flags & JV_F_COMPACT)) ? (jv_codes *)v->u.items : NULL; }
+/* 1 and the hash of its text if the array was read as a hashed matrix ('character_data', threaded reader) */
+int jv_matrix_text_hash(const jv *v, uint64_t *h1, uint64_t *h2, size_t *text_len);
+/* hands `codes` (malloc'd) to the cache under that hash; returns the shared record with one reference for the caller */
+jv_codes *json_codes_publish(uint64_t h1, uint64_t h2, size_t text_len, void *codes, int code_bytes, int64_t rows, int row_len, int max_code);
+void json_codes_retain(jv_codes *d);
+void json_codes_release(jv_codes *d);
 
 /*
  * json_unpack_ex(..., JSON_STRICT, "{s:o, s?o ...}") equivalent: keys is a

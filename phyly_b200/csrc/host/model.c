@@ -23,7 +23,8 @@ void plf_model_clear(plf_model *m)
 {
     free(m->indptr); free(m->indices); free(m->order); free(m->idx_to_user); free(m->preorder);
     free(m->rate_matrix); free(m->edge_rate_user); free(m->root_custom);
-    free(m->mix_rates); free(m->mix_prior); free(m->defs); free(m->codes);
+    free(m->mix_rates); free(m->mix_prior); free(m->defs);
+    if (m->codes_shared) json_codes_release(m->codes_shared); else free(m->codes);
     plf_model_init(m);
 }
 
@@ -259,7 +260,7 @@ finish:
 }
 
 /* one thread's share of parsemodel.c:590-615: rows [S tid / T, S (tid+1) / T) */
-typedef struct { int kind, actual; } cd_fault;
+typedef struct { int kind, actual, max_code; } cd_fault;
 typedef struct { const jv *rows; int64_t S; int N, K, wide; void *codes; cd_fault *faults; } cd_job;
 
 static void cd_worker(int tid, int nthreads, void *ctx)
@@ -280,6 +281,7 @@ static void cd_worker(int tid, int nthreads, void *ctx)
             if (y[j].u.i < 0) { f->kind = 4; return; }
             if (y[j].u.i >= job->K) { f->kind = 5; return; }
             if (job->wide) c32[j] = (int)y[j].u.i; else c8[j] = (unsigned char)y[j].u.i;
+            if ((int)y[j].u.i > f->max_code) f->max_code = (int)y[j].u.i;
         }
     }
 }
@@ -305,6 +307,35 @@ static int parse_character_data(plf_model *m, const jv *data, const jv *defs)
     /* rows -> codes, several threads for an alignment-sized matrix; the first offence in row-major order is the one
      * reported, as in the reference's single loop */
     const int wide = m->K > 256;
+    jv_codes *cached = jv_compact_codes(data);
+    if (cached) {
+        /* the reader recognised the text of the matrix read last time (json.h): every row is an array of row_len
+         * non-negative integers, the largest being max_code */
+        m->S = cached->rows;
+        if (m->S > 0 && cached->row_len != N) {
+            fprintf(stderr, "%s: failed to match the number of nodes: (actual: %d desired: %d)\n", name, cached->row_len, N);
+            return -1;
+        }
+        if (m->S > 0 && cached->max_code >= m->K) {
+            fprintf(stderr, "%s: character indices must each be less than the character count (%d)\n", name, m->K);
+            return -1;
+        }
+        if (cached->code_bytes == (wide ? 4 : 1)) {
+            json_codes_retain(cached);
+            m->codes = cached->codes; m->code_bytes = cached->code_bytes; m->codes_shared = cached;
+        } else {
+            /* the definitions crossed 256 rows since: same codes, other width */
+            const size_t cnt = (size_t)m->S * N;
+            void *conv = malloc((wide ? sizeof(int) : 1) * (cnt + 1));
+            if (!conv) { fprintf(stderr, "%s: out of memory\n", name); return -1; }
+            for (size_t i = 0; i < cnt; i++) {
+                const int v = cached->code_bytes == 1 ? ((const unsigned char *)cached->codes)[i] : ((const int *)cached->codes)[i];
+                if (wide) ((int *)conv)[i] = v; else ((unsigned char *)conv)[i] = (unsigned char)v;
+            }
+            m->codes = conv; m->code_bytes = wide ? 4 : 1;
+        }
+        return 0;
+    }
     const size_t total = (size_t)m->S * N;
     void *codes = malloc((wide ? sizeof(int) : 1) * (total + 1));
     if (!codes) { fprintf(stderr, "%s: out of memory\n", name); return -1; }
@@ -327,7 +358,10 @@ static int parse_character_data(plf_model *m, const jv *data, const jv *defs)
         free(faults); free(codes);
         return -1;
     }
+    int *faults_max = malloc(sizeof(int) * (size_t)nthreads);
+    for (int t = 0; faults_max && t < nthreads; t++) faults_max[t] = faults[t].max_code;
     free(faults);
+    if (!faults_max) { fprintf(stderr, "%s: out of memory\n", name); free(codes); return -1; }
     if (m->K == 0) {   /* only reachable with zero sites */
         free(m->defs);
         m->defs = malloc(sizeof(double) * (n > 0 ? n : 1));
@@ -335,6 +369,19 @@ static int parse_character_data(plf_model *m, const jv *data, const jv *defs)
         m->K = 1;
     }
     m->codes = codes; m->code_bytes = wide ? 4 : 1;
+    {
+        /* a large matrix whose text the reader has hashed: share the codes with the reader's cache, so that the same text
+         * in the next call costs neither reading nor conversion (nor, in drivers.c, an upload) */
+        uint64_t h1, h2;
+        size_t text_len;
+        if (m->S > 0 && jv_matrix_text_hash(data, &h1, &h2, &text_len)) {
+            int max_code = 0;
+            for (int t = 0; t < nthreads; t++) if (faults_max[t] > max_code) max_code = faults_max[t];
+            jv_codes *d = json_codes_publish(h1, h2, text_len, codes, m->code_bytes, m->S, N, max_code);
+            if (d) m->codes_shared = d;
+        }
+        free(faults_max);
+    }
     return 0;
 }
 

@@ -39,6 +39,7 @@ typedef struct {
     double *defs;          /* [K][n] */
     void *codes;           /* [S][N], uint8 if K <= 256 else int32 */
     int code_bytes;
+    struct jv_codes *codes_shared;   /* non-NULL: `codes` belongs to the reader's data cache (json.h); one reference held */
 } plf_model;
 
 void plf_model_init(plf_model *m);

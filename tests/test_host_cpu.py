@@ -292,6 +292,7 @@ def test_threaded_matrix_reader_matches_the_general_route(monkeypatch, capfd):
     want = _code_sums(codes)
     monkeypatch.setenv("ARBPLF_JSON_TRACE", "1")
     monkeypatch.setenv("ARBPLF_HOST_THREADS", "4")
+    monkeypatch.setenv("ARBPLF_NO_DATA_CACHE", "1")      # (the cache of the last character_data has its own test)
     capfd.readouterr()
     A.arbplf_model_summary(text)
     assert "json: matrix of 6000 rows read by 4 threads" in capfd.readouterr().err       # the route under test is taken
@@ -317,7 +318,7 @@ def test_threaded_matrix_reader_matches_the_general_route(monkeypatch, capfd):
     monkeypatch.setenv("ARBPLF_JSON_TRACE", "1")
     capfd.readouterr()
     s = json.loads(A.arbplf_model_summary(moved))
-    assert "json: matrix of 6000 rows" in capfd.readouterr().err
+    assert "json: matrix of 6000 rows read by" in capfd.readouterr().err
     monkeypatch.delenv("ARBPLF_JSON_TRACE")
     assert (s["codes_sum"], s["codes_weighted_sum"]) == want
     # a short document (general route) with the same rows gives the same bytes
@@ -395,3 +396,70 @@ def test_threaded_matrix_reader_steps_aside_for_anything_else():
         assert sb[k] == ss[k], k
     assert (sb["codes_sum"], sb["codes_weighted_sum"]) == _code_sums(c2)
     assert ok_edges["site_count"] == 6000
+
+
+def test_character_data_cache(monkeypatch, capfd):
+    """The reader keeps the codes of the last large character_data matrix under a hash of its text (host/json.h): the
+    same bytes in the next document are not read again, any other bytes are; what the model parser makes of a cached
+    matrix (node count, definition count) is checked like a freshly read one."""
+    import phyly_b200.arbplf as A
+    monkeypatch.delenv("ARBPLF_NO_DATA_CACHE", raising=False)
+    monkeypatch.setenv("ARBPLF_JSON_TRACE", "1")
+    text, codes = _big_document(5000, seed=11)
+    want = _code_sums(codes)
+
+    def summary(t):
+        capfd.readouterr()
+        out = json.loads(A.arbplf_model_summary(t))
+        return out, capfd.readouterr().err
+
+    s1, err1 = summary(text)
+    assert "read by" in err1 and "taken from the cache" not in err1
+    s2, err2 = summary(text)
+    assert "character_data of 5000 rows taken from the cache" in err2 and "read by" not in err2
+    assert s1 == s2 and (s2["codes_sum"], s2["codes_weighted_sum"]) == want
+    # other edge rates, same alignment: still the cached codes
+    doc = json.loads(text[:text.index('"character_data"')].rstrip(", ") + "}}")
+    rates = doc["model_and_data"]["edge_rate_coefficients"]
+    changed = text.replace(json.dumps(rates), json.dumps([r * 1.5 for r in rates]), 1)
+    assert changed != text
+    s3, err3 = summary(changed)
+    assert "taken from the cache" in err3
+    assert (s3["codes_sum"], s3["codes_weighted_sum"]) == want
+    assert s3["edge_rates_csr"] != s1["edge_rates_csr"]
+    # one code differs (same length): read afresh, and the earlier text is no longer the cached one
+    i = text.index("]]", text.index('"character_data"')) - 1
+    assert text[i] in "01234"
+    other = text[:i] + ("0" if text[i] != "0" else "1") + text[i + 1:]
+    codes2 = codes.copy()
+    codes2[-1, -1] = int(other[i])
+    s4, err4 = summary(other)
+    assert "read by" in err4 and "taken from the cache" not in err4
+    assert (s4["codes_sum"], s4["codes_weighted_sum"]) == _code_sums(codes2)
+    s5, err5 = summary(text)
+    assert "read by" in err5
+    assert (s5["codes_sum"], s5["codes_weighted_sum"]) == want
+    # a cached matrix against a tree with another node count / fewer definitions: the parser's own errors
+    s6, err6 = summary(text)
+    assert "taken from the cache" in err6
+    fewer_defs = text.replace(json.dumps(doc["model_and_data"]["character_definitions"]),
+                              json.dumps(doc["model_and_data"]["character_definitions"][:4]), 1)
+    assert fewer_defs != text
+    with pytest.raises(RuntimeError):
+        A.arbplf_model_summary(fewer_defs)
+    assert "less than the character count" in capfd.readouterr().err
+    summary(text)
+    import bench
+    doc_small, N_small = bench.model_document(20)
+    md = dict(doc_small["model_and_data"])
+    head = json.dumps({"model_and_data": md})
+    j = text.index('"character_data"')
+    k = text.index("]]", j) + 2
+    grafted = head[:head.index('"character_data"')] + text[j:k] + "}}"
+    with pytest.raises(RuntimeError):
+        A.arbplf_model_summary(grafted)
+    assert "failed to match the number of nodes" in capfd.readouterr().err
+    # switched off
+    monkeypatch.setenv("ARBPLF_NO_DATA_CACHE", "1")
+    s7, err7 = summary(text)
+    assert "taken from the cache" not in err7 and (s7["codes_sum"], s7["codes_weighted_sum"]) == want

@@ -374,3 +374,60 @@ def test_large_tables_are_written_by_several_threads_in_the_same_bytes(monkeypat
     want = O.run_ll({"model_and_data": md}, mode="fp64")
     for k, i in enumerate(idx):
         assert abs(fwd["data"][i][1] - want["data"][k][1]) <= 1e-11 * abs(want["data"][k][1])
+
+
+def test_repeated_calls_keep_the_alignment_on_the_device(monkeypatch, capfd):
+    """An optimiser's loop: the same large document again and again with other edge rates.  From the second call on the
+    reader recognises the character_data text (host/json.h) and the driver neither re-reads nor re-uploads it
+    (drivers.c:ctx_load); every answer is the text a cold process gives (ARBPLF_NO_DATA_CACHE=1)."""
+    import phyly_b200.arbplf as A
+    import bench
+    doc, N = bench.model_document(16)
+    S = 40000
+    rng = np.random.default_rng(12)
+    codes = rng.integers(0, 5, (S, N)).astype(np.uint8)
+    for a, b in doc["model_and_data"]["edges"]:
+        codes[:, a] = 4
+    text = bench.json_document_bytes(doc, codes).decode()
+    assert len(text) > (1 << 20)
+    rates = doc["model_and_data"]["edge_rate_coefficients"]
+
+    def variant(scale):
+        return text.replace(json.dumps(rates), json.dumps([r * scale for r in rates]), 1)
+
+    docs = [text, variant(1.25), variant(0.5), text]
+    monkeypatch.setenv("ARBPLF_NO_DATA_CACHE", "1")
+    cold = [A.arbplf_deriv(t) for t in docs]
+    cold_ll = A.arbplf_ll(docs[1].replace(', "site_reduction": {"aggregation": "sum"}', ""))
+    monkeypatch.delenv("ARBPLF_NO_DATA_CACHE")
+    monkeypatch.setenv("ARBPLF_JSON_TRACE", "1")
+    A.arbplf_deriv(docs[0])
+    capfd.readouterr()
+    for t, want in zip(docs, cold):
+        got = A.arbplf_deriv(t)
+        err = capfd.readouterr().err
+        assert "taken from the cache" in err and "no upload" in err
+        assert got == want
+    # another program on the same alignment, per-site output
+    got_ll = A.arbplf_ll(docs[1].replace(', "site_reduction": {"aggregation": "sum"}', ""))
+    assert "no upload" in capfd.readouterr().err
+    assert got_ll == cold_ll
+    # a different alignment in between, then the first one again: both are uploaded
+    codes2 = codes.copy()
+    codes2[:, -1] = (codes2[:, -1] + 1) % 4
+    text2 = bench.json_document_bytes(doc, codes2).decode()
+    monkeypatch.setenv("ARBPLF_NO_DATA_CACHE", "1")
+    want2 = A.arbplf_deriv(text2)
+    monkeypatch.delenv("ARBPLF_NO_DATA_CACHE")
+    capfd.readouterr()
+    assert A.arbplf_deriv(text2) == want2
+    assert "no upload" not in capfd.readouterr().err
+    assert A.arbplf_deriv(text) == cold[0]
+    assert "no upload" not in capfd.readouterr().err
+    assert A.arbplf_deriv(text) == cold[0]
+    assert "no upload" in capfd.readouterr().err
+    # a failed call in between forgets what the engine holds
+    with pytest.raises(RuntimeError):
+        A.arbplf_deriv(text.replace('"site_reduction": {"aggregation": "sum"}', '"site_reduction": {"aggregation": "nonsense"}'))
+    capfd.readouterr()
+    assert A.arbplf_deriv(text) == cold[0]
