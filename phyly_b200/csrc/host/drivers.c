@@ -880,7 +880,7 @@ static void *warm_engine(void *unused)
 int arbplf_run_stdio(char *(*f)(const char *, int *))
 {
     pthread_t warm;
-    const int warming = pthread_create(&warm, NULL, warm_engine, NULL) == 0;
+    const int warming = !getenv("ARBPLF_NO_WARMUP") && pthread_create(&warm, NULL, warm_engine, NULL) == 0;
     size_t cap = 1 << 16, len = 0;
     char *s = malloc(cap);
     if (!s) { if (warming) pthread_join(warm, NULL); return -1; }
