@@ -652,8 +652,8 @@ int plf_derive(plf_derived *d, const plf_model *m)
     memset(d, 0, sizeof(*d));
     const int n = m->n, C = plf_model_category_count(m), E = m->E;
     d->n = n; d->C = C; d->E = E;
-    d->cat_rates = calloc(C, sizeof(double));
-    d->cat_prior = calloc(C, sizeof(double));
+    d->cat_rates = calloc((size_t)(C > 0 ? C : 1), sizeof(double));
+    d->cat_prior = calloc((size_t)(C > 0 ? C : 1), sizeof(double));
     long double expect = 1;
     /* rate_mixture_summarize, rate_mixture.c:287-339 */
     if (m->mix_mode == MIX_NONE) { d->cat_rates[0] = 1; d->cat_prior[0] = 1; }
