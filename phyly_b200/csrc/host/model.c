@@ -687,13 +687,13 @@ int plf_derive(plf_derived *d, const plf_model *m)
     /* equilibrium, if needed */
     long double *pi = NULL;
     if (m->root_mode == PLF_ROOT_EQUILIBRIUM || m->use_eq_divisor) {
-        pi = malloc(sizeof(long double) * n);
+        pi = malloc(sizeof(long double) * (size_t)(n > 0 ? n : 1));
         if (equilibrium(pi, m->rate_matrix, n)) {
             fprintf(stderr, "error: the equilibrium distribution of the rate matrix is not uniquely defined\n");
             free(pi);
             return -1;
         }
-        d->equilibrium = malloc(sizeof(double) * n);
+        d->equilibrium = malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
         for (int i = 0; i < n; i++) d->equilibrium[i] = (double)pi[i];
     }
     /* rate divisor, cross_site_ws.c:174-191 */
