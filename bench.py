@@ -663,11 +663,15 @@ def run_ours(args):
     # ---- weak scaling beside it (N > 1 only): every rank owns a whole alignment of args.sites patterns ----
     weak = None
     if world > 1:
-        mw = measure(0, S_total, max(3, min(args.steps, 20)), False, False)
-        (ms_w,) = max_over_ranks([mw["ms"]])
+        mw = measure(0, S_total, max(3, min(args.steps, 20)), True, False)
+        ms_w, ms_w_e2e = max_over_ranks([mw["ms"], mw["ms_e2e"]])
         weak = {"scaling": "weak", "sites_per_gpu": S_total, "steps": mw["steps"], "ms_per_step": ms_w / mw["steps"],
                 "value": float(S_total) * Eg * C * world * mw["steps"] / (ms_w * 1e-3), "unit": "updates/s",
-                "kernel_ms": mw["kern_ms"]}
+                "kernel_ms": mw["kern_ms"],
+                "e2e": {"value": float(S_total) * Eg * C * world * mw["e2e_steps"] / (ms_w_e2e * 1e-3), "unit": "updates/s",
+                        "ms_per_step": ms_w_e2e / mw["e2e_steps"], "steps": mw["e2e_steps"],
+                        "h2d_bytes_per_step": int(S_total * row_bytes + 8 * S_total + 8 * Eg),
+                        "note": "every rank uploads a whole alignment every step; bytes are per GPU"}}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
