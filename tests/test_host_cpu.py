@@ -463,3 +463,23 @@ def test_character_data_cache(monkeypatch, capfd):
     monkeypatch.setenv("ARBPLF_NO_DATA_CACHE", "1")
     s7, err7 = summary(text)
     assert "taken from the cache" not in err7 and (s7["codes_sum"], s7["codes_weighted_sum"]) == want
+
+
+def test_pack4_layout():
+    """phyly_b200.engine.pack4 builds PLF_CODES_PACKED4 rows (include/plf.h): node 2j in the low, node 2j + 1 in the high
+    nibble of byte j, rows of (N + 1) // 2 bytes, for odd and even node counts; codes above 15 are refused."""
+    from phyly_b200.engine import pack4, CODES_PACKED4
+    assert CODES_PACKED4 == 0
+    rng = np.random.default_rng(4)
+    for N in (1, 2, 7, 8, 127):
+        codes = rng.integers(0, 16, (33, N)).astype(np.uint8)
+        p = pack4(codes)
+        assert p.shape == (33, (N + 1) // 2) and p.dtype == np.uint8
+        for nd in range(N):
+            assert np.array_equal((p[:, nd >> 1] >> ((nd & 1) * 4)) & 15, codes[:, nd])
+        if N % 2:
+            assert np.all(p[:, -1] >> 4 == 0)
+        out = np.empty_like(p)
+        assert pack4(codes, out=out) is out and np.array_equal(out, p)
+    with pytest.raises(ValueError):
+        pack4(np.array([[16, 0]], dtype=np.uint8))
