@@ -173,3 +173,77 @@ def test_relabelled_nodes_and_reordered_edges():
     ma = _values(O.run_marginal({"model_and_data": md}, mode="fp64")).reshape(S, N, 4)
     mb = _values(O.run_marginal({"model_and_data": new}, mode="fp64")).reshape(S, N, 4)
     assert np.allclose(mb[:, node_map, :], ma, rtol=1e-10, atol=1e-13)
+
+
+def _codon_problem(taxa=5, S=3, seed=3):
+    """61-state GY94-style model (bench.codon_model) on a small tree with observed codons at the leaves."""
+    import bench
+    Q, pi = bench.codon_model()
+    n = Q.shape[0]
+    edges, N = bench.yule_tree(taxa, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    defs = np.vstack([np.eye(n), np.ones((1, n))])
+    parents = {a for a, b in edges}
+    data = [[int(rng.integers(0, n)) if a not in parents else n for a in range(N)] for _ in range(S)]
+    return {"edges": edges, "edge_rate_coefficients": [float(x) for x in rng.exponential(0.1, len(edges))],
+            "rate_matrix": Q.tolist(), "root_prior": "equilibrium_distribution", "rate_divisor": "equilibrium_exit_rate",
+            "character_definitions": defs.tolist(), "character_data": data}, pi
+
+
+def test_codon_model_equilibrium_and_finite_differences():
+    """The cfg4 model family has no golden in the reference: the oracle's n-generic code is held to the model's
+    known equilibrium (F3x4 frequencies: the rate matrix is reversible by construction) and to finite differences."""
+    md, pi = _codon_problem()
+    m = O.parse_model(md)
+    be = O.get_backend("fp64")
+    cs = O.cross_site(m, be)
+    got_pi = np.array([float(x) for x in O.root_prior_vector(m, cs, be)])
+    assert np.allclose(got_pi, pi, rtol=1e-11)
+    doc = {"model_and_data": md, "site_reduction": {"aggregation": "sum"}}
+    grad = _values(O.run_deriv(doc, mode="fp64"))
+    t0 = list(md["edge_rate_coefficients"])
+    for e in (0, len(t0) // 2, len(t0) - 1):
+        h = 1e-5 * max(t0[e], 0.05)
+        vals = []
+        for sgn in (+1, -1):
+            t = list(t0)
+            t[e] += sgn * h
+            md["edge_rate_coefficients"] = t
+            vals.append(_values(O.run_ll(doc, mode="fp64"))[0])
+        md["edge_rate_coefficients"] = list(t0)
+        assert abs((vals[0] - vals[1]) / (2 * h) - grad[e]) <= 1e-6 * max(1.0, abs(grad[e]))
+    # marginals are distributions, leaves with an observed codon are certain
+    marg = O.run_marginal({"model_and_data": md}, mode="fp64")
+    S, N = len(md["character_data"]), len(md["character_data"][0])
+    mv = _values(marg).reshape(S, N, 61)
+    assert np.allclose(mv.sum(axis=2), 1.0, atol=1e-12)
+    for s in range(S):
+        for a in range(N):
+            code = md["character_data"][s][a]
+            if code < 61:
+                assert abs(mv[s, a, code] - 1.0) < 1e-12
+
+
+def test_twenty_state_mixture_equals_forty_state_block_model():
+    rng = np.random.default_rng(17)
+    n = 20
+    pi = rng.dirichlet(np.ones(n) * 3)
+    R = rng.random((n, n)) + 0.1
+    R = (R + R.T) / 2
+    Q = R * pi[None, :]
+    np.fill_diagonal(Q, 0.0)
+    md = _mixture_problem(53, n=4, ntips=5, S=3)
+    N = len(md["character_data"][0])
+    parents = {a for a, b in md["edges"]}
+    md["rate_matrix"] = Q.tolist()
+    md["root_prior"] = pi.tolist()
+    md["character_definitions"] = np.vstack([np.eye(n), np.ones((1, n))]).tolist()
+    md["character_data"] = [[int(rng.integers(0, n)) if a not in parents else n for a in range(N)] for _ in range(3)]
+    rates, prior = [0.5, 2.0], [0.6, 0.4]
+    mix = dict(md, rate_mixture={"rates": rates, "prior": prior})
+    blk = _block_model(md, rates, prior)
+    assert len(blk["rate_matrix"]) == 40
+    for run in (O.run_ll, O.run_deriv):
+        va = _values(run({"model_and_data": mix}, mode="fp64"))
+        vb = _values(run({"model_and_data": blk}, mode="fp64"))
+        assert np.allclose(va, vb, rtol=1e-10, atol=1e-12 * np.abs(vb).max())
